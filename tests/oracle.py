@@ -1,0 +1,234 @@
+"""ctypes front for oracle/libkatoracle.so — the CPU checker.
+
+Test infrastructure only (see the header of oracle/kat_oracle.c).  Imported by
+tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs; never by the
+product package `kat_b200`.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+REF_DIR = os.path.join(ORACLE_DIR, "_ref")
+REF_KAT = os.path.join(REF_DIR, "kat")
+REF_JELLYFISH = os.path.join(REF_DIR, "kat_jellyfish")
+REF_GENSEQ = os.path.join(REF_DIR, "generate_sequence")
+
+CC_NAMES = [
+    "hash1_total", "hash2_total", "hash3_total",
+    "hash1_distinct", "hash2_distinct", "hash3_distinct",
+    "hash1_only_total", "hash2_only_total",
+    "hash1_only_distinct", "hash2_only_distinct",
+    "shared_hash1_total", "shared_hash2_total", "shared_distinct",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    so = os.path.join(ORACLE_DIR, "libkatoracle.so")
+    src = os.path.join(ORACLE_DIR, "kat_oracle.c")
+    if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "libkatoracle.so"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(so)
+    u8p, u64p, vp = C.c_void_p, C.c_void_p, C.c_void_p
+    L.oracle_parse_file.restype = C.c_long
+    L.oracle_parse_file.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p]
+    L.oracle_table_new.restype = vp
+    L.oracle_table_new.argtypes = [C.c_int, C.c_int]
+    L.oracle_table_free.argtypes = [vp]
+    L.oracle_table_add.argtypes = [vp, u8p, C.c_size_t]
+    L.oracle_table_finish.argtypes = [vp]
+    L.oracle_table_distinct.restype = C.c_uint64
+    L.oracle_table_distinct.argtypes = [vp]
+    L.oracle_table_total.restype = C.c_uint64
+    L.oracle_table_total.argtypes = [vp]
+    L.oracle_table_export.argtypes = [vp, u64p, u64p]
+    L.oracle_lookup.restype = C.c_uint64
+    L.oracle_lookup.argtypes = [vp, C.c_uint64, C.c_int]
+    L.oracle_hist_geometry.argtypes = [C.c_uint64, C.c_uint64, u64p, u64p, u64p]
+    L.oracle_hist.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
+    L.oracle_gcp.argtypes = [vp, C.c_double, C.c_uint32, u64p]
+    L.oracle_comp.argtypes = [vp, vp, vp, C.c_double, C.c_double, C.c_uint32, C.c_uint32,
+                              u64p, u64p, u64p, u64p, u64p, u64p]
+    L.oracle_distances.argtypes = [u64p, u64p, C.c_size_t, C.c_void_p]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def parse_file(data: bytes, k: int, trim5p: int = 0):
+    """a1: file image -> (base stream bytes, status). status 0 ok, -1 unsupported
+    format, -2 invalid fastq (stream truncated as the reference does)."""
+    src = np.frombuffer(data, dtype=np.uint8)
+    out = np.empty(len(data) + 2, dtype=np.uint8)
+    r = lib().oracle_parse_file(_ptr(src) if len(data) else None, len(data), k, trim5p, _ptr(out))
+    if r == -1:
+        return b"", -1
+    if r <= -2:
+        return out[: -(r + 2)].tobytes(), -2
+    return out[:r].tobytes(), 0
+
+
+def parse_files(files, k, trim5p=None):
+    """Whole input group -> list of per-file base streams (single-producer
+    semantics: an invalid FASTQ ends the group, cooperative_pool2.hpp:249-260)."""
+    trim5p = trim5p or [0] * len(files)
+    if len(trim5p) == 1 and len(files) > 1:
+        trim5p = trim5p * len(files)
+    chunks = []
+    for path, t in zip(files, trim5p):
+        if isinstance(path, (bytes, bytearray)):
+            data = bytes(path)
+        else:
+            import gzip
+            with open(path, "rb") as f:
+                data = f.read()
+            if data[:2] == b"\x1f\x8b":
+                data = gzip.decompress(data)
+        s, st = parse_file(data, k, t)
+        if st == -1:
+            break
+        chunks.append(s)
+        if st == -2:
+            break
+    return chunks
+
+
+class Table:
+    """Exact k-mer multiset (sorted keys + counts)."""
+
+    def __init__(self, k, canonical=True):
+        self.k, self.canonical = k, bool(canonical)
+        self.h = lib().oracle_table_new(k, int(canonical))
+        if not self.h:
+            raise ValueError("k out of range")
+        self._done = False
+
+    def add(self, bases: bytes):
+        a = np.frombuffer(bases, dtype=np.uint8)
+        if len(a):
+            lib().oracle_table_add(self.h, _ptr(a), len(a))
+        return self
+
+    def finish(self):
+        if not self._done:
+            lib().oracle_table_finish(self.h)
+            self._done = True
+        return self
+
+    @classmethod
+    def from_chunks(cls, chunks, k, canonical=True):
+        t = cls(k, canonical)
+        for c in chunks:
+            t.add(c)
+        return t.finish()
+
+    @classmethod
+    def from_files(cls, files, k, canonical=True, trim5p=None):
+        return cls.from_chunks(parse_files(files, k, trim5p), k, canonical)
+
+    @property
+    def distinct(self):
+        return int(lib().oracle_table_distinct(self.h))
+
+    @property
+    def total(self):
+        return int(lib().oracle_table_total(self.h))
+
+    def export(self):
+        n = self.distinct
+        keys = np.empty(n, dtype=np.uint64)
+        counts = np.empty(n, dtype=np.uint64)
+        lib().oracle_table_export(self.h, _ptr(keys), _ptr(counts))
+        return keys, counts
+
+    def lookup(self, key, canonicalise=False):
+        return int(lib().oracle_lookup(self.h, int(key), int(canonicalise)))
+
+    def hist(self, low=1, high=10000, inc=1):
+        b, c, n = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        lib().oracle_hist_geometry(low, high, C.byref(b), C.byref(c), C.byref(n))
+        bins = np.zeros(n.value, dtype=np.uint64)
+        lib().oracle_hist(self.h, b.value, c.value, inc, n.value, _ptr(bins))
+        return b.value, bins
+
+    def gcp(self, cvg_scale=1.0, cvg_bins=1000):
+        mx = np.zeros((self.k, cvg_bins + 1), dtype=np.uint64)
+        lib().oracle_gcp(self.h, cvg_scale, cvg_bins, _ptr(mx))
+        return mx
+
+    def __del__(self):
+        try:
+            if self.h:
+                lib().oracle_table_free(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+def comp(t1, t2, t3=None, d1_scale=1.0, d2_scale=1.0, d1_bins=1001, d2_bins=1001):
+    n = min(d1_bins, d2_bins)
+    main = np.zeros((d1_bins, d2_bins), dtype=np.uint64)
+    extra = [np.zeros((d1_bins, d2_bins), dtype=np.uint64) for _ in range(3)] if t3 else [None] * 3
+    counters = np.zeros(13, dtype=np.uint64)
+    spectra = np.zeros((4, n), dtype=np.uint64)
+    lib().oracle_comp(t1.h, t2.h, t3.h if t3 else None, d1_scale, d2_scale, d1_bins, d2_bins,
+                      _ptr(main), *[(_ptr(e) if e is not None else None) for e in extra],
+                      _ptr(counters), _ptr(spectra))
+    return {"main": main, "ends": extra[0], "middle": extra[1], "mixed": extra[2],
+            "counters": dict(zip(CC_NAMES, (int(x) for x in counters))), "spectra": spectra}
+
+
+def distances(s1, s2):
+    s1 = np.ascontiguousarray(s1, dtype=np.uint64)
+    s2 = np.ascontiguousarray(s2, dtype=np.uint64)
+    out = np.zeros(5, dtype=np.float64)
+    lib().oracle_distances(_ptr(s1), _ptr(s2), len(s1), _ptr(out))
+    return out
+
+
+def have_ref():
+    return os.access(REF_KAT, os.X_OK)
+
+
+def run_ref(args, cwd=None, timeout=3600):
+    """Run the unmodified reference `kat` (oracle/_ref/kat)."""
+    return subprocess.run([REF_KAT] + list(args), cwd=cwd, stdout=subprocess.PIPE,
+                          stderr=subprocess.STDOUT, timeout=timeout, text=True)
+
+
+def read_hist(path):
+    """.hist body -> (labels, values) numpy arrays."""
+    lab, val = [], []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#") or not line.strip():
+                continue
+            a, b = line.split()
+            lab.append(int(a)); val.append(int(b))
+    return np.array(lab, dtype=np.uint64), np.array(val, dtype=np.uint64)
+
+
+def read_mx(path):
+    """.mx -> (header dict, matrix)."""
+    hdr, rows = {}, []
+    with open(path) as f:
+        for line in f:
+            if line.startswith("#"):
+                if ":" in line:
+                    k, v = line[1:].split(":", 1)
+                    hdr[k.strip()] = v.strip()
+                continue
+            if line.strip():
+                rows.append(np.array(line.split(), dtype=np.uint64))
+    return hdr, np.vstack(rows) if rows else np.zeros((0, 0), dtype=np.uint64)
