@@ -1,0 +1,215 @@
+/*
+ * katgpu.h — C-ABI of libkatgpu, the Blackwell (sm_100a) k-mer spectra engine
+ * that replaces the counting + histogram hot path behind `kat hist`,
+ * `kat gcp` and `kat comp` (TGAC/KAT 2.4.2).
+ *
+ * The reference has no FFI for this path: the seam is the C++ class boundary
+ * between libkat's InputHandler/JellyfishHelper (producer of the hash) and the
+ * three tools' *Slice workers (consumers).  Each entry point below names the
+ * reference interface it replaces (file:line relative to the KAT tree;
+ * JFI = deps/jellyfish-2.2.0/include/jellyfish).  INTEGRATION.md shows the
+ * binding a KAT maintainer would add.
+ *
+ * Conventions: plain C; opaque handles; every call returns a katgpu_status
+ * (0 = ok, < 0 = error) and leaves a human-readable message for
+ * katgpu_last_error() (thread-local) — no exception crosses the ABI.  The
+ * caller owns all output buffers (row-major uint64_t, host memory unless the
+ * name says _device).  The library owns device memory and streams.  One
+ * in-flight call per context; one context per GPU per process.  There is NO
+ * CPU fallback: without a CUDA device katgpu_init fails with
+ * KATGPU_ERR_NO_DEVICE.
+ */
+#ifndef KATGPU_H
+#define KATGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KATGPU_VERSION 100 /* 0.1.0 */
+
+typedef int katgpu_status;
+enum {
+    KATGPU_OK = 0,
+    KATGPU_ERR_INVALID = -1,   /* bad argument (k out of 1..32, null pointer, ...)      */
+    KATGPU_ERR_CUDA = -2,      /* CUDA runtime error, text in katgpu_last_error()       */
+    KATGPU_ERR_HASH_FULL = -3, /* table full and growth disabled: the reference's
+                                  std::runtime_error("Hash full"), JFI/hash_counter.hpp:199 */
+    KATGPU_ERR_NOMEM = -4,     /* device or host allocation failed                      */
+    KATGPU_ERR_NO_DEVICE = -5, /* no CUDA device: the product has no CPU path           */
+    KATGPU_ERR_STATE = -6,     /* call made in the wrong state (feed after end, ...)    */
+    KATGPU_ERR_OVERFLOW = -7   /* internal side table exhausted (count-overflow keys)   */
+};
+
+typedef struct katgpu_ctx katgpu_ctx;     /* one GPU: device, streams, staging buffers */
+typedef struct katgpu_table katgpu_table; /* one counted input: replaces the pair
+                                             HashCounter + LargeHashArrayPtr held by
+                                             InputHandler (lib/include/kat/input_handler.hpp:53-55) */
+
+/* Last error text of the calling thread ("" if none). */
+const char *katgpu_last_error(void);
+int katgpu_version(void);
+/* Number of visible CUDA devices (0 when there is no driver/GPU). */
+int katgpu_device_count(void);
+
+/* Context on CUDA device `device` (ordinal as CUDA sees it). */
+katgpu_status katgpu_init(int device, katgpu_ctx **out);
+void katgpu_shutdown(katgpu_ctx *ctx);
+
+/* Pinned host memory for callers that want full PCIe rate on katgpu_count_feed. */
+katgpu_status katgpu_host_alloc(size_t bytes, void **out);
+void katgpu_host_free(void *p);
+
+/* ---- counting: replaces InputHandler::count (lib/src/input_handler.cc:180-202),
+ * i.e. `new HashCounter(hashSize, 2k, 7, threads)` + JellyfishHelper::countSeqFile /
+ * countSlice (lib/src/jellyfish_helper.cc:219-246, 202-211) with its
+ * mer_iterator (JFI/mer_iterator.hpp:59-89) and hash_counter::add
+ * (JFI/hash_counter.hpp:98-130).
+ *
+ *   k              mer length, 1..32 (one 64-bit word; mer_dna::k, jellyfish_helper.cc:229)
+ *   canonical      count min(m, revcomp(m)) (InputHandler::canonical)
+ *   hash_size      initial number of table slots, rounded up to a power of two
+ *                  (InputHandler::hashSize, `-H`, default 1e8)
+ *   allow_grow     0 = the reference's --disable_hash_grow: a full table is
+ *                  KATGPU_ERR_HASH_FULL; 1 = double and rehash
+ *                  (hash_counter::double_size, JFI/hash_counter.hpp:204-244)
+ */
+katgpu_status katgpu_count_begin(katgpu_ctx *ctx, int k, int canonical, uint64_t hash_size,
+                                 int allow_grow, katgpu_table **out);
+
+/* Feed `n` bytes of base stream — exactly what the reference parser hands to
+ * mer_iterator (JFI/mer_overlap_sequence_parser.hpp:189-246): sequence
+ * characters with one 'N' between records.  A/a C/c G/g T/t are bases; every
+ * other byte breaks the k-mer run (JFI/mer_dna.hpp:46-63).  No k-mer spans two
+ * calls (the reference never spans two files, :149).  `bases` is HOST memory;
+ * the host->device copies are pipelined inside the call. */
+katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n);
+/* Same, for a stream already resident in device memory (16-byte aligned). */
+katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *bases_dev, size_t n);
+/* Finish counting (hash_counter::done, JFI/hash_counter.hpp:173-176).
+ * n_distinct / n_total (k-mer instances) may be NULL. */
+katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct, uint64_t *n_total);
+void katgpu_table_free(katgpu_table *t);
+
+/* ---- table walks ------------------------------------------------------------ */
+
+/* Histogram::binSlice + merge (src/histogram.cc:183-199, 146-160): for every
+ * distinct k-mer with count v: v < base -> bin 0; v > ceil -> bin nb-1; else
+ * bin (v-base)/inc.  bins_out[nb_buckets]. */
+katgpu_status katgpu_hist(katgpu_table *t, uint64_t base, uint64_t ceil, uint64_t inc,
+                          uint64_t nb_buckets, uint64_t *bins_out);
+
+/* Gcp::analyseSlice + merge (src/gcp.cc:179-197): mx_out[k][cvg_bins+1],
+ * row = #G+#C of the stored k-mer, col = min(ceil(count*cvg_scale), cvg_bins).
+ * k-mers with GC == k fall outside the k rows and are dropped, as the
+ * reference's ThreadedSparseMatrix(k, ...) does (src/gcp.cc:93,
+ * lib/include/kat/sparse_matrix.hpp:324-335). */
+katgpu_status katgpu_gcp(katgpu_table *t, double cvg_scale, uint32_t cvg_bins, uint64_t *mx_out);
+
+/* Comp::compareSlice + merge (src/comp.cc:387-484) with the CompCounters update
+ * rules (lib/src/comp_counters.cc:91-140).  t3 may be NULL (2-input mode); then
+ * ends/middle/mixed may be NULL.  Matrices are [d1_bins][d2_bins]; spectra are
+ * 4 arrays of min(d1_bins,d2_bins): spectrum1, spectrum2, shared_spectrum1,
+ * shared_spectrum2. */
+typedef struct katgpu_comp_counters {
+    uint64_t hash1_total, hash2_total, hash3_total;
+    uint64_t hash1_distinct, hash2_distinct, hash3_distinct;
+    uint64_t hash1_only_total, hash2_only_total;
+    uint64_t hash1_only_distinct, hash2_only_distinct;
+    uint64_t shared_hash1_total, shared_hash2_total, shared_distinct;
+} katgpu_comp_counters;
+
+katgpu_status katgpu_comp(katgpu_table *t1, katgpu_table *t2, katgpu_table *t3, double d1_scale,
+                          double d2_scale, uint32_t d1_bins, uint32_t d2_bins, uint64_t *main_mx,
+                          uint64_t *ends_mx, uint64_t *middle_mx, uint64_t *mixed_mx,
+                          katgpu_comp_counters *counters, uint64_t *spectra);
+
+/* JellyfishHelper::getCount (lib/src/jellyfish_helper.cc:189-194): counts_out[i]
+ * = count of keys[i] (2 bits per base, first base most significant, as
+ * jellyfish::mer_dna packs them), 0 if absent; the probe key is replaced by
+ * min(key, revcomp) iff canonicalise. */
+katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, size_t n, int canonicalise,
+                            uint64_t *counts_out);
+
+/* Every (key, count) of the table, unordered: what region_slice/eager_slice
+ * iteration yields (JFI/large_hash_array.hpp:487-503,
+ * JFI/large_hash_iterator.hpp:56-64,194-206).  Writes at most `cap` pairs and
+ * returns the total number of distinct k-mers in *n_out. */
+katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t *counts_out,
+                                  size_t cap, uint64_t *n_out);
+
+/* ---- table introspection / multi-GPU plumbing ---------------------------------- */
+
+typedef struct katgpu_table_info {
+    int k, canonical;
+    uint64_t slots;        /* current capacity                                  */
+    uint64_t bytes;        /* device bytes held by the table                     */
+    uint64_t n_distinct, n_total;
+    uint32_t count_bits;   /* width of the in-slot count field                   */
+    uint32_t grow_events;  /* number of doublings so far                          */
+    uint64_t overflow_keys;/* keys whose count left the in-slot field             */
+} katgpu_table_info;
+katgpu_status katgpu_table_get_info(katgpu_table *t, katgpu_table_info *out);
+
+/* Testing hook: cap the in-slot count field to `bits` (>=2) for tables created
+ * afterwards, to exercise the exact-overflow side table at small sizes.  0 = auto. */
+void katgpu_debug_set_count_bits(int bits);
+
+/* Multi-GPU (one process per GPU).  Every distinct k-mer must be owned by
+ * exactly one rank before histograms become additive:
+ *   1. katgpu_route_device: extract + canonicalise + hash this rank's base
+ *      stream and write each k-mer's 64-bit hashed key into the bucket of its
+ *      owner rank: out_dev[r] (device pointers, possibly peer-mapped memory of
+ *      rank r) with capacity cap_keys each; counts_out[r] = keys written.
+ *   2. the caller exchanges the buckets (NCCL all-to-all or peer writes);
+ *   3. katgpu_insert_hashed_device inserts received hashed keys.
+ * After that hist/gcp/comp outputs of the ranks add up (one all-reduce). */
+katgpu_status katgpu_route_device(katgpu_table *t, const void *bases_dev, size_t n, int n_ranks,
+                                  void *const *out_dev, uint64_t cap_keys, uint64_t *counts_out);
+katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void *hashed_dev, uint64_t n);
+/* CUDA IPC export/import of a device buffer (64-byte handle), so that rank r's
+ * receive bucket can be written directly over NVLink by its peers. */
+katgpu_status katgpu_device_alloc(katgpu_ctx *ctx, size_t bytes, void **out_dev);
+void katgpu_device_free(katgpu_ctx *ctx, void *dev);
+katgpu_status katgpu_ipc_export(void *dev, void *handle64);
+katgpu_status katgpu_ipc_import(const void *handle64, void **out_dev);
+void katgpu_ipc_close(void *dev);
+katgpu_status katgpu_synchronize(katgpu_ctx *ctx);
+
+/* ---- measurement ------------------------------------------------------------ */
+
+/* Kernel launches issued by this context since creation (bench `gpu_launches`). */
+uint64_t katgpu_launch_count(katgpu_ctx *ctx);
+/* Per-kernel CUDA-event timing on the library's own stream.  enable=1 starts
+ * recording (and clears), katgpu_profile_get returns accumulated milliseconds
+ * and launch count for a kernel family: "count", "hist", "gcp", "comp",
+ * "route", "insert", "memset". */
+katgpu_status katgpu_profile_enable(katgpu_ctx *ctx, int enable);
+katgpu_status katgpu_profile_get(katgpu_ctx *ctx, const char *family, double *ms_total,
+                                 uint64_t *launches);
+
+/* Deterministic synthetic reads: genome of `genome_len`
+ * i.i.d. bases from seed_g; read i is a `read_len` substring at a uniform
+ * position, strand uniform, per-base substitution rate sub_rate, per-base N
+ * rate n_rate, all drawn from a counter-based RNG keyed by (seed_r, i) so any
+ * shard [first_read, first_read+n_reads) is reproducible on its own.  Output
+ * is the base stream (read, 'N', read, 'N', ...), n_reads*(read_len+1) bytes,
+ * into device memory (katgpu_synth_reads_device) or host memory
+ * (katgpu_synth_reads_host: same bytes, computed on the CPU, for the oracle). */
+katgpu_status katgpu_synth_reads_device(katgpu_ctx *ctx, uint64_t genome_len, uint64_t seed_g,
+                                        uint64_t seed_r, uint64_t first_read, uint64_t n_reads,
+                                        uint32_t read_len, double sub_rate, double n_rate,
+                                        void *out_dev);
+katgpu_status katgpu_synth_reads_host(uint64_t genome_len, uint64_t seed_g, uint64_t seed_r,
+                                      uint64_t first_read, uint64_t n_reads, uint32_t read_len,
+                                      double sub_rate, double n_rate, char *out);
+katgpu_status katgpu_memcpy_d2h(katgpu_ctx *ctx, void *dst_host, const void *src_dev, size_t n);
+katgpu_status katgpu_memcpy_h2d(katgpu_ctx *ctx, void *dst_dev, const void *src_host, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KATGPU_H */

@@ -1,0 +1,871 @@
+// katgpu_api.cu — C-ABI of libkatgpu (include/katgpu.h): contexts, table
+// lifetime (allocation, admission control, doubling), the host->device feed
+// pipeline and the launch glue around the kernels.
+#include "../../include/katgpu.h"
+#include "count_kernels.cuh"
+#include "reduce_kernels.cuh"
+#include "synth.cuh"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace katgpu;
+
+static thread_local char g_err[512] = "";
+static int g_debug_count_bits = 0;
+
+static katgpu_status fail(katgpu_status st, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return st;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(e__ == cudaErrorMemoryAllocation ? KATGPU_ERR_NOMEM : KATGPU_ERR_CUDA, "%s: %s (%s:%d)", \
+                        #call, cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
+    } while (0)
+#define KT(call)                          \
+    do {                                  \
+        katgpu_status s__ = (call);       \
+        if (s__ != KATGPU_OK) return s__; \
+    } while (0)
+
+struct ProfSpan {
+    std::string family;
+    cudaEvent_t a, b;
+};
+
+struct katgpu_ctx {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    int bps[2] = {1, 1}; // resident CTAs per SM of the extract kernels
+    unsigned int *tile_counter = nullptr; // device
+    unsigned long long *route_cursors = nullptr; // device [kMaxRanks] + overflow flag after
+    // host feed staging
+    uint8_t *chunk[2] = {nullptr, nullptr};
+    size_t chunk_cap = 0;
+    cudaEvent_t chunk_free[2] = {nullptr, nullptr}, chunk_ready[2] = {nullptr, nullptr};
+    TableCounters *h_ctr = nullptr; // pinned mirror
+    uint64_t launches = 0;
+    bool profiling = false;
+    std::vector<ProfSpan> spans;
+    std::map<std::string, std::pair<double, uint64_t>> prof;
+};
+
+struct katgpu_table {
+    katgpu_ctx *ctx = nullptr;
+    TableGeom g{};
+    uint64_t n_slots = 0;
+    bool allow_grow = true, ended = false;
+    uint32_t grow_events = 0;
+    int count_bits_cap = 0;
+    uint64_t n_total_carry = 0; // not used: n_total lives in the device counter block
+};
+
+static const size_t kChunkBytes = 128u << 20; // host feed granularity
+static const uint64_t kSpillCap = 1u << 20;   // (hashed key, count) pairs
+
+// ---- profiling helpers ----
+struct ProfScope {
+    katgpu_ctx *c;
+    cudaStream_t st;
+    ProfSpan sp;
+    bool on;
+    ProfScope(katgpu_ctx *ctx, const char *family, cudaStream_t s) : c(ctx), st(s), on(ctx->profiling) {
+        if (on) {
+            sp.family = family;
+            cudaEventCreate(&sp.a);
+            cudaEventCreate(&sp.b);
+            cudaEventRecord(sp.a, st);
+        }
+    }
+    ~ProfScope() {
+        if (on) {
+            cudaEventRecord(sp.b, st);
+            c->spans.push_back(sp);
+        }
+    }
+};
+static void prof_collect(katgpu_ctx *c) {
+    for (auto &sp : c->spans) {
+        cudaEventSynchronize(sp.b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, sp.a, sp.b);
+        auto &e = c->prof[sp.family];
+        e.first += ms;
+        e.second += 1;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    c->spans.clear();
+}
+
+// ---- basics ----
+extern "C" const char *katgpu_last_error(void) { return g_err; }
+extern "C" int katgpu_version(void) { return KATGPU_VERSION; }
+extern "C" int katgpu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+extern "C" void katgpu_debug_set_count_bits(int bits) { g_debug_count_bits = bits; }
+
+extern "C" katgpu_status katgpu_init(int device, katgpu_ctx **out) {
+    if (!out) return fail(KATGPU_ERR_INVALID, "katgpu_init: out is NULL");
+    *out = nullptr;
+    int n = katgpu_device_count();
+    if (n <= 0)
+        return fail(KATGPU_ERR_NO_DEVICE, "katgpu_init: no CUDA device visible; libkatgpu has no CPU path");
+    if (device < 0 || device >= n) return fail(KATGPU_ERR_INVALID, "katgpu_init: device %d out of range (%d devices)", device, n);
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10)
+        return fail(KATGPU_ERR_NO_DEVICE, "katgpu_init: device %d is sm_%d%d; libkatgpu is built for sm_100a only", device,
+                    prop.major, prop.minor);
+    katgpu_ctx *c = new (std::nothrow) katgpu_ctx();
+    if (!c) return fail(KATGPU_ERR_NOMEM, "katgpu_init: out of host memory");
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CU(extract_configure(kModeInsert, &c->bps[0]));
+    CU(extract_configure(kModeRoute, &c->bps[1]));
+    if (c->bps[0] < 1 || c->bps[1] < 1) return fail(KATGPU_ERR_CUDA, "katgpu_init: extract kernel does not fit on an SM");
+    CU(cudaMalloc(&c->tile_counter, 256));
+    CU(cudaMalloc(&c->route_cursors, 256));
+    CU(cudaMallocHost(&c->h_ctr, sizeof(TableCounters)));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&c->chunk_free[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c->chunk_ready[i], cudaEventDisableTiming));
+    }
+    *out = c;
+    return KATGPU_OK;
+}
+
+extern "C" void katgpu_shutdown(katgpu_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->copy_stream);
+    prof_collect(c);
+    for (int i = 0; i < 2; i++) {
+        if (c->chunk[i]) cudaFree(c->chunk[i]);
+        if (c->chunk_free[i]) cudaEventDestroy(c->chunk_free[i]);
+        if (c->chunk_ready[i]) cudaEventDestroy(c->chunk_ready[i]);
+    }
+    if (c->tile_counter) cudaFree(c->tile_counter);
+    if (c->route_cursors) cudaFree(c->route_cursors);
+    if (c->h_ctr) cudaFreeHost(c->h_ctr);
+    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->copy_stream);
+    delete c;
+}
+
+extern "C" katgpu_status katgpu_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(KATGPU_ERR_INVALID, "katgpu_host_alloc: out is NULL");
+    CU(cudaMallocHost(out, bytes ? bytes : 1));
+    return KATGPU_OK;
+}
+extern "C" void katgpu_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+extern "C" katgpu_status katgpu_device_alloc(katgpu_ctx *c, size_t bytes, void **out) {
+    if (!c || !out) return fail(KATGPU_ERR_INVALID, "katgpu_device_alloc: NULL argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMalloc(out, bytes ? bytes : 1));
+    return KATGPU_OK;
+}
+extern "C" void katgpu_device_free(katgpu_ctx *c, void *dev) {
+    if (c) cudaSetDevice(c->device);
+    if (dev) cudaFree(dev);
+}
+extern "C" katgpu_status katgpu_ipc_export(void *dev, void *handle64) {
+    if (!dev || !handle64) return fail(KATGPU_ERR_INVALID, "katgpu_ipc_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle is 64 bytes");
+    CU(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle64), dev));
+    return KATGPU_OK;
+}
+extern "C" katgpu_status katgpu_ipc_import(const void *handle64, void **out) {
+    if (!handle64 || !out) return fail(KATGPU_ERR_INVALID, "katgpu_ipc_import: NULL argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    CU(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return KATGPU_OK;
+}
+extern "C" void katgpu_ipc_close(void *dev) {
+    if (dev) cudaIpcCloseMemHandle(dev);
+}
+extern "C" katgpu_status katgpu_synchronize(katgpu_ctx *c) {
+    if (!c) return fail(KATGPU_ERR_INVALID, "katgpu_synchronize: NULL context");
+    CU(cudaStreamSynchronize(c->copy_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KATGPU_OK;
+}
+extern "C" katgpu_status katgpu_memcpy_d2h(katgpu_ctx *c, void *dst, const void *src, size_t n) {
+    if (!c) return fail(KATGPU_ERR_INVALID, "katgpu_memcpy_d2h: NULL context");
+    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KATGPU_OK;
+}
+extern "C" katgpu_status katgpu_memcpy_h2d(katgpu_ctx *c, void *dst, const void *src, size_t n) {
+    if (!c) return fail(KATGPU_ERR_INVALID, "katgpu_memcpy_h2d: NULL context");
+    CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KATGPU_OK;
+}
+extern "C" uint64_t katgpu_launch_count(katgpu_ctx *c) { return c ? c->launches : 0; }
+extern "C" katgpu_status katgpu_profile_enable(katgpu_ctx *c, int enable) {
+    if (!c) return fail(KATGPU_ERR_INVALID, "katgpu_profile_enable: NULL context");
+    CU(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    c->prof.clear();
+    c->profiling = enable != 0;
+    return KATGPU_OK;
+}
+extern "C" katgpu_status katgpu_profile_get(katgpu_ctx *c, const char *family, double *ms, uint64_t *launches) {
+    if (!c || !family) return fail(KATGPU_ERR_INVALID, "katgpu_profile_get: NULL argument");
+    CU(cudaStreamSynchronize(c->stream));
+    prof_collect(c);
+    auto it = c->prof.find(family);
+    if (ms) *ms = it == c->prof.end() ? 0.0 : it->second.first;
+    if (launches) *launches = it == c->prof.end() ? 0 : it->second.second;
+    return KATGPU_OK;
+}
+
+// ---- table geometry ----
+static uint64_t inv_mod_2_64(uint64_t a) { // Newton iteration, a odd
+    uint64_t x = a;
+    for (int i = 0; i < 6; i++) x *= 2 - a * x;
+    return x;
+}
+static int ceil_log2(uint64_t v) {
+    int l = 0;
+    while (l < 63 && (1ULL << l) < v) l++;
+    return l;
+}
+
+// Fill every field of g except the pointers.  Lb = log2(buckets).
+static katgpu_status make_geom(int k, int canonical, int Lb, int count_bits_cap, TableGeom &g) {
+    const int b = 2 * k;
+    if (Lb > b) Lb = b;
+    if (Lb < 1) Lb = 1;
+    const int rbits = b - Lb;
+    int cbits = 64 - (rbits + kProbeBits + 1);
+    if (count_bits_cap >= 2 && count_bits_cap < cbits) cbits = count_bits_cap;
+    if (cbits < 2) return fail(KATGPU_ERR_INVALID, "table geometry: no room for a count field (k=%d, Lb=%d)", k, Lb);
+    g.k = k;
+    g.b = b;
+    g.Lb = Lb;
+    g.rbits = rbits;
+    g.cbits = cbits;
+    g.cshift = 64 - cbits;
+    g.sh = (b + 1) / 2;
+    g.canonical = canonical ? 1 : 0;
+    g.rmask = rbits ? ((1ULL << rbits) - 1) : 0;
+    g.tagmask = (1ULL << (rbits + kProbeBits)) - 1;
+    g.kmask = b == 64 ? ~0ULL : ((1ULL << b) - 1);
+    g.bmask = (1ULL << Lb) - 1;
+    g.cmax = (1ULL << cbits) - 1;
+    g.m1inv = inv_mod_2_64(kMixM1);
+    g.m2inv = inv_mod_2_64(kMixM2);
+    g.spill_cap = kSpillCap;
+    return KATGPU_OK;
+}
+// Smallest Lb that leaves a count field of at least 16 bits (so that count
+// overflow into the side table is rare), and at least 2^10 buckets.
+static int min_Lb(int k) {
+    const int b = 2 * k;
+    int lb = b - (64 - kProbeBits - 1 - 16);
+    if (lb < 10) lb = 10;
+    if (lb > b) lb = b;
+    return lb;
+}
+
+static katgpu_status alloc_table_storage(katgpu_ctx *c, TableGeom &g, uint64_t &n_slots) {
+    n_slots = (uint64_t)kSlotsPerBucket << g.Lb;
+    void *p = nullptr;
+    CU(cudaMalloc(&p, n_slots * sizeof(uint64_t)));
+    g.slots = (uint64_t *)p;
+    CU(cudaMalloc(&p, ((size_t)kOvfCap + 1) * 2 * sizeof(uint64_t)));
+    g.ovf = (uint64_t *)p;
+    CU(cudaMalloc(&p, (size_t)kSpillCap * 2 * sizeof(uint64_t)));
+    g.spill = (uint64_t *)p;
+    CU(cudaMalloc(&p, sizeof(TableCounters)));
+    g.ctr = (TableCounters *)p;
+    {
+        ProfScope ps(c, "memset", c->stream);
+        CU(cudaMemsetAsync(g.slots, 0, n_slots * sizeof(uint64_t), c->stream));
+        CU(cudaMemsetAsync(g.ovf, 0, ((size_t)kOvfCap + 1) * 2 * sizeof(uint64_t), c->stream));
+        CU(cudaMemsetAsync(g.ctr, 0, sizeof(TableCounters), c->stream));
+    }
+    return KATGPU_OK;
+}
+static void free_table_storage(TableGeom &g) {
+    if (g.slots) cudaFree(g.slots);
+    if (g.ovf) cudaFree(g.ovf);
+    if (g.spill) cudaFree(g.spill);
+    if (g.ctr) cudaFree(g.ctr);
+    g.slots = g.ovf = g.spill = nullptr;
+    g.ctr = nullptr;
+}
+
+extern "C" katgpu_status katgpu_count_begin(katgpu_ctx *c, int k, int canonical, uint64_t hash_size, int allow_grow,
+                                            katgpu_table **out) {
+    if (!c || !out) return fail(KATGPU_ERR_INVALID, "katgpu_count_begin: NULL argument");
+    *out = nullptr;
+    if (k < 1 || k > 32) return fail(KATGPU_ERR_INVALID, "katgpu_count_begin: k=%d outside 1..32 (one 64-bit word per k-mer)", k);
+    CU(cudaSetDevice(c->device));
+    katgpu_table *t = new (std::nothrow) katgpu_table();
+    if (!t) return fail(KATGPU_ERR_NOMEM, "katgpu_count_begin: out of host memory");
+    t->ctx = c;
+    t->allow_grow = allow_grow != 0;
+    t->count_bits_cap = g_debug_count_bits;
+    int Lb = ceil_log2(std::max<uint64_t>(hash_size, 1)) - 2; // slots -> buckets
+    Lb = std::max(Lb, min_Lb(k));
+    katgpu_status st = make_geom(k, canonical, Lb, t->count_bits_cap, t->g);
+    if (st == KATGPU_OK) st = alloc_table_storage(c, t->g, t->n_slots);
+    if (st != KATGPU_OK) {
+        free_table_storage(t->g);
+        delete t;
+        return st;
+    }
+    *out = t;
+    return KATGPU_OK;
+}
+
+extern "C" void katgpu_table_free(katgpu_table *t) {
+    if (!t) return;
+    cudaSetDevice(t->ctx->device);
+    cudaStreamSynchronize(t->ctx->stream);
+    free_table_storage(t->g);
+    delete t;
+}
+
+// Read the device counter block (synchronises the compute stream).
+static katgpu_status read_counters(katgpu_table *t, TableCounters &out) {
+    katgpu_ctx *c = t->ctx;
+    CU(cudaMemcpyAsync(c->h_ctr, t->g.ctr, sizeof(TableCounters), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    out = *c->h_ctr;
+    return KATGPU_OK;
+}
+
+// Double the table (hash_counter::double_size, JFI/hash_counter.hpp:204-244)
+// and replay any parked keys.
+static katgpu_status grow_table(katgpu_table *t, const TableCounters &cur) {
+    katgpu_ctx *c = t->ctx;
+    if ((int)t->g.Lb >= (int)t->g.b) return fail(KATGPU_ERR_HASH_FULL, "Hash full: table already covers the whole %u-bit key space", t->g.b);
+    TableGeom ng{};
+    KT(make_geom(t->g.k, t->g.canonical, t->g.Lb + 1, t->count_bits_cap, ng));
+    uint64_t new_slots = 0;
+    katgpu_status st = alloc_table_storage(c, ng, new_slots);
+    if (st != KATGPU_OK) {
+        free_table_storage(ng);
+        return st;
+    }
+    const int grid = c->sm_count * 8;
+    {
+        ProfScope ps(c, "rehash", c->stream);
+        launch_rehash(t->g, ng, t->n_slots, grid, c->stream);
+        c->launches++;
+        const uint64_t nsp = std::min<uint64_t>(cur.spill_n, kSpillCap);
+        if (nsp) {
+            launch_insert_pairs(ng, t->g.spill, nsp, grid, c->stream);
+            c->launches++;
+        }
+    }
+    // carry the instance counter over (n_distinct is recomputed by the rehash)
+    CU(cudaMemcpyAsync(&ng.ctr->n_total, &t->g.ctr->n_total, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    free_table_storage(t->g);
+    t->g = ng;
+    t->n_slots = new_slots;
+    t->grow_events++;
+    return KATGPU_OK;
+}
+
+static const double kMaxLoad = 0.80;  // grow beyond this
+static const double kHardLoad = 0.90; // never admit more k-mers than this could hold
+
+// After a launch: replay spills (growing), check the overflow side table.
+static katgpu_status settle(katgpu_table *t, TableCounters &ctr) {
+    KT(read_counters(t, ctr));
+    if (ctr.ovf_full) return fail(KATGPU_ERR_OVERFLOW, "count-overflow side table exhausted (%u keys)", kOvfCap);
+    while (ctr.spill_n > 0) {
+        if (ctr.spill_n > kSpillCap)
+            return fail(KATGPU_ERR_HASH_FULL, "Hash full: %llu keys could not be placed (spill list holds %llu)", ctr.spill_n, (unsigned long long)kSpillCap);
+        if (!t->allow_grow) return fail(KATGPU_ERR_HASH_FULL, "Hash full");
+        KT(grow_table(t, ctr));
+        KT(read_counters(t, ctr));
+    }
+    return KATGPU_OK;
+}
+
+// How many k-mer starts may be admitted now; grows the table when the answer
+// would be too small.  Worst case every admitted k-mer is a new key.
+static katgpu_status admit(katgpu_table *t, TableCounters &ctr, uint64_t want, uint64_t &granted) {
+    for (;;) {
+        const double slots = (double)t->n_slots;
+        const bool full_space = (int)t->g.Lb >= (int)t->g.b; // bijective: cannot overflow
+        if (full_space) {
+            granted = want;
+            return KATGPU_OK;
+        }
+        const uint64_t hard = (uint64_t)(slots * kHardLoad);
+        const uint64_t room = ctr.n_distinct < hard ? hard - ctr.n_distinct : 0;
+        const bool over_soft = (double)ctr.n_distinct > slots * kMaxLoad;
+        const uint64_t min_chunk = std::min<uint64_t>(want, std::max<uint64_t>(t->n_slots / 64, 4096));
+        if (room >= min_chunk && !(over_soft && t->allow_grow)) {
+            granted = std::min(want, room);
+            return KATGPU_OK;
+        }
+        if (!t->allow_grow) {
+            if (room > 0) {
+                granted = std::min(want, room);
+                return KATGPU_OK;
+            }
+            return fail(KATGPU_ERR_HASH_FULL, "Hash full");
+        }
+        KT(grow_table(t, ctr));
+        KT(read_counters(t, ctr));
+    }
+}
+
+static katgpu_status launch_extract_insert(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts) {
+    katgpu_ctx *c = t->ctx;
+    ExtractParams P{};
+    P.g = t->g;
+    P.bases = dev;
+    P.n_valid = n_valid;
+    P.n_starts = n_starts;
+    P.tile_counter = c->tile_counter;
+    P.n_tiles = (int)((n_starts + kTile - 1) / kTile);
+    P.tma_ok = (reinterpret_cast<uintptr_t>(dev) & 15) == 0;
+    if (P.n_tiles == 0) return KATGPU_OK;
+    CU(cudaMemsetAsync(c->tile_counter, 0, sizeof(unsigned int), c->stream));
+    const int grid = std::min(P.n_tiles, c->sm_count * c->bps[0]);
+    {
+        ProfScope ps(c, "count", c->stream);
+        launch_extract(kModeInsert, P, grid, c->stream);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    return KATGPU_OK;
+}
+
+// Count a device-resident stream, in admission-controlled sub-launches.
+static katgpu_status feed_device_range(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
+                                       TableCounters &ctr) {
+    // a k-mer start needs k bases
+    if (n_valid < (uint64_t)t->g.k) return KATGPU_OK;
+    n_starts = std::min(n_starts, n_valid - t->g.k + 1);
+    uint64_t done = 0;
+    while (done < n_starts) {
+        uint64_t granted = 0;
+        KT(admit(t, ctr, n_starts - done, granted));
+        if (granted < n_starts - done) granted = std::max<uint64_t>(granted / kTile * kTile, kTile); // keep TMA alignment
+        granted = std::min(granted, n_starts - done);
+        KT(launch_extract_insert(t, dev + done, n_valid - done, granted));
+        done += granted;
+        if (done < n_starts || true) KT(settle(t, ctr));
+    }
+    return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *bases_dev, size_t n) {
+    if (!t || (!bases_dev && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_feed_device: NULL argument");
+    if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_feed_device: table already finished");
+    CU(cudaSetDevice(t->ctx->device));
+    TableCounters ctr;
+    KT(read_counters(t, ctr));
+    return feed_device_range(t, (const uint8_t *)bases_dev, n, n, ctr);
+}
+
+extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n) {
+    if (!t || (!bases && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_feed: NULL argument");
+    if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_feed: table already finished");
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    if (n == 0) return KATGPU_OK;
+    const size_t chunk = std::min(kChunkBytes, (n + 4095) / 4096 * 4096);
+    if (c->chunk_cap < chunk + kHalo) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(cudaStreamSynchronize(c->copy_stream));
+        for (int i = 0; i < 2; i++) {
+            if (c->chunk[i]) cudaFree(c->chunk[i]);
+            c->chunk[i] = nullptr;
+            void *p = nullptr;
+            CU(cudaMalloc(&p, chunk + kHalo + 64));
+            c->chunk[i] = (uint8_t *)p;
+        }
+        c->chunk_cap = chunk + kHalo;
+    }
+    TableCounters ctr;
+    KT(read_counters(t, ctr));
+    // chunk i holds host bytes [i*chunk, (i+1)*chunk + halo): k-mers starting in
+    // the first `chunk` positions are counted from it, the halo feeds their tails.
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    auto issue_copy = [&](size_t i) -> katgpu_status {
+        const int b = (int)(i & 1);
+        const size_t off = i * chunk;
+        const size_t len = std::min(n - off, chunk + kHalo);
+        CU(cudaStreamWaitEvent(c->copy_stream, c->chunk_free[b], 0));
+        CU(cudaMemcpyAsync(c->chunk[b], bases + off, len, cudaMemcpyHostToDevice, c->copy_stream));
+        CU(cudaEventRecord(c->chunk_ready[b], c->copy_stream));
+        return KATGPU_OK;
+    };
+    // the free events start out "complete": record them once on an idle stream
+    CU(cudaEventRecord(c->chunk_free[0], c->stream));
+    CU(cudaEventRecord(c->chunk_free[1], c->stream));
+    KT(issue_copy(0));
+    for (size_t i = 0; i < n_chunks; i++) {
+        const int b = (int)(i & 1);
+        if (i + 1 < n_chunks) KT(issue_copy(i + 1)); // overlaps kernel i
+        const size_t off = i * chunk;
+        const size_t len = std::min(n - off, chunk + kHalo);
+        const size_t starts = std::min(n - off, chunk);
+        CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
+        KT(feed_device_range(t, c->chunk[b], len, starts, ctr));
+        CU(cudaEventRecord(c->chunk_free[b], c->stream));
+    }
+    return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct, uint64_t *n_total) {
+    if (!t) return fail(KATGPU_ERR_INVALID, "katgpu_count_end: NULL table");
+    CU(cudaSetDevice(t->ctx->device));
+    TableCounters ctr;
+    KT(settle(t, ctr));
+    t->ended = true;
+    if (n_distinct) *n_distinct = ctr.n_distinct;
+    if (n_total) *n_total = ctr.n_total;
+    return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_table_get_info(katgpu_table *t, katgpu_table_info *out) {
+    if (!t || !out) return fail(KATGPU_ERR_INVALID, "katgpu_table_get_info: NULL argument");
+    CU(cudaSetDevice(t->ctx->device));
+    TableCounters ctr;
+    KT(read_counters(t, ctr));
+    out->k = t->g.k;
+    out->canonical = t->g.canonical;
+    out->slots = t->n_slots;
+    out->bytes = t->n_slots * 8 + ((uint64_t)kOvfCap + 1) * 16 + kSpillCap * 16 + sizeof(TableCounters);
+    out->n_distinct = ctr.n_distinct;
+    out->n_total = ctr.n_total;
+    out->count_bits = t->g.cbits;
+    out->grow_events = t->grow_events;
+    out->overflow_keys = ctr.ovf_n;
+    return KATGPU_OK;
+}
+
+// ---- multi-GPU plumbing ----
+extern "C" katgpu_status katgpu_route_device(katgpu_table *t, const void *bases_dev, size_t n, int n_ranks,
+                                             void *const *out_dev, uint64_t cap_keys, uint64_t *counts_out) {
+    if (!t || !out_dev || !counts_out || (!bases_dev && n)) return fail(KATGPU_ERR_INVALID, "katgpu_route_device: NULL argument");
+    if (n_ranks < 1 || n_ranks > kMaxRanks) return fail(KATGPU_ERR_INVALID, "katgpu_route_device: n_ranks=%d outside 1..%d", n_ranks, kMaxRanks);
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    for (int r = 0; r < n_ranks; r++) counts_out[r] = 0;
+    if (n < (size_t)t->g.k) return KATGPU_OK;
+    ExtractParams P{};
+    P.g = t->g;
+    P.bases = (const uint8_t *)bases_dev;
+    P.n_valid = n;
+    P.n_starts = n - t->g.k + 1;
+    P.tile_counter = c->tile_counter;
+    P.n_tiles = (int)((P.n_starts + kTile - 1) / kTile);
+    P.tma_ok = (reinterpret_cast<uintptr_t>(bases_dev) & 15) == 0;
+    P.n_ranks = (uint32_t)n_ranks;
+    for (int r = 0; r < n_ranks; r++) P.out[r] = (uint64_t *)out_dev[r];
+    P.cursors = c->route_cursors;
+    P.out_cap = cap_keys;
+    P.route_overflow = reinterpret_cast<unsigned int *>(c->route_cursors + kMaxRanks);
+    CU(cudaMemsetAsync(c->tile_counter, 0, sizeof(unsigned int), c->stream));
+    CU(cudaMemsetAsync(c->route_cursors, 0, 256, c->stream));
+    const int grid = std::min(P.n_tiles, c->sm_count * c->bps[1]);
+    {
+        ProfScope ps(c, "route", c->stream);
+        launch_extract(kModeRoute, P, grid, c->stream);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    unsigned long long h[kMaxRanks + 1];
+    CU(cudaMemcpyAsync(h, c->route_cursors, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    for (int r = 0; r < n_ranks; r++) counts_out[r] = h[r];
+    if ((unsigned int)h[kMaxRanks] != 0)
+        return fail(KATGPU_ERR_INVALID, "katgpu_route_device: an owner bucket overflowed its capacity of %llu keys", (unsigned long long)cap_keys);
+    return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void *hashed_dev, uint64_t n) {
+    if (!t || (!hashed_dev && n)) return fail(KATGPU_ERR_INVALID, "katgpu_insert_hashed_device: NULL argument");
+    if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_insert_hashed_device: table already finished");
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    TableCounters ctr;
+    KT(read_counters(t, ctr));
+    const uint64_t *hs = (const uint64_t *)hashed_dev;
+    uint64_t done = 0;
+    while (done < n) {
+        uint64_t granted = 0;
+        KT(admit(t, ctr, n - done, granted));
+        const int grid = (int)std::min<uint64_t>((granted + 256 * kUnroll - 1) / (256 * kUnroll), (uint64_t)c->sm_count * 8);
+        {
+            ProfScope ps(c, "insert", c->stream);
+            launch_insert_hashed(t->g, hs + done, granted, grid, c->stream);
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+        done += granted;
+        KT(settle(t, ctr));
+    }
+    return KATGPU_OK;
+}
+
+// ---- table walks ----
+static katgpu_status finished(katgpu_table *t, const char *who) {
+    if (!t) return fail(KATGPU_ERR_INVALID, "%s: NULL table", who);
+    if (!t->ended) return fail(KATGPU_ERR_STATE, "%s: call katgpu_count_end first", who);
+    return KATGPU_OK;
+}
+
+struct DevBuf { // zeroed device scratch, freed on scope exit
+    void *p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+extern "C" katgpu_status katgpu_hist(katgpu_table *t, uint64_t base, uint64_t ceil_, uint64_t inc, uint64_t nb,
+                                     uint64_t *bins_out) {
+    KT(finished(t, "katgpu_hist"));
+    if (!bins_out || nb == 0 || inc == 0 || nb > 0x7fffffffULL) return fail(KATGPU_ERR_INVALID, "katgpu_hist: bad arguments");
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    DevBuf d;
+    CU(cudaMalloc(&d.p, nb * 8));
+    CU(cudaMemsetAsync(d.p, 0, nb * 8, c->stream));
+    {
+        ProfScope ps(c, "hist", c->stream);
+        launch_hist(t->g, t->n_slots, base, ceil_, inc, (uint32_t)nb, (unsigned long long *)d.p, c->sm_count * 4, c->stream);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(bins_out, d.p, nb * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_gcp(katgpu_table *t, double cvg_scale, uint32_t cvg_bins, uint64_t *mx_out) {
+    KT(finished(t, "katgpu_gcp"));
+    if (!mx_out) return fail(KATGPU_ERR_INVALID, "katgpu_gcp: NULL output");
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    const size_t cells = (size_t)t->g.k * ((size_t)cvg_bins + 1);
+    DevBuf d;
+    CU(cudaMalloc(&d.p, cells * 8));
+    CU(cudaMemsetAsync(d.p, 0, cells * 8, c->stream));
+    {
+        ProfScope ps(c, "gcp", c->stream);
+        launch_gcp(t->g, t->n_slots, cvg_scale, cvg_bins, (unsigned long long *)d.p, c->sm_count, c->stream);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(mx_out, d.p, cells * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_comp(katgpu_table *t1, katgpu_table *t2, katgpu_table *t3, double d1_scale,
+                                     double d2_scale, uint32_t d1_bins, uint32_t d2_bins, uint64_t *main_mx,
+                                     uint64_t *ends_mx, uint64_t *middle_mx, uint64_t *mixed_mx,
+                                     katgpu_comp_counters *counters, uint64_t *spectra) {
+    KT(finished(t1, "katgpu_comp"));
+    KT(finished(t2, "katgpu_comp"));
+    if (t3) KT(finished(t3, "katgpu_comp"));
+    if (!main_mx || !counters || !spectra || d1_bins == 0 || d2_bins == 0) return fail(KATGPU_ERR_INVALID, "katgpu_comp: bad arguments");
+    if (t3 && (!ends_mx || !middle_mx || !mixed_mx)) return fail(KATGPU_ERR_INVALID, "katgpu_comp: 3-input mode needs ends/middle/mixed outputs");
+    if (t1->g.k != t2->g.k || (t3 && t3->g.k != t1->g.k)) return fail(KATGPU_ERR_INVALID, "katgpu_comp: tables were counted with different k");
+    if (t1->ctx != t2->ctx || (t3 && t3->ctx != t1->ctx)) return fail(KATGPU_ERR_INVALID, "katgpu_comp: tables live on different contexts");
+    katgpu_ctx *c = t1->ctx;
+    CU(cudaSetDevice(c->device));
+    const uint32_t len = std::min(d1_bins, d2_bins);
+    const size_t cells = (size_t)d1_bins * d2_bins;
+    const size_t n_mx = t3 ? 4 : 1;
+    const size_t words = n_mx * cells + 16 + 4 * (size_t)len;
+    DevBuf d;
+    CU(cudaMalloc(&d.p, words * 8));
+    CU(cudaMemsetAsync(d.p, 0, words * 8, c->stream));
+    unsigned long long *base = (unsigned long long *)d.p;
+    CompParams P{};
+    P.d1_scale = d1_scale;
+    P.d2_scale = d2_scale;
+    P.d1_bins = d1_bins;
+    P.d2_bins = d2_bins;
+    P.len = len;
+    P.main_mx = base;
+    P.ends_mx = t3 ? base + cells : nullptr;
+    P.middle_mx = t3 ? base + 2 * cells : nullptr;
+    P.mixed_mx = t3 ? base + 3 * cells : nullptr;
+    P.counters = base + n_mx * cells;
+    unsigned long long *spec = P.counters + 16;
+    const int grid = c->sm_count * 2;
+    {
+        ProfScope ps(c, "comp", c->stream);
+        // pass 1: walk hash1, probe hash2 (canonicalised iff input 2 is canonical, src/comp.cc:400) and hash3
+        P.pass = 1;
+        P.ga = t1->g;
+        P.n_slots = t1->n_slots;
+        P.gb = t2->g;
+        P.canon_b = t2->g.canonical;
+        P.have_c = t3 != nullptr;
+        if (t3) {
+            P.gc = t3->g;
+            P.canon_c = t3->g.canonical;
+        }
+        P.spec_walk = spec;
+        P.spec_shared1 = spec + 2 * (size_t)len;
+        P.spec_shared2 = spec + 3 * (size_t)len;
+        launch_comp(P, grid, c->stream);
+        // pass 2: walk hash2, probe hash1 — always canonicalised (src/comp.cc:447)
+        P.pass = 2;
+        P.ga = t2->g;
+        P.n_slots = t2->n_slots;
+        P.gb = t1->g;
+        P.canon_b = 1;
+        P.have_c = 0;
+        P.spec_walk = spec + len;
+        launch_comp(P, grid, c->stream);
+        c->launches += 2;
+        if (t3) { // pass 3: hash3 totals (src/comp.cc:466-479)
+            P.pass = 3;
+            P.ga = t3->g;
+            P.n_slots = t3->n_slots;
+            launch_comp(P, grid, c->stream);
+            c->launches++;
+        }
+    }
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(main_mx, P.main_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (t3) {
+        CU(cudaMemcpyAsync(ends_mx, P.ends_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(middle_mx, P.middle_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(mixed_mx, P.mixed_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
+    }
+    static_assert(sizeof(katgpu_comp_counters) == 13 * 8, "counter block layout");
+    CU(cudaMemcpyAsync(counters, P.counters, sizeof(katgpu_comp_counters), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(spectra, spec, 4 * (size_t)len * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, size_t n, int canonicalise,
+                                       uint64_t *counts_out) {
+    KT(finished(t, "katgpu_lookup"));
+    if ((!keys || !counts_out) && n) return fail(KATGPU_ERR_INVALID, "katgpu_lookup: NULL argument");
+    if (n == 0) return KATGPU_OK;
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    DevBuf dk, dc;
+    CU(cudaMalloc(&dk.p, n * 8));
+    CU(cudaMalloc(&dc.p, n * 8));
+    CU(cudaMemcpyAsync(dk.p, keys, n * 8, cudaMemcpyHostToDevice, c->stream));
+    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
+    launch_lookup(t->g, (const uint64_t *)dk.p, n, canonicalise, (uint64_t *)dc.p, grid, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(counts_out, dc.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t *counts_out, size_t cap,
+                                             uint64_t *n_out) {
+    KT(finished(t, "katgpu_table_export"));
+    if (!n_out || ((!keys_out || !counts_out) && cap)) return fail(KATGPU_ERR_INVALID, "katgpu_table_export: NULL argument");
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    DevBuf dk, dc, dn;
+    CU(cudaMalloc(&dk.p, std::max<size_t>(cap, 1) * 8));
+    CU(cudaMalloc(&dc.p, std::max<size_t>(cap, 1) * 8));
+    CU(cudaMalloc(&dn.p, 8));
+    CU(cudaMemsetAsync(dn.p, 0, 8, c->stream));
+    launch_export(t->g, t->n_slots, (uint64_t *)dk.p, (uint64_t *)dc.p, cap, (unsigned long long *)dn.p, c->sm_count * 8, c->stream);
+    c->launches++;
+    CU(cudaGetLastError());
+    unsigned long long n = 0;
+    CU(cudaMemcpyAsync(&n, dn.p, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    *n_out = n;
+    const size_t m = std::min<size_t>(cap, n);
+    if (m) {
+        CU(cudaMemcpy(keys_out, dk.p, m * 8, cudaMemcpyDeviceToHost));
+        CU(cudaMemcpy(counts_out, dc.p, m * 8, cudaMemcpyDeviceToHost));
+    }
+    return KATGPU_OK;
+}
+
+// ---- synthetic reads ----
+__global__ void synth_kernel(SynthParams p, char *out) {
+    const uint64_t per = (uint64_t)p.read_len + 1;
+    const uint64_t total = p.n_reads * per;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = i / per;
+        out[i] = synth_byte(p, p.first_read + r, (uint32_t)(i - r * per));
+    }
+}
+static katgpu_status synth_params(uint64_t genome_len, uint64_t seed_g, uint64_t seed_r, uint64_t first_read,
+                                  uint64_t n_reads, uint32_t read_len, double sub_rate, double n_rate, SynthParams &p) {
+    if (read_len == 0 || genome_len < read_len || sub_rate < 0 || sub_rate > 1 || n_rate < 0 || n_rate > 1)
+        return fail(KATGPU_ERR_INVALID, "katgpu_synth_reads: bad parameters");
+    p.genome_len = genome_len;
+    p.seed_g = seed_g;
+    p.seed_r = seed_r;
+    p.first_read = first_read;
+    p.n_reads = n_reads;
+    p.read_len = read_len;
+    p.thr_sub = (uint32_t)(sub_rate * 16777216.0);
+    p.thr_n = (uint32_t)(n_rate * 16777216.0);
+    return KATGPU_OK;
+}
+extern "C" katgpu_status katgpu_synth_reads_device(katgpu_ctx *c, uint64_t genome_len, uint64_t seed_g, uint64_t seed_r,
+                                                   uint64_t first_read, uint64_t n_reads, uint32_t read_len,
+                                                   double sub_rate, double n_rate, void *out_dev) {
+    if (!c || !out_dev) return fail(KATGPU_ERR_INVALID, "katgpu_synth_reads_device: NULL argument");
+    SynthParams p;
+    KT(synth_params(genome_len, seed_g, seed_r, first_read, n_reads, read_len, sub_rate, n_rate, p));
+    CU(cudaSetDevice(c->device));
+    if (n_reads) synth_kernel<<<c->sm_count * 16, 256, 0, c->stream>>>(p, (char *)out_dev);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->stream));
+    return KATGPU_OK;
+}
+extern "C" katgpu_status katgpu_synth_reads_host(uint64_t genome_len, uint64_t seed_g, uint64_t seed_r, uint64_t first_read,
+                                                 uint64_t n_reads, uint32_t read_len, double sub_rate, double n_rate,
+                                                 char *out) {
+    if (!out) return fail(KATGPU_ERR_INVALID, "katgpu_synth_reads_host: NULL argument");
+    SynthParams p;
+    KT(synth_params(genome_len, seed_g, seed_r, first_read, n_reads, read_len, sub_rate, n_rate, p));
+    const uint64_t per = (uint64_t)read_len + 1;
+    for (uint64_t r = 0; r < n_reads; r++)
+        for (uint32_t j = 0; j <= read_len; j++) out[r * per + j] = synth_byte(p, first_read + r, j);
+    return KATGPU_OK;
+}

@@ -1,0 +1,239 @@
+"""GPU parity: libkatgpu (through the C-ABI) vs the CPU oracle on identical
+seeded inputs.  Integer work: the bar is bit-exact equality."""
+import numpy as np
+import pytest
+
+import oracle as O
+import seqgen
+import kat_b200
+from kat_b200 import binding as B
+
+pytestmark = pytest.mark.gpu
+
+
+def ora_table(chunks, k, canonical=True):
+    return O.Table.from_chunks([bytes(c) for c in chunks], k, canonical)
+
+
+def gpu_table(ctx, chunks, k, canonical=True, hash_size=1 << 16, allow_grow=True):
+    return ctx.count([np.ascontiguousarray(c) for c in chunks], k, canonical, hash_size, allow_grow)
+
+
+def assert_same_multiset(gt, ot):
+    keys, counts, n = gt.export()
+    okeys, ocounts = ot.export()
+    assert n == ot.distinct == gt.n_distinct
+    assert gt.n_total == ot.total
+    assert np.array_equal(keys, okeys)
+    assert np.array_equal(counts, ocounts)
+
+
+@pytest.mark.parametrize("k", [1, 2, 5, 13, 15, 16, 17, 21, 27, 31, 32])
+@pytest.mark.parametrize("canonical", [True, False])
+def test_count_matches_oracle(ctx, k, canonical):
+    s = seqgen.random_stream(60_000, seed=100 + k)
+    gt = gpu_table(ctx, [s], k, canonical)
+    ot = ora_table([s], k, canonical)
+    assert_same_multiset(gt, ot)
+    base, bins = gt.hist()
+    obase, obins = ot.hist()
+    assert base == obase and np.array_equal(bins, obins)
+    assert int(bins.sum()) == ot.distinct
+
+
+@pytest.mark.parametrize("n", [0, 1, 26, 27, 28, 31, 32, 33, 8191, 8192, 8193, 8192 + 31, 8192 + 32, 8192 + 33,
+                               3 * 8192, 3 * 8192 + 17])
+def test_ragged_sizes(ctx, n):
+    """Empty, shorter than k, and sizes around the 8 KiB TMA tile / 32 B halo."""
+    s = seqgen.random_stream(n, seed=n + 7, n_rate=0.002)
+    gt = gpu_table(ctx, [s], 27)
+    ot = ora_table([s], 27)
+    assert_same_multiset(gt, ot)
+
+
+def test_no_kmer_spans_feeds(ctx):
+    a = seqgen.random_stream(5000, 1, n_rate=0.0, junk_rate=0.0)
+    b = seqgen.random_stream(7000, 2, n_rate=0.0, junk_rate=0.0)
+    gt = gpu_table(ctx, [a, b], 21)
+    assert_same_multiset(gt, ora_table([a, b], 21))
+    joined = gpu_table(ctx, [np.concatenate([a, b])], 21)
+    assert joined.n_total == gt.n_total + 20
+
+
+def test_device_feed_equals_host_feed(ctx):
+    s = seqgen.genome_reads(50_000, 4000, 150, seed=5)
+    d = ctx.device_alloc(s.size)
+    try:
+        ctx.h2d(d, s)
+        t = ctx.count_begin(27, True, 1 << 18)
+        t.feed_device(d, s.size).end()
+        assert_same_multiset(t, ora_table([s], 27))
+        # unaligned device pointer: falls back to the guarded loader
+        t2 = ctx.count_begin(27, True, 1 << 18)
+        t2.feed_device(d + 3, s.size - 3).end()
+        assert_same_multiset(t2, ora_table([s[3:]], 27))
+    finally:
+        ctx.device_free(d)
+
+
+def test_high_multiplicity_and_hist_params(ctx):
+    s = np.concatenate([seqgen.genome_reads(20_000, 6000, 150, seed=9), seqgen.low_complexity(400, 150, seed=3)])
+    gt = gpu_table(ctx, [s], 21)
+    ot = ora_table([s], 21)
+    assert_same_multiset(gt, ot)
+    for low, high, inc in [(1, 10000, 1), (2, 6, 2), (5, 50, 5), (1, 3, 1), (10, 10, 1), (3, 100000, 7)]:
+        base, bins = gt.hist(low, high, inc)
+        obase, obins = ot.hist(low, high, inc)
+        assert base == obase and np.array_equal(bins, obins), (low, high, inc)
+
+
+def test_count_overflow_side_table(ctx):
+    """Force a 3-bit in-slot count field: every 8th increment carries into the
+    exact side table (the reference's large-value chaining, large_hash_array.hpp:668-686)."""
+    B.lib().katgpu_debug_set_count_bits(3)
+    try:
+        s = np.concatenate([seqgen.low_complexity(300, 104, seed=1), seqgen.genome_reads(3000, 2000, 100, seed=2)])
+        gt = gpu_table(ctx, [s], 5)
+        ot = ora_table([s], 5)
+        assert gt.info()["count_bits"] == 3 and gt.info()["overflow_keys"] > 0
+        assert_same_multiset(gt, ot)
+        assert np.array_equal(gt.hist()[1], ot.hist()[1])
+        assert np.array_equal(gt.gcp(), ot.gcp())
+        g2 = gpu_table(ctx, [s], 17)
+        o2 = ora_table([s], 17)
+        assert_same_multiset(g2, o2)
+        # growth with overflowed keys present
+        g3 = gpu_table(ctx, [s], 17, hash_size=4096)
+        assert g3.info()["grow_events"] > 0
+        assert_same_multiset(g3, o2)
+    finally:
+        B.lib().katgpu_debug_set_count_bits(0)
+
+
+def test_exact_large_count(ctx):
+    """300 reads of 104 x 'A', k=5: one k-mer with count 30000."""
+    s = np.tile(np.frombuffer(b"A" * 104 + b"N", dtype=np.uint8), 300)
+    gt = gpu_table(ctx, [s], 5)
+    keys, counts, n = gt.export()
+    assert n == 1 and keys[0] == 0 and counts[0] == 30000
+
+
+def test_table_growth_and_hash_full(ctx):
+    s = seqgen.random_stream(400_000, seed=77, n_rate=0.001)
+    ot = ora_table([s], 27)
+    gt = gpu_table(ctx, [s], 27, hash_size=4096, allow_grow=True)
+    assert gt.info()["grow_events"] >= 5
+    assert_same_multiset(gt, ot)
+    with pytest.raises(kat_b200.KatGpuError) as e:
+        gpu_table(ctx, [s], 27, hash_size=4096, allow_grow=False)
+    assert e.value.status == -3 and "Hash full" in str(e.value)
+
+
+@pytest.mark.parametrize("k,scale,bins", [(17, 1.0, 1000), (5, 0.5, 3), (21, 0.1, 50), (27, 2.5, 1000), (9, 1.0, 20)])
+def test_gcp(ctx, k, scale, bins):
+    s = np.concatenate([seqgen.genome_reads(30_000, 5000, 150, seed=k), seqgen.low_complexity(50, 150, seed=k),
+                        np.frombuffer(b"N" + b"GC" * 40 + b"N" + b"G" * 60 + b"N", dtype=np.uint8)])
+    gt = gpu_table(ctx, [s], k)
+    ot = ora_table([s], k)
+    assert np.array_equal(gt.gcp(scale, bins), ot.gcp(scale, bins))
+
+
+@pytest.mark.parametrize("canon", [(True, True), (False, False), (False, True), (True, False)])
+@pytest.mark.parametrize("scales", [(1.0, 1.0, 1001, 1001), (0.5, 2.0, 40, 60), (1.0, 0.25, 300, 20)])
+def test_comp_two_inputs(ctx, canon, scales):
+    d1s, d2s, d1b, d2b = scales
+    a = seqgen.genome_reads(40_000, 6000, 150, seed=11)
+    b = np.concatenate([seqgen.genome_reads(40_000, 3000, 150, seed=11)[: 3000 * 151 // 2],
+                        seqgen.genome_reads(30_000, 2000, 150, seed=12)])
+    k = 21
+    g1, g2 = gpu_table(ctx, [a], k, canon[0]), gpu_table(ctx, [b], k, canon[1])
+    o1, o2 = ora_table([a], k, canon[0]), ora_table([b], k, canon[1])
+    gr = B.comp(g1, g2, None, d1s, d2s, d1b, d2b)
+    orr = O.comp(o1, o2, None, d1s, d2s, d1b, d2b)
+    assert gr["counters"] == orr["counters"]
+    assert np.array_equal(gr["spectra"], orr["spectra"])
+    assert np.array_equal(gr["main"], orr["main"])
+
+
+def test_comp_three_inputs(ctx):
+    k = 17
+    a = seqgen.genome_reads(30_000, 5000, 150, seed=21)
+    b = seqgen.genome_reads(30_000, 400, 150, seed=21, sub_rate=0.0)
+    c = seqgen.genome_reads(30_000, 300, 150, seed=22, sub_rate=0.0)
+    g = [gpu_table(ctx, [x], k) for x in (a, b, c)]
+    o = [ora_table([x], k) for x in (a, b, c)]
+    gr = B.comp(*g, 1.0, 1.0, 200, 150)
+    orr = O.comp(*o, 1.0, 1.0, 200, 150)
+    assert gr["counters"] == orr["counters"]
+    for name in ("main", "ends", "middle", "mixed", "spectra"):
+        assert np.array_equal(gr[name], orr[name]), name
+
+
+def test_lookup(ctx):
+    s = seqgen.genome_reads(20_000, 3000, 150, seed=31)
+    for canonical in (True, False):
+        gt = gpu_table(ctx, [s], 27, canonical)
+        ot = ora_table([s], 27, canonical)
+        keys, _ = ot.export()
+        rng = np.random.default_rng(1)
+        probe = np.concatenate([keys[:2000], rng.integers(0, 1 << 54, 2000, dtype=np.uint64)])
+        for canon_probe in (False, True):
+            got = gt.lookup(probe, canon_probe)
+            want = np.array([ot.lookup(int(x), canon_probe) for x in probe], dtype=np.uint64)
+            assert np.array_equal(got, want)
+
+
+def test_synth_reads_device_equals_host(ctx):
+    n_reads, L = 5000, 150
+    host = B.synth_reads_host(1_000_000, 1, 2, 12345, n_reads, L)
+    d = ctx.device_alloc(host.size)
+    try:
+        ctx.synth_reads_device(d, 1_000_000, 1, 2, 12345, n_reads, L)
+        dev = np.empty_like(host)
+        ctx.d2h(dev, d)
+        assert np.array_equal(host, dev)
+        t = ctx.count_begin(27, True, 1 << 20)
+        t.feed_device(d, host.size).end()
+        assert_same_multiset(t, ora_table([host], 27))
+    finally:
+        ctx.device_free(d)
+
+
+def test_route_then_insert_equals_direct(ctx):
+    """Single-process model of the multi-GPU exchange: route to R owner buckets,
+    insert every bucket into its own table; the union must equal direct counting
+    and every key must land in exactly one table."""
+    s = seqgen.genome_reads(60_000, 8000, 150, seed=41)
+    k, R = 27, 4
+    d = ctx.device_alloc(s.size)
+    cap = s.size  # generous
+    outs = [ctx.device_alloc(cap * 8) for _ in range(R)]
+    try:
+        ctx.h2d(d, s)
+        router = ctx.count_begin(k, True, 1 << 12)
+        counts = router.route_device(d, s.size, outs, cap)
+        ot = ora_table([s], k)
+        assert sum(counts) == ot.total
+        tables = []
+        for r in range(R):
+            t = ctx.count_begin(k, True, 1 << 18)
+            t.insert_hashed_device(outs[r], counts[r])
+            t.end()
+            tables.append(t)
+        allk, allc = [], []
+        for t in tables:
+            kk, cc, n = t.export()
+            allk.append(kk); allc.append(cc)
+        kk = np.concatenate(allk); cc = np.concatenate(allc)
+        assert len(np.unique(kk)) == len(kk) == ot.distinct  # one owner per key
+        order = np.argsort(kk)
+        okeys, ocounts = ot.export()
+        assert np.array_equal(kk[order], okeys) and np.array_equal(cc[order], ocounts)
+        # additivity of the reductions after ownership partitioning
+        bins = sum(t.hist()[1] for t in tables)
+        assert np.array_equal(bins, ot.hist()[1])
+        assert np.array_equal(sum(t.gcp() for t in tables), ot.gcp())
+    finally:
+        ctx.device_free(d)
+        for o in outs:
+            ctx.device_free(o)
