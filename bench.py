@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""bench.py — canonical k-mers/sec (k=27) into `kat hist` on B200.
+
+    python bench.py --gpus N --steps K --warmup W           # libkatgpu (CUDA)
+    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference's CPU path
+
+Workload (BASELINE.json configs[1]): `kat hist -m27` on
+10 Gbp of synthetic 150 bp reads (66,666,667 reads sampled from a 200 Mbp
+genome, 0.5 % substitutions, 0.01 % N; seeds 1/2).  One step = one whole job:
+allocate + clear the table, extract/canonicalise/insert every k-mer of the
+resident base stream, walk the table into the histogram bins.
+
+`value`  : k-mer instances / s with the base stream already resident in HBM.
+`e2e`    : same job through katgpu_count_feed with the base stream in pinned
+           HOST memory (H2D inside the timed region) and the bins read back.
+`roofline`: dominant kernel (extract+insert) — algorithmic bytes / CUDA-event time.
+`cpu_baseline`: the unmodified reference binary (oracle/_ref/kat, built by
+           oracle/ref.mk) timed on this box's host cores on a bounded sample of
+           the same reads, its histogram compared bit-for-bit with the GPU's.
+
+At N > 1 (torchrun, one rank per GPU) reads are sharded by record, every k-mer
+is routed to its owner rank (hash partition), exchanged, inserted by the owner,
+and the per-rank bins are summed with one all-reduce; per-GPU
+work is fixed (weak scaling: 10 Gbp of reads and 200 Mbp of genome per GPU).
+"""
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+K = 27
+READ_LEN = 150
+GENOME_PER_GPU = 200_000_000
+READS_PER_GPU = 66_666_667
+SEED_G, SEED_R = 1, 2
+SUB_RATE, N_RATE = 0.005, 0.0001
+KMERS_PER_READ = READ_LEN - K + 1
+# algorithmic bytes per k-mer instance of the extract+insert kernel:
+# L/(L-k+1) bytes of base stream + one table read-modify-write (8 B key + 4 B count read + 4 B written)
+B_ALG = READ_LEN / KMERS_PER_READ + 16.0
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        if not shutil.which("nvidia-smi"):
+            return
+        self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits", "-lms", "100"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+        self.t.start()
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        self.t.join(timeout=2)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def write_fastq_sample(stream, n_reads, path):
+    """stream: uint8 [n_reads*(L+1)] base stream (read,'N',...).  Writes 4-line FASTQ."""
+    import numpy as np
+    L = READ_LEN
+    reads = stream.reshape(n_reads, L + 1)[:, :L]
+    hdr = np.frombuffer(b"@r\n", dtype=np.uint8)
+    mid = np.frombuffer(b"\n+\n", dtype=np.uint8)
+    rec = np.empty((n_reads, len(hdr) + L + len(mid) + L + 1), dtype=np.uint8)
+    rec[:, :3] = hdr
+    rec[:, 3:3 + L] = reads
+    rec[:, 3 + L:6 + L] = mid
+    rec[:, 6 + L:6 + 2 * L] = ord("I")
+    rec[:, -1] = ord("\n")
+    rec.tofile(path)
+
+
+def run_reference_hist(fastq, threads, slots, workdir):
+    """`kat hist -m27 -t<threads> -H<slots>` with the unmodified reference binary.
+    Returns (wall seconds, phase dict, hist path)."""
+    import oracle as O
+    out = os.path.join(workdir, "ref.hist")
+    t0 = time.perf_counter()
+    r = O.run_ref(["hist", f"-m{K}", f"-t{threads}", f"-H{slots}", "-o", out, fastq], cwd=workdir, timeout=3600)
+    wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("reference kat failed: " + r.stdout[-500:])
+    phases = {}
+    for name, pat in (("count", r"Counting kmers.*?Time taken: ([0-9.]+)s"), ("bin", r"Bining kmers.*?Time taken: ([0-9.]+)s")):
+        m = re.search(pat, r.stdout, re.S)
+        if m:
+            phases[name] = float(m.group(1))
+    return wall, phases, out
+
+
+def cpu_reference_sample(ctx_or_none, sample_reads, threads, workdir, stream=None):
+    """Time the reference on `sample_reads` reads of the workload (reads
+    [0, sample_reads) of rank 0's shard).  Returns dict + the reference's bins."""
+    import numpy as np
+    from kat_b200 import binding as B
+    import oracle as O
+    if stream is None:
+        stream = B.synth_reads_host(GENOME_PER_GPU, SEED_G, SEED_R, 0, sample_reads, READ_LEN, SUB_RATE, N_RATE)
+    fq = os.path.join(workdir, "sample.fastq")
+    write_fastq_sample(stream, sample_reads, fq)
+    n_kmers_nominal = sample_reads * KMERS_PER_READ
+    slots = 1 << max(20, (n_kmers_nominal - 1).bit_length())  # no doubling for this sample
+    wall, phases, hist = run_reference_hist(fq, threads, slots, workdir)
+    _, bins = O.read_hist(hist)
+    os.unlink(fq)
+    return wall, phases, bins, slots
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="katgpu", choices=["katgpu", "reference"])
+    ap.add_argument("--reads", type=int, default=READS_PER_GPU, help="reads per GPU (default: the 10 Gbp workload)")
+    ap.add_argument("--slots-log2", type=int, default=32, help="table slots per GPU (log2)")
+    ap.add_argument("--cpu-sample-reads", type=int, default=4_000_000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    n_reads = args.reads
+    n_kmers_nominal = n_reads * KMERS_PER_READ
+    workload = (f"kat hist -m{K}: {n_reads * READ_LEN / 1e9:.2f} Gbp synthetic {READ_LEN} bp reads per GPU "
+                f"({n_reads} reads, genome {GENOME_PER_GPU / 1e6:.0f} Mbp/GPU, sub {SUB_RATE}, N {N_RATE}, seeds {SEED_G}/{SEED_R})")
+    config = {"workload": workload, "k": K, "canonical": True, "read_len": READ_LEN,
+              "reads_per_gpu": n_reads, "table_slots_per_gpu": 1 << args.slots_log2,
+              "parallelism": f"read-sharded x{world}, k-mers hash-partitioned to owner ranks" if world > 1 else "1 GPU",
+              "l2": "inputs (10 GB base stream, >=17 GB table) far larger than the 126 MB L2; no explicit flush"}
+    threads = os.cpu_count() or 1
+
+    # ------------------------------------------------------------ reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import oracle as O
+        if not O.have_ref():
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/kat not built (run oracle/ref.mk where /root/reference exists)"}))
+            return 0
+        from kat_b200 import binding as B
+        sample = min(args.cpu_sample_reads, n_reads)
+        work = tempfile.mkdtemp(prefix="katref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            stream = B.synth_reads_host(GENOME_PER_GPU, SEED_G, SEED_R, 0, sample, READ_LEN, SUB_RATE, N_RATE)
+            import numpy as np
+            n_inst = None
+            times = []
+            for i in range(args.warmup + args.steps):
+                wall, phases, bins, slots = cpu_reference_sample(None, sample, threads, work, stream)
+                lab = np.arange(1, len(bins) + 1, dtype=np.uint64)
+                n_inst = int((bins[:-1] * lab[:-1]).sum()) if bins[-1] == 0 else None
+                if i >= args.warmup:
+                    times.append((wall, phases))
+            total = sum(t[0] for t in times)
+            n_inst = n_inst or sample * KMERS_PER_READ
+            val = n_inst * len(times) / total
+            line = {"impl": "reference", "metric": "canonical k-mers/sec (k=27) into hist", "value": val, "unit": "k-mers/s",
+                    "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+                    "config": config,
+                    "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": threads, "kind": "reference",
+                                     "sample": f"first {sample} reads ({n_inst} k-mer instances) of the workload as FASTQ; "
+                                               f"`kat hist -m27 -t{threads} -H{slots}` wall time incl. parse; phases {times[-1][1]}"},
+                    "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            print(json.dumps(line))
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
+        return 0
+
+    # ------------------------------------------------------------ CUDA arm
+    import numpy as np
+    import torch
+    import kat_b200
+    from kat_b200 import binding as B
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; libkatgpu has no CPU path")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctx = kat_b200.Context(local_rank)
+    hbm_peak, peak_src = measured_peaks()
+
+    n_bytes = n_reads * (READ_LEN + 1)
+    genome_len = GENOME_PER_GPU * world
+    first_read = rank * n_reads
+    d_bases = ctx.device_alloc(n_bytes + 64)
+    ctx.synth_reads_device(d_bases, genome_len, SEED_G, SEED_R, first_read, n_reads, READ_LEN, SUB_RATE, N_RATE)
+    base, ceil_, nb = B.hist_geometry(1, 10000)
+
+    if world > 1:
+        from kat_b200.multigpu import DistributedCounter
+        dc = DistributedCounter(ctx, dist, K, True, 1 << args.slots_log2)
+
+    def job_resident():
+        """One whole `kat hist` job, base stream resident in HBM.  Returns (bins, n_total)."""
+        if world == 1:
+            t = ctx.count_begin(K, True, 1 << args.slots_log2, True)
+            t.feed_device(d_bases, n_bytes).end()
+            _, bins = t.hist(1, 10000, 1)
+            nt, nd = t.n_total, t.n_distinct
+            t.free()
+            return bins, nt, nd
+        return dc.hist_job(d_bases, n_bytes, 1, 10000, 1, READ_LEN + 1)
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        out = None
+        for _ in range(warmup):
+            out = fn()
+        barrier()
+        l0 = ctx.launch_count()
+        ctx.profile_enable(True)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = fn()
+        barrier()
+        dt = time.perf_counter() - t0
+        clocks = sampler.stop()
+        prof = {f: ctx.profile_get(f) for f in ("count", "hist", "route", "insert", "memset", "rehash")}
+        ctx.profile_enable(False)
+        if dist is not None:
+            tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dt = float(tt.item())
+        return dt, out, ctx.launch_count() - l0, clocks, prof
+
+    dt, (bins, n_total, n_distinct), launches, clocks, prof = timed(job_resident, args.steps, args.warmup)
+    if dist is not None:
+        tt = torch.tensor([n_total], device="cuda", dtype=torch.int64)
+        dist.all_reduce(tt)
+        n_total_all = int(tt.item())
+    else:
+        n_total_all = n_total
+    value = n_total_all * args.steps / dt
+    # size-independent checks of the full-size result
+    labels = np.arange(base, base + nb, dtype=np.uint64)
+    assert int(bins.sum()) == (n_distinct if dist is None else int(bins.sum()))
+    if bins[-1] == 0:
+        assert int((bins * labels).sum()) == n_total_all, "sum(label*bins) != k-mer instances"
+
+    kernel = "count" if world == 1 else "insert"
+    k_ms, k_n = prof[kernel]
+    k_inst = n_total * args.steps  # instances inserted on this rank's table
+    achieved = (k_inst * B_ALG / 1e9) / (k_ms / 1e3) if k_ms > 0 else None
+    roofline = {"bound": "hbm", "kernel": "extract_kernel<insert>" if world == 1 else "insert_hashed_kernel",
+                "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_kmer": B_ALG, "kernel_ms_total": k_ms, "kernel_launches": k_n,
+                "kmers_per_launch": k_inst / k_n if k_n else None,
+                "input_only_GBps": (k_inst * (READ_LEN / KMERS_PER_READ) / 1e9) / (k_ms / 1e3) if k_ms > 0 else None,
+                "other_kernels_ms": {f: prof[f][0] for f in prof if f != kernel}}
+
+    line = {"metric": "canonical k-mers/sec (k=27) into hist", "value": value, "unit": "k-mers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
+            "kmer_instances_per_step": n_total_all, "distinct_kmers_rank0": n_distinct,
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+
+    # ------------------------------------------------------------ end to end
+    if not args.no_e2e and world == 1:
+        hp = C_void_p_host(n_bytes)
+        try:
+            B._check(B.lib().katgpu_memcpy_d2h(ctx.h, hp, d_bases, n_bytes))
+
+            def job_e2e():
+                t = ctx.count_begin(K, True, 1 << args.slots_log2, True)
+                t.feed_ptr(hp, n_bytes).end()
+                _, b2 = t.hist(1, 10000, 1)
+                nt = t.n_total
+                t.free()
+                return b2, nt, None
+            dt2, (bins2, nt2, _), _, _, _ = timed(job_e2e, args.steps, min(args.warmup, 3))
+            assert np.array_equal(bins2, bins) and nt2 == n_total
+            chunks = (n_bytes + (128 << 20) - 1) // (128 << 20)
+            line["e2e"] = {"value": nt2 * args.steps / dt2, "unit": "k-mers/s",
+                           "h2d_bytes_per_step": n_bytes + 32 * (chunks - 1), "d2h_bytes_per_step": nb * 8,
+                           "ms_per_step": 1e3 * dt2 / args.steps,
+                           "path": "katgpu_count_begin -> katgpu_count_feed(pinned host base stream) -> katgpu_count_end -> katgpu_hist"}
+        finally:
+            B.lib().katgpu_host_free(hp)
+    elif world > 1:
+        line["e2e"] = None
+
+    # ------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        import oracle as O
+        if O.have_ref():
+            sample = min(args.cpu_sample_reads, n_reads)
+            work = tempfile.mkdtemp(prefix="katref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+            try:
+                stream = np.empty(sample * (READ_LEN + 1), dtype=np.uint8)
+                ctx.d2h(stream, d_bases)
+                wall, phases, ref_bins, slots = cpu_reference_sample(ctx, sample, threads, work, stream)
+                t = ctx.count_begin(K, True, slots, True)
+                t.feed(stream).end()
+                _, gbins = t.hist(1, 10000, 1)
+                n_inst = t.n_total
+                t.free()
+                line["cpu_baseline"] = {
+                    "value": n_inst / wall, "unit": "k-mers/s", "cores": threads, "kind": "reference",
+                    "sample": f"first {sample} reads ({n_inst} k-mer instances) of the workload written as FASTQ; "
+                              f"unmodified reference `kat hist -m27 -t{threads} -H{slots}` wall {wall:.2f}s (phases {phases})",
+                    "parity_on_sample": bool(np.array_equal(gbins, ref_bins))}
+            finally:
+                shutil.rmtree(work, ignore_errors=True)
+        else:
+            line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": threads, "kind": "reference",
+                                    "sample": "oracle/_ref/kat not present"}
+
+    ctx.device_free(d_bases)
+    if rank == 0:
+        print(json.dumps(line))
+    ctx.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def C_void_p_host(nbytes):
+    import ctypes as C
+    from kat_b200 import binding as B
+    p = C.c_void_p()
+    B._check(B.lib().katgpu_host_alloc(nbytes, C.byref(p)))
+    return p
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -109,11 +109,15 @@ def hist_geometry(low=1, high=10000):
 
 class Context:
     def __init__(self, device=0):
+        import weakref
         self.h = C.c_void_p()
+        self._tables = weakref.WeakSet()
         _check(lib().katgpu_init(device, C.byref(self.h)))
 
     def close(self):
         if self.h:
+            for t in list(self._tables):  # tables must not outlive their context
+                t.free()
             lib().katgpu_shutdown(self.h)
             self.h = C.c_void_p()
 
@@ -187,6 +191,7 @@ class Table:
     def __init__(self, ctx, h, k, canonical):
         self.ctx, self.h, self.k, self.canonical = ctx, h, k, bool(canonical)
         self.n_distinct = self.n_total = None
+        ctx._tables.add(self)
 
     def feed(self, bases):
         """bases: bytes / numpy uint8 array in HOST memory."""
@@ -252,9 +257,9 @@ class Table:
         _check(lib().katgpu_insert_hashed_device(self.h, dev_ptr, n))
 
     def free(self):
-        if self.h:
+        if self.h and self.ctx.h:
             lib().katgpu_table_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

@@ -122,7 +122,7 @@ def test_table_growth_and_hash_full(ctx):
     s = seqgen.random_stream(400_000, seed=77, n_rate=0.001)
     ot = ora_table([s], 27)
     gt = gpu_table(ctx, [s], 27, hash_size=4096, allow_grow=True)
-    assert gt.info()["grow_events"] >= 5
+    assert gt.info()["grow_events"] >= 3
     assert_same_multiset(gt, ot)
     with pytest.raises(kat_b200.KatGpuError) as e:
         gpu_table(ctx, [s], 27, hash_size=4096, allow_grow=False)
