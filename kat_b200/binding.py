@@ -17,7 +17,7 @@ class KatGpuError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libkatgpu.so")
+    return os.environ.get("KATGPU_LIB") or os.path.join(_HERE, "lib", "libkatgpu.so")
 
 
 class TableInfo(C.Structure):

@@ -92,7 +92,7 @@ __device__ __forceinline__ bool cut_kmer(uint64_t hi, uint64_t lo, uint64_t bad4
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(kThreads, MODE == kModeInsert ? 3 : 2)
+__global__ void __launch_bounds__(kThreads, MODE == kModeInsert ? KATGPU_MIN_CTAS : 2)
     extract_kernel(const __grid_constant__ ExtractParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ExtractSmem &S = *reinterpret_cast<ExtractSmem *>(smem_raw);

@@ -8,7 +8,13 @@ constexpr int kTile = 8192;          // k-mer start positions per tile
 constexpr int kHalo = 32;            // >= k-1 bases of look-ahead, keeps TMA sizes 16-byte multiples
 constexpr int kGroups = kTile / 16;  // 16-base groups per tile
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;           // independent bucket loads in flight per thread
+#ifndef KATGPU_UNROLL
+#define KATGPU_UNROLL 4
+#endif
+#ifndef KATGPU_MIN_CTAS
+#define KATGPU_MIN_CTAS 3
+#endif
+constexpr int kUnroll = KATGPU_UNROLL; // independent bucket loads in flight per thread
 constexpr int kMaxRanks = 8;         // one NVSwitch box
 constexpr int kModeInsert = 0;
 constexpr int kModeRoute = 1;

@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -137,6 +138,14 @@ extern "C" katgpu_status katgpu_init(int device, katgpu_ctx **out) {
     if (prop.major < 10)
         return fail(KATGPU_ERR_NO_DEVICE, "katgpu_init: device %d is sm_%d%d; libkatgpu is built for sm_100a only", device,
                     prop.major, prop.minor);
+    // Random 32-byte bucket probes: ask L2 to fetch 32-byte sectors from HBM instead of
+    // promoting every miss to 64/128 bytes (a hint; KATGPU_L2_FETCH_BYTES overrides).
+    {
+        size_t gran = 32;
+        if (const char *e = getenv("KATGPU_L2_FETCH_BYTES")) gran = (size_t)atoi(e);
+        if (gran) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gran);
+        cudaGetLastError();
+    }
     katgpu_ctx *c = new (std::nothrow) katgpu_ctx();
     if (!c) return fail(KATGPU_ERR_NOMEM, "katgpu_init: out of host memory");
     c->device = device;
@@ -284,6 +293,7 @@ static katgpu_status make_geom(int k, int canonical, int Lb, int count_bits_cap,
     g.m1inv = inv_mod_2_64(kMixM1);
     g.m2inv = inv_mod_2_64(kMixM2);
     g.spill_cap = kSpillCap;
+    g.add_bound = ~0ULL; // set per launch
     return KATGPU_OK;
 }
 // Smallest Lb that leaves a count field of at least 16 bits (so that count
@@ -451,6 +461,7 @@ static katgpu_status launch_extract_insert(katgpu_table *t, const uint8_t *dev, 
     katgpu_ctx *c = t->ctx;
     ExtractParams P{};
     P.g = t->g;
+    P.g.add_bound = n_starts; // every k-mer of this launch could hit the same slot
     P.bases = dev;
     P.n_valid = n_valid;
     P.n_starts = n_starts;
@@ -630,7 +641,9 @@ extern "C" katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void
         const int grid = (int)std::min<uint64_t>((granted + 256 * kUnroll - 1) / (256 * kUnroll), (uint64_t)c->sm_count * 8);
         {
             ProfScope ps(c, "insert", c->stream);
-            launch_insert_hashed(t->g, hs + done, granted, grid, c->stream);
+            TableGeom gl = t->g;
+            gl.add_bound = granted;
+            launch_insert_hashed(gl, hs + done, granted, grid, c->stream);
         }
         c->launches++;
         CU(cudaGetLastError());

@@ -57,6 +57,7 @@ struct TableGeom {
     uint64_t cmax;     // (1 << cbits) - 1
     uint64_t m1inv, m2inv;
     uint64_t spill_cap;
+    uint64_t add_bound; // upper bound on the increments any one slot can receive in this launch
     uint32_t k, b, Lb, rbits, cshift, cbits, sh, canonical;
 };
 
@@ -145,7 +146,15 @@ static __device__ __noinline__ uint64_t ovf_get(const TableGeom &g, uint64_t h) 
 }
 
 // Add `cnt` (< 2^cbits) to an occupied slot; handles the wrap exactly.
-__device__ __forceinline__ void slot_add(const TableGeom &g, uint64_t *slot, uint64_t h, uint64_t cnt) {
+// `seen` is a value of the slot word read during this launch.  Counts only
+// grow, so the field can end the launch no higher than field(seen) + add_bound:
+// when that cannot carry, a fire-and-forget RED replaces the ATOM round trip.
+__device__ __forceinline__ void slot_add(const TableGeom &g, uint64_t *slot, uint64_t h, uint64_t cnt,
+                                         uint64_t seen) {
+    if ((seen >> g.cshift) + g.add_bound <= g.cmax && g.add_bound <= g.cmax) {
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(slot), "l"(cnt << g.cshift) : "memory");
+        return;
+    }
     unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long *>(slot),
                                        (unsigned long long)(cnt << g.cshift));
     if (((old >> g.cshift) + cnt) > g.cmax) { // this add carried out of the field
@@ -182,7 +191,7 @@ __device__ __forceinline__ int insert_hashed(const TableGeom &g, uint64_t h, uin
                 w = old;
             }
             if ((w & g.tagmask) == want) {
-                if (low) slot_add(g, bp + s, h, low);
+                if (low) slot_add(g, bp + s, h, low, w);
                 if (carries) {
                     atomicOr(reinterpret_cast<unsigned long long *>(bp + s), 1ULL << (g.rbits + kProbeBits));
                     ovf_add(g, h, carries);
