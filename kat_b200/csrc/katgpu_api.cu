@@ -3,6 +3,7 @@
 // pipeline and the launch glue around the kernels.
 #include "../../include/katgpu.h"
 #include "count_kernels.cuh"
+#include "partition_kernels.cuh"
 #include "reduce_kernels.cuh"
 #include "synth.cuh"
 
@@ -11,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
 #include <map>
 #include <new>
 #include <string>
@@ -51,6 +53,7 @@ struct katgpu_ctx {
     int sm_count = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     int bps[2] = {1, 1}; // resident CTAs per SM of the extract kernels
+    int bps_part = 1;    // ... of the partition kernel
     unsigned int *tile_counter = nullptr; // device
     unsigned long long *route_cursors = nullptr; // device [kMaxRanks] + overflow flag after
     // host feed staging
@@ -71,7 +74,12 @@ struct katgpu_table {
     bool allow_grow = true, ended = false;
     uint32_t grow_events = 0;
     int count_bits_cap = 0;
-    uint64_t n_total_carry = 0; // not used: n_total lives in the device counter block
+    // keys partitioned by table slice, waiting for the next sweep (partitioned path)
+    uint64_t *pend_keys = nullptr;
+    uint32_t *pend_seglen = nullptr, *pend_hll = nullptr;
+    uint32_t pend_Pb = 0, pend_segs = 0, pend_seg_cap = 0;
+    double pend_fill = 0;      // conservative estimate of the fullest segment (keys)
+    uint64_t pend_bound = 0;   // upper bound on pending k-mer instances
 };
 
 static const size_t kChunkBytes = 128u << 20; // host feed granularity
@@ -154,6 +162,9 @@ extern "C" katgpu_status katgpu_init(int device, katgpu_ctx **out) {
     CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     CU(extract_configure(kModeInsert, &c->bps[0]));
     CU(extract_configure(kModeRoute, &c->bps[1]));
+    CU(partition_configure(&c->bps_part));
+    if (c->bps_part < 1) return fail(KATGPU_ERR_CUDA, "katgpu_init: partition kernel does not fit on an SM");
+    if (c->bps_part > 2) c->bps_part = 2;
     if (c->bps[0] < 1 || c->bps[1] < 1) return fail(KATGPU_ERR_CUDA, "katgpu_init: extract kernel does not fit on an SM");
     CU(cudaMalloc(&c->tile_counter, 256));
     CU(cudaMalloc(&c->route_cursors, 256));
@@ -363,6 +374,9 @@ extern "C" void katgpu_table_free(katgpu_table *t) {
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     free_table_storage(t->g);
+    if (t->pend_keys) cudaFree(t->pend_keys);
+    if (t->pend_seglen) cudaFree(t->pend_seglen);
+    if (t->pend_hll) cudaFree(t->pend_hll);
     delete t;
 }
 
@@ -377,11 +391,11 @@ static katgpu_status read_counters(katgpu_table *t, TableCounters &out) {
 
 // Double the table (hash_counter::double_size, JFI/hash_counter.hpp:204-244)
 // and replay any parked keys.
-static katgpu_status grow_table(katgpu_table *t, const TableCounters &cur) {
+static katgpu_status grow_table(katgpu_table *t, const TableCounters &cur, int target_Lb = 0) {
     katgpu_ctx *c = t->ctx;
     if ((int)t->g.Lb >= (int)t->g.b) return fail(KATGPU_ERR_HASH_FULL, "Hash full: table already covers the whole %u-bit key space", t->g.b);
     TableGeom ng{};
-    KT(make_geom(t->g.k, t->g.canonical, t->g.Lb + 1, t->count_bits_cap, ng));
+    KT(make_geom(t->g.k, t->g.canonical, std::max<int>(t->g.Lb + 1, target_Lb), t->count_bits_cap, ng));
     uint64_t new_slots = 0;
     katgpu_status st = alloc_table_storage(c, ng, new_slots);
     if (st != KATGPU_OK) {
@@ -480,12 +494,174 @@ static katgpu_status launch_extract_insert(katgpu_table *t, const uint8_t *dev, 
     return KATGPU_OK;
 }
 
+// ---- partitioned (L2-resident) counting path ----------------------------------
+static int count_path_mode() { // 0 auto, 1 direct, 2 partition
+    const char *e = getenv("KATGPU_COUNT_PATH");
+    if (!e) return 0;
+    if (!strcmp(e, "direct")) return 1;
+    if (!strcmp(e, "partition")) return 2;
+    return 0;
+}
+static bool use_partition(const katgpu_table *t, uint64_t kmers_hint) {
+    const int m = count_path_mode();
+    if (m == 1 || t->g.Lb < 6) return false;
+    if (m == 2) return true;
+    // worth it once the table is far larger than L2 and the batch amortises one table pass
+    return t->n_slots * 8 >= (512ull << 20) && kmers_hint >= (32ull << 20);
+}
+
+static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) {
+    ok = true;
+    if (t->pend_keys) return KATGPU_OK;
+    katgpu_ctx *c = t->ctx;
+    const uint64_t table_bytes = t->n_slots * 8;
+    int Pb = ceil_log2(std::max<uint64_t>(1, table_bytes / (32ull << 20)));
+    Pb = std::max(1, std::min(Pb, 9));
+    Pb = std::min<int>(Pb, (int)t->g.Lb - 2);
+    const uint64_t nparts = 1ull << Pb, n_segs = (uint64_t)c->sm_count * c->bps_part;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    const uint64_t budget_keys = (uint64_t)((double)free_b * 0.70 / 8.0);
+    uint64_t want = (uint64_t)((double)std::max<uint64_t>(kmers_hint, t->n_slots / 4) * 1.12) + nparts * n_segs * 256;
+    want = std::min(want, budget_keys);
+    uint64_t seg_cap = want / (nparts * n_segs) / 16 * 16;
+    if (seg_cap < 256) {
+        ok = false; // not enough memory for a useful pending buffer: use the direct path
+        return KATGPU_OK;
+    }
+    seg_cap = std::min<uint64_t>(seg_cap, 0x7fffffffu / 16 * 16);
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, nparts * n_segs * seg_cap * 8);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        ok = false;
+        return KATGPU_OK;
+    }
+    t->pend_keys = (uint64_t *)p;
+    CU(cudaMalloc(&p, nparts * n_segs * 4));
+    t->pend_seglen = (uint32_t *)p;
+    CU(cudaMalloc(&p, kHllM * 4));
+    t->pend_hll = (uint32_t *)p;
+    CU(cudaMemsetAsync(t->pend_seglen, 0, nparts * n_segs * 4, c->stream));
+    CU(cudaMemsetAsync(t->pend_hll, 0, kHllM * 4, c->stream));
+    t->pend_Pb = Pb;
+    t->pend_segs = (uint32_t)n_segs;
+    t->pend_seg_cap = (uint32_t)seg_cap;
+    t->pend_fill = 0;
+    t->pend_bound = 0;
+    return KATGPU_OK;
+}
+
+static double hll_estimate(const uint32_t *reg, int m) {
+    double z = 0;
+    int zeros = 0;
+    for (int i = 0; i < m; i++) {
+        z += std::ldexp(1.0, -(int)reg[i]);
+        zeros += reg[i] == 0;
+    }
+    const double alpha = 0.7213 / (1.0 + 1.079 / m);
+    double e = alpha * m * (double)m / z;
+    if (e <= 2.5 * m && zeros > 0) e = m * std::log((double)m / zeros);
+    return e;
+}
+
+// Insert every pending key, slice by slice (sweep_kernel), after sizing the table
+// for the estimated number of new distinct keys.
+static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
+    if (!t->pend_keys || t->pend_bound == 0) return KATGPU_OK;
+    katgpu_ctx *c = t->ctx;
+    uint32_t h_hll[kHllM];
+    CU(cudaMemcpyAsync(h_hll, t->pend_hll, sizeof h_hll, cudaMemcpyDeviceToHost, c->stream));
+    KT(read_counters(t, ctr)); // synchronises
+    const double est_new = std::min((double)t->pend_bound, hll_estimate(h_hll, kHllM) * (double)(1u << kHllSampleShift) * 1.12 + 4096.0);
+    if ((int)t->g.Lb < (int)t->g.b) {
+        const double need = (double)ctr.n_distinct + est_new;
+        if (need > kMaxLoad * (double)t->n_slots) {
+            if (t->allow_grow) {
+                int lb = t->g.Lb;
+                while (lb < (int)t->g.b && need > 0.70 * (double)((uint64_t)kSlotsPerBucket << lb)) lb++;
+                KT(grow_table(t, ctr, lb));
+                KT(read_counters(t, ctr));
+            } else if ((double)ctr.n_distinct + est_new / 1.12 * 0.9 > (double)t->n_slots)
+                return fail(KATGPU_ERR_HASH_FULL, "Hash full");
+        }
+    }
+    SweepParams P{};
+    P.g = t->g;
+    const double per_part = t->pend_fill * (double)t->pend_segs; // keys that can target one slot
+    P.g.add_bound = per_part < 1.8e19 ? (uint64_t)per_part + 1 : ~0ULL;
+    P.keys = t->pend_keys;
+    P.seglen = t->pend_seglen;
+    P.seg_cap = t->pend_seg_cap;
+    P.n_segs = t->pend_segs;
+    P.part_lo = 0;
+    P.part_hi = 1u << t->pend_Pb;
+    P.split = 2;
+    {
+        ProfScope ps(c, "sweep", c->stream);
+        launch_sweep(P, c->stream);
+    }
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemsetAsync(t->pend_seglen, 0, ((size_t)1 << t->pend_Pb) * t->pend_segs * 4, c->stream));
+    CU(cudaMemsetAsync(t->pend_hll, 0, kHllM * 4, c->stream));
+    t->pend_fill = 0;
+    t->pend_bound = 0;
+    return settle(t, ctr);
+}
+
+static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
+                                      TableCounters &ctr) {
+    katgpu_ctx *c = t->ctx;
+    const double m = (double)kTile / (double)(1u << t->pend_Pb);
+    const double need_per_tile = m + 4.0 * std::sqrt(m) + 4.0; // mean + 4 sigma + padding, per CTA tile per slice
+    uint64_t done = 0;
+    while (done < n_starts) {
+        const double room = (double)t->pend_seg_cap - t->pend_fill;
+        const uint64_t cta_tiles = room > need_per_tile ? (uint64_t)(room / need_per_tile) : 0;
+        if (cta_tiles == 0) {
+            KT(sweep_pending(t, ctr));
+            continue;
+        }
+        const uint64_t max_starts = cta_tiles * t->pend_segs * (uint64_t)kTile;
+        const uint64_t take = std::min(n_starts - done, max_starts);
+        PartitionParams P{};
+        P.g = t->g;
+        P.bases = dev + done;
+        P.n_valid = n_valid - done;
+        P.n_starts = take;
+        P.n_tiles = (int)((take + kTile - 1) / kTile);
+        P.tma_ok = (reinterpret_cast<uintptr_t>(dev + done) & 15) == 0;
+        P.Pb = t->pend_Pb;
+        P.seg_cap = t->pend_seg_cap;
+        P.keys = t->pend_keys;
+        P.seglen = t->pend_seglen;
+        P.hll = t->pend_hll;
+        {
+            ProfScope ps(c, "partition", c->stream);
+            launch_partition(P, (int)t->pend_segs, c->stream);
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+        t->pend_fill += (double)((P.n_tiles + t->pend_segs - 1) / t->pend_segs) * need_per_tile;
+        t->pend_bound += take;
+        done += take;
+    }
+    return KATGPU_OK;
+}
+
 // Count a device-resident stream, in admission-controlled sub-launches.
 static katgpu_status feed_device_range(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
-                                       TableCounters &ctr) {
+                                       TableCounters &ctr, uint64_t kmers_hint) {
     // a k-mer start needs k bases
     if (n_valid < (uint64_t)t->g.k) return KATGPU_OK;
     n_starts = std::min(n_starts, n_valid - t->g.k + 1);
+    if (use_partition(t, kmers_hint)) {
+        bool ok = false;
+        KT(pend_alloc(t, kmers_hint, ok));
+        if (ok) return feed_partitioned(t, dev, n_valid, n_starts, ctr);
+    }
+    KT(sweep_pending(t, ctr)); // keep insertion order irrelevant but the table consistent
     uint64_t done = 0;
     while (done < n_starts) {
         uint64_t granted = 0;
@@ -505,7 +681,7 @@ extern "C" katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *b
     CU(cudaSetDevice(t->ctx->device));
     TableCounters ctr;
     KT(read_counters(t, ctr));
-    return feed_device_range(t, (const uint8_t *)bases_dev, n, n, ctr);
+    return feed_device_range(t, (const uint8_t *)bases_dev, n, n, ctr, n);
 }
 
 extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n) {
@@ -552,7 +728,7 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
         const size_t len = std::min(n - off, chunk + kHalo);
         const size_t starts = std::min(n - off, chunk);
         CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
-        KT(feed_device_range(t, c->chunk[b], len, starts, ctr));
+        KT(feed_device_range(t, c->chunk[b], len, starts, ctr, n));
         CU(cudaEventRecord(c->chunk_free[b], c->stream));
     }
     return KATGPU_OK;
@@ -562,8 +738,17 @@ extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct,
     if (!t) return fail(KATGPU_ERR_INVALID, "katgpu_count_end: NULL table");
     CU(cudaSetDevice(t->ctx->device));
     TableCounters ctr;
+    KT(read_counters(t, ctr));
+    KT(sweep_pending(t, ctr));
     KT(settle(t, ctr));
     t->ended = true;
+    if (t->pend_keys) { // the pending-key buffer is only needed while counting
+        cudaFree(t->pend_keys);
+        cudaFree(t->pend_seglen);
+        cudaFree(t->pend_hll);
+        t->pend_keys = nullptr;
+        t->pend_seglen = t->pend_hll = nullptr;
+    }
     if (n_distinct) *n_distinct = ctr.n_distinct;
     if (n_total) *n_total = ctr.n_total;
     return KATGPU_OK;
@@ -633,6 +818,7 @@ extern "C" katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void
     CU(cudaSetDevice(c->device));
     TableCounters ctr;
     KT(read_counters(t, ctr));
+    KT(sweep_pending(t, ctr));
     const uint64_t *hs = (const uint64_t *)hashed_dev;
     uint64_t done = 0;
     while (done < n) {

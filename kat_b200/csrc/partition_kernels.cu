@@ -1,0 +1,291 @@
+// partition_kernels.cu — the L2-resident counting path.
+//
+// Measured on B200: inserting k-mers in read order makes every probe a random
+// HBM line fetch and tops out at ~15.6 G inserts/s whatever the occupancy
+// (profiles/r1_v0_count_kernel_ncu.txt).  So counting is split in two
+// streaming phases, the GPU analogue of the reference's slice-wise table
+// ownership (JFI/large_hash_array.hpp:487-503) applied to *insertion*:
+//
+//   P  partition_kernel  extract + canonicalise + hash (as extract_kernel) and
+//      bucket the 64-bit hashed keys by the table slice they will land in
+//      (top Pb bits of the hash).  Per tile: warp-level match.any ranking ->
+//      per-warp counters -> one block scan -> counting sort in shared memory
+//      -> coalesced 32-byte-aligned appends to this CTA's private segment of
+//      every slice (no global atomics).
+//   S  sweep_kernel  walks the slices in order; all CTAs work on the same
+//      slice at (nearly) the same time, so the 32-64 MB of table it covers
+//      stays in the 126 MB L2: bucket loads and atomics hit L2, HBM only sees
+//      the key stream (8 B/k-mer, sequential) and one read + write-back of the
+//      table.
+#include "partition_kernels.cuh"
+#include "extract.cuh"
+
+namespace katgpu {
+
+constexpr uint64_t kSentinel = ~0ULL; // padding key (segments are appended in multiples of 4 keys)
+
+struct __align__(128) PartSmem {
+    uint8_t ascii[kTile + kHalo];
+    uint32_t W[kGroups + 2];
+    uint32_t B[kGroups + 2];
+    uint64_t mbar;
+    uint32_t off[kMaxParts + 2];                  // exclusive prefix of per-partition counts (+dummy bin)
+    uint32_t gcur[kMaxParts];                     // this CTA's append cursor per partition (keys)
+    uint16_t wcnt[kPartThreads / 32][kMaxParts + 2]; // per-warp per-partition counts -> warp prefixes
+    uint32_t wscan[kPartThreads / 32];
+    uint32_t hll[kHllM];
+    uint64_t stage[kTile];
+};
+
+__device__ __forceinline__ uint64_t hll_hash(uint64_t h) {
+    uint64_t x = h * 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 32;
+    x *= 0xD6E8FEB86659FD93ULL;
+    x ^= x >> 32;
+    return x;
+}
+
+__global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid_constant__ PartitionParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    PartSmem &S = *reinterpret_cast<PartSmem *>(smem_raw);
+    const TableGeom &g = P.g;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t k = g.k;
+    const uint32_t nparts = 1u << P.Pb;
+    const uint32_t pshift = g.b - P.Pb;
+
+    for (uint32_t i = tid; i < nparts; i += kPartThreads) S.gcur[i] = P.seglen[(size_t)i * gridDim.x + blockIdx.x];
+    for (uint32_t i = tid; i < (uint32_t)kHllM; i += kPartThreads) S.hll[i] = 0;
+    for (uint32_t i = tid; i < (kPartThreads / 32) * (kMaxParts + 2); i += kPartThreads) (&S.wcnt[0][0])[i] = 0;
+    auto tile_tma = [&](int t) { return P.tma_ok && ((uint64_t)(t + 1) * kTile + kHalo <= P.n_valid); };
+    int tile = blockIdx.x; // static striding: per-CTA segment fill is predictable
+    if (tid == 0) {
+        mbar_init(&S.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < P.n_tiles && tile_tma(tile)) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&S.mbar, kTile + kHalo);
+            tma_load_1d(S.ascii, P.bases + (uint64_t)tile * kTile, kTile + kHalo, &S.mbar);
+        }
+    }
+    __syncthreads();
+    uint32_t parity = 0;
+    unsigned long long direct_new = 0, direct_total = 0;
+
+    for (; tile < P.n_tiles; tile += gridDim.x) {
+        const uint64_t tile_base = (uint64_t)tile * kTile;
+        if (tile_tma(tile)) {
+            while (!mbar_try_wait(&S.mbar, parity)) {
+            }
+            parity ^= 1;
+        } else {
+            for (int i = tid; i < (kTile + kHalo); i += kPartThreads) {
+                const uint64_t p = tile_base + i;
+                S.ascii[i] = p < P.n_valid ? P.bases[p] : (uint8_t)0;
+            }
+            __syncthreads();
+        }
+        for (int gi = tid; gi < kGroups + 2; gi += kPartThreads) {
+            const uint4 v = reinterpret_cast<const uint4 *>(S.ascii)[gi];
+            uint32_t c0, c1, c2, c3, b0, b1, b2, b3;
+            pack4(v.x, c0, b0);
+            pack4(v.y, c1, b1);
+            pack4(v.z, c2, b2);
+            pack4(v.w, c3, b3);
+            S.W[gi] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+            S.B[gi] = (b0 << 12) | (b1 << 8) | (b2 << 4) | b3;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            const int nt = tile + gridDim.x;
+            if (nt < P.n_tiles && tile_tma(nt)) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&S.mbar, kTile + kHalo);
+                tma_load_1d(S.ascii, P.bases + (uint64_t)nt * kTile, kTile + kHalo, &S.mbar);
+            }
+        }
+        // ---- A: hash 16 k-mers per thread, rank them inside (warp, partition) ----
+        const int gi = tid; // kGroups == kPartThreads
+        const uint64_t p0 = tile_base + (uint64_t)gi * 16;
+        const uint64_t hi = ((uint64_t)S.W[gi] << 32) | S.W[gi + 1];
+        const uint64_t lo = (uint64_t)S.W[gi + 2] << 32;
+        const uint64_t bad48 = ((uint64_t)S.B[gi] << 32) | ((uint64_t)S.B[gi + 1] << 16) | S.B[gi + 2];
+        const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
+        uint64_t hh[16];
+        uint32_t rk[8]; // 16-bit rank inside (warp, partition), two per register
+#pragma unroll
+        for (uint32_t r = 0; r < 16; r++) {
+            uint64_t fwd;
+            const bool ok = cut_kmer(hi, lo, bad48, r, k, fwd) && (r < nst);
+            uint64_t key = fwd;
+            if (g.canonical) {
+                const uint64_t rc = revcomp_kmer(fwd, k);
+                key = rc < fwd ? rc : fwd;
+            }
+            const uint64_t h = mix_key(g, key);
+            if (ok && h == kSentinel) { // the one hash value that doubles as padding (k = 32 only)
+                Bucket bk = {};
+                direct_new += insert_hashed(g, h, 1, bk, false) == 1;
+                direct_total++;
+            }
+            hh[r] = ok ? h : kSentinel;
+            const uint32_t part = hh[r] != kSentinel ? (uint32_t)(h >> pshift) : nparts; // dummy bin for non-k-mers
+            const uint32_t peers = __match_any_sync(0xffffffffu, part);
+            const int leader = __ffs(peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader) {
+                old = S.wcnt[warp][part];
+                S.wcnt[warp][part] = (uint16_t)(old + __popc(peers));
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            const uint32_t rank = old + __popc(peers & ((1u << lane) - 1));
+            if (r & 1) rk[r >> 1] |= rank << 16;
+            else rk[r >> 1] = rank;
+            __syncwarp();
+            // distinct-key estimate: HyperLogLog over a 1/16 sample of the key space
+            if (ok && (h & ((1u << kHllSampleShift) - 1)) == 0) {
+                const uint64_t x = hll_hash(h);
+                atomicMax(&S.hll[x >> (64 - kHllBits)], (uint32_t)__clzll((x << kHllBits) | (1ULL << (kHllBits - 1))) + 1);
+            }
+        }
+        __syncthreads();
+        // ---- B: per-partition totals over warps, then block scan over partitions ----
+        uint32_t mine = 0;
+        if ((uint32_t)tid < nparts) { // one partition column per thread (nparts <= kPartThreads)
+            uint32_t run = 0;
+#pragma unroll
+            for (int w = 0; w < kPartThreads / 32; w++) {
+                const uint32_t t = S.wcnt[w][tid];
+                S.wcnt[w][tid] = (uint16_t)run;
+                run += t;
+            }
+            mine = run;
+        }
+        uint32_t inc = mine;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += t;
+        }
+        if (lane == 31) S.wscan[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+#pragma unroll
+        for (int w = 0; w < kPartThreads / 32; w++)
+            if (w < warp) wbase += S.wscan[w];
+        if ((uint32_t)tid < nparts) S.off[tid] = wbase + inc - mine;
+        if ((uint32_t)tid == nparts - 1) S.off[nparts] = wbase + inc; // total
+        __syncthreads();
+        // ---- C: counting-sort scatter into the stage ----
+#pragma unroll
+        for (uint32_t r = 0; r < 16; r++) {
+            const uint64_t h = hh[r];
+            if (h != kSentinel) {
+                const uint32_t part = (uint32_t)(h >> pshift);
+                const uint32_t rank = (rk[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
+                S.stage[S.off[part] + S.wcnt[warp][part] + rank] = h;
+            }
+        }
+        __syncthreads();
+        // ---- D: append each partition's run (padded to 4 keys = 32 B) to this CTA's segment ----
+        for (uint32_t part = warp; part < nparts; part += kPartThreads / 32) {
+            const uint32_t o = S.off[part], n = S.off[part + 1] - o;
+            if (n == 0) continue;
+            const uint32_t n_out = (n + 3) & ~3u;
+            const uint32_t cur = S.gcur[part];
+            if (cur + n_out <= P.seg_cap) {
+                uint64_t *dst = P.keys + ((size_t)part * gridDim.x + blockIdx.x) * P.seg_cap + cur;
+                for (uint32_t j = lane; j < n_out; j += 32) dst[j] = j < n ? S.stage[o + j] : kSentinel;
+                if (lane == 0) S.gcur[part] = cur + n_out;
+            } else {
+                // segment full: insert these keys the slow (random-access) way; never lose a k-mer
+                for (uint32_t j = lane; j < n; j += 32) {
+                    Bucket bk = {};
+                    direct_new += insert_hashed(g, S.stage[o + j], 1, bk, false) == 1;
+                    direct_total++;
+                }
+            }
+        }
+        // reset the per-warp counters for the next tile
+        for (uint32_t i = tid; i < (kPartThreads / 32) * (kMaxParts + 2); i += kPartThreads) (&S.wcnt[0][0])[i] = 0;
+        __syncthreads();
+    }
+    for (uint32_t i = tid; i < nparts; i += kPartThreads) P.seglen[(size_t)i * gridDim.x + blockIdx.x] = S.gcur[i];
+    for (uint32_t i = tid; i < (uint32_t)kHllM; i += kPartThreads)
+        if (S.hll[i]) atomicMax(P.hll + i, S.hll[i]);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        direct_total += __shfl_down_sync(0xffffffffu, direct_total, d);
+        direct_new += __shfl_down_sync(0xffffffffu, direct_new, d);
+    }
+    if (lane == 0) {
+        if (direct_total) atomicAdd(&g.ctr->n_total, direct_total);
+        if (direct_new) atomicAdd(&g.ctr->n_distinct, direct_new);
+    }
+}
+
+// Streaming load of pending keys: do not let them displace the table slice in L2.
+__device__ __forceinline__ uint64_t ld_key_stream(const uint64_t *p, uint64_t policy) {
+    uint64_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.u64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+    return v;
+}
+
+__global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) sweep_kernel(const __grid_constant__ SweepParams P) {
+    const TableGeom &g = P.g;
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    unsigned long long my_new = 0, my_total = 0;
+    // CTA -> (segment, piece): the same for every partition, so all CTAs advance
+    // through the slices in step and the slice being filled stays in L2.
+    const uint32_t seg = blockIdx.x / P.split, piece = blockIdx.x % P.split;
+    for (uint32_t part = P.part_lo; part < P.part_hi; part++) {
+        const size_t sidx = (size_t)part * P.n_segs + seg;
+        const uint32_t len = P.seglen[sidx];
+        const uint32_t per = ((len + P.split - 1) / P.split + 3) & ~3u;
+        const uint32_t lo = min(len, piece * per), hi = min(len, lo + per);
+        const uint64_t *keys = P.keys + sidx * P.seg_cap;
+        for (uint32_t base = lo; base < hi; base += kSweepThreads * kUnroll) {
+            uint64_t h[kUnroll];
+            bool ok[kUnroll];
+            Bucket bk[kUnroll];
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                const uint32_t i = base + u * kSweepThreads + threadIdx.x;
+                h[u] = i < hi ? ld_key_stream(keys + i, pol) : kSentinel;
+                ok[u] = h[u] != kSentinel;
+                if (ok[u]) bk[u] = load_bucket(g.slots + (((h[u] >> g.rbits) & g.bmask) << 2));
+            }
+#pragma unroll
+            for (int u = 0; u < kUnroll; u++) {
+                if (ok[u]) {
+                    my_new += insert_hashed(g, h[u], 1, bk[u], true) == 1;
+                    my_total++;
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        my_total += __shfl_down_sync(0xffffffffu, my_total, d);
+        my_new += __shfl_down_sync(0xffffffffu, my_new, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (my_total) atomicAdd(&g.ctr->n_total, my_total);
+        if (my_new) atomicAdd(&g.ctr->n_distinct, my_new);
+    }
+}
+
+size_t partition_smem_bytes() { return sizeof(PartSmem); }
+
+cudaError_t partition_configure(int *blocks_per_sm) {
+    cudaError_t e = cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem));
+    if (e != cudaSuccess) return e;
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, partition_kernel, kPartThreads, sizeof(PartSmem));
+}
+void launch_partition(const PartitionParams &P, int grid, cudaStream_t st) {
+    partition_kernel<<<grid, kPartThreads, sizeof(PartSmem), st>>>(P);
+}
+void launch_sweep(const SweepParams &P, cudaStream_t st) { sweep_kernel<<<P.n_segs * P.split, kSweepThreads, 0, st>>>(P); }
+
+} // namespace katgpu

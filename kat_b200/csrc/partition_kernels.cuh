@@ -1,0 +1,46 @@
+// partition_kernels.cuh — declarations of the L2-resident counting path.
+#pragma once
+#include "count_kernels.cuh"
+
+namespace katgpu {
+
+constexpr int kPartThreads = 512;  // == kGroups: one 16-base group per thread per tile
+constexpr int kMaxParts = 512;     // table slices (Pb <= 9)
+constexpr int kHllBits = 10;       // HyperLogLog registers for the distinct-key estimate
+constexpr int kHllM = 1 << kHllBits;
+constexpr int kHllSampleShift = 4; // 1/16 of the key space is sampled
+#ifndef KATGPU_SWEEP_THREADS
+#define KATGPU_SWEEP_THREADS 256
+#endif
+#ifndef KATGPU_SWEEP_MIN_CTAS
+#define KATGPU_SWEEP_MIN_CTAS 4
+#endif
+constexpr int kSweepThreads = KATGPU_SWEEP_THREADS;
+constexpr int kSweepMinCtas = KATGPU_SWEEP_MIN_CTAS;
+
+struct PartitionParams {
+    TableGeom g;
+    const uint8_t *bases;
+    uint64_t n_valid, n_starts;
+    int n_tiles, tma_ok;
+    uint32_t Pb;        // log2(partitions)
+    uint32_t seg_cap;   // keys per (partition, CTA) segment, multiple of 16
+    uint64_t *keys;     // [partition][cta][seg_cap]
+    uint32_t *seglen;   // [partition][cta] keys appended so far (multiples of 4)
+    uint32_t *hll;      // [kHllM]
+};
+
+struct SweepParams {
+    TableGeom g;
+    const uint64_t *keys;
+    const uint32_t *seglen;
+    uint32_t seg_cap, n_segs, part_lo, part_hi;
+    uint32_t split; // CTAs per segment
+};
+
+size_t partition_smem_bytes();
+cudaError_t partition_configure(int *blocks_per_sm);
+void launch_partition(const PartitionParams &P, int grid, cudaStream_t st);
+void launch_sweep(const SweepParams &P, cudaStream_t st);
+
+} // namespace katgpu

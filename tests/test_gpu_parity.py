@@ -11,6 +11,14 @@ from kat_b200 import binding as B
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(autouse=True, params=["direct", "partition"])
+def count_path(request, monkeypatch):
+    """Every case runs through both counting paths of libkatgpu: extract+insert in
+    read order ("direct") and partition-by-slice + L2-resident sweep ("partition")."""
+    monkeypatch.setenv("KATGPU_COUNT_PATH", request.param)
+    return request.param
+
+
 def ora_table(chunks, k, canonical=True):
     return O.Table.from_chunks([bytes(c) for c in chunks], k, canonical)
 
