@@ -79,6 +79,7 @@ struct katgpu_table {
     uint32_t *pend_seglen = nullptr, *pend_hll = nullptr;
     uint32_t pend_Pb = 0, pend_segs = 0, pend_seg_cap = 0;
     double pend_fill = 0;      // conservative estimate of the fullest segment (keys)
+    uint64_t pend_tiles = 0;   // tiles each CTA has partitioned since the last sweep
     uint64_t pend_bound = 0;   // upper bound on pending k-mer instances
 };
 
@@ -515,7 +516,9 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     if (t->pend_keys) return KATGPU_OK;
     katgpu_ctx *c = t->ctx;
     const uint64_t table_bytes = t->n_slots * 8;
-    int Pb = ceil_log2(std::max<uint64_t>(1, table_bytes / (32ull << 20)));
+    uint64_t slice_mb = 32; // table bytes swept at a time; must stay L2-resident
+    if (const char *e = getenv("KATGPU_SLICE_MB")) slice_mb = std::max(1, atoi(e));
+    int Pb = ceil_log2(std::max<uint64_t>(1, table_bytes / (slice_mb << 20)));
     Pb = std::max(1, std::min(Pb, 9));
     Pb = std::min<int>(Pb, (int)t->g.Lb - 2);
     const uint64_t nparts = 1ull << Pb, n_segs = (uint64_t)c->sm_count * c->bps_part;
@@ -525,7 +528,10 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     uint64_t want = (uint64_t)((double)std::max<uint64_t>(kmers_hint, t->n_slots / 4) * 1.12) + nparts * n_segs * 256;
     want = std::min(want, budget_keys);
     uint64_t seg_cap = want / (nparts * n_segs) / 16 * 16;
-    if (seg_cap < 256) {
+    const double m_tile = (double)kTile / (double)nparts; // keys one tile sends to one slice
+    const uint64_t min_cap = ((uint64_t)(2.2 * (m_tile + 4.0 * std::sqrt(m_tile) + 4.0)) + 255) / 16 * 16;
+    seg_cap = std::max(seg_cap, min_cap);
+    if (nparts * n_segs * seg_cap > budget_keys) {
         ok = false; // not enough memory for a useful pending buffer: use the direct path
         return KATGPU_OK;
     }
@@ -597,6 +603,7 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
     P.part_lo = 0;
     P.part_hi = 1u << t->pend_Pb;
     P.split = 2;
+    if (const char *e = getenv("KATGPU_SWEEP_SPLIT")) P.split = std::max(1, atoi(e));
     {
         ProfScope ps(c, "sweep", c->stream);
         launch_sweep(P, c->stream);
@@ -606,6 +613,7 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
     CU(cudaMemsetAsync(t->pend_seglen, 0, ((size_t)1 << t->pend_Pb) * t->pend_segs * 4, c->stream));
     CU(cudaMemsetAsync(t->pend_hll, 0, kHllM * 4, c->stream));
     t->pend_fill = 0;
+    t->pend_tiles = 0;
     t->pend_bound = 0;
     return settle(t, ctr);
 }
@@ -613,13 +621,25 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
 static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
                                       TableCounters &ctr) {
     katgpu_ctx *c = t->ctx;
+    // keys one CTA tile sends to one slice: mean m (every position a k-mer) + up to 3 padding keys;
+    // after T tiles the fullest segment holds about T*(m+2) + 4*sqrt(T*m) (a segment that still
+    // overflows falls back to direct insertion inside the kernel, so this only has to be a good guess)
     const double m = (double)kTile / (double)(1u << t->pend_Pb);
-    const double need_per_tile = m + 4.0 * std::sqrt(m) + 4.0; // mean + 4 sigma + padding, per CTA tile per slice
+    auto fill_after = [&](uint64_t tiles) { return (double)tiles * (m + 2.0) + 4.0 * std::sqrt((double)tiles * m); };
     uint64_t done = 0;
     while (done < n_starts) {
-        const double room = (double)t->pend_seg_cap - t->pend_fill;
-        const uint64_t cta_tiles = room > need_per_tile ? (uint64_t)(room / need_per_tile) : 0;
+        uint64_t cta_tiles = 0; // largest T with fill_after(pend_tiles + T) <= seg_cap
+        {
+            const double cap = (double)t->pend_seg_cap;
+            uint64_t lo = 0, hi = (uint64_t)(cap / (m + 2.0)) + 1;
+            while (lo < hi) {
+                const uint64_t mid = (lo + hi + 1) / 2;
+                if (fill_after(mid) <= cap) lo = mid; else hi = mid - 1;
+            }
+            cta_tiles = lo > t->pend_tiles ? lo - t->pend_tiles : 0;
+        }
         if (cta_tiles == 0) {
+            if (t->pend_tiles == 0) return fail(KATGPU_ERR_INVALID, "internal: pending segments smaller than one tile");
             KT(sweep_pending(t, ctr));
             continue;
         }
@@ -643,7 +663,8 @@ static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint6
         }
         c->launches++;
         CU(cudaGetLastError());
-        t->pend_fill += (double)((P.n_tiles + t->pend_segs - 1) / t->pend_segs) * need_per_tile;
+        t->pend_tiles += (P.n_tiles + t->pend_segs - 1) / t->pend_segs;
+        t->pend_fill = fill_after(t->pend_tiles);
         t->pend_bound += take;
         done += take;
     }

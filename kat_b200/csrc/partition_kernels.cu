@@ -245,22 +245,22 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) sweep_kernel(con
         const uint32_t per = ((len + P.split - 1) / P.split + 3) & ~3u;
         const uint32_t lo = min(len, piece * per), hi = min(len, lo + per);
         const uint64_t *keys = P.keys + sidx * P.seg_cap;
-        for (uint32_t base = lo; base < hi; base += kSweepThreads * kUnroll) {
-            uint64_t h[kUnroll];
-            bool ok[kUnroll];
-            Bucket bk[kUnroll];
+        for (uint32_t base = lo; base < hi; base += kSweepThreads * kSweepUnroll) {
+            uint64_t h[kSweepUnroll];
+            bool ok[kSweepUnroll];
+            Bucket bk[kSweepUnroll];
 #pragma unroll
-            for (int u = 0; u < kUnroll; u++) {
+            for (int u = 0; u < kSweepUnroll; u++) {
                 const uint32_t i = base + u * kSweepThreads + threadIdx.x;
                 h[u] = i < hi ? ld_key_stream(keys + i, pol) : kSentinel;
                 ok[u] = h[u] != kSentinel;
                 if (ok[u]) bk[u] = load_bucket(g.slots + (((h[u] >> g.rbits) & g.bmask) << 2));
             }
 #pragma unroll
-            for (int u = 0; u < kUnroll; u++) {
+            for (int u = 0; u < kSweepUnroll; u++) {
                 if (ok[u]) {
-                    my_new += insert_hashed(g, h[u], 1, bk[u], true) == 1;
                     my_total++;
+                    my_new += insert_hashed(g, h[u], 1, bk[u], true) == 1;
                 }
             }
         }

@@ -17,6 +17,10 @@ constexpr int kHllSampleShift = 4; // 1/16 of the key space is sampled
 #endif
 constexpr int kSweepThreads = KATGPU_SWEEP_THREADS;
 constexpr int kSweepMinCtas = KATGPU_SWEEP_MIN_CTAS;
+#ifndef KATGPU_SWEEP_UNROLL
+#define KATGPU_SWEEP_UNROLL 2
+#endif
+constexpr int kSweepUnroll = KATGPU_SWEEP_UNROLL;
 
 struct PartitionParams {
     TableGeom g;

@@ -99,9 +99,10 @@ struct Bucket {
 };
 // One 32-byte sector, L2-coherent (other SMs update it with atomics).
 __device__ __forceinline__ Bucket load_bucket(const uint64_t *p) {
-    Bucket r;
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(r.s[0]), "=l"(r.s[1]) : "l"(p));
-    asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(r.s[2]), "=l"(r.s[3]) : "l"(p + 2));
+    Bucket r; // one 256-bit request (LDG.E.256, sm_100+): a single sector transaction per probe
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];"
+                 : "=l"(r.s[0]), "=l"(r.s[1]), "=l"(r.s[2]), "=l"(r.s[3])
+                 : "l"(p));
     return r;
 }
 __device__ __forceinline__ void prefetch_bucket_l2(const uint64_t *p) {
@@ -207,6 +208,32 @@ __device__ __forceinline__ int insert_hashed(const TableGeom &g, uint64_t h, uin
         g.spill[2 * at + 1] = cnt;
     }
     return -1;
+}
+
+// Out-of-line general insert (claims, later probes, overflow): keeps the hot
+// loops of the streaming kernels small.  Returns like insert_hashed.
+static __device__ __noinline__ int insert_hashed_slow(const TableGeom &g, uint64_t h, uint64_t cnt) {
+    Bucket bk = {};
+    return insert_hashed(g, h, cnt, bk, false);
+}
+
+// Hot path of an insertion whose home bucket `bk` is already loaded: if the key
+// sits in its home bucket and the in-slot count cannot carry in this launch,
+// one fire-and-forget RED finishes it.  Returns false when the general path is needed.
+__device__ __forceinline__ bool insert_fast_hit(const TableGeom &g, uint64_t h, const Bucket &bk) {
+    if (g.add_bound > g.cmax) return false;
+    const uint64_t want = (h & g.rmask) | (1ULL << g.rbits); // probe 0
+    uint64_t *bp = g.slots + (((h >> g.rbits) & g.bmask) << 2);
+#pragma unroll
+    for (int s = 0; s < kSlotsPerBucket; s++) {
+        const uint64_t w = bk.s[s];
+        if ((w & g.tagmask) == want) {
+            if ((w >> g.cshift) + g.add_bound > g.cmax) return false;
+            asm volatile("red.global.add.u64 [%0], %1;" ::"l"(bp + s), "l"(1ULL << g.cshift) : "memory");
+            return true;
+        }
+    }
+    return false;
 }
 
 // Exact count of hashed key h (0 if absent).

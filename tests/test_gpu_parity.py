@@ -126,11 +126,11 @@ def test_exact_large_count(ctx):
     assert n == 1 and keys[0] == 0 and counts[0] == 30000
 
 
-def test_table_growth_and_hash_full(ctx):
+def test_table_growth_and_hash_full(ctx, count_path):
     s = seqgen.random_stream(400_000, seed=77, n_rate=0.001)
     ot = ora_table([s], 27)
     gt = gpu_table(ctx, [s], 27, hash_size=4096, allow_grow=True)
-    assert gt.info()["grow_events"] >= 3
+    assert gt.info()["grow_events"] >= (3 if count_path == "direct" else 1)  # the partitioned path sizes once from its HLL estimate
     assert_same_multiset(gt, ot)
     with pytest.raises(kat_b200.KatGpuError) as e:
         gpu_table(ctx, [s], 27, hash_size=4096, allow_grow=False)
