@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeInsert ? KATGPU_MIN_CTA
             // number of k-mer starts this thread owns (stream end / chunk overlap)
             const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
 
+            uint64_t rc = 0; // rolled reverse complement of the current k-mer
             if (MODE == kModeInsert) {
 #pragma unroll 1
                 for (uint32_t r0 = 0; r0 < 16; r0 += kUnroll) {
@@ -112,18 +113,14 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeInsert ? KATGPU_MIN_CTA
                     for (int u = 0; u < kUnroll; u++) {
                         uint64_t fwd;
                         ok[u] = cut_kmer(hi, lo, bad48, r0 + u, k, fwd) && (r0 + u < nst);
-                        uint64_t key = fwd;
-                        if (g.canonical) {
-                            const uint64_t rc = revcomp_kmer(fwd, k);
-                            key = rc < fwd ? rc : fwd;
-                        }
-                        h[u] = mix_key(g, key);
+                        rc = (r0 + u) == 0 ? revcomp_kmer(fwd, k) : (rc >> 2) | ((~fwd & 3ULL) << (2 * k - 2));
+                        h[u] = mix_key(g, (g.canonical && rc < fwd) ? rc : fwd);
                         if (ok[u]) bk[u] = load_bucket(g.slots + (((h[u] >> g.rbits) & g.bmask) << 2));
                     }
 #pragma unroll
                     for (int u = 0; u < kUnroll; u++) {
                         if (ok[u]) {
-                            const int res = insert_hashed(g, h[u], 1, bk[u], true);
+                            const int res = insert_home(g, h[u], bk[u]);
                             my_total++;
                             my_new += (res == 1);
                         }
@@ -138,12 +135,8 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeInsert ? KATGPU_MIN_CTA
                 for (uint32_t r = 0; r < 16; r++) {
                     uint64_t fwd;
                     const bool ok = cut_kmer(hi, lo, bad48, r, k, fwd) && (r < nst);
-                    uint64_t key = fwd;
-                    if (g.canonical) {
-                        const uint64_t rc = revcomp_kmer(fwd, k);
-                        key = rc < fwd ? rc : fwd;
-                    }
-                    hh[r] = mix_key(g, key);
+                    rc = r == 0 ? revcomp_kmer(fwd, k) : (rc >> 2) | ((~fwd & 3ULL) << (2 * k - 2));
+                    hh[r] = mix_key(g, (g.canonical && rc < fwd) ? rc : fwd);
                     const uint32_t o = ok ? owner_of(hh[r], P.n_ranks) : 0xFu;
                     owners |= (uint64_t)o << (4 * r);
                     if (ok) {
@@ -254,7 +247,7 @@ __global__ void __launch_bounds__(256) insert_hashed_kernel(const __grid_constan
 #pragma unroll
         for (int u = 0; u < kUnroll; u++) {
             if (ok[u]) {
-                my_new += insert_hashed(g, h[u], 1, bk[u], true) == 1;
+                my_new += insert_home(g, h[u], bk[u]) == 1;
                 my_total++;
             }
         }

@@ -54,6 +54,7 @@ struct katgpu_ctx {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     int bps[2] = {1, 1}; // resident CTAs per SM of the extract kernels
     int bps_part = 1;    // ... of the partition kernel
+    int bps_sweep = 1;   // ... of the sweep kernel
     unsigned int *tile_counter = nullptr; // device
     unsigned long long *route_cursors = nullptr; // device [kMaxRanks] + overflow flag after
     // host feed staging
@@ -65,6 +66,10 @@ struct katgpu_ctx {
     bool profiling = false;
     std::vector<ProfSpan> spans;
     std::map<std::string, std::pair<double, uint64_t>> prof;
+    // freed device blocks kept for reuse: a `kat hist` job after the first one does not pay
+    // cudaMalloc/cudaFree of tens of GB again (the reference likewise keeps its mmap'd arena)
+    std::multimap<size_t, void *> pool;
+    size_t pooled_bytes = 0;
 };
 
 struct katgpu_table {
@@ -76,15 +81,46 @@ struct katgpu_table {
     int count_bits_cap = 0;
     // keys partitioned by table slice, waiting for the next sweep (partitioned path)
     uint64_t *pend_keys = nullptr;
-    uint32_t *pend_seglen = nullptr, *pend_hll = nullptr;
+    uint32_t *pend_seglen = nullptr, *pend_hll = nullptr, *pend_done = nullptr;
     uint32_t pend_Pb = 0, pend_segs = 0, pend_seg_cap = 0;
     double pend_fill = 0;      // conservative estimate of the fullest segment (keys)
     uint64_t pend_tiles = 0;   // tiles each CTA has partitioned since the last sweep
     uint64_t pend_bound = 0;   // upper bound on pending k-mer instances
+    size_t pend_bytes = 0;
 };
 
 static const size_t kChunkBytes = 128u << 20; // host feed granularity
 static const uint64_t kSpillCap = 1u << 20;   // (hashed key, count) pairs
+
+// ---- device block cache ----
+static void pool_flush(katgpu_ctx *c) {
+    for (auto &kv : c->pool) cudaFree(kv.second);
+    c->pool.clear();
+    c->pooled_bytes = 0;
+}
+static cudaError_t pool_alloc(katgpu_ctx *c, size_t bytes, void **out) {
+    bytes = std::max<size_t>(bytes, 256);
+    auto it = c->pool.find(bytes);
+    if (it != c->pool.end()) {
+        *out = it->second;
+        c->pooled_bytes -= bytes;
+        c->pool.erase(it);
+        return cudaSuccess;
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation && !c->pool.empty()) {
+        cudaGetLastError();
+        pool_flush(c);
+        e = cudaMalloc(out, bytes);
+    }
+    return e;
+}
+static void pool_free(katgpu_ctx *c, void *p, size_t bytes) {
+    if (!p) return;
+    bytes = std::max<size_t>(bytes, 256);
+    c->pool.emplace(bytes, p);
+    c->pooled_bytes += bytes;
+}
 
 // ---- profiling helpers ----
 struct ProfScope {
@@ -166,6 +202,7 @@ extern "C" katgpu_status katgpu_init(int device, katgpu_ctx **out) {
     CU(partition_configure(&c->bps_part));
     if (c->bps_part < 1) return fail(KATGPU_ERR_CUDA, "katgpu_init: partition kernel does not fit on an SM");
     if (c->bps_part > 2) c->bps_part = 2;
+    CU(sweep_occupancy(&c->bps_sweep));
     if (c->bps[0] < 1 || c->bps[1] < 1) return fail(KATGPU_ERR_CUDA, "katgpu_init: extract kernel does not fit on an SM");
     CU(cudaMalloc(&c->tile_counter, 256));
     CU(cudaMalloc(&c->route_cursors, 256));
@@ -189,6 +226,7 @@ extern "C" void katgpu_shutdown(katgpu_ctx *c) {
         if (c->chunk_free[i]) cudaEventDestroy(c->chunk_free[i]);
         if (c->chunk_ready[i]) cudaEventDestroy(c->chunk_ready[i]);
     }
+    pool_flush(c);
     if (c->tile_counter) cudaFree(c->tile_counter);
     if (c->route_cursors) cudaFree(c->route_cursors);
     if (c->h_ctr) cudaFreeHost(c->h_ctr);
@@ -208,7 +246,13 @@ extern "C" void katgpu_host_free(void *p) {
 extern "C" katgpu_status katgpu_device_alloc(katgpu_ctx *c, size_t bytes, void **out) {
     if (!c || !out) return fail(KATGPU_ERR_INVALID, "katgpu_device_alloc: NULL argument");
     CU(cudaSetDevice(c->device));
-    CU(cudaMalloc(out, bytes ? bytes : 1));
+    cudaError_t e = cudaMalloc(out, bytes ? bytes : 1);
+    if (e == cudaErrorMemoryAllocation && !c->pool.empty()) { // give cached blocks back first
+        cudaGetLastError();
+        pool_flush(c);
+        e = cudaMalloc(out, bytes ? bytes : 1);
+    }
+    CU(e);
     return KATGPU_OK;
 }
 extern "C" void katgpu_device_free(katgpu_ctx *c, void *dev) {
@@ -321,13 +365,13 @@ static int min_Lb(int k) {
 static katgpu_status alloc_table_storage(katgpu_ctx *c, TableGeom &g, uint64_t &n_slots) {
     n_slots = (uint64_t)kSlotsPerBucket << g.Lb;
     void *p = nullptr;
-    CU(cudaMalloc(&p, n_slots * sizeof(uint64_t)));
+    CU(pool_alloc(c, n_slots * sizeof(uint64_t), &p));
     g.slots = (uint64_t *)p;
-    CU(cudaMalloc(&p, ((size_t)kOvfCap + 1) * 2 * sizeof(uint64_t)));
+    CU(pool_alloc(c, ((size_t)kOvfCap + 1) * 2 * sizeof(uint64_t), &p));
     g.ovf = (uint64_t *)p;
-    CU(cudaMalloc(&p, (size_t)kSpillCap * 2 * sizeof(uint64_t)));
+    CU(pool_alloc(c, (size_t)kSpillCap * 2 * sizeof(uint64_t), &p));
     g.spill = (uint64_t *)p;
-    CU(cudaMalloc(&p, sizeof(TableCounters)));
+    CU(pool_alloc(c, sizeof(TableCounters), &p));
     g.ctr = (TableCounters *)p;
     {
         ProfScope ps(c, "memset", c->stream);
@@ -337,11 +381,11 @@ static katgpu_status alloc_table_storage(katgpu_ctx *c, TableGeom &g, uint64_t &
     }
     return KATGPU_OK;
 }
-static void free_table_storage(TableGeom &g) {
-    if (g.slots) cudaFree(g.slots);
-    if (g.ovf) cudaFree(g.ovf);
-    if (g.spill) cudaFree(g.spill);
-    if (g.ctr) cudaFree(g.ctr);
+static void free_table_storage(katgpu_ctx *c, TableGeom &g) {
+    if (g.slots) pool_free(c, g.slots, ((uint64_t)kSlotsPerBucket << g.Lb) * sizeof(uint64_t));
+    if (g.ovf) pool_free(c, g.ovf, ((size_t)kOvfCap + 1) * 2 * sizeof(uint64_t));
+    if (g.spill) pool_free(c, g.spill, (size_t)kSpillCap * 2 * sizeof(uint64_t));
+    if (g.ctr) pool_free(c, g.ctr, sizeof(TableCounters));
     g.slots = g.ovf = g.spill = nullptr;
     g.ctr = nullptr;
 }
@@ -362,7 +406,7 @@ extern "C" katgpu_status katgpu_count_begin(katgpu_ctx *c, int k, int canonical,
     katgpu_status st = make_geom(k, canonical, Lb, t->count_bits_cap, t->g);
     if (st == KATGPU_OK) st = alloc_table_storage(c, t->g, t->n_slots);
     if (st != KATGPU_OK) {
-        free_table_storage(t->g);
+        free_table_storage(c, t->g);
         delete t;
         return st;
     }
@@ -374,10 +418,11 @@ extern "C" void katgpu_table_free(katgpu_table *t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    free_table_storage(t->g);
-    if (t->pend_keys) cudaFree(t->pend_keys);
+    free_table_storage(t->ctx, t->g);
+    if (t->pend_keys) pool_free(t->ctx, t->pend_keys, t->pend_bytes);
     if (t->pend_seglen) cudaFree(t->pend_seglen);
     if (t->pend_hll) cudaFree(t->pend_hll);
+    if (t->pend_done) cudaFree(t->pend_done);
     delete t;
 }
 
@@ -400,7 +445,7 @@ static katgpu_status grow_table(katgpu_table *t, const TableCounters &cur, int t
     uint64_t new_slots = 0;
     katgpu_status st = alloc_table_storage(c, ng, new_slots);
     if (st != KATGPU_OK) {
-        free_table_storage(ng);
+        free_table_storage(c, ng);
         return st;
     }
     const int grid = c->sm_count * 8;
@@ -418,7 +463,7 @@ static katgpu_status grow_table(katgpu_table *t, const TableCounters &cur, int t
     CU(cudaMemcpyAsync(&ng.ctr->n_total, &t->g.ctr->n_total, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, c->stream));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(c->stream));
-    free_table_storage(t->g);
+    free_table_storage(c, t->g);
     t->g = ng;
     t->n_slots = new_slots;
     t->grow_events++;
@@ -524,7 +569,7 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     const uint64_t nparts = 1ull << Pb, n_segs = (uint64_t)c->sm_count * c->bps_part;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t budget_keys = (uint64_t)((double)free_b * 0.70 / 8.0);
+    const uint64_t budget_keys = (uint64_t)((double)(free_b + c->pooled_bytes) * 0.70 / 8.0);
     uint64_t want = (uint64_t)((double)std::max<uint64_t>(kmers_hint, t->n_slots / 4) * 1.12) + nparts * n_segs * 256;
     want = std::min(want, budget_keys);
     uint64_t seg_cap = want / (nparts * n_segs) / 16 * 16;
@@ -537,17 +582,20 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     }
     seg_cap = std::min<uint64_t>(seg_cap, 0x7fffffffu / 16 * 16);
     void *p = nullptr;
-    cudaError_t e = cudaMalloc(&p, nparts * n_segs * seg_cap * 8);
+    cudaError_t e = pool_alloc(c, nparts * n_segs * seg_cap * 8, &p);
     if (e != cudaSuccess) {
         cudaGetLastError();
         ok = false;
         return KATGPU_OK;
     }
     t->pend_keys = (uint64_t *)p;
+    t->pend_bytes = nparts * n_segs * seg_cap * 8;
     CU(cudaMalloc(&p, nparts * n_segs * 4));
     t->pend_seglen = (uint32_t *)p;
     CU(cudaMalloc(&p, kHllM * 4));
     t->pend_hll = (uint32_t *)p;
+    CU(cudaMalloc(&p, kMaxParts * 4));
+    t->pend_done = (uint32_t *)p;
     CU(cudaMemsetAsync(t->pend_seglen, 0, nparts * n_segs * 4, c->stream));
     CU(cudaMemsetAsync(t->pend_hll, 0, kHllM * 4, c->stream));
     t->pend_Pb = Pb;
@@ -602,8 +650,17 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
     P.n_segs = t->pend_segs;
     P.part_lo = 0;
     P.part_hi = 1u << t->pend_Pb;
-    P.split = 2;
-    if (const char *e = getenv("KATGPU_SWEEP_SPLIT")) P.split = std::max(1, atoi(e));
+    // every sweep CTA must be resident at once (they synchronise slice by slice)
+    const uint32_t resident = (uint32_t)(c->sm_count * c->bps_sweep);
+    P.split = std::max<uint32_t>(1, resident / t->pend_segs);
+    P.window = 1;
+    if (const char *e = getenv("KATGPU_SWEEP_WINDOW")) P.window = (uint32_t)std::max(0, atoi(e));
+    if (P.split * t->pend_segs > resident) P.window = 0; // cannot guarantee co-residency: no barrier
+    P.slice_done = t->pend_done;
+    P.slice_slots = t->n_slots >> t->pend_Pb;
+    P.prefetch = 1;
+    if (const char *e = getenv("KATGPU_SWEEP_PREFETCH")) P.prefetch = (uint32_t)atoi(e);
+    CU(cudaMemsetAsync(t->pend_done, 0, kMaxParts * 4, c->stream));
     {
         ProfScope ps(c, "sweep", c->stream);
         launch_sweep(P, c->stream);
@@ -764,11 +821,12 @@ extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct,
     KT(settle(t, ctr));
     t->ended = true;
     if (t->pend_keys) { // the pending-key buffer is only needed while counting
-        cudaFree(t->pend_keys);
+        pool_free(t->ctx, t->pend_keys, t->pend_bytes);
         cudaFree(t->pend_seglen);
         cudaFree(t->pend_hll);
+        cudaFree(t->pend_done);
         t->pend_keys = nullptr;
-        t->pend_seglen = t->pend_hll = nullptr;
+        t->pend_seglen = t->pend_hll = t->pend_done = nullptr;
     }
     if (n_distinct) *n_distinct = ctr.n_distinct;
     if (n_total) *n_total = ctr.n_total;

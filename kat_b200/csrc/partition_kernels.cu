@@ -37,6 +37,12 @@ struct __align__(128) PartSmem {
     uint64_t stage[kTile];
 };
 
+__device__ __forceinline__ uint64_t sel16(const uint64_t (&a)[16], int i) {
+    uint64_t v = a[0];
+#pragma unroll
+    for (int j = 1; j < 16; j++) v = (i == j) ? a[j] : v;
+    return v;
+}
 __device__ __forceinline__ uint64_t hll_hash(uint64_t h) {
     uint64_t x = h * 0xD6E8FEB86659FD93ULL;
     x ^= x >> 32;
@@ -113,23 +119,21 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
         const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
         uint64_t hh[16];
         uint32_t rk[8]; // 16-bit rank inside (warp, partition), two per register
+        uint32_t hll_mask = 0, sent_mask = 0;
+        uint64_t rc = 0;
 #pragma unroll
         for (uint32_t r = 0; r < 16; r++) {
             uint64_t fwd;
             const bool ok = cut_kmer(hi, lo, bad48, r, k, fwd) && (r < nst);
-            uint64_t key = fwd;
-            if (g.canonical) {
-                const uint64_t rc = revcomp_kmer(fwd, k);
-                key = rc < fwd ? rc : fwd;
-            }
+            // reverse complement, rolled: drop the last base, complement of the new last base on top
+            rc = r == 0 ? revcomp_kmer(fwd, k) : (rc >> 2) | ((~fwd & 3ULL) << (2 * k - 2));
+            const uint64_t key = (g.canonical && rc < fwd) ? rc : fwd;
             const uint64_t h = mix_key(g, key);
-            if (ok && h == kSentinel) { // the one hash value that doubles as padding (k = 32 only)
-                Bucket bk = {};
-                direct_new += insert_hashed(g, h, 1, bk, false) == 1;
-                direct_total++;
-            }
-            hh[r] = ok ? h : kSentinel;
-            const uint32_t part = hh[r] != kSentinel ? (uint32_t)(h >> pshift) : nparts; // dummy bin for non-k-mers
+            const bool real = ok && h != kSentinel;
+            sent_mask |= (uint32_t)(ok && h == kSentinel) << r; // the one hash that doubles as padding (k = 32 only)
+            hll_mask |= (uint32_t)(real && (h & ((1u << kHllSampleShift) - 1)) == 0) << r;
+            hh[r] = real ? h : kSentinel;
+            const uint32_t part = real ? (uint32_t)(h >> pshift) : nparts; // dummy bin for non-k-mers
             const uint32_t peers = __match_any_sync(0xffffffffu, part);
             const int leader = __ffs(peers) - 1;
             uint32_t old = 0;
@@ -142,10 +146,20 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
             if (r & 1) rk[r >> 1] |= rank << 16;
             else rk[r >> 1] = rank;
             __syncwarp();
-            // distinct-key estimate: HyperLogLog over a 1/16 sample of the key space
-            if (ok && (h & ((1u << kHllSampleShift) - 1)) == 0) {
-                const uint64_t x = hll_hash(h);
+        }
+        // rare side work kept out of the unrolled loop
+        if (hll_mask) { // distinct-key estimate: HyperLogLog over a 1/2^kHllSampleShift sample of the key space
+#pragma unroll 1
+            for (uint32_t m = hll_mask; m; m &= m - 1) {
+                const uint64_t x = hll_hash(sel16(hh, __ffs(m) - 1));
                 atomicMax(&S.hll[x >> (64 - kHllBits)], (uint32_t)__clzll((x << kHllBits) | (1ULL << (kHllBits - 1))) + 1);
+            }
+        }
+        if (sent_mask) {
+            for (uint32_t m = sent_mask; m; m &= m - 1) {
+                Bucket bk = {};
+                direct_new += insert_hashed(g, kSentinel, 1, bk, false) == 1;
+                direct_total++;
             }
         }
         __syncthreads();
@@ -240,6 +254,37 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) sweep_kernel(con
     // through the slices in step and the slice being filled stays in L2.
     const uint32_t seg = blockIdx.x / P.split, piece = blockIdx.x % P.split;
     for (uint32_t part = P.part_lo; part < P.part_hi; part++) {
+        // Slice barrier: nobody starts slice `part` before every CTA has finished slice
+        // part - window.  Without it per-SM speed differences let the CTAs drift tens of
+        // slices apart and the table stops being L2-resident (measured: 77 % of bucket
+        // loads missed L2).  All CTAs are co-resident (host checks), so spinning is safe.
+        if (P.window && part >= P.part_lo + P.window) {
+            if (threadIdx.x == 0) {
+                const volatile uint32_t *c = P.slice_done + (part - P.window);
+                while (*c < gridDim.x) __nanosleep(200);
+            }
+            __syncthreads();
+        }
+        // Stream the NEXT slice of the table into L2 with bulk prefetches (one share per CTA):
+        // its first-touch misses would otherwise be random 32-byte HBM reads.
+        if (threadIdx.x == 0 && P.prefetch) {
+            const uint32_t nxt = part == P.part_lo ? part : part + 1; // first iteration: this slice, then one ahead
+            for (uint32_t q = nxt; q <= part + 1 && q < P.part_hi; q++) {
+                const uint64_t slice_bytes = P.slice_slots * 8;
+                const uint64_t share = (slice_bytes / gridDim.x + 15) & ~15ULL;
+                const uint64_t lo_b = (uint64_t)blockIdx.x * share;
+                if (lo_b < slice_bytes) {
+                    const char *pb = reinterpret_cast<const char *>(g.slots + (uint64_t)q * P.slice_slots) + lo_b;
+                    uint64_t left = min(share, slice_bytes - lo_b);
+                    while (left) {
+                        const uint32_t n = left < 32768 ? (uint32_t)left : 32768u;
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pb), "r"(n) : "memory");
+                        pb += n;
+                        left -= n;
+                    }
+                }
+            }
+        }
         const size_t sidx = (size_t)part * P.n_segs + seg;
         const uint32_t len = P.seglen[sidx];
         const uint32_t per = ((len + P.split - 1) / P.split + 3) & ~3u;
@@ -260,9 +305,13 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) sweep_kernel(con
             for (int u = 0; u < kSweepUnroll; u++) {
                 if (ok[u]) {
                     my_total++;
-                    my_new += insert_hashed(g, h[u], 1, bk[u], true) == 1;
+                    my_new += insert_home(g, h[u], bk[u]) == 1;
                 }
             }
+        }
+        if (P.window) {
+            __syncthreads();
+            if (threadIdx.x == 0) atomicAdd(P.slice_done + part, 1u);
         }
     }
 #pragma unroll
@@ -285,6 +334,9 @@ cudaError_t partition_configure(int *blocks_per_sm) {
 }
 void launch_partition(const PartitionParams &P, int grid, cudaStream_t st) {
     partition_kernel<<<grid, kPartThreads, sizeof(PartSmem), st>>>(P);
+}
+cudaError_t sweep_occupancy(int *blocks_per_sm) {
+    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sweep_kernel, kSweepThreads, 0);
 }
 void launch_sweep(const SweepParams &P, cudaStream_t st) { sweep_kernel<<<P.n_segs * P.split, kSweepThreads, 0, st>>>(P); }
 

@@ -8,7 +8,7 @@ constexpr int kPartThreads = 512;  // == kGroups: one 16-base group per thread p
 constexpr int kMaxParts = 512;     // table slices (Pb <= 9)
 constexpr int kHllBits = 10;       // HyperLogLog registers for the distinct-key estimate
 constexpr int kHllM = 1 << kHllBits;
-constexpr int kHllSampleShift = 4; // 1/16 of the key space is sampled
+constexpr int kHllSampleShift = 6; // 1/64 of the key space is sampled
 #ifndef KATGPU_SWEEP_THREADS
 #define KATGPU_SWEEP_THREADS 256
 #endif
@@ -40,11 +40,16 @@ struct SweepParams {
     const uint32_t *seglen;
     uint32_t seg_cap, n_segs, part_lo, part_hi;
     uint32_t split; // CTAs per segment
+    uint32_t window;      // slices the CTAs may be apart (0 = no barrier)
+    uint32_t *slice_done; // [partitions] CTAs that finished each slice
+    uint64_t slice_slots; // table slots per slice
+    uint32_t prefetch;    // bulk-prefetch the next slice into L2
 };
 
 size_t partition_smem_bytes();
 cudaError_t partition_configure(int *blocks_per_sm);
 void launch_partition(const PartitionParams &P, int grid, cudaStream_t st);
+cudaError_t sweep_occupancy(int *blocks_per_sm);
 void launch_sweep(const SweepParams &P, cudaStream_t st);
 
 } // namespace katgpu

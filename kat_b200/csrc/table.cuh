@@ -210,30 +210,44 @@ __device__ __forceinline__ int insert_hashed(const TableGeom &g, uint64_t h, uin
     return -1;
 }
 
-// Out-of-line general insert (claims, later probes, overflow): keeps the hot
-// loops of the streaming kernels small.  Returns like insert_hashed.
-static __device__ __noinline__ int insert_hashed_slow(const TableGeom &g, uint64_t h, uint64_t cnt) {
-    Bucket bk = {};
-    return insert_hashed(g, h, cnt, bk, false);
-}
-
-// Hot path of an insertion whose home bucket `bk` is already loaded: if the key
-// sits in its home bucket and the in-slot count cannot carry in this launch,
-// one fire-and-forget RED finishes it.  Returns false when the general path is needed.
-__device__ __forceinline__ bool insert_fast_hit(const TableGeom &g, uint64_t h, const Bucket &bk) {
-    if (g.add_bound > g.cmax) return false;
+// Insertion with the home bucket already in registers — the hot path of every
+// counting kernel.  Three tiers, the first two branch-free up to one predicated
+// memory instruction so that a warp does not serialise over which slot matched:
+//   1. key present in the home bucket  -> one RED (or ATOM when the count field
+//      could carry in this launch);
+//   2. key absent, home bucket has a free slot -> one CAS into the first free
+//      slot (slots fill in order and never empty, so the key cannot live in a
+//      later probe bucket);
+//   3. anything else (lost CAS race, full home bucket) -> the general loop.
+// Returns 1 if a new slot was claimed, 0 if the key existed, -1 if it was parked.
+__device__ __forceinline__ int insert_home(const TableGeom &g, uint64_t h, const Bucket &bk) {
     const uint64_t want = (h & g.rmask) | (1ULL << g.rbits); // probe 0
     uint64_t *bp = g.slots + (((h >> g.rbits) & g.bmask) << 2);
+    int hit = -1, emp = -1;
+    uint64_t wsel = 0;
 #pragma unroll
-    for (int s = 0; s < kSlotsPerBucket; s++) {
+    for (int s = kSlotsPerBucket - 1; s >= 0; s--) { // descending: the lowest index wins
         const uint64_t w = bk.s[s];
-        if ((w & g.tagmask) == want) {
-            if ((w >> g.cshift) + g.add_bound > g.cmax) return false;
-            asm volatile("red.global.add.u64 [%0], %1;" ::"l"(bp + s), "l"(1ULL << g.cshift) : "memory");
-            return true;
+        const bool m = (w & g.tagmask) == want;
+        hit = m ? s : hit;
+        wsel = m ? w : wsel;
+        emp = (w == 0) ? s : emp;
+    }
+    if (hit >= 0) {
+        slot_add(g, bp + hit, h, 1, wsel);
+        return 0;
+    }
+    if (emp >= 0) {
+        const unsigned long long old = atomicCAS(reinterpret_cast<unsigned long long *>(bp + emp), 0ULL,
+                                                 (unsigned long long)(want | (1ULL << g.cshift)));
+        if (old == 0) return 1;
+        if ((old & g.tagmask) == want) {
+            slot_add(g, bp + emp, h, 1, old);
+            return 0;
         }
     }
-    return false;
+    Bucket none = {};
+    return insert_hashed(g, h, 1, none, false);
 }
 
 // Exact count of hashed key h (0 if absent).

@@ -1,11 +1,6 @@
 #!/bin/bash
-# tuning sweep (run on the GPU box): sweep-kernel shape variants of the partitioned path (256-bit bucket loads)
-P='import json,sys; d=json.loads(sys.stdin.read()); r=d["roofline"]; print("value %.2f G/s  %s  launches %d" % (d["value"]/1e9, {k: round(v/d["steps"],2) for k,v in r["kernel_ms_by_family"].items()}, d["gpu_launches"]))'
-for v in default t256c4u2 t256c4u1 t512c2u2 t256c4u8; do
-    lib=$PWD/kat_b200/lib/variants/libkatgpu_$v.so; [ $v = default ] && lib=$PWD/kat_b200/lib/libkatgpu.so
-    sp=2; [ $v = t512c2u2 ] && sp=1
-    echo -n "$v split=$sp : "
-    KATGPU_LIB=$lib KATGPU_COUNT_PATH=partition KATGPU_SWEEP_SPLIT=$sp timeout 200 python bench.py --reads 8000000 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --slots-log2 30 2>/dev/null | python -c "$P"
-done
-echo -n "direct path (256-bit loads): "
-KATGPU_COUNT_PATH=direct timeout 200 python bench.py --reads 8000000 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --slots-log2 30 2>/dev/null | python -c "$P"
+P='import json,sys; d=json.loads(sys.stdin.read()); r=d["roofline"]; print("value %.2f G/s ms/step %.1f  %s other %s launches %d" % (d["value"]/1e9, d["ms_per_step"], {k: round(v/d["steps"],2) for k,v in r["kernel_ms_by_family"].items()}, {k: round(v/d["steps"],2) for k,v in r["other_kernels_ms"].items() if v}, d["gpu_launches"]))'
+for pf in 0 1; do echo -n "partition 5Gbp prefetch=$pf: "; KATGPU_SWEEP_PREFETCH=$pf KATGPU_COUNT_PATH=partition timeout 200 python bench.py --reads 33000000 --steps 2 --warmup 1 --no-cpu-baseline --no-e2e --slots-log2 30 2>/dev/null | python -c "$P"; done
+echo -n "full auto: "; timeout 600 python bench.py --steps 3 --warmup 2 --no-cpu-baseline 2>gpurun_out/b_full4.err | tee gpurun_out/b_full4.json | python -c "$P"; tail -2 gpurun_out/b_full4.err
+python -c "
+import json; d=json.load(open('gpurun_out/b_full4.json')); print('e2e', d['e2e']['value']/1e9, d['e2e']['ms_per_step'])"
