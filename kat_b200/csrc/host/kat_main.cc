@@ -1,0 +1,702 @@
+// kat_main.cc — `kat hist | gcp | comp` front-end over libkatgpu.
+//
+// Mirrors the reference's CLI surface and output files for the three spectra
+// tools (src/kat.cc:178-305, src/histogram.cc:257-369, src/gcp.cc:255-370,
+// src/comp.cc:633-843) and its libkat helpers (InputHandler:
+// lib/src/input_handler.cc; SparseMatrix printing: lib/include/kat/sparse_matrix.hpp;
+// CompCounters::printCounts: lib/src/comp_counters.cc:144-206; distance metrics:
+// lib/include/kat/distance_metrics.hpp).  Counting and the table walks run on
+// the GPU through the C-ABI of include/katgpu.h; this file only parses
+// arguments, reads sequence files, and writes the text outputs byte for byte
+// as the reference does.  Not supported (reference features outside the hot
+// path): jellyfish-hash inputs (LOAD mode), -d/--dump_hash, plotting.
+#include <glob.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <map>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "katgpu.h"
+#include "seq_parser.hpp"
+
+using std::cerr;
+using std::cout;
+using std::endl;
+using std::string;
+using std::vector;
+
+namespace {
+
+const char *kVersion = "2.4.2-katgpu0.1";
+
+struct KatError : std::runtime_error {
+    int code;
+    KatError(int c, const string &m) : std::runtime_error(m), code(c) {}
+};
+void gpu_check(katgpu_status st) {
+    if (st == KATGPU_ERR_HASH_FULL) throw KatError(5, "Hash full"); // std::runtime_error("Hash full") -> exit 5 (src/kat.cc:292)
+    if (st != KATGPU_OK) throw KatError(4, string("katgpu: ") + katgpu_last_error());
+}
+
+// ---- tiny option parser (boost::program_options stand-in) ----------------------
+struct OptSpec {
+    char shortname;     // 0 = none
+    const char *longname;
+    bool takes_value;
+};
+struct Parsed {
+    std::map<string, string> val;
+    vector<string> positional;
+    bool has(const string &k) const { return val.count(k) != 0; }
+    string get(const string &k, const string &dflt) const {
+        auto it = val.find(k);
+        return it == val.end() ? dflt : it->second;
+    }
+};
+Parsed parse_args(int argc, char **argv, const vector<OptSpec> &specs) {
+    Parsed p;
+    for (int i = 1; i < argc; i++) {
+        const string a = argv[i];
+        const OptSpec *sp = nullptr;
+        string value;
+        bool have_value = false;
+        if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
+            string name = a.substr(2);
+            const size_t eq = name.find('=');
+            if (eq != string::npos) {
+                value = name.substr(eq + 1);
+                name = name.substr(0, eq);
+                have_value = true;
+            }
+            for (auto &s : specs)
+                if (name == s.longname) sp = &s;
+            if (!sp) throw KatError(1, "Error: Parsing Command Line: unrecognised option '--" + name + "'");
+        } else if (a.size() >= 2 && a[0] == '-' && a != "-") {
+            for (auto &s : specs)
+                if (s.shortname && a[1] == s.shortname) sp = &s;
+            if (!sp) throw KatError(1, "Error: Parsing Command Line: unrecognised option '" + a + "'");
+            if (a.size() > 2) {
+                if (sp->takes_value) {
+                    value = a.substr(2);
+                    have_value = true;
+                } else { // bundled switches: -nv
+                    for (size_t j = 1; j < a.size(); j++) {
+                        const OptSpec *q = nullptr;
+                        for (auto &s : specs)
+                            if (s.shortname && a[j] == s.shortname) q = &s;
+                        if (!q || q->takes_value) throw KatError(1, "Error: Parsing Command Line: bad option bundle '" + a + "'");
+                        p.val[q->longname] = "1";
+                    }
+                    continue;
+                }
+            }
+        } else {
+            p.positional.push_back(a);
+            continue;
+        }
+        if (sp->takes_value) {
+            if (!have_value) {
+                if (i + 1 >= argc) throw KatError(1, string("Error: Parsing Command Line: the required argument for option '--") + sp->longname + "' is missing");
+                value = argv[++i];
+            }
+            p.val[sp->longname] = value;
+        } else
+            p.val[sp->longname] = "1";
+    }
+    return p;
+}
+uint64_t to_u64(const string &s, const char *what) {
+    try {
+        size_t pos = 0;
+        if (s.empty() || s[0] == '-') throw std::invalid_argument(s);
+        // boost::lexical_cast-like: accept plain integers and 1e8-style values
+        const double d = std::stod(s, &pos);
+        if (pos != s.size() || d < 0) throw std::invalid_argument(s);
+        if (s.find_first_of(".eE") == string::npos) return std::stoull(s);
+        return (uint64_t)d;
+    } catch (...) {
+        throw KatError(1, string("Error: Parsing Command Line: the argument ('") + s + "') for option '--" + what + "' is invalid");
+    }
+}
+double to_double(const string &s, const char *what) {
+    try {
+        size_t pos = 0;
+        const double d = std::stod(s, &pos);
+        if (pos != s.size()) throw std::invalid_argument(s);
+        return d;
+    } catch (...) {
+        throw KatError(1, string("Error: Parsing Command Line: the argument ('") + s + "') for option '--" + what + "' is invalid");
+    }
+}
+vector<unsigned> parse_trim(const string &s) {
+    vector<unsigned> v;
+    std::stringstream ss(s);
+    string item;
+    while (std::getline(ss, item, ',')) v.push_back((unsigned)to_u64(item, "5ptrim"));
+    if (v.empty()) v.push_back(0);
+    return v;
+}
+
+// ---- InputHandler (lib/src/input_handler.cc) ------------------------------------
+string leaf(const string &p) {
+    const size_t s = p.find_last_of('/');
+    return s == string::npos ? p : p.substr(s + 1);
+}
+string join(const vector<string> &v, bool leaves) {
+    string s;
+    for (auto &p : v) s += (leaves ? leaf(p) : p) + " ";
+    while (!s.empty() && s.back() == ' ') s.pop_back(); // boost::trim_right_copy
+    return s;
+}
+bool exists(const string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0;
+}
+string lower(string s) {
+    for (auto &c : s) c = (char)tolower((unsigned char)c);
+    return s;
+}
+string ext_of(const string &p) {
+    const string l = leaf(p);
+    const size_t d = l.find_last_of('.');
+    return d == string::npos || d == 0 ? "" : l.substr(d);
+}
+// JellyfishHelper::isSequenceFile (lib/src/jellyfish_helper.cc:270-307): by extension, else by first byte
+bool is_sequence_file(const string &path) {
+    string e = lower(ext_of(path));
+    string stem = path;
+    if (e == ".gz") {
+        stem = path.substr(0, path.size() - 3);
+        e = lower(ext_of(stem));
+    }
+    static const char *kExt[] = {".fastq", ".fq", ".fasta", ".fa", ".fna", ".fas", ".scafseq"};
+    for (auto x : kExt)
+        if (e == x) return true;
+    std::ifstream f(path);
+    char ch = 0;
+    f >> ch;
+    return ch == '>' || ch == '@';
+}
+// InputHandler::globFiles (lib/src/input_handler.cc:245-316): space-separated patterns, brace + tilde expansion
+vector<string> glob_group(const string &group) {
+    vector<string> pats;
+    std::stringstream ss(group);
+    string item;
+    while (std::getline(ss, item, ' '))
+        pats.push_back(item);
+    if (pats.empty()) throw KatError(4, "No input provided for this input group");
+    glob_t g;
+    memset(&g, 0, sizeof g);
+    int i = 0;
+    for (auto &p : pats) {
+        int flags = GLOB_TILDE | GLOB_NOCHECK | GLOB_BRACE;
+        if (i++ > 0) flags |= GLOB_APPEND;
+        if (glob(p.c_str(), flags, nullptr, &g) != 0) throw KatError(4, "Problem globbing input pattern: " + p);
+    }
+    vector<string> out;
+    for (size_t j = 0; j < g.gl_pathc; j++) out.push_back(g.gl_pathv[j]);
+    if (g.gl_pathc) globfree(&g);
+    if (out.empty()) out.push_back(pats[0]);
+    return out;
+}
+
+struct Input {
+    vector<string> files;
+    vector<unsigned> trim5p;
+    bool canonical = true;
+    uint64_t hash_size = 100000000ULL; // DEFAULT_HASH_SIZE, lib/include/kat/jellyfish_helper.hpp:76
+    int index = 1;
+    katgpu_table *table = nullptr;
+    uint64_t n_distinct = 0, n_total = 0;
+
+    void set_trim(const vector<unsigned> &t) { // InputHandler::set5pTrim
+        if (t.empty()) trim5p.assign(files.size(), 0);
+        else if (t.size() == 1) trim5p.assign(files.size(), t[0]);
+        else if (t.size() == files.size()) trim5p = t;
+        else throw KatError(4, "Inconsistent number of inputs and trimming settings.  Please establish your inputs before trying to set trimming vector.  Also ensure you have the same number of input files to trimming settings.");
+    }
+    void validate() const { // InputHandler::validateInput
+        for (auto &p : files) {
+            if (!exists(p)) throw KatError(4, "Could not find input file at: " + p + "; please check the path and try again.");
+            if (!is_sequence_file(p))
+                throw KatError(4, "Input " + p + " is not a FastA/FastQ file: jellyfish hash inputs (LOAD mode) are outside this GPU build's scope");
+        }
+    }
+};
+
+struct Timer {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double secs() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+void phase_done(const Timer &t) {
+    char b[64];
+    snprintf(b, sizeof b, "  Time taken: %.1fs\n\n", t.secs()); // auto_cpu_timer(1, "  Time taken: %ws\n\n")
+    cout << " done." << b;
+    cout.flush();
+}
+
+// InputHandler::count (lib/src/input_handler.cc:180-202) on the GPU
+void count_input(katgpu_ctx *ctx, Input &in, int k, bool allow_grow) {
+    Timer t;
+    cout << "Input " << in.index << " is a sequence file.  Counting kmers for input " << in.index << " (" << join(in.files, false) << ") ...";
+    cout.flush();
+    gpu_check(katgpu_count_begin(ctx, k, in.canonical ? 1 : 0, in.hash_size, allow_grow ? 1 : 0, &in.table));
+    std::vector<unsigned char> raw;
+    std::string bases;
+    for (size_t i = 0; i < in.files.size(); i++) {
+        string err;
+        if (!kat_host::read_file(in.files[i], raw, err)) throw KatError(4, err);
+        bases.clear();
+        const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), k, in.trim5p[i], bases);
+        if (st == kat_host::ParseStatus::UnsupportedFormat) {
+            cerr << "warning: " << in.files[i] << ": Unsupported format (the reference silently stops reading this input here)" << endl;
+            break;
+        }
+        if (!bases.empty()) gpu_check(katgpu_count_feed(in.table, bases.data(), bases.size()));
+        if (st == kat_host::ParseStatus::InvalidFastq) {
+            cerr << "warning: " << in.files[i] << ": Invalid fastq sequence; like the reference, the rest of this input is ignored" << endl;
+            break;
+        }
+    }
+    gpu_check(katgpu_count_end(in.table, &in.n_distinct, &in.n_total));
+    phase_done(t);
+}
+
+void ensure_parent_dir(const string &prefix) { // KatFS::ensureDirectoryExists(absolute(prefix).parent_path())
+    string p = prefix;
+    if (p.empty() || p[0] != '/') {
+        char cwd[4096];
+        if (!getcwd(cwd, sizeof cwd)) return;
+        p = string(cwd) + "/" + p;
+    }
+    const size_t s = p.find_last_of('/');
+    if (s == string::npos || s == 0) return;
+    const string dir = p.substr(0, s);
+    string cur;
+    std::stringstream ss(dir);
+    string part;
+    while (std::getline(ss, part, '/')) {
+        if (part.empty()) continue;
+        cur += "/" + part;
+        if (!exists(cur) && mkdir(cur.c_str(), 0777) != 0 && !exists(cur))
+            throw KatError(4, "Could not create output directory: " + dir);
+    }
+}
+
+// SparseMatrix::printMatrix / getMaxVal (lib/include/kat/sparse_matrix.hpp:162-173,269-277)
+void print_matrix(std::ostream &out, const vector<uint64_t> &mx, uint32_t rows, uint32_t cols) {
+    for (uint32_t i = 0; i < rows; i++) {
+        out << mx[(size_t)i * cols];
+        for (uint32_t j = 1; j < cols; j++) out << " " << mx[(size_t)i * cols + j];
+        out << endl;
+    }
+}
+uint64_t max_val(const vector<uint64_t> &mx) {
+    uint64_t m = 0;
+    for (auto v : mx) m = std::max(m, v);
+    return m;
+}
+// boost::filesystem::path::operator<< : quoted, '&' escapes '"' and '&'
+string quoted_path(const string &p) {
+    string s = "\"";
+    for (char c : p) {
+        if (c == '"' || c == '&') s += '&';
+        s += c;
+    }
+    return s + "\"";
+}
+
+// Distance metrics with the reference's arithmetic (lib/include/kat/distance_metrics.hpp:50-126)
+double minkowski(const vector<uint64_t> &a, const vector<uint64_t> &b, int p) {
+    uint64_t sum = 0;
+    for (size_t i = 0; i < a.size(); i++) {
+        const uint64_t diff = a[i] < b[i] ? b[i] - a[i] : a[i] - b[i];
+        sum += std::pow(diff, p); // double -> uint64 at every step, as the reference
+    }
+    return p == 1 ? (double)sum : std::pow((double)sum, 1.0 / (double)p);
+}
+double cosine(const vector<uint64_t> &a, const vector<uint64_t> &b) {
+    double dot = 0.0, da = 0.0, db = 0.0;
+    for (size_t i = 0; i < a.size(); i++) {
+        dot += a[i] * b[i]; // uint64 product (wraps) before the double add, as the reference
+        da += std::pow(a[i], 2);
+        db += std::pow(b[i], 2);
+    }
+    return 1.0 - (dot / (std::sqrt(da) * std::sqrt(db)));
+}
+double canberra(const vector<uint64_t> &a, const vector<uint64_t> &b) {
+    double sum = 0.0;
+    for (size_t i = 0; i < a.size(); i++) {
+        const double diff = (double)a[i] - (double)b[i];
+        const double s = a[i] + b[i];
+        if (s > 0) sum += std::abs(diff) / s;
+    }
+    return sum;
+}
+double jaccard(const vector<uint64_t> &a, const vector<uint64_t> &b) {
+    double mn = 0.0, mx = 0.0;
+    for (size_t i = 0; i < a.size(); i++) mn += std::min(a[i], b[i]);
+    for (size_t i = 0; i < a.size(); i++) mx += std::max(a[i], b[i]);
+    return 1.0 - (mn / mx);
+}
+void print_distances(std::ostream &out, const vector<uint64_t> &a, const vector<uint64_t> &b) {
+    out << " - Manhattan distance: " << minkowski(a, b, 1) << endl;
+    out << " - Euclidean distance: " << minkowski(a, b, 2) << endl;
+    out << " - Cosine distance: " << cosine(a, b) << endl;
+    out << " - Canberra distance: " << canberra(a, b) << endl;
+    out << " - Jaccard distance: " << jaccard(a, b) << endl;
+}
+
+struct Ctx {
+    katgpu_ctx *c = nullptr;
+    Ctx() {
+        int dev = 0;
+        if (const char *e = getenv("KATGPU_DEVICE")) dev = atoi(e);
+        gpu_check(katgpu_init(dev, &c));
+    }
+    ~Ctx() { katgpu_shutdown(c); }
+};
+
+// =============================== kat hist ========================================
+int hist_main(int argc, char **argv) {
+    const vector<OptSpec> specs = {{'o', "output_prefix", true}, {'t', "threads", true}, {'l', "low", true}, {'h', "high", true},
+                                   {'i', "inc", true}, {0, "5ptrim", true}, {'N', "non_canonical", false}, {'m', "mer_len", true},
+                                   {'H', "hash_size", true}, {'d', "dump_hash", false}, {'p', "output_type", true},
+                                   {'v', "verbose", false}, {0, "help", false}};
+    const Parsed a = parse_args(argc, argv, specs);
+    if (a.has("help") || argc <= 1) {
+        cout << "Usage: kat hist [options] (<input>)+\n\nCreate an histogram of k-mer occurrences from the input.\n\n"
+                "Options: -o prefix (kat.hist) -t threads -l low (1) -h high (10000) -i inc (1) --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -v --help\n" << endl;
+        return 1;
+    }
+    if (a.has("dump_hash")) throw KatError(4, "-d/--dump_hash (jellyfish hash output) is outside this GPU build's scope");
+    const uint64_t low = to_u64(a.get("low", "1"), "low"), high = to_u64(a.get("high", "10000"), "high"), inc = to_u64(a.get("inc", "1"), "inc");
+    const int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
+    Timer total;
+    cout << "Running KAT in HIST mode" << endl << "------------------------" << endl << endl;
+    Input in;
+    in.files = a.positional;
+    in.set_trim(parse_trim(a.get("5ptrim", "0")));
+    in.canonical = !a.has("non_canonical");
+    in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
+    const string prefix = a.get("output_prefix", "kat.hist");
+    // Histogram ctor, src/histogram.cc:57-71, src/histogram.hpp:172-178
+    const uint64_t base = low > 1 ? (1 >= low ? 1 : low - 1) : 1, ceil = high + 1, nb = ceil + 1 - base;
+    if (high < low) throw KatError(4, "High count value must be >= to low count value.  High: " + std::to_string(high) + "; Low: " + std::to_string(low));
+    if (inc == 0) throw KatError(4, "Increment must be >= 1");
+    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    in.validate();
+    ensure_parent_dir(prefix);
+    Ctx ctx;
+    count_input(ctx.c, in, k, true);
+    vector<uint64_t> bins(nb);
+    {
+        Timer t;
+        cout << "Bining kmers ...";
+        cout.flush();
+        gpu_check(katgpu_hist(in.table, base, ceil, inc, nb, bins.data()));
+        phase_done(t);
+    }
+    {
+        Timer t;
+        cout << "Saving results to disk ...";
+        cout.flush();
+        std::ofstream out(prefix.c_str());
+        out << "# Title:" << k << "-mer spectra for: " << join(in.files, true) << endl;
+        out << "# XLabel:" << k << "-mer frequency" << endl;
+        out << "# YLabel:# distinct " << k << "-mers" << endl;
+        out << "# Kmer value:" << k << endl;
+        out << "# Input 1:" << join(in.files, false) << endl;
+        out << "###" << endl;
+        uint64_t col = base;
+        for (uint64_t i = 0; i < nb; i++, col += inc) out << col << " " << bins[i] << "\n";
+        out.close();
+        phase_done(t);
+    }
+    katgpu_table_free(in.table);
+    char b[96];
+    snprintf(b, sizeof b, "KAT HIST completed.\nTotal runtime: %.1fs\n\n", total.secs());
+    cout << b;
+    return 0;
+}
+
+// =============================== kat gcp =========================================
+int gcp_main(int argc, char **argv) {
+    const vector<OptSpec> specs = {{'o', "output_prefix", true}, {'t', "threads", true}, {'x', "cvg_scale", true}, {'y', "cvg_bins", true},
+                                   {0, "5ptrim", true}, {'N', "non_canonical", false}, {'m', "mer_len", true}, {'H', "hash_size", true},
+                                   {'d', "dump_hash", false}, {'p', "output_type", true}, {'v', "verbose", false}, {0, "help", false}};
+    const Parsed a = parse_args(argc, argv, specs);
+    if (a.has("help") || argc <= 1) {
+        cout << "Usage: kat gcp [options] (<input>)+\n\nCompares GC content and K-mer coverage from the input.\n\n"
+                "Options: -o prefix (kat-gcp) -t threads -x cvg_scale (1.0) -y cvg_bins (1000) --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -v --help\n" << endl;
+        return 1;
+    }
+    if (a.has("dump_hash")) throw KatError(4, "-d/--dump_hash (jellyfish hash output) is outside this GPU build's scope");
+    const double scale = to_double(a.get("cvg_scale", "1.0"), "cvg_scale");
+    const uint32_t bins = (uint32_t)to_u64(a.get("cvg_bins", "1000"), "cvg_bins");
+    const int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
+    Timer total;
+    cout << "Running KAT in GCP mode" << endl << "------------------------" << endl << endl;
+    Input in;
+    in.files = a.positional;
+    in.set_trim(parse_trim(a.get("5ptrim", "0")));
+    in.canonical = !a.has("non_canonical");
+    in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
+    const string prefix = a.get("output_prefix", "kat-gcp");
+    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    in.validate();
+    ensure_parent_dir(prefix);
+    Ctx ctx;
+    count_input(ctx.c, in, k, true);
+    vector<uint64_t> mx((size_t)k * (bins + 1));
+    {
+        Timer t;
+        cout << "Analysing kmers in hash ...";
+        cout.flush();
+        gpu_check(katgpu_gcp(in.table, scale, bins, mx.data()));
+        phase_done(t);
+    }
+    {
+        Timer t;
+        cout << "Saving results to disk ...";
+        cout.flush();
+        std::ofstream out((prefix + ".mx").c_str());
+        out << "# Title:K-mer coverage vs GC count plot for: " << join(in.files, true) << endl;
+        out << "# XLabel:" << k << "-mer frequency" << endl;
+        out << "# YLabel:GC count" << endl;
+        out << "# ZLabel:# distinct " << k << "-mers" << endl;
+        out << "# Columns:" << bins + 1 << endl;
+        out << "# Rows:" << k << endl;
+        out << "# MaxVal:" << max_val(mx) << endl;
+        out << "# Transpose:0" << endl;
+        out << "# Kmer value:" << k << endl;
+        out << "# Input 1:" << join(in.files, false) << endl;
+        out << "###" << endl;
+        print_matrix(out, mx, (uint32_t)k, bins + 1);
+        out.close();
+        phase_done(t);
+    }
+    katgpu_table_free(in.table);
+    char b[96];
+    snprintf(b, sizeof b, "KAT GCP completed.\nTotal runtime: %.1fs\n\n", total.secs());
+    cout << b;
+    return 0;
+}
+
+// =============================== kat comp ========================================
+void print_comp_counts(std::ostream &out, const katgpu_comp_counters &c, const string &p1, const string &p2, const string &p3,
+                       const vector<uint64_t> &sp1, const vector<uint64_t> &sp2, const vector<uint64_t> &ssp1,
+                       const vector<uint64_t> &ssp2) { // CompCounters::printCounts, lib/src/comp_counters.cc:144-206
+    out << "K-mer statistics for: " << endl;
+    out << " - Hash 1: " << quoted_path(p1) << endl;
+    out << " - Hash 2: " << quoted_path(p2) << endl;
+    if (c.hash3_total > 0) out << " - Hash 3: " << quoted_path(p3) << endl;
+    out << endl;
+    out << "Total K-mers in: " << endl;
+    out << " - Hash 1: " << c.hash1_total << endl;
+    out << " - Hash 2: " << c.hash2_total << endl;
+    if (c.hash3_total > 0) out << " - Hash 3: " << c.hash3_total << endl;
+    out << endl;
+    out << "Distinct K-mers in:" << endl;
+    out << " - Hash 1: " << c.hash1_distinct << endl;
+    out << " - Hash 2: " << c.hash2_distinct << endl;
+    if (c.hash3_total > 0) out << " - Hash 3: " << c.hash3_distinct << endl;
+    out << endl;
+    out << "Total K-mers only found in:" << endl;
+    out << " - Hash 1: " << c.hash1_only_total << endl;
+    out << " - Hash 2: " << c.hash2_only_total << endl;
+    out << endl;
+    out << "Distinct K-mers only found in:" << endl;
+    out << " - Hash 1: " << c.hash1_only_distinct << endl;
+    out << " - Hash 2: " << c.hash2_only_distinct << endl << endl;
+    out << "Shared K-mers:" << endl;
+    out << " - Total shared found in hash 1: " << c.shared_hash1_total << endl;
+    out << " - Total shared found in hash 2: " << c.shared_hash2_total << endl;
+    out << " - Distinct shared K-mers: " << c.shared_distinct << endl << endl;
+    out << "Distance between spectra 1 and 2 (all k-mers):" << endl;
+    print_distances(out, sp1, sp2);
+    out << endl;
+    out << "Distance between spectra 1 and 2 (shared k-mers):" << endl;
+    print_distances(out, ssp1, ssp2);
+    out << endl;
+}
+
+int comp_main(int argc, char **argv) {
+    const vector<OptSpec> specs = {{'o', "output_prefix", true}, {'t', "threads", true}, {'x', "d1_scale", true}, {'y', "d2_scale", true},
+                                   {'i', "d1_bins", true}, {'j', "d2_bins", true}, {0, "d1_5ptrim", true}, {0, "d2_5ptrim", true},
+                                   {'N', "non_canonical_1", false}, {'O', "non_canonical_2", false}, {'P', "non_canonical_3", false},
+                                   {'m', "mer_len", true}, {'H', "hash_size_1", true}, {'I', "hash_size_2", true}, {'J', "hash_size_3", true},
+                                   {'d', "dump_hashes", false}, {'g', "disable_hash_grow", false}, {'n', "density_plot", false},
+                                   {'p', "output_type", true}, {'h', "output_hists", false}, {'v', "verbose", false}, {0, "help", false}};
+    const Parsed a = parse_args(argc, argv, specs);
+    if (a.has("help") || argc <= 1) {
+        cout << "Usage: kat comp [options] <input_1> <input_2> [<input_3>]\n\nCompares jellyfish K-mer count hashes.\n\n"
+                "Options: -o prefix (kat-comp) -t threads -x d1_scale -y d2_scale -i d1_bins (1001) -j d2_bins (1001) --d1_5ptrim --d2_5ptrim "
+                "-N -O -P -m mer_len (27) -H -I -J hash sizes (1e8) -g -n -h -v --help\n" << endl;
+        return 1;
+    }
+    if (a.has("dump_hashes")) throw KatError(4, "-d/--dump_hashes (jellyfish hash output) is outside this GPU build's scope");
+    Timer total;
+    cout << "Running KAT in COMP mode" << endl << "------------------------" << endl << endl;
+    if (a.positional.size() < 1) throw KatError(4, "Nothing specified for input group 1");
+    if (a.positional.size() < 2) throw KatError(4, "Nothing specified for input group 2");
+    const bool three = a.positional.size() >= 3;
+    const int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
+    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    const double d1s = to_double(a.get("d1_scale", "1.0"), "d1_scale"), d2s = to_double(a.get("d2_scale", "1.0"), "d2_scale");
+    const uint32_t d1b = (uint32_t)to_u64(a.get("d1_bins", "1001"), "d1_bins"), d2b = (uint32_t)to_u64(a.get("d2_bins", "1001"), "d2_bins");
+    if (d1b == 0 || d2b == 0) throw KatError(4, "d1_bins and d2_bins must be >= 1");
+    Input in[3];
+    const char *nc[3] = {"non_canonical_1", "non_canonical_2", "non_canonical_3"};
+    const char *hs[3] = {"hash_size_1", "hash_size_2", "hash_size_3"};
+    for (int i = 0; i < (three ? 3 : 2); i++) {
+        in[i].files = glob_group(a.positional[i]);
+        in[i].index = i + 1;
+        in[i].canonical = !a.has(nc[i]);
+        in[i].hash_size = to_u64(a.get(hs[i], "100000000"), hs[i]);
+    }
+    in[0].set_trim(parse_trim(a.get("d1_5ptrim", "0")));
+    in[1].set_trim(parse_trim(a.get("d2_5ptrim", "0")));
+    if (three) in[2].set_trim({});
+    const string prefix = a.get("output_prefix", "kat-comp");
+    for (int i = 0; i < (three ? 3 : 2); i++) in[i].validate();
+    ensure_parent_dir(prefix);
+    Ctx ctx;
+    for (int i = 0; i < (three ? 3 : 2); i++) count_input(ctx.c, in[i], k, !a.has("disable_hash_grow"));
+    const size_t cells = (size_t)d1b * d2b, len = std::min(d1b, d2b);
+    vector<uint64_t> main_mx(cells), ends, middle, mixed, spectra(4 * len);
+    if (three) {
+        ends.resize(cells);
+        middle.resize(cells);
+        mixed.resize(cells);
+    }
+    katgpu_comp_counters cc;
+    {
+        Timer t;
+        cout << "Comparing hashes ...";
+        cout.flush();
+        gpu_check(katgpu_comp(in[0].table, in[1].table, three ? in[2].table : nullptr, d1s, d2s, d1b, d2b, main_mx.data(),
+                              three ? ends.data() : nullptr, three ? middle.data() : nullptr, three ? mixed.data() : nullptr, &cc,
+                              spectra.data()));
+        phase_done(t);
+    }
+    const vector<uint64_t> sp1(spectra.begin(), spectra.begin() + len), sp2(spectra.begin() + len, spectra.begin() + 2 * len),
+        ssp1(spectra.begin() + 2 * len, spectra.begin() + 3 * len), ssp2(spectra.begin() + 3 * len, spectra.end());
+    const string p1 = in[0].files[0], p2 = in[1].files[0], p3 = three ? in[2].files[0] : "";
+    {
+        Timer t;
+        cout << "Saving results to disk ...";
+        cout.flush();
+        {
+            std::ofstream out((prefix + "-main.mx").c_str()); // Comp::printMainMatrix, src/comp.cc:308-326
+            out << "# Title:K-mer comparison plot" << endl
+                << "# XLabel:" << k << "-mer frequency for: " << join(in[0].files, true) << endl
+                << "# YLabel:" << k << "-mer frequency for: " << join(in[1].files, true) << endl
+                << "# ZLabel:# distinct " << k << "-mers" << endl
+                << "# Columns:" << d2b << endl
+                << "# Rows:" << d1b << endl
+                << "# MaxVal:" << max_val(main_mx) << endl
+                << "# Transpose:1" << endl
+                << "# Kmer value:" << k << endl
+                << "# Input 1:" << join(in[0].files, false) << endl
+                << "# Input 2:" << join(in[1].files, false) << endl
+                << "###" << endl;
+            print_matrix(out, main_mx, d1b, d2b);
+        }
+        if (three) { // src/comp.cc:330-356
+            std::ofstream e((prefix + "-ends.mx").c_str());
+            e << "# Each row represents K-mer frequency for: " << p1 << endl;
+            e << "# Each column represents K-mer frequency for sequence ends: " << p3 << endl;
+            print_matrix(e, ends, d1b, d2b);
+            std::ofstream m((prefix + "-middle.mx").c_str());
+            m << "# Each row represents K-mer frequency for: " << p1 << endl;
+            m << "# Each column represents K-mer frequency for sequence middles: " << p2 << endl;
+            print_matrix(m, middle, d1b, d2b);
+            std::ofstream x((prefix + "-mixed.mx").c_str());
+            x << "# Each row represents K-mer frequency for hash file 1: " << p1 << endl;
+            x << "# Each column represents K-mer frequency for mixed: " << p2 << " and " << p3 << endl;
+            print_matrix(x, mixed, d1b, d2b);
+        }
+        {
+            std::ofstream out((prefix + ".stats").c_str());
+            print_comp_counts(out, cc, p1, p2, p3, sp1, sp2, ssp1, ssp2);
+        }
+        if (a.has("output_hists")) { // Comp::printHist, src/comp.cc:235-246
+            for (int i = 0; i < 2; i++) {
+                std::ofstream out((prefix + "." + std::to_string(i + 1) + ".hist").c_str());
+                out << "# Title:" << k << "-mer spectra for: " << join(in[i].files, false) << endl;
+                out << "# XLabel:" << k << "-mer frequency" << endl;
+                out << "# YLabel:# distinct " << k << "-mers" << endl;
+                out << "###" << endl;
+                const vector<uint64_t> &h = i == 0 ? sp1 : sp2;
+                for (uint64_t j = 0; j < h.size(); j++) out << j << " " << h[j] << "\n";
+            }
+        }
+        phase_done(t);
+    }
+    cout << endl << "Summary statistics" << endl << "------------------" << endl << endl;
+    print_comp_counts(cout, cc, p1, p2, p3, sp1, sp2, ssp1, ssp2);
+    for (int i = 0; i < (three ? 3 : 2); i++) katgpu_table_free(in[i].table);
+    char b[96];
+    snprintf(b, sizeof b, "KAT COMP completed.\nTotal runtime: %.1fs\n\n", total.secs());
+    cout << b;
+    return 0;
+}
+
+} // namespace
+
+int main(int argc, char **argv) {
+    try {
+        if (argc < 2 || !strcmp(argv[1], "--help") || !strcmp(argv[1], "-h")) {
+            cout << "The K-mer Analysis Toolkit (KAT), GPU spectra engine.\n\nUsage: kat <mode> [options]\n\n"
+                    "Modes: hist, gcp, comp (counting and spectra on the GPU through libkatgpu).\n"
+                    "sect, cold, filter and plot are not part of this build.\n" << endl;
+            return 1;
+        }
+        if (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V")) {
+            cout << "kat " << kVersion << endl;
+            return 0;
+        }
+        const string mode = argv[1];
+        if (mode == "_parse") { // test hook, no GPU involved: dump the base stream of one file to stdout
+            const Parsed a = parse_args(argc - 1, argv + 1, {{'m', "mer_len", true}, {0, "5ptrim", true}});
+            if (a.positional.size() != 1) throw KatError(1, "usage: kat _parse -m K [--5ptrim X] <file>");
+            std::vector<unsigned char> raw;
+            string err, bases;
+            if (!kat_host::read_file(a.positional[0], raw, err)) throw KatError(4, err);
+            const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), (int)to_u64(a.get("mer_len", "27"), "mer_len"),
+                                                          (unsigned)to_u64(a.get("5ptrim", "0"), "5ptrim"), bases);
+            fwrite(bases.data(), 1, bases.size(), stdout);
+            return st == kat_host::ParseStatus::Ok ? 0 : st == kat_host::ParseStatus::UnsupportedFormat ? 2 : 3;
+        }
+        cout << "Kmer Analysis Toolkit (KAT) V" << kVersion << endl << endl;
+        if (mode == "hist") return hist_main(argc - 1, argv + 1);
+        if (mode == "gcp") return gcp_main(argc - 1, argv + 1);
+        if (mode == "comp") return comp_main(argc - 1, argv + 1);
+        if (mode == "sect" || mode == "cold" || mode == "filter" || mode == "plot")
+            throw KatError(4, "KAT mode '" + mode + "' is outside this GPU build's scope (hist, gcp, comp)");
+        throw KatError(4, "Unrecognised KAT mode: " + mode);
+    } catch (const KatError &e) {
+        cerr << (e.code == 5 ? "Error: " : "") << e.what() << endl;
+        return e.code;
+    } catch (const std::exception &e) {
+        cerr << "Error: " << e.what() << endl;
+        return 5;
+    } catch (...) {
+        cerr << "Error: Exception of unknown type!" << endl;
+        return 7;
+    }
+}

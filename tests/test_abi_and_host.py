@@ -1,0 +1,103 @@
+"""CPU-only checks of the product's boundary: the C-ABI library loads and exports
+every symbol include/katgpu.h declares, refuses to run without a GPU (no CPU
+fallback), and the C++ front-end's FASTA/FASTQ reader emits the reference's base
+stream (checked against the oracle on the golden inputs and on random files)."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import golden_util as G
+import oracle as O
+import kat_b200
+from kat_b200 import binding as B
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KAT = os.path.join(ROOT, "kat_b200", "bin", "kat")
+
+
+def test_every_declared_symbol_is_exported_and_bound():
+    hdr = open(os.path.join(ROOT, "include", "katgpu.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(katgpu_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    lib = B.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), name + " declared in katgpu.h but not exported by libkatgpu.so"
+    assert declared == set(B.SIGNATURES), declared ^ set(B.SIGNATURES)
+    assert lib.katgpu_version() == 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    assert B.lib().katgpu_device_count() == 0
+    with pytest.raises(kat_b200.KatGpuError) as e:
+        kat_b200.Context(0)
+    assert e.value.status == -5 and "no CPU path" in str(e.value)
+    r = subprocess.run([KAT, "hist", "-m5", os.path.join(G.GOLDEN, "inputs", "edge1.fa")], capture_output=True, text=True)
+    assert r.returncode == 4 and "no CPU path" in r.stderr
+
+
+def test_product_does_not_reference_the_oracle():
+    """The shipped path must not import, link or exec anything under oracle/."""
+    for base, _, files in os.walk(os.path.join(ROOT, "kat_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cc", ".hpp", ".h")):
+                txt = open(os.path.join(base, f), errors="ignore").read()
+                assert "libkatoracle" not in txt and "import oracle" not in txt and "oracle/" not in txt.replace("oracle/_ref", ""), f
+    out = subprocess.run(["ldd", B.lib_path()], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+def _kat_parse(path, k, trim=0):
+    r = subprocess.run([KAT, "_parse", "-m", str(k), "--5ptrim", str(trim), path], capture_output=True)
+    return r.stdout, {0: 0, 2: -1, 3: -2}[r.returncode]
+
+
+@pytest.mark.parametrize("name", sorted(os.listdir(os.path.join(G.GOLDEN, "inputs"))))
+@pytest.mark.parametrize("k,trim", [(5, 0), (21, 0), (27, 3), (32, 7)])
+def test_host_parser_matches_oracle_on_golden_inputs(name, k, trim):
+    import gzip
+    path = os.path.join(G.GOLDEN, "inputs", name)
+    data = open(path, "rb").read()
+    if data[:2] == b"\x1f\x8b":
+        data = gzip.decompress(data)
+    want, st = O.parse_file(data, k, trim)
+    got, gst = _kat_parse(path, k, trim)
+    if st == -2:
+        assert gst == -2  # the front-end reports it; what was emitted before matches
+    assert (got, gst) == (want, st)
+
+
+def _random_file(rng, fastq):
+    out = bytearray()
+    for i in range(int(rng.integers(1, 40))):
+        n = int(rng.integers(0, 9000)) if rng.random() < 0.15 else int(rng.integers(0, 300))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTacgtNRY-", dtype=np.uint8), n, p=[.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .01, .01]))
+        width = int(rng.integers(1, 200)) if rng.random() < 0.5 else max(n, 1)
+        lines = [seq[j:j + width] for j in range(0, n, width)] or [b""]
+        if fastq:
+            out += b"@r%d some text\n" % i + b"\n".join(lines) + b"\n+\n"
+            q = bytes(rng.choice(np.frombuffer(b"I@+>#5", dtype=np.uint8), n))
+            out += b"\n".join(q[j:j + width] for j in range(0, n, width)) + b"\n"
+        else:
+            out += b">c%d\n" % i + b"\n".join(lines) + b"\n"
+            if rng.random() < 0.2:
+                out += b"\n"
+    if rng.random() < 0.3 and out.endswith(b"\n"):
+        out = out[:-1]
+    return bytes(out)
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_host_parser_matches_oracle_on_random_files(seed, tmp_path):
+    rng = np.random.default_rng(seed)
+    data = _random_file(rng, fastq=seed % 2 == 0)
+    p = tmp_path / ("r.fq" if seed % 2 == 0 else "r.fa")
+    p.write_bytes(data)
+    for k, trim in [(5, 0), (27, 0), (21, int(rng.integers(1, 12)))]:
+        assert _kat_parse(str(p), k, trim) == O.parse_file(data, k, trim), (seed, k, trim)
