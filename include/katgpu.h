@@ -89,6 +89,11 @@ katgpu_status katgpu_count_begin(katgpu_ctx *ctx, int k, int canonical, uint64_t
 katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n);
 /* Same, for a stream already resident in device memory (16-byte aligned). */
 katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *bases_dev, size_t n);
+/* Optional hint: about `expected_kmers` k-mer instances will be fed before
+ * katgpu_count_end.  Lets the library size its pending-key buffer once (the
+ * partitioned counting path inserts slice by slice; fewer, larger sweeps are
+ * cheaper).  Never changes results. */
+katgpu_status katgpu_count_reserve(katgpu_table *t, uint64_t expected_kmers);
 /* Finish counting (hash_counter::done, JFI/hash_counter.hpp:173-176).
  * n_distinct / n_total (k-mer instances) may be NULL. */
 katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct, uint64_t *n_total);

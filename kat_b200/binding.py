@@ -48,6 +48,7 @@ SIGNATURES = {
     "katgpu_count_begin": (_i, [_vp, _i, _i, _u64, _i, C.POINTER(_vp)]),
     "katgpu_count_feed": (_i, [_vp, _vp, _sz]),
     "katgpu_count_feed_device": (_i, [_vp, _vp, _sz]),
+    "katgpu_count_reserve": (_i, [_vp, _u64]),
     "katgpu_count_end": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "katgpu_table_free": (None, [_vp]),
     "katgpu_hist": (_i, [_vp, _u64, _u64, _u64, _u64, _vp]),
@@ -206,6 +207,10 @@ class Table:
 
     def feed_device(self, dev_ptr, n):
         _check(lib().katgpu_count_feed_device(self.h, dev_ptr, n))
+        return self
+
+    def reserve(self, expected_kmers):
+        _check(lib().katgpu_count_reserve(self.h, int(expected_kmers)))
         return self
 
     def end(self):

@@ -676,7 +676,7 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
 }
 
 static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
-                                      TableCounters &ctr) {
+                                      TableCounters &ctr, const uint64_t *in_keys = nullptr) {
     katgpu_ctx *c = t->ctx;
     // keys one CTA tile sends to one slice: mean m (every position a k-mer) + up to 3 padding keys;
     // after T tiles the fullest segment holds about T*(m+2) + 4*sqrt(T*m) (a segment that still
@@ -704,11 +704,13 @@ static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint6
         const uint64_t take = std::min(n_starts - done, max_starts);
         PartitionParams P{};
         P.g = t->g;
-        P.bases = dev + done;
+        P.bases = in_keys ? nullptr : dev + done;
         P.n_valid = n_valid - done;
         P.n_starts = take;
+        P.in_keys = in_keys ? in_keys + done : nullptr;
+        P.n_keys = take;
         P.n_tiles = (int)((take + kTile - 1) / kTile);
-        P.tma_ok = (reinterpret_cast<uintptr_t>(dev + done) & 15) == 0;
+        P.tma_ok = !in_keys && (reinterpret_cast<uintptr_t>(dev + done) & 15) == 0;
         P.Pb = t->pend_Pb;
         P.seg_cap = t->pend_seg_cap;
         P.keys = t->pend_keys;
@@ -812,6 +814,17 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
     return KATGPU_OK;
 }
 
+extern "C" katgpu_status katgpu_count_reserve(katgpu_table *t, uint64_t expected_kmers) {
+    if (!t) return fail(KATGPU_ERR_INVALID, "katgpu_count_reserve: NULL table");
+    if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_reserve: table already finished");
+    CU(cudaSetDevice(t->ctx->device));
+    if (use_partition(t, expected_kmers)) {
+        bool ok = false;
+        KT(pend_alloc(t, expected_kmers, ok));
+    }
+    return KATGPU_OK;
+}
+
 extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct, uint64_t *n_total) {
     if (!t) return fail(KATGPU_ERR_INVALID, "katgpu_count_end: NULL table");
     CU(cudaSetDevice(t->ctx->device));
@@ -897,8 +910,13 @@ extern "C" katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void
     CU(cudaSetDevice(c->device));
     TableCounters ctr;
     KT(read_counters(t, ctr));
-    KT(sweep_pending(t, ctr));
     const uint64_t *hs = (const uint64_t *)hashed_dev;
+    if (use_partition(t, n)) { // partition the received keys by table slice; inserted at the next sweep
+        bool ok = false;
+        KT(pend_alloc(t, n, ok));
+        if (ok) return feed_partitioned(t, nullptr, n, n, ctr, hs);
+    }
+    KT(sweep_pending(t, ctr));
     uint64_t done = 0;
     while (done < n) {
         uint64_t granted = 0;

@@ -51,6 +51,9 @@ __device__ __forceinline__ uint64_t hll_hash(uint64_t h) {
     return x;
 }
 
+// KEYS = false: tiles of the base stream (extract + hash);  KEYS = true: tiles of already
+// hashed keys (the owner side of the multi-GPU exchange).
+template <bool KEYS>
 __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid_constant__ PartitionParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     PartSmem &S = *reinterpret_cast<PartSmem *>(smem_raw);
@@ -65,7 +68,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
     for (uint32_t i = tid; i < (kPartThreads / 32) * (kMaxParts + 2); i += kPartThreads) (&S.wcnt[0][0])[i] = 0;
     auto tile_tma = [&](int t) { return P.tma_ok && ((uint64_t)(t + 1) * kTile + kHalo <= P.n_valid); };
     int tile = blockIdx.x; // static striding: per-CTA segment fill is predictable
-    if (tid == 0) {
+    if (!KEYS && tid == 0) {
         mbar_init(&S.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (tile < P.n_tiles && tile_tma(tile)) {
@@ -80,6 +83,10 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
 
     for (; tile < P.n_tiles; tile += gridDim.x) {
         const uint64_t tile_base = (uint64_t)tile * kTile;
+        uint64_t hh[16];
+        uint32_t rk[8]; // 16-bit rank inside (warp, partition), two per register
+        uint32_t hll_mask = 0, sent_mask = 0;
+        if (!KEYS) {
         if (tile_tma(tile)) {
             while (!mbar_try_wait(&S.mbar, parity)) {
             }
@@ -117,9 +124,6 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
         const uint64_t lo = (uint64_t)S.W[gi + 2] << 32;
         const uint64_t bad48 = ((uint64_t)S.B[gi] << 32) | ((uint64_t)S.B[gi + 1] << 16) | S.B[gi + 2];
         const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
-        uint64_t hh[16];
-        uint32_t rk[8]; // 16-bit rank inside (warp, partition), two per register
-        uint32_t hll_mask = 0, sent_mask = 0;
         uint64_t rc = 0;
 #pragma unroll
         for (uint32_t r = 0; r < 16; r++) {
@@ -129,10 +133,24 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
             rc = r == 0 ? revcomp_kmer(fwd, k) : (rc >> 2) | ((~fwd & 3ULL) << (2 * k - 2));
             const uint64_t key = (g.canonical && rc < fwd) ? rc : fwd;
             const uint64_t h = mix_key(g, key);
-            const bool real = ok && h != kSentinel;
             sent_mask |= (uint32_t)(ok && h == kSentinel) << r; // the one hash that doubles as padding (k = 32 only)
+            hh[r] = ok ? h : kSentinel;
+        }
+        } else {
+#pragma unroll
+            for (uint32_t r = 0; r < 16; r++) { // coalesced: consecutive threads read consecutive keys
+                const uint64_t i = tile_base + (uint64_t)r * kPartThreads + tid;
+                const bool ok = i < P.n_keys;
+                const uint64_t h = ok ? __ldg(P.in_keys + i) : kSentinel;
+                sent_mask |= (uint32_t)(ok && h == kSentinel) << r;
+                hh[r] = h;
+            }
+        }
+#pragma unroll
+        for (uint32_t r = 0; r < 16; r++) {
+            const uint64_t h = hh[r];
+            const bool real = h != kSentinel;
             hll_mask |= (uint32_t)(real && (h & ((1u << kHllSampleShift) - 1)) == 0) << r;
-            hh[r] = real ? h : kSentinel;
             const uint32_t part = real ? (uint32_t)(h >> pshift) : nparts; // dummy bin for non-k-mers
             const uint32_t peers = __match_any_sync(0xffffffffu, part);
             const int leader = __ffs(peers) - 1;
@@ -328,12 +346,20 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) sweep_kernel(con
 size_t partition_smem_bytes() { return sizeof(PartSmem); }
 
 cudaError_t partition_configure(int *blocks_per_sm) {
-    cudaError_t e = cudaFuncSetAttribute(partition_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem));
+    cudaError_t e = cudaFuncSetAttribute(partition_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem));
     if (e != cudaSuccess) return e;
-    return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, partition_kernel, kPartThreads, sizeof(PartSmem));
+    e = cudaFuncSetAttribute(partition_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PartSmem));
+    if (e != cudaSuccess) return e;
+    int a = 0, b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, partition_kernel<false>, kPartThreads, sizeof(PartSmem));
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, partition_kernel<true>, kPartThreads, sizeof(PartSmem));
+    *blocks_per_sm = a < b ? a : b;
+    return e;
 }
 void launch_partition(const PartitionParams &P, int grid, cudaStream_t st) {
-    partition_kernel<<<grid, kPartThreads, sizeof(PartSmem), st>>>(P);
+    if (P.in_keys) partition_kernel<true><<<grid, kPartThreads, sizeof(PartSmem), st>>>(P);
+    else partition_kernel<false><<<grid, kPartThreads, sizeof(PartSmem), st>>>(P);
 }
 cudaError_t sweep_occupancy(int *blocks_per_sm) {
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, sweep_kernel, kSweepThreads, 0);

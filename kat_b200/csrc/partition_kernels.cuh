@@ -32,6 +32,8 @@ struct PartitionParams {
     uint64_t *keys;     // [partition][cta][seg_cap]
     uint32_t *seglen;   // [partition][cta] keys appended so far (multiples of 4)
     uint32_t *hll;      // [kHllM]
+    const uint64_t *in_keys; // non-null: partition these hashed keys instead of the base stream
+    uint64_t n_keys;
 };
 
 struct SweepParams {

@@ -32,8 +32,10 @@ class GpuEngine:
         self.table = None
         self.device = torch.device("cuda", torch.cuda.current_device())
 
-    def begin(self):
+    def begin(self, expected_kmers=0):
         self.table = self.ctx.count_begin(self.k, self.canonical, self.slots, True)
+        if expected_kmers:
+            self.table.reserve(expected_kmers)
 
     def alloc_keys(self, n):
         return self.torch.empty(max(n, 1), dtype=self.torch.int64, device=self.device)
@@ -91,7 +93,8 @@ class DistributedCounter:
         """Route / exchange / insert the local base stream in batches.  Batches
         end on record boundaries when record_len is given (no k-mer is cut)."""
         e, dist, W = self.engine, self.dist, self.world
-        e.begin()
+        # with a uniform owner hash every rank receives about what it routes
+        e.begin(n_bytes)
         step = self.batch_bytes
         if record_len:  # whole records per batch, and 16-byte aligned batch starts (TMA path)
             unit = record_len * 16

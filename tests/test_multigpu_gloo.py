@@ -22,7 +22,7 @@ class NumpyEngine:
     def __init__(self, bases, k, canonical):
         self.bases, self.k, self.canonical = bases, k, canonical
 
-    def begin(self):
+    def begin(self, expected_kmers=0):
         self.h = []
 
     def alloc_keys(self, n):
