@@ -154,6 +154,15 @@ def cpu_reference_sample(ctx_or_none, sample_reads, threads, workdir, stream=Non
 
 
 def main():
+    # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner)
+    # are sent to stderr, the result goes to the saved descriptor.
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+    def emit(obj):
+        real_stdout.write(json.dumps(obj) + "\n")
+        real_stdout.flush()
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -185,7 +194,7 @@ def main():
             return 0
         import oracle as O
         if not O.have_ref():
-            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/kat not built (run oracle/ref.mk where /root/reference exists)"}))
+            emit({"impl": "reference", "unavailable": "oracle/_ref/kat not built (run oracle/ref.mk where /root/reference exists)"})
             return 0
         from kat_b200 import binding as B
         sample = min(args.cpu_sample_reads, n_reads)
@@ -212,7 +221,7 @@ def main():
                                      "sample": f"first {sample} reads ({n_inst} k-mer instances) of the workload as FASTQ; "
                                                f"`kat hist -m27 -t{threads} -H{slots}` wall time incl. parse; phases {times[-1][1]}"},
                     "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-            print(json.dumps(line))
+            emit(line)
         finally:
             shutil.rmtree(work, ignore_errors=True)
         return 0
@@ -302,7 +311,8 @@ def main():
     # K1 (extract + canonicalise + insert) is either one kernel (extract_kernel<insert>,
     # family "count") or the pair partition_kernel + sweep_kernel; its algorithmic bytes are B_ALG per k-mer.
     if world > 1:
-        fam, kname = ["route", "insert"], "extract_kernel<route> + insert_hashed_kernel"
+        fam = [f for f in ("route", "partition", "sweep", "insert") if prof[f][1] > 0]
+        kname = "extract_kernel<route> + partition_kernel<keys> + sweep_kernel (K1 + K5; NCCL exchange between route and partition not included)"
     elif prof["partition"][1] > 0:
         fam, kname = ["partition", "sweep"], "partition_kernel + sweep_kernel (K1 split in two streaming phases)"
     else:
@@ -379,7 +389,7 @@ def main():
 
     ctx.device_free(d_bases)
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
