@@ -102,7 +102,8 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeInsert ? KATGPU_MIN_CTA
             // number of k-mer starts this thread owns (stream end / chunk overlap)
             const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
 
-            uint64_t rc = 0; // rolled reverse complement of the current k-mer
+            Roll16 roll;
+            roll.init(hi, lo, bad48, k, nst);
             if (MODE == kModeInsert) {
 #pragma unroll 1
                 for (uint32_t r0 = 0; r0 < 16; r0 += kUnroll) {
@@ -111,10 +112,9 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeInsert ? KATGPU_MIN_CTA
                     Bucket bk[kUnroll];
 #pragma unroll
                     for (int u = 0; u < kUnroll; u++) {
-                        uint64_t fwd;
-                        ok[u] = cut_kmer(hi, lo, bad48, r0 + u, k, fwd) && (r0 + u < nst);
-                        rc = (r0 + u) == 0 ? revcomp_kmer(fwd, k) : (rc >> 2) | ((~fwd & 3ULL) << (2 * k - 2));
-                        h[u] = mix_key(g, (g.canonical && rc < fwd) ? rc : fwd);
+                        if (r0 + u > 0) roll.step(r0 + u, g.kmask);
+                        ok[u] = roll.ok(r0 + u);
+                        h[u] = mix_key(g, roll.key(g.canonical));
                         if (ok[u]) bk[u] = load_bucket(g.slots + (((h[u] >> g.rbits) & g.bmask) << 2));
                     }
 #pragma unroll
@@ -133,10 +133,9 @@ __global__ void __launch_bounds__(kThreads, MODE == kModeInsert ? KATGPU_MIN_CTA
                 unsigned long long c0 = 0, c1 = 0; // 16-bit fields: owners 0-3, 4-7
 #pragma unroll
                 for (uint32_t r = 0; r < 16; r++) {
-                    uint64_t fwd;
-                    const bool ok = cut_kmer(hi, lo, bad48, r, k, fwd) && (r < nst);
-                    rc = r == 0 ? revcomp_kmer(fwd, k) : (rc >> 2) | ((~fwd & 3ULL) << (2 * k - 2));
-                    hh[r] = mix_key(g, (g.canonical && rc < fwd) ? rc : fwd);
+                    if (r > 0) roll.step(r, g.kmask);
+                    const bool ok = roll.ok(r);
+                    hh[r] = mix_key(g, roll.key(g.canonical));
                     const uint32_t o = ok ? owner_of(hh[r], P.n_ranks) : 0xFu;
                     owners |= (uint64_t)o << (4 * r);
                     if (ok) {

@@ -61,4 +61,45 @@ __device__ __forceinline__ bool cut_kmer(uint64_t hi, uint64_t lo, uint64_t bad4
 }
 
 
+
+// 16 valid-start flags of one thread at once: start r is a k-mer iff none of the k
+// invalid bits [r, r+k) is set.  OR over a window of k by doubling (bit 47-t of bad48 =
+// base t).  Returns bit (15 - r) = start r is valid.
+__device__ __forceinline__ uint32_t valid_starts16(uint64_t bad48, uint32_t k) {
+    uint64_t w = bad48; // window 1
+    uint32_t len = 1;
+#pragma unroll
+    for (int d = 0; d < 5; d++) {
+        if (2 * len <= k) {
+            w |= w << len;
+            len *= 2;
+        }
+    }
+    w |= w << (k - len); // two windows of `len` cover a window of k (len <= k < 2 len)
+    return (uint32_t)(~w >> 32) & 0xFFFFu;
+}
+
+// Rolling extraction state of one thread: the 16 k-mers starting at the 16 bases of its
+// group, forward and reverse complement (JFI/mer_dna.hpp:330-378 shift_left/shift_right).
+struct Roll16 {
+    uint64_t fwd, rc, nextw;
+    uint32_t okm, topsh;
+    __device__ __forceinline__ void init(uint64_t hi, uint64_t lo, uint64_t bad48, uint32_t k, uint32_t nst) {
+        okm = valid_starts16(bad48, k);
+        okm &= nst >= 16 ? 0xFFFFu : (0xFFFFu << (16 - nst)) & 0xFFFFu;
+        nextw = k < 32 ? ((hi << (2 * k)) | (lo >> (64 - 2 * k))) : lo; // bases k .. k+15, base k on top
+        fwd = hi >> (64 - 2 * k);
+        rc = revcomp_kmer(fwd, k);
+        topsh = 2 * k - 2;
+    }
+    // advance from start r-1 to start r (r >= 1): base r+k-1 enters, base r-1 leaves
+    __device__ __forceinline__ void step(uint32_t r, uint64_t kmask) {
+        const uint64_t c = (nextw >> (64 - 2 * r)) & 3ULL;
+        fwd = ((fwd << 2) | c) & kmask;
+        rc = (rc >> 2) | ((c ^ 3ULL) << topsh);
+    }
+    __device__ __forceinline__ bool ok(uint32_t r) const { return (okm >> (15 - r)) & 1u; }
+    __device__ __forceinline__ uint64_t key(bool canonical) const { return (canonical && rc < fwd) ? rc : fwd; }
+};
+
 } // namespace katgpu

@@ -312,6 +312,12 @@ extern "C" katgpu_status katgpu_profile_get(katgpu_ctx *c, const char *family, d
     return KATGPU_OK;
 }
 
+// Per-launch bound on the increments one slot can receive -> when RED is provably safe.
+static void set_add_bound(TableGeom &g, uint64_t bound) {
+    g.add_bound = bound;
+    g.red_below = bound <= g.cmax ? g.cmax - bound + 1 : 0;
+}
+
 // ---- table geometry ----
 static uint64_t inv_mod_2_64(uint64_t a) { // Newton iteration, a odd
     uint64_t x = a;
@@ -349,7 +355,8 @@ static katgpu_status make_geom(int k, int canonical, int Lb, int count_bits_cap,
     g.m1inv = inv_mod_2_64(kMixM1);
     g.m2inv = inv_mod_2_64(kMixM2);
     g.spill_cap = kSpillCap;
-    g.add_bound = ~0ULL; // set per launch
+    g.add_bound = ~0ULL; // set per launch (set_add_bound)
+    g.red_below = 0;
     return KATGPU_OK;
 }
 // Smallest Lb that leaves a count field of at least 16 bits (so that count
@@ -521,7 +528,7 @@ static katgpu_status launch_extract_insert(katgpu_table *t, const uint8_t *dev, 
     katgpu_ctx *c = t->ctx;
     ExtractParams P{};
     P.g = t->g;
-    P.g.add_bound = n_starts; // every k-mer of this launch could hit the same slot
+    set_add_bound(P.g, n_starts); // every k-mer of this launch could hit the same slot
     P.bases = dev;
     P.n_valid = n_valid;
     P.n_starts = n_starts;
@@ -627,7 +634,7 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
     uint32_t h_hll[kHllM];
     CU(cudaMemcpyAsync(h_hll, t->pend_hll, sizeof h_hll, cudaMemcpyDeviceToHost, c->stream));
     KT(read_counters(t, ctr)); // synchronises
-    const double est_new = std::min((double)t->pend_bound, hll_estimate(h_hll, kHllM) * (double)(1u << kHllSampleShift) * 1.12 + 4096.0);
+    const double est_new = std::min((double)t->pend_bound, hll_estimate(h_hll, kHllM) * (double)(1u << kHllSampleShift) * 1.25 + 4096.0);
     if ((int)t->g.Lb < (int)t->g.b) {
         const double need = (double)ctr.n_distinct + est_new;
         if (need > kMaxLoad * (double)t->n_slots) {
@@ -636,14 +643,14 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
                 while (lb < (int)t->g.b && need > 0.70 * (double)((uint64_t)kSlotsPerBucket << lb)) lb++;
                 KT(grow_table(t, ctr, lb));
                 KT(read_counters(t, ctr));
-            } else if ((double)ctr.n_distinct + est_new / 1.12 * 0.9 > (double)t->n_slots)
+            } else if ((double)ctr.n_distinct + est_new / 1.25 * 0.8 > (double)t->n_slots)
                 return fail(KATGPU_ERR_HASH_FULL, "Hash full");
         }
     }
     SweepParams P{};
     P.g = t->g;
     const double per_part = t->pend_fill * (double)t->pend_segs; // keys that can target one slot
-    P.g.add_bound = per_part < 1.8e19 ? (uint64_t)per_part + 1 : ~0ULL;
+    set_add_bound(P.g, per_part < 1.8e19 ? (uint64_t)per_part + 1 : ~0ULL);
     P.keys = t->pend_keys;
     P.seglen = t->pend_seglen;
     P.seg_cap = t->pend_seg_cap;
@@ -925,7 +932,7 @@ extern "C" katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void
         {
             ProfScope ps(c, "insert", c->stream);
             TableGeom gl = t->g;
-            gl.add_bound = granted;
+            set_add_bound(gl, granted);
             launch_insert_hashed(gl, hs + done, granted, grid, c->stream);
         }
         c->launches++;

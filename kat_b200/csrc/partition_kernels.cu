@@ -24,17 +24,21 @@ namespace katgpu {
 
 constexpr uint64_t kSentinel = ~0ULL; // padding key (segments are appended in multiples of 4 keys)
 
+constexpr int kStageCap = kTile + 3 * kMaxParts; // every slice run is padded to a multiple of 4 keys
+
 struct __align__(128) PartSmem {
     uint8_t ascii[kTile + kHalo];
     uint32_t W[kGroups + 2];
     uint32_t B[kGroups + 2];
     uint64_t mbar;
-    uint32_t off[kMaxParts + 2];                  // exclusive prefix of per-partition counts (+dummy bin)
-    uint32_t gcur[kMaxParts];                     // this CTA's append cursor per partition (keys)
-    uint16_t wcnt[kPartThreads / 32][kMaxParts + 2]; // per-warp per-partition counts -> warp prefixes
+    uint32_t off[kMaxParts + 2];                     // exclusive prefix of the PADDED per-slice counts
+    uint32_t gcur[kMaxParts];                        // this CTA's append cursor per slice (keys)
+    uint16_t wcnt[kPartThreads / 32][kMaxParts + 2]; // per-warp per-slice counts -> warp prefixes
     uint32_t wscan[kPartThreads / 32];
+    uint8_t ovf[kMaxParts];                          // this tile's run does not fit the slice segment
+    uint32_t any_ovf;
     uint32_t hll[kHllM];
-    uint64_t stage[kTile];
+    uint64_t stage[kStageCap];
 };
 
 __device__ __forceinline__ uint64_t sel16(const uint64_t (&a)[16], int i) {
@@ -62,6 +66,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
     const uint32_t k = g.k;
     const uint32_t nparts = 1u << P.Pb;
     const uint32_t pshift = g.b - P.Pb;
+    const bool sentinel_possible = g.b == 64; // only then can a real hash equal the padding value
 
     for (uint32_t i = tid; i < nparts; i += kPartThreads) S.gcur[i] = P.seglen[(size_t)i * gridDim.x + blockIdx.x];
     for (uint32_t i = tid; i < (uint32_t)kHllM; i += kPartThreads) S.hll[i] = 0;
@@ -84,73 +89,72 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
     for (; tile < P.n_tiles; tile += gridDim.x) {
         const uint64_t tile_base = (uint64_t)tile * kTile;
         uint64_t hh[16];
-        uint32_t rk[8]; // 16-bit rank inside (warp, partition), two per register
+        uint32_t rk[8]; // 16-bit rank inside (warp, slice), two per register
         uint32_t hll_mask = 0, sent_mask = 0;
         if (!KEYS) {
-        if (tile_tma(tile)) {
-            while (!mbar_try_wait(&S.mbar, parity)) {
+            if (tile_tma(tile)) {
+                while (!mbar_try_wait(&S.mbar, parity)) {
+                }
+                parity ^= 1;
+            } else {
+                for (int i = tid; i < (kTile + kHalo); i += kPartThreads) {
+                    const uint64_t p = tile_base + i;
+                    S.ascii[i] = p < P.n_valid ? P.bases[p] : (uint8_t)0;
+                }
+                __syncthreads();
             }
-            parity ^= 1;
-        } else {
-            for (int i = tid; i < (kTile + kHalo); i += kPartThreads) {
-                const uint64_t p = tile_base + i;
-                S.ascii[i] = p < P.n_valid ? P.bases[p] : (uint8_t)0;
+            for (int gi = tid; gi < kGroups + 2; gi += kPartThreads) {
+                const uint4 v = reinterpret_cast<const uint4 *>(S.ascii)[gi];
+                uint32_t c0, c1, c2, c3, b0, b1, b2, b3;
+                pack4(v.x, c0, b0);
+                pack4(v.y, c1, b1);
+                pack4(v.z, c2, b2);
+                pack4(v.w, c3, b3);
+                S.W[gi] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+                S.B[gi] = (b0 << 12) | (b1 << 8) | (b2 << 4) | b3;
             }
             __syncthreads();
-        }
-        for (int gi = tid; gi < kGroups + 2; gi += kPartThreads) {
-            const uint4 v = reinterpret_cast<const uint4 *>(S.ascii)[gi];
-            uint32_t c0, c1, c2, c3, b0, b1, b2, b3;
-            pack4(v.x, c0, b0);
-            pack4(v.y, c1, b1);
-            pack4(v.z, c2, b2);
-            pack4(v.w, c3, b3);
-            S.W[gi] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
-            S.B[gi] = (b0 << 12) | (b1 << 8) | (b2 << 4) | b3;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            const int nt = tile + gridDim.x;
-            if (nt < P.n_tiles && tile_tma(nt)) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&S.mbar, kTile + kHalo);
-                tma_load_1d(S.ascii, P.bases + (uint64_t)nt * kTile, kTile + kHalo, &S.mbar);
+            if (tid == 0) {
+                const int nt = tile + gridDim.x;
+                if (nt < P.n_tiles && tile_tma(nt)) {
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    mbar_expect_tx(&S.mbar, kTile + kHalo);
+                    tma_load_1d(S.ascii, P.bases + (uint64_t)nt * kTile, kTile + kHalo, &S.mbar);
+                }
             }
-        }
-        // ---- A: hash 16 k-mers per thread, rank them inside (warp, partition) ----
-        const int gi = tid; // kGroups == kPartThreads
-        const uint64_t p0 = tile_base + (uint64_t)gi * 16;
-        const uint64_t hi = ((uint64_t)S.W[gi] << 32) | S.W[gi + 1];
-        const uint64_t lo = (uint64_t)S.W[gi + 2] << 32;
-        const uint64_t bad48 = ((uint64_t)S.B[gi] << 32) | ((uint64_t)S.B[gi + 1] << 16) | S.B[gi + 2];
-        const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
-        uint64_t rc = 0;
+            // ---- A1: 16 rolled canonical k-mers per thread -> hashed keys ----
+            const int gi = tid; // kGroups == kPartThreads
+            const uint64_t p0 = tile_base + (uint64_t)gi * 16;
+            const uint64_t hi = ((uint64_t)S.W[gi] << 32) | S.W[gi + 1];
+            const uint64_t lo = (uint64_t)S.W[gi + 2] << 32;
+            const uint64_t bad48 = ((uint64_t)S.B[gi] << 32) | ((uint64_t)S.B[gi + 1] << 16) | S.B[gi + 2];
+            const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
+            Roll16 roll;
+            roll.init(hi, lo, bad48, k, nst);
 #pragma unroll
-        for (uint32_t r = 0; r < 16; r++) {
-            uint64_t fwd;
-            const bool ok = cut_kmer(hi, lo, bad48, r, k, fwd) && (r < nst);
-            // reverse complement, rolled: drop the last base, complement of the new last base on top
-            rc = r == 0 ? revcomp_kmer(fwd, k) : (rc >> 2) | ((~fwd & 3ULL) << (2 * k - 2));
-            const uint64_t key = (g.canonical && rc < fwd) ? rc : fwd;
-            const uint64_t h = mix_key(g, key);
-            sent_mask |= (uint32_t)(ok && h == kSentinel) << r; // the one hash that doubles as padding (k = 32 only)
-            hh[r] = ok ? h : kSentinel;
-        }
+            for (uint32_t r = 0; r < 16; r++) {
+                if (r > 0) roll.step(r, g.kmask);
+                const uint64_t h = mix_key(g, roll.key(g.canonical));
+                const bool ok = roll.ok(r);
+                if (sentinel_possible) sent_mask |= (uint32_t)(ok && h == kSentinel) << r;
+                hh[r] = ok ? h : kSentinel;
+            }
         } else {
 #pragma unroll
             for (uint32_t r = 0; r < 16; r++) { // coalesced: consecutive threads read consecutive keys
                 const uint64_t i = tile_base + (uint64_t)r * kPartThreads + tid;
                 const bool ok = i < P.n_keys;
                 const uint64_t h = ok ? __ldg(P.in_keys + i) : kSentinel;
-                sent_mask |= (uint32_t)(ok && h == kSentinel) << r;
+                if (sentinel_possible) sent_mask |= (uint32_t)(ok && h == kSentinel) << r;
                 hh[r] = h;
             }
         }
+        // ---- A2: rank every key inside its (warp, slice) ----
 #pragma unroll
         for (uint32_t r = 0; r < 16; r++) {
             const uint64_t h = hh[r];
             const bool real = h != kSentinel;
-            hll_mask |= (uint32_t)(real && (h & ((1u << kHllSampleShift) - 1)) == 0) << r;
+            hll_mask |= (uint32_t)(real && ((uint32_t)h & ((1u << kHllSampleShift) - 1)) == 0) << r;
             const uint32_t part = real ? (uint32_t)(h >> pshift) : nparts; // dummy bin for non-k-mers
             const uint32_t peers = __match_any_sync(0xffffffffu, part);
             const int leader = __ffs(peers) - 1;
@@ -165,7 +169,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
             else rk[r >> 1] = rank;
             __syncwarp();
         }
-        // rare side work kept out of the unrolled loop
+        // rare side work kept out of the unrolled loops
         if (hll_mask) { // distinct-key estimate: HyperLogLog over a 1/2^kHllSampleShift sample of the key space
 #pragma unroll 1
             for (uint32_t m = hll_mask; m; m &= m - 1) {
@@ -173,17 +177,18 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
                 atomicMax(&S.hll[x >> (64 - kHllBits)], (uint32_t)__clzll((x << kHllBits) | (1ULL << (kHllBits - 1))) + 1);
             }
         }
-        if (sent_mask) {
+        if (sent_mask) { // a real key that equals the padding value (k = 32 only): insert it directly
             for (uint32_t m = sent_mask; m; m &= m - 1) {
                 Bucket bk = {};
                 direct_new += insert_hashed(g, kSentinel, 1, bk, false) == 1;
                 direct_total++;
             }
         }
+        if (tid == 0) S.any_ovf = 0;
         __syncthreads();
-        // ---- B: per-partition totals over warps, then block scan over partitions ----
+        // ---- B: per-slice totals over warps, padded to 4 keys, then block scan over slices ----
         uint32_t mine = 0;
-        if ((uint32_t)tid < nparts) { // one partition column per thread (nparts <= kPartThreads)
+        if ((uint32_t)tid < nparts) { // one slice column per thread (nparts <= kPartThreads)
             uint32_t run = 0;
 #pragma unroll
             for (int w = 0; w < kPartThreads / 32; w++) {
@@ -191,9 +196,13 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
                 S.wcnt[w][tid] = (uint16_t)run;
                 run += t;
             }
-            mine = run;
+            mine = (run + 3) & ~3u;
+            const bool o = S.gcur[tid] + mine > P.seg_cap;
+            S.ovf[tid] = o;
+            if (o) S.any_ovf = 1;
+            mine |= run << 16; // low 16 bits: padded count, high 16: real count
         }
-        uint32_t inc = mine;
+        uint32_t inc = mine & 0xFFFFu;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
             const uint32_t t = __shfl_up_sync(0xffffffffu, inc, d);
@@ -205,8 +214,13 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
 #pragma unroll
         for (int w = 0; w < kPartThreads / 32; w++)
             if (w < warp) wbase += S.wscan[w];
-        if ((uint32_t)tid < nparts) S.off[tid] = wbase + inc - mine;
-        if ((uint32_t)tid == nparts - 1) S.off[nparts] = wbase + inc; // total
+        if ((uint32_t)tid < nparts) {
+            const uint32_t padded = mine & 0xFFFFu, real_n = mine >> 16;
+            const uint32_t o = wbase + inc - padded;
+            S.off[tid] = o;
+            for (uint32_t j = real_n; j < padded; j++) S.stage[o + j] = kSentinel; // <= 3 pad keys
+            if ((uint32_t)tid == nparts - 1) S.off[nparts] = wbase + inc; // total (padded)
+        }
         __syncthreads();
         // ---- C: counting-sort scatter into the stage ----
 #pragma unroll
@@ -219,25 +233,40 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
             }
         }
         __syncthreads();
-        // ---- D: append each partition's run (padded to 4 keys = 32 B) to this CTA's segment ----
-        for (uint32_t part = warp; part < nparts; part += kPartThreads / 32) {
-            const uint32_t o = S.off[part], n = S.off[part + 1] - o;
-            if (n == 0) continue;
-            const uint32_t n_out = (n + 3) & ~3u;
-            const uint32_t cur = S.gcur[part];
-            if (cur + n_out <= P.seg_cap) {
-                uint64_t *dst = P.keys + ((size_t)part * gridDim.x + blockIdx.x) * P.seg_cap + cur;
-                for (uint32_t j = lane; j < n_out; j += 32) dst[j] = j < n ? S.stage[o + j] : kSentinel;
-                if (lane == 0) S.gcur[part] = cur + n_out;
-            } else {
-                // segment full: insert these keys the slow (random-access) way; never lose a k-mer
+        // ---- D: flat, coalesced append: stage[i] goes to its slice's segment of this CTA ----
+        {
+            const uint32_t total = S.off[nparts];
+            for (uint32_t i = tid; i < total; i += kPartThreads) {
+                const uint64_t h = S.stage[i];
+                uint32_t part;
+                if (h != kSentinel) part = (uint32_t)(h >> pshift);
+                else { // padding: find its slice by bisection on the run starts
+                    uint32_t lo_p = 0, hi_p = nparts; // largest p with off[p] <= i
+                    while (hi_p - lo_p > 1) {
+                        const uint32_t mid = (lo_p + hi_p) >> 1;
+                        if (S.off[mid] <= i) lo_p = mid; else hi_p = mid;
+                    }
+                    part = lo_p;
+                }
+                if (!S.ovf[part])
+                    P.keys[((size_t)part * gridDim.x + blockIdx.x) * P.seg_cap + S.gcur[part] + (i - S.off[part])] = h;
+            }
+        }
+        if (S.any_ovf) { // some segment is full: insert that run the slow (random-access) way; never lose a k-mer
+            for (uint32_t part = warp; part < nparts; part += kPartThreads / 32) {
+                if (!S.ovf[part]) continue;
+                const uint32_t o = S.off[part], n = S.off[part + 1] - o;
                 for (uint32_t j = lane; j < n; j += 32) {
+                    const uint64_t h = S.stage[o + j];
+                    if (h == kSentinel) continue;
                     Bucket bk = {};
-                    direct_new += insert_hashed(g, S.stage[o + j], 1, bk, false) == 1;
+                    direct_new += insert_hashed(g, h, 1, bk, false) == 1;
                     direct_total++;
                 }
             }
         }
+        __syncthreads();
+        if ((uint32_t)tid < nparts && !S.ovf[tid]) S.gcur[tid] += mine & 0xFFFFu;
         // reset the per-warp counters for the next tile
         for (uint32_t i = tid; i < (kPartThreads / 32) * (kMaxParts + 2); i += kPartThreads) (&S.wcnt[0][0])[i] = 0;
         __syncthreads();

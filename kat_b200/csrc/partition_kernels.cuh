@@ -6,7 +6,7 @@ namespace katgpu {
 
 constexpr int kPartThreads = 512;  // == kGroups: one 16-base group per thread per tile
 constexpr int kMaxParts = 512;     // table slices (Pb <= 9)
-constexpr int kHllBits = 10;       // HyperLogLog registers for the distinct-key estimate
+constexpr int kHllBits = 8;        // HyperLogLog registers for the distinct-key estimate (6.5 % std error)
 constexpr int kHllM = 1 << kHllBits;
 constexpr int kHllSampleShift = 6; // 1/64 of the key space is sampled
 #ifndef KATGPU_SWEEP_THREADS

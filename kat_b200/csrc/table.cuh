@@ -58,6 +58,7 @@ struct TableGeom {
     uint64_t m1inv, m2inv;
     uint64_t spill_cap;
     uint64_t add_bound; // upper bound on the increments any one slot can receive in this launch
+    uint64_t red_below; // derived: a count field below this cannot carry in this launch (0 = never)
     uint32_t k, b, Lb, rbits, cshift, cbits, sh, canonical;
 };
 
@@ -152,7 +153,7 @@ static __device__ __noinline__ uint64_t ovf_get(const TableGeom &g, uint64_t h) 
 // when that cannot carry, a fire-and-forget RED replaces the ATOM round trip.
 __device__ __forceinline__ void slot_add(const TableGeom &g, uint64_t *slot, uint64_t h, uint64_t cnt,
                                          uint64_t seen) {
-    if ((seen >> g.cshift) + g.add_bound <= g.cmax && g.add_bound <= g.cmax) {
+    if ((seen >> g.cshift) < g.red_below) {
         asm volatile("red.global.add.u64 [%0], %1;" ::"l"(slot), "l"(cnt << g.cshift) : "memory");
         return;
     }
