@@ -169,7 +169,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="katgpu", choices=["katgpu", "reference"])
     ap.add_argument("--reads", type=int, default=READS_PER_GPU, help="reads per GPU (default: the 10 Gbp workload)")
-    ap.add_argument("--slots-log2", type=int, default=31, help="table slots per GPU (log2)")
+    ap.add_argument("--slots-log2", type=int, default=0, help="table slots per GPU (log2)")
     ap.add_argument("--cpu-sample-reads", type=int, default=4_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -177,6 +177,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.slots_log2 == 0:  # load ~0.28 on one GPU; 2^31 when the exchange buffers also need HBM
+        args.slots_log2 = 32 if world == 1 else 31
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_reads = args.reads
     n_kmers_nominal = n_reads * KMERS_PER_READ

@@ -33,7 +33,7 @@ struct __align__(128) PartSmem {
     uint64_t mbar;
     uint32_t off[kMaxParts + 2];                     // exclusive prefix of the PADDED per-slice counts
     uint32_t gcur[kMaxParts];                        // this CTA's append cursor per slice (keys)
-    uint16_t wcnt[kPartThreads / 32][kMaxParts + 2]; // per-warp per-slice counts -> warp prefixes
+    uint32_t cnt[kMaxParts];                         // keys of this tile per slice (shared atomics hand out ranks)
     uint32_t wscan[kPartThreads / 32];
     uint8_t ovf[kMaxParts];                          // this tile's run does not fit the slice segment
     uint32_t any_ovf;
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
 
     for (uint32_t i = tid; i < nparts; i += kPartThreads) S.gcur[i] = P.seglen[(size_t)i * gridDim.x + blockIdx.x];
     for (uint32_t i = tid; i < (uint32_t)kHllM; i += kPartThreads) S.hll[i] = 0;
-    for (uint32_t i = tid; i < (kPartThreads / 32) * (kMaxParts + 2); i += kPartThreads) (&S.wcnt[0][0])[i] = 0;
+    for (uint32_t i = tid; i < (uint32_t)kMaxParts; i += kPartThreads) S.cnt[i] = 0;
     auto tile_tma = [&](int t) { return P.tma_ok && ((uint64_t)(t + 1) * kTile + kHalo <= P.n_valid); };
     int tile = blockIdx.x; // static striding: per-CTA segment fill is predictable
     if (!KEYS && tid == 0) {
@@ -149,25 +149,16 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
                 hh[r] = h;
             }
         }
-        // ---- A2: rank every key inside its (warp, slice) ----
+        // ---- A2: rank every key inside its slice: one shared-memory atomic per key ----
 #pragma unroll
         for (uint32_t r = 0; r < 16; r++) {
             const uint64_t h = hh[r];
             const bool real = h != kSentinel;
             hll_mask |= (uint32_t)(real && ((uint32_t)h & ((1u << kHllSampleShift) - 1)) == 0) << r;
-            const uint32_t part = real ? (uint32_t)(h >> pshift) : nparts; // dummy bin for non-k-mers
-            const uint32_t peers = __match_any_sync(0xffffffffu, part);
-            const int leader = __ffs(peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader) {
-                old = S.wcnt[warp][part];
-                S.wcnt[warp][part] = (uint16_t)(old + __popc(peers));
-            }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            const uint32_t rank = old + __popc(peers & ((1u << lane) - 1));
+            uint32_t rank = 0;
+            if (real) rank = atomicAdd(&S.cnt[(uint32_t)(h >> pshift)], 1u);
             if (r & 1) rk[r >> 1] |= rank << 16;
             else rk[r >> 1] = rank;
-            __syncwarp();
         }
         // rare side work kept out of the unrolled loops
         if (hll_mask) { // distinct-key estimate: HyperLogLog over a 1/2^kHllSampleShift sample of the key space
@@ -189,13 +180,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
         // ---- B: per-slice totals over warps, padded to 4 keys, then block scan over slices ----
         uint32_t mine = 0;
         if ((uint32_t)tid < nparts) { // one slice column per thread (nparts <= kPartThreads)
-            uint32_t run = 0;
-#pragma unroll
-            for (int w = 0; w < kPartThreads / 32; w++) {
-                const uint32_t t = S.wcnt[w][tid];
-                S.wcnt[w][tid] = (uint16_t)run;
-                run += t;
-            }
+            const uint32_t run = S.cnt[tid];
             mine = (run + 3) & ~3u;
             const bool o = S.gcur[tid] + mine > P.seg_cap;
             S.ovf[tid] = o;
@@ -229,7 +214,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
             if (h != kSentinel) {
                 const uint32_t part = (uint32_t)(h >> pshift);
                 const uint32_t rank = (rk[r >> 1] >> ((r & 1) * 16)) & 0xFFFFu;
-                S.stage[S.off[part] + S.wcnt[warp][part] + rank] = h;
+                S.stage[S.off[part] + rank] = h;
             }
         }
         __syncthreads();
@@ -238,18 +223,15 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
             const uint32_t total = S.off[nparts];
             for (uint32_t i = tid; i < total; i += kPartThreads) {
                 const uint64_t h = S.stage[i];
-                uint32_t part;
-                if (h != kSentinel) part = (uint32_t)(h >> pshift);
-                else { // padding: find its slice by bisection on the run starts
-                    uint32_t lo_p = 0, hi_p = nparts; // largest p with off[p] <= i
-                    while (hi_p - lo_p > 1) {
-                        const uint32_t mid = (lo_p + hi_p) >> 1;
-                        if (S.off[mid] <= i) lo_p = mid; else hi_p = mid;
-                    }
-                    part = lo_p;
-                }
+                if (h == kSentinel) continue; // padding slot: its slice's column thread writes it below
+                const uint32_t part = (uint32_t)(h >> pshift);
                 if (!S.ovf[part])
                     P.keys[((size_t)part * gridDim.x + blockIdx.x) * P.seg_cap + S.gcur[part] + (i - S.off[part])] = h;
+            }
+            if ((uint32_t)tid < nparts && !S.ovf[tid]) { // <= 3 sentinel keys keep every append a multiple of 32 bytes
+                const uint32_t padded = mine & 0xFFFFu, real_n = mine >> 16;
+                uint64_t *dst = P.keys + ((size_t)tid * gridDim.x + blockIdx.x) * P.seg_cap + S.gcur[tid];
+                for (uint32_t j = real_n; j < padded; j++) dst[j] = kSentinel;
             }
         }
         if (S.any_ovf) { // some segment is full: insert that run the slow (random-access) way; never lose a k-mer
@@ -266,9 +248,10 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
             }
         }
         __syncthreads();
-        if ((uint32_t)tid < nparts && !S.ovf[tid]) S.gcur[tid] += mine & 0xFFFFu;
-        // reset the per-warp counters for the next tile
-        for (uint32_t i = tid; i < (kPartThreads / 32) * (kMaxParts + 2); i += kPartThreads) (&S.wcnt[0][0])[i] = 0;
+        if ((uint32_t)tid < nparts) {
+            if (!S.ovf[tid]) S.gcur[tid] += mine & 0xFFFFu;
+            S.cnt[tid] = 0; // for the next tile
+        }
         __syncthreads();
     }
     for (uint32_t i = tid; i < nparts; i += kPartThreads) P.seglen[(size_t)i * gridDim.x + blockIdx.x] = S.gcur[i];
@@ -348,6 +331,7 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) sweep_kernel(con
                 ok[u] = h[u] != kSentinel;
                 if (ok[u]) bk[u] = load_bucket(g.slots + (((h[u] >> g.rbits) & g.bmask) << 2));
             }
+#if !KATGPU_SWEEP_TWOSTAGE
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++) {
                 if (ok[u]) {
@@ -355,6 +339,20 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) sweep_kernel(con
                     my_new += insert_home(g, h[u], bk[u]) == 1;
                 }
             }
+#else
+            InsertTicket tk[kSweepUnroll];
+#pragma unroll
+            for (int u = 0; u < kSweepUnroll; u++) { // issue every key's RED / CAS ...
+                tk[u].state = 0;
+                if (ok[u]) {
+                    my_total++;
+                    tk[u] = insert_issue(g, h[u], bk[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < kSweepUnroll; u++) // ... then look at the CAS results
+                if (ok[u] && tk[u].state) my_new += insert_finish(g, h[u], tk[u]) == 1;
+#endif
         }
         if (P.window) {
             __syncthreads();

@@ -6,9 +6,9 @@ namespace katgpu {
 
 constexpr int kPartThreads = 512;  // == kGroups: one 16-base group per thread per tile
 constexpr int kMaxParts = 512;     // table slices (Pb <= 9)
-constexpr int kHllBits = 8;        // HyperLogLog registers for the distinct-key estimate (6.5 % std error)
+constexpr int kHllBits = 10;       // HyperLogLog registers for the distinct-key estimate (3.3 % std error)
 constexpr int kHllM = 1 << kHllBits;
-constexpr int kHllSampleShift = 6; // 1/64 of the key space is sampled
+constexpr int kHllSampleShift = 10; // 1/1024 of the key space is sampled
 #ifndef KATGPU_SWEEP_THREADS
 #define KATGPU_SWEEP_THREADS 256
 #endif
@@ -21,6 +21,9 @@ constexpr int kSweepMinCtas = KATGPU_SWEEP_MIN_CTAS;
 #define KATGPU_SWEEP_UNROLL 2
 #endif
 constexpr int kSweepUnroll = KATGPU_SWEEP_UNROLL;
+#ifndef KATGPU_SWEEP_TWOSTAGE
+#define KATGPU_SWEEP_TWOSTAGE 0
+#endif
 
 struct PartitionParams {
     TableGeom g;

@@ -226,13 +226,25 @@ __device__ __forceinline__ int insert_home(const TableGeom &g, uint64_t h, const
     uint64_t *bp = g.slots + (((h >> g.rbits) & g.bmask) << 2);
     int hit = -1, emp = -1;
     uint64_t wsel = 0;
+    if (g.tagmask <= 0xFFFFFFFFULL) { // tag (rem + probe) fits 32 bits: half the compare work (uniform branch)
+        const uint32_t want32 = (uint32_t)want, mask32 = (uint32_t)g.tagmask;
 #pragma unroll
-    for (int s = kSlotsPerBucket - 1; s >= 0; s--) { // descending: the lowest index wins
-        const uint64_t w = bk.s[s];
-        const bool m = (w & g.tagmask) == want;
-        hit = m ? s : hit;
-        wsel = m ? w : wsel;
-        emp = (w == 0) ? s : emp;
+        for (int s = kSlotsPerBucket - 1; s >= 0; s--) { // descending: the lowest index wins
+            const uint64_t w = bk.s[s];
+            const bool m = ((uint32_t)w & mask32) == want32;
+            hit = m ? s : hit;
+            wsel = m ? w : wsel;
+            emp = (w == 0) ? s : emp;
+        }
+    } else {
+#pragma unroll
+        for (int s = kSlotsPerBucket - 1; s >= 0; s--) {
+            const uint64_t w = bk.s[s];
+            const bool m = (w & g.tagmask) == want;
+            hit = m ? s : hit;
+            wsel = m ? w : wsel;
+            emp = (w == 0) ? s : emp;
+        }
     }
     if (hit >= 0) {
         slot_add(g, bp + hit, h, 1, wsel);
@@ -244,6 +256,57 @@ __device__ __forceinline__ int insert_home(const TableGeom &g, uint64_t h, const
         if (old == 0) return 1;
         if ((old & g.tagmask) == want) {
             slot_add(g, bp + emp, h, 1, old);
+            return 0;
+        }
+    }
+    Bucket none = {};
+    return insert_hashed(g, h, 1, none, false);
+}
+
+// Two-stage form of insert_home for software pipelining: stage 1 issues the one memory
+// operation of the common cases (RED on a hit, CAS on a claim) without waiting for it;
+// stage 2 looks at the CAS result once other keys' operations are in flight as well.
+struct InsertTicket {
+    unsigned long long old; // CAS result (state 1)
+    uint32_t state;         // 0 done (existing key), 1 CAS issued, 2 needs the general path
+    uint32_t slot;
+};
+__device__ __forceinline__ InsertTicket insert_issue(const TableGeom &g, uint64_t h, const Bucket &bk) {
+    const uint64_t want = (h & g.rmask) | (1ULL << g.rbits);
+    uint64_t *bp = g.slots + (((h >> g.rbits) & g.bmask) << 2);
+    int hit = -1, emp = -1;
+    uint64_t wsel = 0;
+#pragma unroll
+    for (int s = kSlotsPerBucket - 1; s >= 0; s--) {
+        const uint64_t w = bk.s[s];
+        const bool m = (w & g.tagmask) == want;
+        hit = m ? s : hit;
+        wsel = m ? w : wsel;
+        emp = (w == 0) ? s : emp;
+    }
+    InsertTicket t;
+    t.old = 0;
+    t.slot = 0;
+    t.state = 2;
+    if (hit >= 0) {
+        slot_add(g, bp + hit, h, 1, wsel);
+        t.state = 0;
+    } else if (emp >= 0) {
+        t.old = atomicCAS(reinterpret_cast<unsigned long long *>(bp + emp), 0ULL,
+                          (unsigned long long)(want | (1ULL << g.cshift)));
+        t.state = 1;
+        t.slot = (uint32_t)emp;
+    }
+    return t;
+}
+// Returns 1 if a new slot was claimed, 0 if the key existed, -1 if it was parked.
+__device__ __forceinline__ int insert_finish(const TableGeom &g, uint64_t h, const InsertTicket &t) {
+    if (t.state == 0) return 0;
+    if (t.state == 1) {
+        if (t.old == 0) return 1;
+        const uint64_t want = (h & g.rmask) | (1ULL << g.rbits);
+        if ((t.old & g.tagmask) == want) {
+            slot_add(g, g.slots + (((h >> g.rbits) & g.bmask) << 2) + t.slot, h, 1, t.old);
             return 0;
         }
     }
