@@ -48,6 +48,8 @@ struct ProfSpan {
     cudaEvent_t a, b;
 };
 
+static const int kRing = 24; // host-feed staging ring: lets the copy engine run ahead of a mid-feed sweep
+
 struct katgpu_ctx {
     int device = 0;
     int sm_count = 0;
@@ -58,9 +60,10 @@ struct katgpu_ctx {
     unsigned int *tile_counter = nullptr; // device
     unsigned long long *route_cursors = nullptr; // device [kMaxRanks] + overflow flag after
     // host feed staging
-    uint8_t *chunk[2] = {nullptr, nullptr};
+    uint8_t *chunk[kRing] = {};
     size_t chunk_cap = 0;
-    cudaEvent_t chunk_free[2] = {nullptr, nullptr}, chunk_ready[2] = {nullptr, nullptr};
+    int chunk_n = 0;          // staging buffers currently allocated (2 .. kRing)
+    cudaEvent_t chunk_free[kRing] = {}, chunk_ready[kRing] = {};
     TableCounters *h_ctr = nullptr; // pinned mirror
     uint64_t launches = 0;
     bool profiling = false;
@@ -207,7 +210,7 @@ extern "C" katgpu_status katgpu_init(int device, katgpu_ctx **out) {
     CU(cudaMalloc(&c->tile_counter, 256));
     CU(cudaMalloc(&c->route_cursors, 256));
     CU(cudaMallocHost(&c->h_ctr, sizeof(TableCounters)));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kRing; i++) {
         CU(cudaEventCreateWithFlags(&c->chunk_free[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&c->chunk_ready[i], cudaEventDisableTiming));
     }
@@ -221,7 +224,7 @@ extern "C" void katgpu_shutdown(katgpu_ctx *c) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
     prof_collect(c);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kRing; i++) {
         if (c->chunk[i]) cudaFree(c->chunk[i]);
         if (c->chunk_free[i]) cudaEventDestroy(c->chunk_free[i]);
         if (c->chunk_ready[i]) cudaEventDestroy(c->chunk_ready[i]);
@@ -778,25 +781,30 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
     CU(cudaSetDevice(c->device));
     if (n == 0) return KATGPU_OK;
     const size_t chunk = std::min(kChunkBytes, (n + 4095) / 4096 * 4096);
-    if (c->chunk_cap < chunk + kHalo) {
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    const int ring = (int)std::min<size_t>(kRing, std::max<size_t>(2, n_chunks));
+    if (c->chunk_cap < chunk + kHalo || c->chunk_n < ring) {
         CU(cudaStreamSynchronize(c->stream));
         CU(cudaStreamSynchronize(c->copy_stream));
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kRing; i++) {
             if (c->chunk[i]) cudaFree(c->chunk[i]);
             c->chunk[i] = nullptr;
+        }
+        const size_t cap = std::max(c->chunk_cap, chunk + kHalo);
+        for (int i = 0; i < ring; i++) {
             void *p = nullptr;
-            CU(cudaMalloc(&p, chunk + kHalo + 64));
+            CU(cudaMalloc(&p, cap + 64));
             c->chunk[i] = (uint8_t *)p;
         }
-        c->chunk_cap = chunk + kHalo;
+        c->chunk_cap = cap;
+        c->chunk_n = ring;
     }
     TableCounters ctr;
     KT(read_counters(t, ctr));
     // chunk i holds host bytes [i*chunk, (i+1)*chunk + halo): k-mers starting in
     // the first `chunk` positions are counted from it, the halo feeds their tails.
-    const size_t n_chunks = (n + chunk - 1) / chunk;
     auto issue_copy = [&](size_t i) -> katgpu_status {
-        const int b = (int)(i & 1);
+        const int b = (int)(i % ring);
         const size_t off = i * chunk;
         const size_t len = std::min(n - off, chunk + kHalo);
         CU(cudaStreamWaitEvent(c->copy_stream, c->chunk_free[b], 0));
@@ -805,18 +813,21 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
         return KATGPU_OK;
     };
     // the free events start out "complete": record them once on an idle stream
-    CU(cudaEventRecord(c->chunk_free[0], c->stream));
-    CU(cudaEventRecord(c->chunk_free[1], c->stream));
-    KT(issue_copy(0));
+    for (int b = 0; b < ring; b++) CU(cudaEventRecord(c->chunk_free[b], c->stream));
+    // With the partitioned path and a long feed, insert the first half of the keys while the
+    // second half is still crossing PCIe: the copy engine keeps filling the ring during the sweep.
+    const size_t mid_sweep_at = (n_chunks >= 16 && use_partition(t, n)) ? n_chunks / 2 : (size_t)-1;
+    size_t issued = 0;
     for (size_t i = 0; i < n_chunks; i++) {
-        const int b = (int)(i & 1);
-        if (i + 1 < n_chunks) KT(issue_copy(i + 1)); // overlaps kernel i
+        while (issued < n_chunks && issued < i + (size_t)ring) KT(issue_copy(issued++)); // run ahead of the kernels
+        const int b = (int)(i % ring);
         const size_t off = i * chunk;
         const size_t len = std::min(n - off, chunk + kHalo);
         const size_t starts = std::min(n - off, chunk);
         CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
         KT(feed_device_range(t, c->chunk[b], len, starts, ctr, n));
         CU(cudaEventRecord(c->chunk_free[b], c->stream));
+        if (i + 1 == mid_sweep_at) KT(sweep_pending(t, ctr));
     }
     return KATGPU_OK;
 }

@@ -73,7 +73,7 @@ class GpuEngine:
 
 
 class DistributedCounter:
-    def __init__(self, ctx, dist, k, canonical=True, slots=1 << 31, batch_bytes=1 << 30, engine=None):
+    def __init__(self, ctx, dist, k, canonical=True, slots=1 << 31, batch_bytes=1 << 29, engine=None):
         self.dist = dist
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.k = k
@@ -83,15 +83,18 @@ class DistributedCounter:
         self._cap = 0
 
     def _buffers(self, cap):
+        """Two send and two receive bucket sets: batch b+1 is routed and batch b-1 is
+        inserted while batch b is on the wire."""
         if cap > self._cap:
-            self._send = [self.engine.alloc_keys(cap) for _ in range(self.world)]
-            self._recv = [self.engine.alloc_keys(cap) for _ in range(self.world)]
+            self._send = [[self.engine.alloc_keys(cap) for _ in range(self.world)] for _ in range(2)]
+            self._recv = [[self.engine.alloc_keys(cap) for _ in range(self.world)] for _ in range(2)]
             self._cap = cap
         return self._send, self._recv
 
     def count(self, bases_ptr, n_bytes, record_len=None):
-        """Route / exchange / insert the local base stream in batches.  Batches
-        end on record boundaries when record_len is given (no k-mer is cut)."""
+        """Route / exchange / insert the local base stream in batches, software-pipelined:
+        route(b+1) and insert(b-1) overlap the exchange of batch b.  Batches end on record
+        boundaries when record_len is given (no k-mer is cut)."""
         e, dist, W = self.engine, self.dist, self.world
         # with a uniform owner hash every rank receives about what it routes
         e.begin(n_bytes)
@@ -106,26 +109,36 @@ class DistributedCounter:
         n_batches = int(e.from_tensor(nbt)[0])
         cap = int(step / W * 1.25) + KMERS_SLACK
         send, recv = self._buffers(cap)
-        off = 0
-        for _ in range(n_batches):
+
+        def route(b):
+            off = min(n_bytes, b * step)
             n = max(0, min(step, n_bytes - off))
-            counts = e.route(bases_ptr + off, n, send, cap) if n else [0] * W
-            off += n
+            counts = e.route(bases_ptr + off, n, send[b & 1], cap) if n else [0] * W
             sc = e.to_tensor(np.array(counts))
             rc = e.to_tensor(np.zeros(W))
             dist.all_to_all_single(rc, sc)
             rcounts = [int(x) for x in e.from_tensor(rc)]
             if max(rcounts) > cap:
                 raise B.KatGpuError(-1, "receive bucket too small for this batch")
-            self._exchange(send, counts, recv, rcounts)
+            return counts, rcounts
+
+        cnt = route(0)
+        works = self._exchange_start(send[0], cnt[0], recv[0], cnt[1])
+        for b in range(n_batches):
+            nxt = route(b + 1) if b + 1 < n_batches else None  # overlaps exchange b
+            for w in works:
+                w.wait()
             e.sync_exchange()
-            for r in range(W):
-                e.insert(recv[r], rcounts[r])
+            if nxt is not None:
+                works = self._exchange_start(send[(b + 1) & 1], nxt[0], recv[(b + 1) & 1], nxt[1])
+            for r in range(W):  # overlaps exchange b+1
+                e.insert(recv[b & 1][r], cnt[1][r])
+            cnt = nxt
         return e.end()
 
-    def _exchange(self, send, counts, recv, rcounts):
+    def _exchange_start(self, send, counts, recv, rcounts):
         """Ragged all-to-all as grouped point-to-point (what NCCL's all-to-all is
-        underneath); works on NCCL and gloo alike."""
+        underneath); works on NCCL and gloo alike.  Returns the pending work handles."""
         dist, W, me = self.dist, self.world, self.rank
         ops = []
         for d in range(1, W):
@@ -136,9 +149,7 @@ class DistributedCounter:
                 ops.append(dist.P2POp(dist.irecv, recv[frm][: rcounts[frm]], frm))
         if rcounts[me]:
             recv[me][: rcounts[me]].copy_(send[me][: counts[me]])
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
+        return dist.batch_isend_irecv(ops) if ops else []
 
     def _allreduce_u64(self, arr):
         t = self.engine.to_tensor(arr.reshape(-1))
