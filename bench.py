@@ -48,6 +48,9 @@ KMERS_PER_READ = READ_LEN - K + 1
 # algorithmic bytes per k-mer instance of the extract+insert kernel:
 # L/(L-k+1) bytes of base stream + one table read-modify-write (8 B key + 4 B count read + 4 B written)
 B_ALG = READ_LEN / KMERS_PER_READ + 16.0
+# measured DRAM bytes per k-mer instance of K1 = partition_kernel + sweep_kernel, from the ncu --set full
+# captures summarised in profiles/r1_v2_partition_sweep_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum)
+TRAFFIC_B_PER_KMER_PARTITIONED = 26.0
 
 
 def measured_peaks():
@@ -61,13 +64,15 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  The sampler process
+    is started early (NVML start-up contends with the CUDA driver for a moment) and only the
+    samples that arrive between mark_begin() and mark_end() are used."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.t0, self.t1 = index, None, [], None, None
 
     def start(self):
         if not shutil.which("nvidia-smi"):
@@ -75,17 +80,27 @@ class ClockSampler:
         self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
                                       "--format=csv,noheader,nounits", "-lms", "100"],
                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-        self.t = threading.Thread(target=lambda: self.lines.extend(self.proc.stdout), daemon=True)
+
+        def pump():
+            for ln in self.proc.stdout:
+                self.lines.append((time.perf_counter(), ln))
+        self.t = threading.Thread(target=pump, daemon=True)
         self.t.start()
 
-    def stop(self):
+    def mark_begin(self):
+        self.t0, self.t1 = time.perf_counter(), None
+
+    def mark_end(self):
+        self.t1 = time.perf_counter()
+
+    def summary(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        self.t.join(timeout=2)
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        for ts, ln in list(self.lines):
+            if self.t0 is None or ts < self.t0 or (self.t1 is not None and ts > self.t1 + 0.11):
+                continue
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -99,6 +114,10 @@ class ClockSampler:
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
 
 
 def write_fastq_sample(stream, n_reads, path):
@@ -242,6 +261,8 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     ctx = kat_b200.Context(local_rank)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     hbm_peak, peak_src = measured_peaks()
 
     n_bytes = n_reads * (READ_LEN + 1)
@@ -280,14 +301,14 @@ def main():
         barrier()
         l0 = ctx.launch_count()
         ctx.profile_enable(True)
-        sampler = ClockSampler(local_rank)
-        sampler.start()
+        sampler.mark_begin()
         t0 = time.perf_counter()
         for _ in range(steps):
             out = fn()
         barrier()
         dt = time.perf_counter() - t0
-        clocks = sampler.stop()
+        sampler.mark_end()
+        clocks = sampler.summary()
         prof = {f: ctx.profile_get(f) for f in ("count", "partition", "sweep", "hist", "route", "insert", "memset", "rehash")}
         ctx.profile_enable(False)
         if dist is not None:
@@ -322,10 +343,12 @@ def main():
     k_ms = sum(prof[f][0] for f in fam)
     k_n = max(prof[f][1] for f in fam)
     k_inst = n_total * args.steps  # instances inserted on this rank's table
-    achieved = (k_inst * B_ALG / 1e9) / (k_ms / 1e3) if k_ms > 0 else None
+    achieved = (k_inst * B_ALG / 1e9) / (k_ms / 1e3) if k_ms > 0 else None  # GB/s; per launch: bytes/launch over ms/launch
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": (TRAFFIC_B_PER_KMER_PARTITIONED * k_inst / max(k_n, 1)) if fam == ["partition", "sweep"] else None,
+                "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum of both kernels at 5 Gbp, scaled per k-mer (profiles/r1_v2_partition_sweep_ncu.txt)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_kmer": B_ALG, "kernel_ms_total": k_ms, "kernel_launches": k_n,
                 "kernel_ms_by_family": {f: prof[f][0] for f in fam},
                 "kmers_per_launch": k_inst / k_n if k_n else None,
@@ -390,6 +413,7 @@ def main():
                                     "sample": "oracle/_ref/kat not present"}
 
     ctx.device_free(d_bases)
+    sampler.stop()
     if rank == 0:
         emit(line)
     ctx.close()

@@ -8,6 +8,7 @@
 #include "synth.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -87,13 +88,25 @@ struct katgpu_table {
     uint32_t *pend_seglen = nullptr, *pend_hll = nullptr, *pend_done = nullptr;
     uint32_t pend_Pb = 0, pend_segs = 0, pend_seg_cap = 0;
     double pend_fill = 0;      // conservative estimate of the fullest segment (keys)
-    uint64_t pend_tiles = 0;   // tiles each CTA has partitioned since the last sweep
+    uint64_t pend_tiles = 0;   // tiles the busiest CTA has partitioned since the last sweep
+    uint64_t pend_total_tiles = 0; // all tiles since the last sweep (also the CTA rotation)
     uint64_t pend_bound = 0;   // upper bound on pending k-mer instances
     size_t pend_bytes = 0;
 };
 
 static const size_t kChunkBytes = 128u << 20; // host feed granularity
 static const uint64_t kSpillCap = 1u << 20;   // (hashed key, count) pairs
+
+// KATGPU_TRACE=1: wall-clock of every host-side phase to stderr (debugging aid).
+struct TraceScope {
+    const char *name;
+    std::chrono::steady_clock::time_point t0;
+    bool on;
+    explicit TraceScope(const char *n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("KATGPU_TRACE") != nullptr) {}
+    ~TraceScope() {
+        if (on) fprintf(stderr, "[katgpu] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
+};
 
 // ---- device block cache ----
 static void pool_flush(katgpu_ctx *c) {
@@ -373,6 +386,7 @@ static int min_Lb(int k) {
 }
 
 static katgpu_status alloc_table_storage(katgpu_ctx *c, TableGeom &g, uint64_t &n_slots) {
+    TraceScope trace__("  alloc_table_storage");
     n_slots = (uint64_t)kSlotsPerBucket << g.Lb;
     void *p = nullptr;
     CU(pool_alloc(c, n_slots * sizeof(uint64_t), &p));
@@ -402,6 +416,7 @@ static void free_table_storage(katgpu_ctx *c, TableGeom &g) {
 
 extern "C" katgpu_status katgpu_count_begin(katgpu_ctx *c, int k, int canonical, uint64_t hash_size, int allow_grow,
                                             katgpu_table **out) {
+    TraceScope trace__("katgpu_count_begin");
     if (!c || !out) return fail(KATGPU_ERR_INVALID, "katgpu_count_begin: NULL argument");
     *out = nullptr;
     if (k < 1 || k > 32) return fail(KATGPU_ERR_INVALID, "katgpu_count_begin: k=%d outside 1..32 (one 64-bit word per k-mer)", k);
@@ -425,6 +440,7 @@ extern "C" katgpu_status katgpu_count_begin(katgpu_ctx *c, int k, int canonical,
 }
 
 extern "C" void katgpu_table_free(katgpu_table *t) {
+    TraceScope trace__("katgpu_table_free");
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
@@ -567,6 +583,7 @@ static bool use_partition(const katgpu_table *t, uint64_t kmers_hint) {
 }
 
 static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) {
+    TraceScope trace__("  pend_alloc");
     ok = true;
     if (t->pend_keys) return KATGPU_OK;
     katgpu_ctx *c = t->ctx;
@@ -580,12 +597,17 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t budget_keys = (uint64_t)((double)(free_b + c->pooled_bytes) * 0.70 / 8.0);
-    uint64_t want = (uint64_t)((double)std::max<uint64_t>(kmers_hint, t->n_slots / 4) * 1.12) + nparts * n_segs * 256;
-    want = std::min(want, budget_keys);
-    uint64_t seg_cap = want / (nparts * n_segs) / 16 * 16;
+    // Size every (slice, CTA) segment from the same fill model feed_partitioned() uses, so that a
+    // feed of `kmers_hint` positions fits in ONE partition round (each extra round = one more full
+    // pass over the table in the sweep).
     const double m_tile = (double)kTile / (double)nparts; // keys one tile sends to one slice
+    const uint64_t hint = std::max<uint64_t>(kmers_hint, t->n_slots / 4);
+    const uint64_t cta_tiles = ((hint + kTile - 1) / kTile + n_segs - 1) / n_segs + 1;
+    uint64_t seg_cap = (uint64_t)(((double)cta_tiles * (m_tile + 2.0) + 4.0 * std::sqrt((double)cta_tiles * m_tile)) * 1.02) + 64;
+    seg_cap = (seg_cap + 15) / 16 * 16;
     const uint64_t min_cap = ((uint64_t)(2.2 * (m_tile + 4.0 * std::sqrt(m_tile) + 4.0)) + 255) / 16 * 16;
     seg_cap = std::max(seg_cap, min_cap);
+    if (nparts * n_segs * seg_cap > budget_keys) seg_cap = std::max(min_cap, budget_keys / (nparts * n_segs) / 16 * 16);
     if (nparts * n_segs * seg_cap > budget_keys) {
         ok = false; // not enough memory for a useful pending buffer: use the direct path
         return KATGPU_OK;
@@ -632,6 +654,7 @@ static double hll_estimate(const uint32_t *reg, int m) {
 // Insert every pending key, slice by slice (sweep_kernel), after sizing the table
 // for the estimated number of new distinct keys.
 static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
+    TraceScope trace__("  sweep_pending");
     if (!t->pend_keys || t->pend_bound == 0) return KATGPU_OK;
     katgpu_ctx *c = t->ctx;
     uint32_t h_hll[kHllM];
@@ -681,6 +704,7 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
     CU(cudaMemsetAsync(t->pend_hll, 0, kHllM * 4, c->stream));
     t->pend_fill = 0;
     t->pend_tiles = 0;
+    t->pend_total_tiles = 0;
     t->pend_bound = 0;
     return settle(t, ctr);
 }
@@ -721,6 +745,7 @@ static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint6
         P.n_keys = take;
         P.n_tiles = (int)((take + kTile - 1) / kTile);
         P.tma_ok = !in_keys && (reinterpret_cast<uintptr_t>(dev + done) & 15) == 0;
+        P.cta_rot = (uint32_t)(t->pend_total_tiles % t->pend_segs);
         P.Pb = t->pend_Pb;
         P.seg_cap = t->pend_seg_cap;
         P.keys = t->pend_keys;
@@ -732,7 +757,8 @@ static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint6
         }
         c->launches++;
         CU(cudaGetLastError());
-        t->pend_tiles += (P.n_tiles + t->pend_segs - 1) / t->pend_segs;
+        t->pend_total_tiles += (uint64_t)P.n_tiles;
+        t->pend_tiles = (t->pend_total_tiles + t->pend_segs - 1) / t->pend_segs;
         t->pend_fill = fill_after(t->pend_tiles);
         t->pend_bound += take;
         done += take;
@@ -766,6 +792,7 @@ static katgpu_status feed_device_range(katgpu_table *t, const uint8_t *dev, uint
 }
 
 extern "C" katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *bases_dev, size_t n) {
+    TraceScope trace__("katgpu_count_feed_device");
     if (!t || (!bases_dev && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_feed_device: NULL argument");
     if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_feed_device: table already finished");
     CU(cudaSetDevice(t->ctx->device));
@@ -775,6 +802,7 @@ extern "C" katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *b
 }
 
 extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n) {
+    TraceScope trace__("katgpu_count_feed");
     if (!t || (!bases && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_feed: NULL argument");
     if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_feed: table already finished");
     katgpu_ctx *c = t->ctx;
@@ -844,6 +872,7 @@ extern "C" katgpu_status katgpu_count_reserve(katgpu_table *t, uint64_t expected
 }
 
 extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct, uint64_t *n_total) {
+    TraceScope trace__("katgpu_count_end");
     if (!t) return fail(KATGPU_ERR_INVALID, "katgpu_count_end: NULL table");
     CU(cudaSetDevice(t->ctx->device));
     TableCounters ctr;
@@ -970,6 +999,7 @@ struct DevBuf { // zeroed device scratch, freed on scope exit
 
 extern "C" katgpu_status katgpu_hist(katgpu_table *t, uint64_t base, uint64_t ceil_, uint64_t inc, uint64_t nb,
                                      uint64_t *bins_out) {
+    TraceScope trace__("katgpu_hist");
     KT(finished(t, "katgpu_hist"));
     if (!bins_out || nb == 0 || inc == 0 || nb > 0x7fffffffULL) return fail(KATGPU_ERR_INVALID, "katgpu_hist: bad arguments");
     katgpu_ctx *c = t->ctx;

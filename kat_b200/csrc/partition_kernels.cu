@@ -72,7 +72,9 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
     for (uint32_t i = tid; i < (uint32_t)kHllM; i += kPartThreads) S.hll[i] = 0;
     for (uint32_t i = tid; i < (uint32_t)kMaxParts; i += kPartThreads) S.cnt[i] = 0;
     auto tile_tma = [&](int t) { return P.tma_ok && ((uint64_t)(t + 1) * kTile + kHalo <= P.n_valid); };
-    int tile = blockIdx.x; // static striding: per-CTA segment fill is predictable
+    // static striding (per-CTA segment fill is predictable), rotated so that successive launches
+    // hand their first tiles to different CTAs
+    int tile = (int)((blockIdx.x + gridDim.x - P.cta_rot % gridDim.x) % gridDim.x);
     if (!KEYS && tid == 0) {
         mbar_init(&S.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

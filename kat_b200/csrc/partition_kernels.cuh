@@ -30,6 +30,7 @@ struct PartitionParams {
     const uint8_t *bases;
     uint64_t n_valid, n_starts;
     int n_tiles, tma_ok;
+    uint32_t cta_rot;   // CTA that takes tile 0 (rotates between launches so segments fill evenly)
     uint32_t Pb;        // log2(partitions)
     uint32_t seg_cap;   // keys per (partition, CTA) segment, multiple of 16
     uint64_t *keys;     // [partition][cta][seg_cap]
