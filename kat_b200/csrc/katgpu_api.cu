@@ -692,6 +692,8 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
     P.slice_done = t->pend_done;
     P.slice_slots = t->n_slots >> t->pend_Pb;
     P.prefetch = 1;
+    P.experiment = 0;
+    if (const char *e = getenv("KATGPU_SWEEP_EXPERIMENT")) P.experiment = (uint32_t)atoi(e); // measurement only
     if (const char *e = getenv("KATGPU_SWEEP_PREFETCH")) P.prefetch = (uint32_t)atoi(e);
     CU(cudaMemsetAsync(t->pend_done, 0, kMaxParts * 4, c->stream));
     {

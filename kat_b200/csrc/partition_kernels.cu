@@ -33,6 +33,7 @@ struct __align__(128) PartSmem {
     uint64_t mbar;
     uint32_t off[kMaxParts + 2];                     // exclusive prefix of the PADDED per-slice counts
     uint32_t gcur[kMaxParts];                        // this CTA's append cursor per slice (keys)
+    int64_t sbase[kMaxParts];                        // this tile: key index in P.keys of stage[0]-relative slot 0 of the slice
     uint32_t cnt[kMaxParts];                         // keys of this tile per slice (shared atomics hand out ranks)
     uint32_t wscan[kPartThreads / 32];
     uint8_t ovf[kMaxParts];                          // this tile's run does not fit the slice segment
@@ -205,6 +206,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
             const uint32_t padded = mine & 0xFFFFu, real_n = mine >> 16;
             const uint32_t o = wbase + inc - padded;
             S.off[tid] = o;
+            S.sbase[tid] = (int64_t)(((size_t)tid * gridDim.x + blockIdx.x) * P.seg_cap + S.gcur[tid]) - (int64_t)o;
             for (uint32_t j = real_n; j < padded; j++) S.stage[o + j] = kSentinel; // <= 3 pad keys
             if ((uint32_t)tid == nparts - 1) S.off[nparts] = wbase + inc; // total (padded)
         }
@@ -227,8 +229,7 @@ __global__ void __launch_bounds__(kPartThreads, 2) partition_kernel(const __grid
                 const uint64_t h = S.stage[i];
                 if (h == kSentinel) continue; // padding slot: its slice's column thread writes it below
                 const uint32_t part = (uint32_t)(h >> pshift);
-                if (!S.ovf[part])
-                    P.keys[((size_t)part * gridDim.x + blockIdx.x) * P.seg_cap + S.gcur[part] + (i - S.off[part])] = h;
+                if (!S.ovf[part]) P.keys[S.sbase[part] + (int64_t)i] = h;
             }
             if ((uint32_t)tid < nparts && !S.ovf[tid]) { // <= 3 sentinel keys keep every append a multiple of 32 bytes
                 const uint32_t padded = mine & 0xFFFFu, real_n = mine >> 16;
@@ -334,6 +335,17 @@ __global__ void __launch_bounds__(kSweepThreads, kSweepMinCtas) sweep_kernel(con
                 if (ok[u]) bk[u] = load_bucket(g.slots + (((h[u] >> g.rbits) & g.bmask) << 2));
             }
 #if !KATGPU_SWEEP_TWOSTAGE
+            if (P.experiment) { // measurement aid: 1 = key + bucket loads only, 2 = plus a blind RED on slot 0
+#pragma unroll
+                for (int u = 0; u < kSweepUnroll; u++) {
+                    if (ok[u]) {
+                        my_total += (bk[u].s[0] ^ bk[u].s[1] ^ bk[u].s[2] ^ bk[u].s[3]) == 0x123456789ULL;
+                        if (P.experiment == 2)
+                            asm volatile("red.global.add.u64 [%0], %1;" ::"l"(g.slots + (((h[u] >> g.rbits) & g.bmask) << 2)), "l"(1ULL << g.cshift) : "memory");
+                    }
+                }
+                continue;
+            }
 #pragma unroll
             for (int u = 0; u < kSweepUnroll; u++) {
                 if (ok[u]) {

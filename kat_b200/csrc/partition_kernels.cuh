@@ -50,6 +50,7 @@ struct SweepParams {
     uint32_t *slice_done; // [partitions] CTAs that finished each slice
     uint64_t slice_slots; // table slots per slice
     uint32_t prefetch;    // bulk-prefetch the next slice into L2
+    uint32_t experiment;  // 0 = normal; 1/2 = measurement aids (results are WRONG), see sweep_kernel
 };
 
 size_t partition_smem_bytes();

@@ -19,8 +19,6 @@ def mix_key(x, k):
         x = x ^ (x >> sh)
         x = (x * _M1) & km
         x = x ^ (x >> sh)
-        x = (x * _M2) & km
-        x = x ^ (x >> sh)
     return x
 
 

@@ -207,12 +207,13 @@ def test_synth_reads_device_equals_host(ctx):
         ctx.device_free(d)
 
 
-def test_route_then_insert_equals_direct(ctx):
+@pytest.mark.parametrize("R", [2, 3, 4, 8])
+def test_route_then_insert_equals_direct(ctx, R):
     """Single-process model of the multi-GPU exchange: route to R owner buckets,
     insert every bucket into its own table; the union must equal direct counting
     and every key must land in exactly one table."""
     s = seqgen.genome_reads(60_000, 8000, 150, seed=41)
-    k, R = 27, 4
+    k = 27
     d = ctx.device_alloc(s.size)
     cap = s.size  # generous
     outs = [ctx.device_alloc(cap * 8) for _ in range(R)]
