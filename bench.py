@@ -327,9 +327,11 @@ def main():
     value = n_total_all * args.steps / dt
     # size-independent checks of the full-size result
     labels = np.arange(base, base + nb, dtype=np.uint64)
-    assert int(bins.sum()) == (n_distinct if dist is None else int(bins.sum()))
+    # KATGPU_SWEEP_EXPERIMENT runs (measurement aids with deliberately wrong results) skip the checks
+    nocheck = bool(os.environ.get("KATGPU_SWEEP_EXPERIMENT"))
+    assert nocheck or int(bins.sum()) == (n_distinct if dist is None else int(bins.sum()))
     if bins[-1] == 0:
-        assert int((bins * labels).sum()) == n_total_all, "sum(label*bins) != k-mer instances"
+        assert nocheck or int((bins * labels).sum()) == n_total_all, "sum(label*bins) != k-mer instances"
 
     # K1 (extract + canonicalise + insert) is either one kernel (extract_kernel<insert>,
     # family "count") or the pair partition_kernel + sweep_kernel; its algorithmic bytes are B_ALG per k-mer.

@@ -94,6 +94,13 @@ katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *bases_dev, s
  * partitioned counting path inserts slice by slice; fewer, larger sweeps are
  * cheaper).  Never changes results. */
 katgpu_status katgpu_count_reserve(katgpu_table *t, uint64_t expected_kmers);
+/* Add `n` (k-mer, count) records to the table: count[keys[i]] += counts[i] — what
+ * HashLoader::loadHash does with every record of a jellyfish hash file
+ * (`hash->add(reader.key(), reader.val())`, lib/src/jellyfish_helper.cc:176-178;
+ * array_base::add, JFI/large_hash_array.hpp:298-302).  keys are 2 bits per base,
+ * first base most significant, < 4^k; they are stored as given (a hash dumped
+ * from canonical counting already holds canonical k-mers).  HOST pointers. */
+katgpu_status katgpu_count_add_pairs(katgpu_table *t, const uint64_t *keys, const uint64_t *counts, size_t n);
 /* Finish counting (hash_counter::done, JFI/hash_counter.hpp:173-176).
  * n_distinct / n_total (k-mer instances) may be NULL. */
 katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct, uint64_t *n_total);

@@ -49,6 +49,7 @@ SIGNATURES = {
     "katgpu_count_feed": (_i, [_vp, _vp, _sz]),
     "katgpu_count_feed_device": (_i, [_vp, _vp, _sz]),
     "katgpu_count_reserve": (_i, [_vp, _u64]),
+    "katgpu_count_add_pairs": (_i, [_vp, _vp, _vp, _sz]),
     "katgpu_count_end": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "katgpu_table_free": (None, [_vp]),
     "katgpu_hist": (_i, [_vp, _u64, _u64, _u64, _u64, _vp]),
@@ -207,6 +208,15 @@ class Table:
 
     def feed_device(self, dev_ptr, n):
         _check(lib().katgpu_count_feed_device(self.h, dev_ptr, n))
+        return self
+
+    def add_pairs(self, keys, counts):
+        """(k-mer, count) records in HOST memory: count[keys[i]] += counts[i] (HashLoader::loadHash)."""
+        k = np.ascontiguousarray(keys, dtype=np.uint64)
+        c = np.ascontiguousarray(counts, dtype=np.uint64)
+        assert k.size == c.size
+        if k.size:
+            _check(lib().katgpu_count_add_pairs(self.h, _ptr(k), _ptr(c), k.size))
         return self
 
     def reserve(self, expected_kmers):

@@ -276,6 +276,28 @@ __global__ void __launch_bounds__(256) insert_pairs_kernel(const __grid_constant
     if ((threadIdx.x & 31) == 0 && my_new) atomicAdd(&g.ctr->n_distinct, my_new);
 }
 
+// Add (k-mer, count) records: the LOAD path (HashLoader::loadHash, lib/src/jellyfish_helper.cc:176-178).
+__global__ void __launch_bounds__(256) add_pairs_kernel(const __grid_constant__ TableGeom g, const uint64_t *__restrict__ keys,
+                                                        const uint64_t *__restrict__ counts, uint64_t n) {
+    unsigned long long my_new = 0, my_total = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t c = counts[i];
+        if (c == 0) continue; // add(key, 0) of the reference creates the key with count 0, which no walk reports
+        Bucket bk = {};
+        my_new += insert_hashed(g, mix_key(g, keys[i] & g.kmask), c, bk, false) == 1;
+        my_total += c;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        my_new += __shfl_down_sync(0xffffffffu, my_new, d);
+        my_total += __shfl_down_sync(0xffffffffu, my_total, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (my_new) atomicAdd(&g.ctr->n_distinct, my_new);
+        if (my_total) atomicAdd(&g.ctr->n_total, my_total);
+    }
+}
+
 // Table doubling (the role of hash_counter::double_size, JFI/hash_counter.hpp:204-244):
 // walk the old table, re-insert every (hashed key, exact count) into the new one.
 __global__ void __launch_bounds__(256) rehash_kernel(const __grid_constant__ TableGeom old_g,
@@ -323,6 +345,9 @@ void launch_insert_hashed(const TableGeom &g, const uint64_t *hs, uint64_t n, in
 }
 void launch_insert_pairs(const TableGeom &g, const uint64_t *pairs, uint64_t n, int grid, cudaStream_t st) {
     insert_pairs_kernel<<<grid, 256, 0, st>>>(g, pairs, n);
+}
+void launch_add_pairs(const TableGeom &g, const uint64_t *keys, const uint64_t *counts, uint64_t n, int grid, cudaStream_t st) {
+    add_pairs_kernel<<<grid, 256, 0, st>>>(g, keys, counts, n);
 }
 void launch_rehash(const TableGeom &old_g, const TableGeom &new_g, uint64_t n_slots, int grid, cudaStream_t st) {
     rehash_kernel<<<grid, 256, 0, st>>>(old_g, new_g, n_slots);

@@ -40,6 +40,7 @@ cudaError_t extract_configure(int mode, int *blocks_per_sm);
 void launch_extract(int mode, const ExtractParams &P, int grid, cudaStream_t st);
 void launch_insert_hashed(const TableGeom &g, const uint64_t *hs, uint64_t n, int grid, cudaStream_t st);
 void launch_insert_pairs(const TableGeom &g, const uint64_t *pairs, uint64_t n, int grid, cudaStream_t st);
+void launch_add_pairs(const TableGeom &g, const uint64_t *keys, const uint64_t *counts, uint64_t n, int grid, cudaStream_t st);
 void launch_rehash(const TableGeom &old_g, const TableGeom &new_g, uint64_t n_slots, int grid, cudaStream_t st);
 
 } // namespace katgpu

@@ -102,4 +102,65 @@ struct Roll16 {
     __device__ __forceinline__ uint64_t key(bool canonical) const { return (canonical && rc < fwd) ? rc : fwd; }
 };
 
+// ---- window extraction (partition / route kernels) ------------------------------------
+// A thread owns the 16 k-mer starts of one 16-base group and sees the 48-base window
+// w2:w1:w0 (w2 = bases 0-15, first base in the top bits).  Instead of rolling one k-mer into
+// the next (a serial chain of 64-bit shifts by run-time amounts), both strands are prepared
+// once as 96-bit strings from which k-mer r is a CONSTANT funnel shift away:
+//   F = W >> 2(33-k)            fwd(r) = (F >> 2(15-r)) & kmask
+//   R = revcomp(W) (base 0 low) rc(r)  = (R >> 2r)      & kmask
+// (JFI/mer_dna.hpp:330-378 shift_left/shift_right define the two strands; 3 instructions per
+// strand per k-mer instead of ~9, and the 16 k-mers are independent.)
+__device__ __forceinline__ uint32_t revcomp16(uint32_t w) { // 16 bases: reverse the order, complement
+    const uint32_t x = __brev(~w);                          // bit pairs now in place but bit-swapped
+    return ((x << 1) & 0xAAAAAAAAu) | ((x >> 1) & 0x55555555u);
+}
+struct Cut16 {
+    uint32_t f0, f1, f2, r0, r1, r2, okm;
+    __device__ __forceinline__ void init(uint32_t w2, uint32_t w1, uint32_t w0, uint64_t bad48, uint32_t k, uint32_t nst) {
+        okm = valid_starts16(bad48, k);
+        okm &= nst >= 16 ? 0xFFFFu : (0xFFFFu << (16 - nst)) & 0xFFFFu;
+        r0 = revcomp16(w2);
+        r1 = revcomp16(w1);
+        r2 = revcomp16(w0);
+        const uint32_t s = 2 * (33 - k); // 2 .. 64 (uniform)
+        uint32_t a0 = w0, a1 = w1, a2 = w2;
+        if (s >= 64) {
+            a0 = w2, a1 = 0, a2 = 0;
+        } else if (s >= 32) {
+            a0 = w1, a1 = w2, a2 = 0;
+        }
+        f0 = __funnelshift_r(a0, a1, s);
+        f1 = __funnelshift_r(a1, a2, s);
+        f2 = a2 >> (s & 31);
+    }
+    __device__ __forceinline__ bool ok(uint32_t r) const { return (okm >> (15 - r)) & 1u; }
+    // canonical (or forward) k-mer r as two words; r is a compile-time constant after unrolling
+    template <bool CANON, bool WIDE>
+    __device__ __forceinline__ void key(uint32_t r, uint32_t kmask_lo, uint32_t kmask_hi, uint32_t &lo, uint32_t &hi) const {
+        uint32_t flo = __funnelshift_r(f0, f1, 2 * (15 - r));
+        const uint32_t fhi = __funnelshift_r(f1, f2, 2 * (15 - r)) & kmask_hi;
+        if (!WIDE) flo &= kmask_lo;
+        lo = flo, hi = fhi;
+        if (CANON) {
+            uint32_t rlo = __funnelshift_r(r0, r1, 2 * r);
+            const uint32_t rhi = __funnelshift_r(r1, r2, 2 * r) & kmask_hi;
+            if (!WIDE) rlo &= kmask_lo;
+            const bool rc_smaller = rhi < fhi || (rhi == fhi && rlo < flo); // mer_dna::operator< (JFI/mer_dna.hpp:235-258)
+            lo = rc_smaller ? rlo : flo;
+            hi = rc_smaller ? rhi : fhi;
+        }
+    }
+};
+// mix_key (table.cuh) on a key held as two words; sh = g.sh in [1, 32].
+template <bool WIDE>
+__device__ __forceinline__ uint64_t mix_words(uint32_t lo, uint32_t hi, uint32_t sh, uint32_t kmask_lo, uint32_t kmask_hi) {
+    lo ^= __funnelshift_rc(lo, hi, sh); // low word of x >> sh (the high word of x >> sh is 0: b - sh <= 32)
+    const uint64_t x = (((uint64_t)hi << 32) | lo) * kMixM1;
+    uint32_t xl = (uint32_t)x;
+    const uint32_t xh = (uint32_t)(x >> 32) & kmask_hi;
+    if (!WIDE) xl &= kmask_lo;
+    return ((uint64_t)xh << 32) | xl;
+}
+
 } // namespace katgpu

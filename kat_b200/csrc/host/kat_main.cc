@@ -8,8 +8,9 @@
 // lib/include/kat/distance_metrics.hpp).  Counting and the table walks run on
 // the GPU through the C-ABI of include/katgpu.h; this file only parses
 // arguments, reads sequence files, and writes the text outputs byte for byte
-// as the reference does.  Not supported (reference features outside the hot
-// path): jellyfish-hash inputs (LOAD mode), -d/--dump_hash, plotting.
+// as the reference does.  Jellyfish-hash inputs (LOAD mode, InputHandler::loadHash) and
+// -d/--dump_hash (InputHandler::dump) read and write the reference's "binary/sorted" files
+// (jf_format.cc).  Not supported (outside the hot path): plotting.
 #include <glob.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -30,6 +31,7 @@
 #include <vector>
 
 #include "katgpu.h"
+#include "jf_format.hpp"
 #include "seq_parser.hpp"
 
 using std::cerr;
@@ -219,6 +221,7 @@ struct Input {
     bool canonical = true;
     uint64_t hash_size = 100000000ULL; // DEFAULT_HASH_SIZE, lib/include/kat/jellyfish_helper.hpp:76
     int index = 1;
+    bool load_mode = false; // InputMode::LOAD: the (first) input is a jellyfish hash
     katgpu_table *table = nullptr;
     uint64_t n_distinct = 0, n_total = 0;
 
@@ -228,11 +231,12 @@ struct Input {
         else if (t.size() == files.size()) trim5p = t;
         else throw KatError(4, "Inconsistent number of inputs and trimming settings.  Please establish your inputs before trying to set trimming vector.  Also ensure you have the same number of input files to trimming settings.");
     }
-    void validate() const { // InputHandler::validateInput
+    void validate() { // InputHandler::validateInput (lib/src/input_handler.cc:99-136)
         for (auto &p : files) {
             if (!exists(p)) throw KatError(4, "Could not find input file at: " + p + "; please check the path and try again.");
-            if (!is_sequence_file(p))
-                throw KatError(4, "Input " + p + " is not a FastA/FastQ file: jellyfish hash inputs (LOAD mode) are outside this GPU build's scope");
+            // `start` is never cleared in the reference, so the mode is simply that of the last
+            // file and the "Cannot mix sequence files and jellyfish hashes" check cannot fire
+            load_mode = !is_sequence_file(p);
         }
     }
 };
@@ -272,6 +276,86 @@ void count_input(katgpu_ctx *ctx, Input &in, int k, bool allow_grow) {
         }
     }
     gpu_check(katgpu_count_end(in.table, &in.n_distinct, &in.n_total));
+    phase_done(t);
+}
+
+// InputHandler::loadHeader + loadHash (lib/src/input_handler.cc:138-142,204-219) via
+// HashLoader::loadHash (lib/src/jellyfish_helper.cc:97-187): only the FIRST file of the group is
+// read; k and the canonical flag come from its header.  Returns the file's mer length.
+kat_host::JfHeader read_jf_header(const string &path, std::ifstream &f) {
+    f.open(path.c_str(), std::ios::in | std::ios::binary);
+    kat_host::JfHeader h;
+    string err;
+    if (!f.good() || !kat_host::jf_read_header(f, h, err)) throw KatError(4, "Failed to parse header of file: " + path);
+    if (h.format == "bloomcounter")
+        throw KatError(4, "KAT does not currently support bloom counted kmer hashes.  Please create a binary hash with jellyfish or KAT and use that instead.");
+    if (h.format == "text/sorted")
+        throw KatError(4, "Processing a text format hash will be painfully slow, so we don't support it.  Please create a binary hash with jellyfish or KAT and use that instead.");
+    if (h.format != "binary/sorted") throw KatError(4, "Unknown format '" + h.format + "'");
+    return h;
+}
+int load_input(katgpu_ctx *ctx, Input &in) {
+    std::ifstream f;
+    const kat_host::JfHeader h = read_jf_header(in.files[0], f);
+    const int k = (int)(h.key_len / 2);
+    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); the hash holds " + std::to_string(k) + "-mers");
+    struct stat st;
+    uint64_t n_records = 0;
+    if (stat(in.files[0].c_str(), &st) == 0 && (uint64_t)st.st_size >= h.offset) {
+        const uint64_t data = (uint64_t)st.st_size - h.offset;
+        if (data % h.record_bytes())
+            throw KatError(4, "Size of database (" + std::to_string(data) + ") must be a multiple of the length of a record (" + std::to_string(h.record_bytes()) + ")");
+        n_records = data / h.record_bytes();
+    }
+    in.canonical = h.canonical;
+    // the reference sizes the new array at 2 * nbRecords rounded up to a power of two (:149-150)
+    gpu_check(katgpu_count_begin(ctx, k, in.canonical ? 1 : 0, std::max<uint64_t>(2 * n_records, 1024), 1, &in.table));
+    string err;
+    katgpu_status first_bad = KATGPU_OK;
+    const bool ok = kat_host::jf_read_records(f, h, (size_t)1 << 22, [&](const uint64_t *keys, const uint64_t *counts, size_t n) {
+        if (first_bad == KATGPU_OK) first_bad = katgpu_count_add_pairs(in.table, keys, counts, n);
+    }, err);
+    gpu_check(first_bad);
+    if (!ok) throw KatError(4, err);
+    gpu_check(katgpu_count_end(in.table, &in.n_distinct, &in.n_total));
+    return k;
+}
+void load_inputs_phase(katgpu_ctx *ctx, Input *ins, int n_in, int &k) { // the "Loading hashes into memory..." phase
+    Timer t;
+    cout << "Loading hashes into memory...";
+    cout.flush();
+    for (int i = 0; i < n_in; i++)
+        if (ins[i].load_mode) {
+            const int kk = load_input(ctx, ins[i]);
+            if (n_in == 1) k = kk; // hist / gcp take merLen from the loaded hash (InputHandler::loadHash)
+        }
+    phase_done(t);
+}
+
+// InputHandler::dump (lib/src/input_handler.cc:221-243): a counted input is written as a
+// jellyfish binary/sorted hash (JellyfishHelper::dumpHash: 4-byte counters, one file), a
+// loaded one is symlinked.
+void dump_input(Input &in, int k, const string &out_path) {
+    struct stat st;
+    if (lstat(out_path.c_str(), &st) == 0) unlink(out_path.c_str());
+    if (in.load_mode) {
+        if (symlink(in.files[0].c_str(), out_path.c_str()) != 0) throw KatError(4, "Could not create symlink " + out_path);
+        return;
+    }
+    Timer t;
+    cout << "Dumping hash to " << out_path << " ...";
+    cout.flush();
+    vector<uint64_t> keys(std::max<uint64_t>(in.n_distinct, 1)), counts(keys.size());
+    uint64_t n = 0;
+    gpu_check(katgpu_table_export(in.table, keys.data(), counts.data(), keys.size(), &n));
+    keys.resize((size_t)std::min<uint64_t>(n, keys.size()));
+    counts.resize(keys.size());
+    kat_host::JfHeader h;
+    kat_host::jf_prepare_dump(h, (unsigned)k, in.canonical, keys.size(), keys, counts);
+    std::ofstream out(out_path.c_str(), std::ios::out | std::ios::binary);
+    kat_host::jf_write_file(out, h, keys, counts);
+    out.close();
+    if (!out.good()) throw KatError(4, "Could not write " + out_path);
     phase_done(t);
 }
 
@@ -382,9 +466,8 @@ int hist_main(int argc, char **argv) {
                 "Options: -o prefix (kat.hist) -t threads -l low (1) -h high (10000) -i inc (1) --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -v --help\n" << endl;
         return 1;
     }
-    if (a.has("dump_hash")) throw KatError(4, "-d/--dump_hash (jellyfish hash output) is outside this GPU build's scope");
     const uint64_t low = to_u64(a.get("low", "1"), "low"), high = to_u64(a.get("high", "10000"), "high"), inc = to_u64(a.get("inc", "1"), "inc");
-    const int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
+    int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
     Timer total;
     cout << "Running KAT in HIST mode" << endl << "------------------------" << endl << endl;
     Input in;
@@ -401,7 +484,8 @@ int hist_main(int argc, char **argv) {
     in.validate();
     ensure_parent_dir(prefix);
     Ctx ctx;
-    count_input(ctx.c, in, k, true);
+    if (in.load_mode) load_inputs_phase(ctx.c, &in, 1, k);
+    else count_input(ctx.c, in, k, true);
     vector<uint64_t> bins(nb);
     {
         Timer t;
@@ -410,6 +494,7 @@ int hist_main(int argc, char **argv) {
         gpu_check(katgpu_hist(in.table, base, ceil, inc, nb, bins.data()));
         phase_done(t);
     }
+    if (a.has("dump_hash")) dump_input(in, k, prefix + "-hash.jf" + std::to_string(k));
     {
         Timer t;
         cout << "Saving results to disk ...";
@@ -444,10 +529,9 @@ int gcp_main(int argc, char **argv) {
                 "Options: -o prefix (kat-gcp) -t threads -x cvg_scale (1.0) -y cvg_bins (1000) --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -v --help\n" << endl;
         return 1;
     }
-    if (a.has("dump_hash")) throw KatError(4, "-d/--dump_hash (jellyfish hash output) is outside this GPU build's scope");
     const double scale = to_double(a.get("cvg_scale", "1.0"), "cvg_scale");
     const uint32_t bins = (uint32_t)to_u64(a.get("cvg_bins", "1000"), "cvg_bins");
-    const int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
+    int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
     Timer total;
     cout << "Running KAT in GCP mode" << endl << "------------------------" << endl << endl;
     Input in;
@@ -460,7 +544,8 @@ int gcp_main(int argc, char **argv) {
     in.validate();
     ensure_parent_dir(prefix);
     Ctx ctx;
-    count_input(ctx.c, in, k, true);
+    if (in.load_mode) load_inputs_phase(ctx.c, &in, 1, k);
+    else count_input(ctx.c, in, k, true);
     vector<uint64_t> mx((size_t)k * (bins + 1));
     {
         Timer t;
@@ -468,6 +553,7 @@ int gcp_main(int argc, char **argv) {
         cout.flush();
         gpu_check(katgpu_gcp(in.table, scale, bins, mx.data()));
         phase_done(t);
+        if (a.has("dump_hash")) dump_input(in, k, prefix + "-hash.jf" + std::to_string(k));
     }
     {
         Timer t;
@@ -548,13 +634,12 @@ int comp_main(int argc, char **argv) {
                 "-N -O -P -m mer_len (27) -H -I -J hash sizes (1e8) -g -n -h -v --help\n" << endl;
         return 1;
     }
-    if (a.has("dump_hashes")) throw KatError(4, "-d/--dump_hashes (jellyfish hash output) is outside this GPU build's scope");
     Timer total;
     cout << "Running KAT in COMP mode" << endl << "------------------------" << endl << endl;
     if (a.positional.size() < 1) throw KatError(4, "Nothing specified for input group 1");
     if (a.positional.size() < 2) throw KatError(4, "Nothing specified for input group 2");
     const bool three = a.positional.size() >= 3;
-    const int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
+    int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
     if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
     const double d1s = to_double(a.get("d1_scale", "1.0"), "d1_scale"), d2s = to_double(a.get("d2_scale", "1.0"), "d2_scale");
     const uint32_t d1b = (uint32_t)to_u64(a.get("d1_bins", "1001"), "d1_bins"), d2b = (uint32_t)to_u64(a.get("d2_bins", "1001"), "d2_bins");
@@ -575,7 +660,31 @@ int comp_main(int argc, char **argv) {
     for (int i = 0; i < (three ? 3 : 2); i++) in[i].validate();
     ensure_parent_dir(prefix);
     Ctx ctx;
-    for (int i = 0; i < (three ? 3 : 2); i++) count_input(ctx.c, in[i], k, !a.has("disable_hash_grow"));
+    const int n_in = three ? 3 : 2;
+    // Comp::execute (src/comp.cc:140-167): count the sequence inputs, then read the headers of
+    // the hash inputs; when every input is a hash the mer length comes from the first header;
+    // every hash must hold k-mers of the mer length in use (InputHandler::validateMerLen).
+    for (int i = 0; i < n_in; i++)
+        if (!in[i].load_mode) count_input(ctx.c, in[i], k, !a.has("disable_hash_grow"));
+    bool any_load = false, all_load = true;
+    vector<unsigned> hash_k(n_in, 0);
+    for (int i = 0; i < n_in; i++) {
+        if (in[i].load_mode) {
+            std::ifstream f;
+            hash_k[i] = read_jf_header(in[i].files[0], f).key_len / 2;
+            any_load = true;
+        } else
+            all_load = false;
+    }
+    if (all_load) k = (int)hash_k[0];
+    for (int i = 0; i < n_in; i++)
+        if (in[i].load_mode && (int)hash_k[i] != k)
+            throw KatError(4, "Cannot process hashes that were created with different K-mer lengths.  Expected: " + std::to_string(k) +
+                                  ".  Key length was " + std::to_string(hash_k[i]) + " for : " + in[i].files[0]);
+    if (any_load) {
+        int k_unused = k;
+        load_inputs_phase(ctx.c, in, n_in, k_unused);
+    }
     const size_t cells = (size_t)d1b * d2b, len = std::min(d1b, d2b);
     vector<uint64_t> main_mx(cells), ends, middle, mixed, spectra(4 * len);
     if (three) {
@@ -593,6 +702,8 @@ int comp_main(int argc, char **argv) {
                               spectra.data()));
         phase_done(t);
     }
+    if (a.has("dump_hashes")) // src/comp.cc:174-179
+        for (int i = 0; i < n_in; i++) dump_input(in[i], k, prefix + "-hash" + std::to_string(in[i].index) + ".jf" + std::to_string(k));
     const vector<uint64_t> sp1(spectra.begin(), spectra.begin() + len), sp2(spectra.begin() + len, spectra.begin() + 2 * len),
         ssp1(spectra.begin() + 2 * len, spectra.begin() + 3 * len), ssp2(spectra.begin() + 3 * len, spectra.end());
     const string p1 = in[0].files[0], p2 = in[1].files[0], p3 = three ? in[2].files[0] : "";
@@ -681,6 +792,51 @@ int main(int argc, char **argv) {
                                                           (unsigned)to_u64(a.get("5ptrim", "0"), "5ptrim"), bases);
             fwrite(bases.data(), 1, bases.size(), stdout);
             return st == kat_host::ParseStatus::Ok ? 0 : st == kat_host::ParseStatus::UnsupportedFormat ? 2 : 3;
+        }
+        if (mode == "_jfdump") { // test hook, no GPU: header summary + records of a jellyfish hash, in file order
+            if (argc != 3) throw KatError(1, "usage: kat _jfdump <hash.jf>");
+            std::ifstream f;
+            const kat_host::JfHeader h = read_jf_header(argv[2], f);
+            const unsigned k = h.key_len / 2;
+            printf("# k=%u canonical=%d counter_len=%u size=%llu format=%s offset=%zu\n", k, h.canonical ? 1 : 0, h.counter_len,
+                   (unsigned long long)h.size, h.format.c_str(), h.offset);
+            string err;
+            uint64_t prev_pos = 0, prev_key = 0, n_seen = 0, unsorted = 0;
+            const bool ok = kat_host::jf_read_records(f, h, 1 << 16, [&](const uint64_t *keys, const uint64_t *counts, size_t n) {
+                string line;
+                for (size_t i = 0; i < n; i++) {
+                    line.clear();
+                    for (unsigned j = 0; j < k; j++) line += "ACGT"[(keys[i] >> (2 * (k - 1 - j))) & 3];
+                    printf("%s %llu\n", line.c_str(), (unsigned long long)counts[i]);
+                    const uint64_t pos = kat_host::jf_position(h, keys[i]);
+                    if (n_seen && (pos < prev_pos || (pos == prev_pos && keys[i] <= prev_key))) unsorted++;
+                    prev_pos = pos, prev_key = keys[i], n_seen++;
+                }
+            }, err);
+            if (!ok) throw KatError(4, err);
+            printf("# records=%llu out_of_order=%llu\n", (unsigned long long)n_seen, (unsigned long long)unsorted);
+            return 0;
+        }
+        if (mode == "_jfwrite") { // test hook, no GPU: "KMER count" lines -> jellyfish binary/sorted hash
+            const Parsed a = parse_args(argc - 1, argv + 1, {{'m', "mer_len", true}, {'N', "non_canonical", false}});
+            if (a.positional.size() != 2) throw KatError(1, "usage: kat _jfwrite -m K [-N] <kmers.txt> <out.jf>");
+            const unsigned k = (unsigned)to_u64(a.get("mer_len", "27"), "mer_len");
+            std::ifstream in(a.positional[0].c_str());
+            vector<uint64_t> keys, counts;
+            string km;
+            uint64_t c;
+            while (in >> km >> c) {
+                if (km.size() != k) throw KatError(4, "k-mer of the wrong length: " + km);
+                uint64_t key = 0;
+                for (char ch : km) key = (key << 2) | (uint64_t)(ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3);
+                keys.push_back(key);
+                counts.push_back(c);
+            }
+            kat_host::JfHeader h;
+            kat_host::jf_prepare_dump(h, k, !a.has("non_canonical"), keys.size(), keys, counts);
+            std::ofstream out(a.positional[1].c_str(), std::ios::out | std::ios::binary);
+            kat_host::jf_write_file(out, h, keys, counts);
+            return out.good() ? 0 : 4;
         }
         cout << "Kmer Analysis Toolkit (KAT) V" << kVersion << endl << endl;
         if (mode == "hist") return hist_main(argc - 1, argv + 1);

@@ -952,6 +952,51 @@ extern "C" katgpu_status katgpu_route_device(katgpu_table *t, const void *bases_
     return KATGPU_OK;
 }
 
+extern "C" katgpu_status katgpu_count_add_pairs(katgpu_table *t, const uint64_t *keys, const uint64_t *counts, size_t n) {
+    if (!t || ((!keys || !counts) && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_add_pairs: NULL argument");
+    if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_add_pairs: table already finished");
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    TableCounters ctr;
+    KT(read_counters(t, ctr));
+    KT(sweep_pending(t, ctr));
+    const size_t kBatch = 1u << 24; // records per staging round (2 x 128 MiB on the device)
+    uint64_t *d_keys = nullptr, *d_counts = nullptr;
+    const size_t cap = std::min(n, kBatch);
+    if (cap == 0) return KATGPU_OK;
+    CU(cudaMalloc((void **)&d_keys, cap * 8));
+    if (cudaMalloc((void **)&d_counts, cap * 8) != cudaSuccess) {
+        cudaFree(d_keys);
+        return fail(KATGPU_ERR_NOMEM, "katgpu_count_add_pairs: out of device memory");
+    }
+    katgpu_status st = KATGPU_OK;
+    size_t done = 0;
+    while (done < n && st == KATGPU_OK) {
+        uint64_t granted = 0;
+        st = admit(t, ctr, std::min(n - done, cap), granted);
+        if (st != KATGPU_OK) break;
+        cudaError_t e = cudaMemcpyAsync(d_keys, keys + done, granted * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(d_counts, counts + done, granted * 8, cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            st = fail(KATGPU_ERR_CUDA, "katgpu_count_add_pairs: %s", cudaGetErrorString(e));
+            break;
+        }
+        {
+            ProfScope ps(c, "insert", c->stream);
+            TableGeom gl = t->g;
+            set_add_bound(gl, ~0ULL); // counts are arbitrary: always the checked (ATOM) add
+            const int grid = (int)std::min<uint64_t>((granted + 255) / 256, (uint64_t)c->sm_count * 8);
+            launch_add_pairs(gl, d_keys, d_counts, granted, grid, c->stream);
+        }
+        c->launches++;
+        done += granted;
+        st = settle(t, ctr); // synchronises: the staging buffers are free again
+    }
+    cudaFree(d_keys);
+    cudaFree(d_counts);
+    return st;
+}
+
 extern "C" katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void *hashed_dev, uint64_t n) {
     if (!t || (!hashed_dev && n)) return fail(KATGPU_ERR_INVALID, "katgpu_insert_hashed_device: NULL argument");
     if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_insert_hashed_device: table already finished");

@@ -62,20 +62,20 @@ struct TableGeom {
     uint32_t k, b, Lb, rbits, cshift, cbits, sh, canonical;
 };
 
-// Bijection on b-bit integers: xorshift, odd multiply mod 2^b, xorshift.  One multiply is
-// enough here: bucket occupancy and slice balance on genome k-mers are indistinguishable from
-// the two-multiply murmur finaliser (measured), and hashing is ~15 % of the extraction kernels.
+// Bijection on b-bit integers: xorshift (folds the first bases into the last), then an odd
+// multiply mod 2^b.  Only the TOP bits of h choose the slice and the bucket, and those depend
+// on every bit of the key; the low bits are merely stored (rem), so no second xorshift is
+// needed (bucket occupancy and slice balance measured equal to the two-round finaliser on
+// E. coli, random and tandem-repeat k-mers).  sh = ceil(b / 2) <= 32, so x >> sh fits the low
+// word: the device fast path (extract.cuh: mix_words) is one funnel shift, one xor, a 64-bit
+// multiply and a mask.
 __host__ __device__ __forceinline__ uint64_t mix_key(const TableGeom &g, uint64_t x) {
     x ^= x >> g.sh;
-    x = (x * kMixM1) & g.kmask;
-    x ^= x >> g.sh;
-    return x;
+    return (x * kMixM1) & g.kmask;
 }
 __host__ __device__ __forceinline__ uint64_t unmix_key(const TableGeom &g, uint64_t x) {
-    x ^= x >> g.sh; // 2*sh >= b: the xorshift is an involution
     x = (x * g.m1inv) & g.kmask;
-    x ^= x >> g.sh;
-    return x;
+    return x ^ (x >> g.sh); // 2*sh >= b: the xorshift is an involution
 }
 // Owner rank of a hashed key: independent of the bucket bits.
 __host__ __device__ __forceinline__ uint32_t owner_of(uint64_t h, uint32_t n_ranks) {

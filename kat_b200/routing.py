@@ -18,7 +18,6 @@ def mix_key(x, k):
     with np.errstate(over="ignore"):
         x = x ^ (x >> sh)
         x = (x * _M1) & km
-        x = x ^ (x >> sh)
     return x
 
 

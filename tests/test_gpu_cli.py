@@ -51,3 +51,75 @@ def test_cli_hash_full_exit_code(workdir):
 def test_cli_missing_input(workdir):
     r = subprocess.run([KAT, "hist", "-m21", "inputs/nope.fa"], cwd=workdir, capture_output=True, text=True)
     assert r.returncode == 4 and "Could not find input file" in r.stderr
+
+
+# ---- jellyfish hashes either side of the path: LOAD mode and -d/--dump_hash -------------------
+import gzip
+import json
+
+JF_MANIFEST = json.load(open(os.path.join(G.GOLDEN, "jf", "cases.json")))
+REF_JF = os.path.join(ROOT, "oracle", "_ref", "kat_jellyfish")
+
+
+@pytest.fixture(scope="module")
+def jf_workdir(tmp_path_factory):
+    d = tmp_path_factory.mktemp("jf_run")
+    shutil.copytree(os.path.join(G.GOLDEN, "inputs"), d / "inputs")
+    os.makedirs(d / "jf")
+    for h in JF_MANIFEST["hashes"]:
+        shutil.copy(os.path.join(G.GOLDEN, "jf", h["name"] + ".jf"), d / "jf")
+    return d
+
+
+def _jf_expected(case, f):
+    p = os.path.join(G.GOLDEN, "jf", "expected", case, f)
+    return open(p, "rb").read() if os.path.exists(p) else gzip.open(p + ".gz", "rb").read()
+
+
+@pytest.mark.parametrize("case", JF_MANIFEST["cases"], ids=lambda c: c["name"])
+def test_cli_load_mode_files_byte_identical(case, jf_workdir):
+    """Hashes written by the reference (its own -d, and jellyfish count) as INPUT of the product's
+    hist / gcp / comp (InputHandler::loadHash): same output files as the reference, byte for byte
+    — including k taken from the hash header and the canonical flag of a loaded input."""
+    out = os.path.join("jf", "expected", case["name"])
+    shutil.rmtree(jf_workdir / out, ignore_errors=True)
+    os.makedirs(jf_workdir / out)
+    r = subprocess.run([KAT] + [a.replace("OUT", out) for a in case["args"]], cwd=jf_workdir, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    assert "Loading hashes into memory..." in r.stdout
+    for f in case["files"]:
+        assert open(jf_workdir / out / f, "rb").read() == _jf_expected(case["name"], f), f"{case['name']}/{f}"
+
+
+@pytest.mark.parametrize("path", ["direct", "partition"])
+def test_cli_dump_hash_is_a_jellyfish_file(path, jf_workdir):
+    """`kat hist -d` writes <prefix>-hash.jf<k>: the same (k-mer, count) records as the reference's
+    own dump of the same input, readable by the unmodified jellyfish, and loadable again."""
+    env = dict(os.environ, KATGPU_COUNT_PATH=path)
+    r = subprocess.run([KAT, "hist", "-m13", "-d", "-o", "dump/h", "inputs/long.fa"], cwd=jf_workdir, capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "Dumping hash to dump/h-hash.jf13 ..." in r.stdout, r.stdout + r.stderr
+    want = sorted(gzip.open(os.path.join(G.GOLDEN, "jf", "long_k13_kat.dump.txt.gz"), "rt").read().splitlines())
+    d = subprocess.run([KAT, "_jfdump", "dump/h-hash.jf13"], cwd=jf_workdir, capture_output=True, text=True)
+    lines = d.stdout.splitlines()
+    assert "canonical=1 counter_len=4" in lines[0] and lines[-1].endswith("out_of_order=0")
+    assert sorted(l for l in lines if not l.startswith("#")) == want
+    if os.access(REF_JF, os.X_OK):
+        j = subprocess.run([REF_JF, "dump", "-c", "dump/h-hash.jf13"], cwd=jf_workdir, capture_output=True, text=True)
+        assert j.returncode == 0 and sorted(j.stdout.splitlines()) == want
+    # and our own LOAD of our own dump reproduces the histogram of the counting run
+    r2 = subprocess.run([KAT, "hist", "-o", "dump/h2", "dump/h-hash.jf13"], cwd=jf_workdir, capture_output=True, text=True, timeout=300)
+    assert r2.returncode == 0, r2.stderr
+    body = lambda p: [l for l in open(jf_workdir / p).read().splitlines() if not l.startswith("#")]
+    assert body("dump/h") == body("dump/h2")
+
+
+def test_cli_comp_dump_hashes_and_symlink(jf_workdir):
+    """comp -d: counted inputs are dumped as <prefix>-hash<i>.jf<k>, loaded ones symlinked
+    (InputHandler::dump, lib/src/input_handler.cc:221-243)."""
+    r = subprocess.run([KAT, "comp", "-m21", "-d", "-i", "40", "-j", "50", "-o", "cd/c", "jf/synthc_k21_jf.jf", "inputs/synth_a.fq"],
+                       cwd=jf_workdir, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert os.path.islink(jf_workdir / "cd" / "c-hash1.jf21")
+    d = subprocess.run([KAT, "_jfdump", "cd/c-hash2.jf21"], cwd=jf_workdir, capture_output=True, text=True)
+    assert d.returncode == 0 and "k=21 canonical=1" in d.stdout.splitlines()[0]
+    assert open(jf_workdir / "cd" / "c-main.mx", "rb").read() == _jf_expected("load_comp_hash_vs_reads_k21", "c-main.mx")

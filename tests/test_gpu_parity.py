@@ -246,3 +246,32 @@ def test_route_then_insert_equals_direct(ctx, R):
         ctx.device_free(d)
         for o in outs:
             ctx.device_free(o)
+
+
+@pytest.mark.parametrize("k", [5, 21, 32])
+def test_add_pairs_is_hash_add(ctx, k):
+    """katgpu_count_add_pairs == `hash->add(key, val)` per record (HashLoader::loadHash): loading the
+    records of a counted table into a fresh one — in two overlapping halves, so counts add — gives
+    the oracle's counts; counts beyond the in-slot field stay exact (forced 3-bit field)."""
+    reads = seqgen.genome_reads(3000, 1500, 90, seed=k)
+    ot = ora_table([reads], k)
+    okeys, ocounts = ot.export()
+    B.lib().katgpu_debug_set_count_bits(3)
+    try:
+        t = ctx.count_begin(k, True, 1 << 10, True)
+        half = len(okeys) // 2
+        t.add_pairs(okeys[:half], ocounts[:half])
+        t.add_pairs(okeys[half:], ocounts[half:] + np.uint64(1 << 34))  # large counts: carried exactly
+        t.add_pairs(okeys[: half // 2], np.full(half // 2, 3, dtype=np.uint64))  # a second add of the same keys
+        t.add_pairs(np.zeros(0, dtype=np.uint64), np.zeros(0, dtype=np.uint64))
+        t.end()
+    finally:
+        B.lib().katgpu_debug_set_count_bits(0)
+    want = ocounts.copy()
+    want[half:] += np.uint64(1 << 34)
+    want[: half // 2] += np.uint64(3)
+    keys, counts, n = t.export()
+    assert n == len(okeys) and np.array_equal(keys, okeys) and np.array_equal(counts, want)
+    assert t.n_total == int(want.sum())
+    _, bins = t.hist(1, 10000, 1)
+    assert int(bins.sum()) == n
