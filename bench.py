@@ -309,7 +309,7 @@ def main():
         dt = time.perf_counter() - t0
         sampler.mark_end()
         clocks = sampler.summary()
-        prof = {f: ctx.profile_get(f) for f in ("count", "partition", "sweep", "hist", "route", "insert", "memset", "rehash")}
+        prof = {f: ctx.profile_get(f) for f in ("count", "partition", "sweep", "bin1", "bin2", "tile", "hist", "route", "insert", "memset", "rehash")}
         ctx.profile_enable(False)
         if dist is not None:
             tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
@@ -336,8 +336,11 @@ def main():
     # K1 (extract + canonicalise + insert) is either one kernel (extract_kernel<insert>,
     # family "count") or the pair partition_kernel + sweep_kernel; its algorithmic bytes are B_ALG per k-mer.
     if world > 1:
-        fam = [f for f in ("route", "partition", "sweep", "insert") if prof[f][1] > 0]
-        kname = "extract_kernel<route> + partition_kernel<keys> + sweep_kernel (K1 + K5; NCCL exchange between route and partition not included)"
+        fam = [f for f in ("route", "partition", "sweep", "bin1", "bin2", "tile", "insert") if prof[f][1] > 0]
+        kname = "extract_kernel<route> + owner-side binning + insertion kernels (K1 + K5; NCCL exchange between route and binning not included)"
+    elif prof["bin1"][1] > 0:
+        fam = [f for f in ("bin1", "bin2", "tile", "insert") if prof[f][1] > 0]
+        kname = "bin_bases_kernel + bin_keys_kernel + tile_insert_kernel (+ general insert of the side list): K1 as two binning passes and shared-memory table tiles"
     elif prof["partition"][1] > 0:
         fam, kname = ["partition", "sweep"], "partition_kernel + sweep_kernel (K1 split in two streaming phases)"
     else:

@@ -4,6 +4,7 @@
 #include "../../include/katgpu.h"
 #include "count_kernels.cuh"
 #include "partition_kernels.cuh"
+#include "tile_kernels.cuh"
 #include "reduce_kernels.cuh"
 #include "synth.cuh"
 
@@ -58,6 +59,7 @@ struct katgpu_ctx {
     int bps[2] = {1, 1}; // resident CTAs per SM of the extract kernels
     int bps_part = 1;    // ... of the partition kernel
     int bps_sweep = 1;   // ... of the sweep kernel
+    int bps_bin1 = 2, bps_tile = 1; // ... of the tiled path's bin_bases / tile_insert kernels
     unsigned int *tile_counter = nullptr; // device
     unsigned long long *route_cursors = nullptr; // device [kMaxRanks] + overflow flag after
     // host feed staging
@@ -91,7 +93,15 @@ struct katgpu_table {
     uint64_t pend_tiles = 0;   // tiles the busiest CTA has partitioned since the last sweep
     uint64_t pend_total_tiles = 0; // all tiles since the last sweep (also the CTA rotation)
     uint64_t pend_bound = 0;   // upper bound on pending k-mer instances
-    size_t pend_bytes = 0;
+    size_t pend_bytes = 0, pend_seglen_bytes = 0;
+    // tiled path (tile_kernels.cu): the pending keys are level-1 segments of the same layout
+    bool tiled = false;
+    uint32_t ring1 = 0;           // staging-ring slots per bin of the level-1 kernels
+    uint64_t *side_keys = nullptr; // side list + its counters {n, reserved} and the deferred-tile list
+    unsigned long long *side_ctr = nullptr;
+    uint32_t *side_deferred = nullptr;
+    uint64_t side_cap = 0;
+    size_t side_bytes = 0;
 };
 
 static const size_t kChunkBytes = 128u << 20; // host feed granularity
@@ -219,6 +229,8 @@ extern "C" katgpu_status katgpu_init(int device, katgpu_ctx **out) {
     if (c->bps_part < 1) return fail(KATGPU_ERR_CUDA, "katgpu_init: partition kernel does not fit on an SM");
     if (c->bps_part > 2) c->bps_part = 2;
     CU(sweep_occupancy(&c->bps_sweep));
+    CU(tile_configure(&c->bps_bin1, &c->bps_tile));
+    if (c->bps_tile < 1) return fail(KATGPU_ERR_CUDA, "katgpu_init: tile kernel does not fit on an SM");
     if (c->bps[0] < 1 || c->bps[1] < 1) return fail(KATGPU_ERR_CUDA, "katgpu_init: extract kernel does not fit on an SM");
     CU(cudaMalloc(&c->tile_counter, 256));
     CU(cudaMalloc(&c->route_cursors, 256));
@@ -353,6 +365,10 @@ static katgpu_status make_geom(int k, int canonical, int Lb, int count_bits_cap,
     if (Lb < 1) Lb = 1;
     const int rbits = b - Lb;
     int cbits = 64 - (rbits + kProbeBits + 1);
+    // The count field never reaches into the low word (cshift >= 32): the tile kernel updates it
+    // with a native 32-bit shared-memory atomic on the high word.  Counts beyond 2^32 - 1 carry
+    // into the exact side table like any other field overflow.
+    if (cbits > 32) cbits = 32;
     if (count_bits_cap >= 2 && count_bits_cap < cbits) cbits = count_bits_cap;
     if (cbits < 2) return fail(KATGPU_ERR_INVALID, "table geometry: no room for a count field (k=%d, Lb=%d)", k, Lb);
     g.k = k;
@@ -439,16 +455,29 @@ extern "C" katgpu_status katgpu_count_begin(katgpu_ctx *c, int k, int canonical,
     return KATGPU_OK;
 }
 
+static void pend_release(katgpu_table *t) {
+    katgpu_ctx *c = t->ctx;
+    if (t->pend_keys) pool_free(c, t->pend_keys, t->pend_bytes);
+    if (t->pend_seglen) pool_free(c, t->pend_seglen, t->pend_seglen_bytes);
+    if (t->pend_hll) pool_free(c, t->pend_hll, kHllM * 4);
+    if (t->pend_done) pool_free(c, t->pend_done, kMaxParts * 4);
+    if (t->side_keys) pool_free(c, t->side_keys, t->side_bytes);
+    if (t->side_ctr) pool_free(c, t->side_ctr, 64);
+    if (t->side_deferred) pool_free(c, t->side_deferred, ((size_t)1 << 20) * 4);
+    t->pend_keys = nullptr;
+    t->pend_seglen = t->pend_hll = t->pend_done = nullptr;
+    t->side_keys = nullptr;
+    t->side_ctr = nullptr;
+    t->side_deferred = nullptr;
+}
+
 extern "C" void katgpu_table_free(katgpu_table *t) {
     TraceScope trace__("katgpu_table_free");
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
     free_table_storage(t->ctx, t->g);
-    if (t->pend_keys) pool_free(t->ctx, t->pend_keys, t->pend_bytes);
-    if (t->pend_seglen) cudaFree(t->pend_seglen);
-    if (t->pend_hll) cudaFree(t->pend_hll);
-    if (t->pend_done) cudaFree(t->pend_done);
+    pend_release(t);
     delete t;
 }
 
@@ -567,19 +596,39 @@ static katgpu_status launch_extract_insert(katgpu_table *t, const uint8_t *dev, 
 }
 
 // ---- partitioned (L2-resident) counting path ----------------------------------
-static int count_path_mode() { // 0 auto, 1 direct, 2 partition
+static int count_path_mode() { // 0 auto, 1 direct, 2 partition (L2 sweep), 3 tiled (shared-memory tiles)
     const char *e = getenv("KATGPU_COUNT_PATH");
     if (!e) return 0;
     if (!strcmp(e, "direct")) return 1;
     if (!strcmp(e, "partition")) return 2;
+    if (!strcmp(e, "tiled")) return 3;
     return 0;
 }
+static const int kAutoPendingPath = 3; // which pending-key path "auto" picks for large jobs (2 = L2 sweep, 3 = tiled)
+static bool tiled_possible(const katgpu_table *t) { return (int)t->g.Lb >= kTileBucketsLog2 + 2; }
 static bool use_partition(const katgpu_table *t, uint64_t kmers_hint) {
+    if (t->pend_keys) return true; // keep the path the pending buffer was built for
     const int m = count_path_mode();
     if (m == 1 || t->g.Lb < 6) return false;
     if (m == 2) return true;
+    if (m == 3) return tiled_possible(t);
     // worth it once the table is far larger than L2 and the batch amortises one table pass
     return t->n_slots * 8 >= (512ull << 20) && kmers_hint >= (32ull << 20);
+}
+static bool want_tiled(const katgpu_table *t) {
+    const int m = count_path_mode();
+    return tiled_possible(t) && (m == 3 || (m == 0 && kAutoPendingPath == 3));
+}
+
+// Staging-ring slots per bin for a binning pass of `tile_keys` keys over F bins: the leftover of
+// the previous flush (< 4) + mean + ~4 sigma, within `max_bytes` of shared memory (a ring that
+// is too small only sends more keys the slow way).
+static uint32_t ring_slots(uint32_t F, uint32_t tile_keys, size_t max_bytes) {
+    const double mean = (double)tile_keys / (double)F;
+    uint64_t R = 4 + (uint64_t)std::ceil(mean + 4.0 * std::sqrt(mean));
+    const uint64_t fit = max_bytes > (size_t)F * 8 + 16 ? (max_bytes - (size_t)F * 8 - 16) / ((size_t)F * 8) : 4;
+    R = std::max<uint64_t>(4, std::min(R, fit));
+    return (uint32_t)R;
 }
 
 static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) {
@@ -587,23 +636,28 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     ok = true;
     if (t->pend_keys) return KATGPU_OK;
     katgpu_ctx *c = t->ctx;
+    const bool tiled = want_tiled(t);
     const uint64_t table_bytes = t->n_slots * 8;
     uint64_t slice_mb = 32; // table bytes swept at a time; must stay L2-resident
     if (const char *e = getenv("KATGPU_SLICE_MB")) slice_mb = std::max(1, atoi(e));
     int Pb = ceil_log2(std::max<uint64_t>(1, table_bytes / (slice_mb << 20)));
     Pb = std::max(1, std::min(Pb, 9));
     Pb = std::min<int>(Pb, (int)t->g.Lb - 2);
-    const uint64_t nparts = 1ull << Pb, n_segs = (uint64_t)c->sm_count * c->bps_part;
+    if (tiled) // level 1 of two: leave at least one bit for level 2 (slice -> 64 KB tile)
+        Pb = std::max(1, std::min(9, (int)t->g.Lb - kTileBucketsLog2 - 1));
+    const uint64_t tile_pos = tiled ? kBinTile : kTile; // positions one CTA bins between two flushes
+    const uint64_t nparts = 1ull << Pb, n_segs = (uint64_t)c->sm_count * (tiled ? c->bps_bin1 : c->bps_part);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    const uint64_t budget_keys = (uint64_t)((double)(free_b + c->pooled_bytes) * 0.70 / 8.0);
+    const uint64_t budget_keys = (uint64_t)((double)(free_b + c->pooled_bytes) * (tiled ? 0.60 : 0.70) / 8.0);
     // Size every (slice, CTA) segment from the same fill model feed_partitioned() uses, so that a
     // feed of `kmers_hint` positions fits in ONE partition round (each extra round = one more full
     // pass over the table in the sweep).
-    const double m_tile = (double)kTile / (double)nparts; // keys one tile sends to one slice
+    const double m_tile = (double)tile_pos / (double)nparts; // keys one tile sends to one slice
+    const double pad = tiled ? 0.0 : 2.0;                    // the L2-sweep path pads every run to 4 keys
     const uint64_t hint = std::max<uint64_t>(kmers_hint, t->n_slots / 4);
-    const uint64_t cta_tiles = ((hint + kTile - 1) / kTile + n_segs - 1) / n_segs + 1;
-    uint64_t seg_cap = (uint64_t)(((double)cta_tiles * (m_tile + 2.0) + 4.0 * std::sqrt((double)cta_tiles * m_tile)) * 1.02) + 64;
+    const uint64_t cta_tiles = ((hint + tile_pos - 1) / tile_pos + n_segs - 1) / n_segs + 1;
+    uint64_t seg_cap = (uint64_t)(((double)cta_tiles * (m_tile + pad) + 4.0 * std::sqrt((double)cta_tiles * m_tile)) * 1.02) + 64;
     seg_cap = (seg_cap + 15) / 16 * 16;
     const uint64_t min_cap = ((uint64_t)(2.2 * (m_tile + 4.0 * std::sqrt(m_tile) + 4.0)) + 255) / 16 * 16;
     seg_cap = std::max(seg_cap, min_cap);
@@ -622,11 +676,14 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     }
     t->pend_keys = (uint64_t *)p;
     t->pend_bytes = nparts * n_segs * seg_cap * 8;
-    CU(cudaMalloc(&p, nparts * n_segs * 4));
+    // small per-job buffers also come from the block cache: cudaMalloc/cudaFree synchronise the
+    // device and were measured at up to 45 ms per job when HBM is nearly full
+    t->pend_seglen_bytes = nparts * n_segs * 4;
+    CU(pool_alloc(c, t->pend_seglen_bytes, &p));
     t->pend_seglen = (uint32_t *)p;
-    CU(cudaMalloc(&p, kHllM * 4));
+    CU(pool_alloc(c, kHllM * 4, &p));
     t->pend_hll = (uint32_t *)p;
-    CU(cudaMalloc(&p, kMaxParts * 4));
+    CU(pool_alloc(c, kMaxParts * 4, &p));
     t->pend_done = (uint32_t *)p;
     CU(cudaMemsetAsync(t->pend_seglen, 0, nparts * n_segs * 4, c->stream));
     CU(cudaMemsetAsync(t->pend_hll, 0, kHllM * 4, c->stream));
@@ -635,6 +692,26 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     t->pend_seg_cap = (uint32_t)seg_cap;
     t->pend_fill = 0;
     t->pend_bound = 0;
+    t->tiled = tiled;
+    if (tiled) {
+        // two CTAs of bin_bases_kernel per SM: ~104 KB each, 16.5 KB of it fixed
+        t->ring1 = ring_slots((uint32_t)nparts, kBinTile, (104u << 10) - 16896);
+        // side list: keys that leave the fast path (~1 % at load 0.3, ~5 % at 0.55)
+        t->side_cap = std::min<uint64_t>(std::max<uint64_t>(hint / 8, 4u << 20), 512u << 20);
+        t->side_bytes = t->side_cap * 8;
+        if (pool_alloc(c, t->side_bytes, &p) != cudaSuccess) {
+            cudaGetLastError();
+            t->side_cap = 1u << 20;
+            t->side_bytes = t->side_cap * 8;
+            CU(pool_alloc(c, t->side_bytes, &p));
+        }
+        t->side_keys = (uint64_t *)p;
+        CU(pool_alloc(c, 64, &p));
+        t->side_ctr = (unsigned long long *)p;
+        CU(cudaMemsetAsync(t->side_ctr, 0, 64, c->stream));
+        CU(pool_alloc(c, ((size_t)1 << 20) * 4, &p));
+        t->side_deferred = (uint32_t *)p;
+    }
     return KATGPU_OK;
 }
 
@@ -649,6 +726,181 @@ static double hll_estimate(const uint32_t *reg, int m) {
     double e = alpha * m * (double)m / z;
     if (e <= 2.5 * m && zeros > 0) e = m * std::log((double)m / zeros);
     return e;
+}
+
+static katgpu_status settle(katgpu_table *t, TableCounters &ctr);
+static katgpu_status admit(katgpu_table *t, TableCounters &ctr, uint64_t want, uint64_t &granted);
+static void set_add_bound(TableGeom &g, uint64_t bound);
+
+// Insert `n` hashed keys held in device memory with the general random-access kernel.
+static katgpu_status insert_hashed_direct(katgpu_table *t, TableCounters &ctr, const uint64_t *hs, uint64_t n) {
+    katgpu_ctx *c = t->ctx;
+    uint64_t done = 0;
+    while (done < n) {
+        uint64_t granted = 0;
+        KT(admit(t, ctr, n - done, granted));
+        const int grid = (int)std::min<uint64_t>((granted + 256 * kUnroll - 1) / (256 * kUnroll), (uint64_t)c->sm_count * 8);
+        {
+            ProfScope ps(c, "insert", c->stream);
+            TableGeom gl = t->g;
+            set_add_bound(gl, granted);
+            launch_insert_hashed(gl, hs + done, granted, grid, c->stream);
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+        done += granted;
+        KT(settle(t, ctr));
+    }
+    return KATGPU_OK;
+}
+
+static SideList side_list_of(const katgpu_table *t) {
+    SideList S{};
+    S.keys = t->side_keys;
+    S.n = t->side_ctr;
+    S.reserved = t->side_ctr + 1;
+    S.cap = t->side_cap;
+    S.deferred = t->side_deferred;
+    S.n_deferred = reinterpret_cast<uint32_t *>(t->side_ctr + 2);
+    S.deferred_cap = 1u << 20;
+    return S;
+}
+
+// The tiled sweep (tile_kernels.cu): for groups of slices, bin the slice's keys by table tile
+// (bin_keys_kernel), then update every tile in shared memory (tile_insert_kernel); finally the
+// side list goes through the general kernel.  Called with the table already sized.
+static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
+    katgpu_ctx *c = t->ctx;
+    const uint32_t F1 = 1u << t->pend_Pb, n_segs = t->pend_segs;
+    const int total_bits = (int)t->g.Lb - kTileBucketsLog2; // table tiles = 2^total_bits
+    const int Pb2 = total_bits - (int)t->pend_Pb;
+    TableGeom gchk = t->g;
+    set_add_bound(gchk, ~0ULL); // rare general-path inserts inside the kernels: always the checked add
+    SideList side = side_list_of(t);
+    bool general = Pb2 < 1 || Pb2 > 10; // (a table grown past 2^32 slots after binning started)
+    if (const char *e = getenv("KATGPU_TILED_GENERAL")) general = general || atoi(e) != 0;
+    if (general) { // insert the level-1 segments as they are, the general way
+        TileParams P{};
+        P.g = gchk;
+        P.keys = t->pend_keys;
+        P.len = t->pend_seglen;
+        P.cap = t->pend_seg_cap;
+        P.parts = 1;
+        P.n_tiles = F1 * n_segs;
+        P.side = side;
+        {
+            ProfScope ps(c, "insert", c->stream);
+            launch_insert_deferred(P, nullptr, P.n_tiles, c->stream);
+        }
+        c->launches++;
+        CU(cudaGetLastError());
+    } else {
+        const uint32_t F2 = 1u << Pb2;
+        // keys a slice can hold at most: sizing from the capacity (not from the current fill) gives
+        // every sweep of a job — and of the next job — the same buffer sizes, so the block cache hits
+        const double slice_keys = std::max(64.0, (double)t->pend_seg_cap * (double)n_segs);
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        double budget = std::min(0.80 * (double)(free_b + c->pooled_bytes), 24.0 * 1024 * 1024 * 1024);
+        if (const char *e = getenv("KATGPU_TILED_GROUP_MB")) budget = std::max(1.0, atof(e)) * 1024 * 1024;
+        uint32_t spg = (uint32_t)std::max(1.0, std::min((double)F1, budget / (slice_keys * 8.0 * 1.3)));
+        const uint32_t want_ctas = (uint32_t)c->sm_count; // bin_keys_kernel: one 1024-thread CTA per SM
+        uint32_t parts = std::max<uint32_t>(1, std::min<uint32_t>(8, (want_ctas + spg - 1) / spg));
+        parts = std::min(parts, n_segs);
+        uint64_t cap2 = 0;
+        for (;;) {
+            const double mean2 = slice_keys / ((double)F2 * parts);
+            cap2 = ((uint64_t)(mean2 + 6.0 * std::sqrt(mean2) + 32.0) + 15) / 16 * 16;
+            if ((double)spg * F2 * parts * cap2 * 8.0 <= budget || spg == 1) break;
+            spg = std::max<uint32_t>(1, spg * 3 / 4);
+        }
+        void *p = nullptr;
+        const size_t bytes2 = (size_t)spg * F2 * parts * cap2 * 8;
+        cudaError_t e2 = pool_alloc(c, bytes2, &p);
+        if (e2 != cudaSuccess) return fail(KATGPU_ERR_NOMEM, "sweep_tiled: cannot allocate %zu bytes for the tile segments", bytes2);
+        uint64_t *keys2 = (uint64_t *)p;
+        const size_t len2_bytes = (size_t)spg * F2 * parts * 4;
+        if (pool_alloc(c, len2_bytes, &p) != cudaSuccess) {
+            pool_free(c, keys2, bytes2);
+            return fail(KATGPU_ERR_NOMEM, "sweep_tiled: out of device memory");
+        }
+        uint32_t *len2 = (uint32_t *)p;
+        // keys binned between two flushes of bin_keys_kernel and its ring (one CTA per SM, <= 200 KB)
+        const uint32_t tile2 = kBin2Threads * kBin2Unroll; // bin_keys_kernel bins chunks of kBin2Unroll keys per thread
+        const uint32_t ring2 = ring_slots(F2, tile2, (196u << 10) - kTileHllM * 4); // one CTA per SM
+        if (getenv("KATGPU_TRACE"))
+            fprintf(stderr, "[katgpu] sweep_tiled: F1=%u F2=%u slices/group=%u parts=%u cap2=%llu ring1=%u ring2=%u tile2=%u level-2 buffer %.1f MB side cap %llu\n",
+                    F1, F2, spg, parts, (unsigned long long)cap2, t->ring1, ring2, tile2, bytes2 / 1048576.0, (unsigned long long)t->side_cap);
+        katgpu_status st = KATGPU_OK;
+        for (uint32_t s0 = 0; s0 < F1 && st == KATGPU_OK; s0 += spg) {
+            const uint32_t ns = std::min(spg, F1 - s0);
+            cudaMemsetAsync(len2, 0, (size_t)ns * F2 * parts * 4, c->stream);
+            BinKeysParams B{};
+            B.g = gchk;
+            B.src_keys = t->pend_keys;
+            B.src_len = t->pend_seglen;
+            B.src_segs = n_segs;
+            B.src_cap = t->pend_seg_cap;
+            B.first_slice = s0;
+            B.parts = parts;
+            B.tile_keys = tile2;
+            B.dst.keys = keys2;
+            B.dst.len = len2;
+            B.dst.cap = (uint32_t)cap2;
+            B.dst.stride = parts;
+            B.dst.shift = t->g.b - t->pend_Pb - Pb2;
+            B.dst.mask = F2 - 1;
+            B.dst.F = F2;
+            B.dst.R = ring2;
+            B.side = side;
+            {
+                ProfScope ps(c, "bin2", c->stream);
+                launch_bin_keys(B, (int)(ns * parts), c->stream);
+            }
+            c->launches++;
+            TileParams P{};
+            P.g = gchk;
+            P.keys = keys2;
+            P.len = len2;
+            P.cap = (uint32_t)cap2;
+            P.parts = parts;
+            P.first_tile = s0 * F2;
+            P.n_tiles = ns * F2;
+            P.side = side;
+            {
+                ProfScope ps(c, "tile", c->stream);
+                launch_tile_insert(P, (int)std::min<uint32_t>(P.n_tiles, (uint32_t)(c->sm_count * c->bps_tile)), c->stream);
+            }
+            c->launches++;
+            // tiles refused for lack of side-list room (pathological inputs): general kernel, then forget them
+            {
+                ProfScope ps(c, "insert", c->stream);
+                launch_insert_deferred(P, side.deferred, side.deferred_cap, c->stream);
+            }
+            c->launches++;
+            cudaMemsetAsync(side.n_deferred, 0, 4, c->stream);
+            if (cudaGetLastError() != cudaSuccess) st = fail(KATGPU_ERR_CUDA, "sweep_tiled: launch failed");
+        }
+        cudaStreamSynchronize(c->stream);
+        pool_free(c, keys2, bytes2);
+        pool_free(c, len2, len2_bytes);
+        KT(st);
+    }
+    // keys that left the fast path: general insertion (may grow the table)
+    unsigned long long side_n = 0;
+    CU(cudaMemcpyAsync(&side_n, t->side_ctr, 8, cudaMemcpyDeviceToHost, c->stream));
+    KT(settle(t, ctr)); // synchronises; spills of the general inserts above
+    side_n = std::min<unsigned long long>(side_n, t->side_cap);
+    if (getenv("KATGPU_TRACE")) fprintf(stderr, "[katgpu] sweep_tiled: %llu keys took the side list\n", side_n);
+    if (side_n) KT(insert_hashed_direct(t, ctr, t->side_keys, side_n));
+    CU(cudaMemsetAsync(t->side_ctr, 0, 64, c->stream));
+    CU(cudaMemsetAsync(t->pend_seglen, 0, ((size_t)1 << t->pend_Pb) * t->pend_segs * 4, c->stream));
+    CU(cudaMemsetAsync(t->pend_hll, 0, kHllM * 4, c->stream));
+    t->pend_fill = 0;
+    t->pend_tiles = 0;
+    t->pend_total_tiles = 0;
+    t->pend_bound = 0;
+    return settle(t, ctr);
 }
 
 // Insert every pending key, slice by slice (sweep_kernel), after sizing the table
@@ -673,6 +925,7 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
                 return fail(KATGPU_ERR_HASH_FULL, "Hash full");
         }
     }
+    if (t->tiled) return sweep_tiled(t, ctr);
     SweepParams P{};
     P.g = t->g;
     const double per_part = t->pend_fill * (double)t->pend_segs; // keys that can target one slot
@@ -717,14 +970,15 @@ static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint6
     // keys one CTA tile sends to one slice: mean m (every position a k-mer) + up to 3 padding keys;
     // after T tiles the fullest segment holds about T*(m+2) + 4*sqrt(T*m) (a segment that still
     // overflows falls back to direct insertion inside the kernel, so this only has to be a good guess)
-    const double m = (double)kTile / (double)(1u << t->pend_Pb);
-    auto fill_after = [&](uint64_t tiles) { return (double)tiles * (m + 2.0) + 4.0 * std::sqrt((double)tiles * m); };
+    const uint64_t tile_pos = t->tiled ? kBinTile : kTile;
+    const double m = (double)tile_pos / (double)(1u << t->pend_Pb), pad = t->tiled ? 0.0 : 2.0;
+    auto fill_after = [&](uint64_t tiles) { return (double)tiles * (m + pad) + 4.0 * std::sqrt((double)tiles * m); };
     uint64_t done = 0;
     while (done < n_starts) {
         uint64_t cta_tiles = 0; // largest T with fill_after(pend_tiles + T) <= seg_cap
         {
             const double cap = (double)t->pend_seg_cap;
-            uint64_t lo = 0, hi = (uint64_t)(cap / (m + 2.0)) + 1;
+            uint64_t lo = 0, hi = (uint64_t)(cap / (m + pad)) + 1;
             while (lo < hi) {
                 const uint64_t mid = (lo + hi + 1) / 2;
                 if (fill_after(mid) <= cap) lo = mid; else hi = mid - 1;
@@ -736,30 +990,71 @@ static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint6
             KT(sweep_pending(t, ctr));
             continue;
         }
-        const uint64_t max_starts = cta_tiles * t->pend_segs * (uint64_t)kTile;
+        const uint64_t max_starts = cta_tiles * t->pend_segs * tile_pos;
         const uint64_t take = std::min(n_starts - done, max_starts);
-        PartitionParams P{};
-        P.g = t->g;
-        P.bases = in_keys ? nullptr : dev + done;
-        P.n_valid = n_valid - done;
-        P.n_starts = take;
-        P.in_keys = in_keys ? in_keys + done : nullptr;
-        P.n_keys = take;
-        P.n_tiles = (int)((take + kTile - 1) / kTile);
-        P.tma_ok = !in_keys && (reinterpret_cast<uintptr_t>(dev + done) & 15) == 0;
-        P.cta_rot = (uint32_t)(t->pend_total_tiles % t->pend_segs);
-        P.Pb = t->pend_Pb;
-        P.seg_cap = t->pend_seg_cap;
-        P.keys = t->pend_keys;
-        P.seglen = t->pend_seglen;
-        P.hll = t->pend_hll;
-        {
+        const uint64_t n_tiles = (take + tile_pos - 1) / tile_pos;
+        const uint32_t cta_rot = (uint32_t)(t->pend_total_tiles % t->pend_segs);
+        if (t->tiled) {
+            BinDst D{};
+            D.keys = t->pend_keys;
+            D.len = t->pend_seglen;
+            D.cap = t->pend_seg_cap;
+            D.stride = t->pend_segs; // segment (slice d, CTA j) = d * n_segs + j
+            D.shift = t->g.b - t->pend_Pb;
+            D.mask = (1u << t->pend_Pb) - 1;
+            D.F = 1u << t->pend_Pb;
+            D.R = t->ring1;
+            TableGeom gchk = t->g;
+            set_add_bound(gchk, ~0ULL);
+            if (in_keys) {
+                BinKeysParams B{};
+                B.g = gchk;
+                B.in_keys = in_keys + done;
+                B.n_keys = take;
+                B.cta_rot = cta_rot;
+                B.tile_keys = kBinTile;
+                B.dst = D;
+                B.side = side_list_of(t);
+                B.hll = t->pend_hll;
+                ProfScope ps(c, "bin1", c->stream);
+                launch_bin_keys(B, (int)t->pend_segs, c->stream);
+            } else {
+                BinBasesParams B{};
+                B.g = gchk;
+                B.bases = dev + done;
+                B.n_valid = n_valid - done;
+                B.n_starts = take;
+                B.n_tiles = (int)n_tiles;
+                B.tma_ok = (reinterpret_cast<uintptr_t>(dev + done) & 15) == 0;
+                B.cta_rot = cta_rot;
+                B.dst = D;
+                B.side = side_list_of(t);
+                B.hll = t->pend_hll;
+                ProfScope ps(c, "bin1", c->stream);
+                launch_bin_bases(B, (int)t->pend_segs, c->stream);
+            }
+        } else {
+            PartitionParams P{};
+            P.g = t->g;
+            P.bases = in_keys ? nullptr : dev + done;
+            P.n_valid = n_valid - done;
+            P.n_starts = take;
+            P.in_keys = in_keys ? in_keys + done : nullptr;
+            P.n_keys = take;
+            P.n_tiles = (int)n_tiles;
+            P.tma_ok = !in_keys && (reinterpret_cast<uintptr_t>(dev + done) & 15) == 0;
+            P.cta_rot = cta_rot;
+            P.Pb = t->pend_Pb;
+            P.seg_cap = t->pend_seg_cap;
+            P.keys = t->pend_keys;
+            P.seglen = t->pend_seglen;
+            P.hll = t->pend_hll;
             ProfScope ps(c, "partition", c->stream);
             launch_partition(P, (int)t->pend_segs, c->stream);
         }
         c->launches++;
         CU(cudaGetLastError());
-        t->pend_total_tiles += (uint64_t)P.n_tiles;
+        t->pend_total_tiles += n_tiles;
         t->pend_tiles = (t->pend_total_tiles + t->pend_segs - 1) / t->pend_segs;
         t->pend_fill = fill_after(t->pend_tiles);
         t->pend_bound += take;
@@ -882,14 +1177,7 @@ extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct,
     KT(sweep_pending(t, ctr));
     KT(settle(t, ctr));
     t->ended = true;
-    if (t->pend_keys) { // the pending-key buffer is only needed while counting
-        pool_free(t->ctx, t->pend_keys, t->pend_bytes);
-        cudaFree(t->pend_seglen);
-        cudaFree(t->pend_hll);
-        cudaFree(t->pend_done);
-        t->pend_keys = nullptr;
-        t->pend_seglen = t->pend_hll = t->pend_done = nullptr;
-    }
+    pend_release(t); // the pending-key buffers are only needed while counting
     if (n_distinct) *n_distinct = ctr.n_distinct;
     if (n_total) *n_total = ctr.n_total;
     return KATGPU_OK;

@@ -1,0 +1,94 @@
+// tile_kernels.cuh — the shared-memory counting path ("tiled"): two binning passes bring every
+// hashed key next to the 64 KB piece of the table (a "tile") it belongs to, then each tile is
+// updated in shared memory and written back once.  See tile_kernels.cu and DESIGN.md §3.
+#pragma once
+#include "count_kernels.cuh"
+
+namespace katgpu {
+
+constexpr int kBinTile = 4096;        // k-mer start positions per tile of the level-1 kernel (256 threads x 16)
+constexpr int kBinGroups = kBinTile / 16;
+constexpr int kBin1Threads = 256;
+constexpr int kBin2Threads = 1024;    // one CTA per SM: 32 warps hide the key-load latency, one bin per thread in the flush
+constexpr int kBin2Unroll = 4;        // keys per thread between two flushes of bin_keys_kernel (4096 per CTA)
+constexpr int kTileThreads = 512;
+constexpr int kTileBucketsLog2 = 11;  // a table tile = 2048 buckets = 8192 slots = 64 KB
+constexpr int kTileBytes = (1 << kTileBucketsLog2) * 32;
+constexpr int kMaxBins = 1024;        // fan-out of one binning pass
+constexpr int kTileHllBits = 10;      // HyperLogLog registers of the level-1 kernel (as partition_kernel)
+constexpr int kTileHllM = 1 << kTileHllBits;
+constexpr int kTileHllSampleShift = 10;
+
+// Keys that cannot take the fast way (a full staging ring or segment; in the tile kernel a full
+// home bucket or a count field about to carry) are parked here and inserted with the general
+// random-access kernel afterwards.  `reserved` lets the tile kernel refuse a tile up front when
+// the list might not hold all of its keys (the tile is then deferred, never dropped).
+struct SideList {
+    uint64_t *keys;
+    unsigned long long *n;        // keys pushed
+    unsigned long long *reserved; // tile kernel: keys that may still be pushed by tiles in flight + n
+    uint64_t cap;
+    uint32_t *deferred;           // tile kernel: ids of tiles left for the general kernel
+    uint32_t *n_deferred;
+    uint32_t deferred_cap;
+};
+
+// Destination of one binning pass: bin d of this CTA goes to segment (d * stride + offset).
+struct BinDst {
+    uint64_t *keys;   // [segment][cap]
+    uint32_t *len;    // [segment] keys present
+    uint32_t cap;     // keys per segment, multiple of 16
+    uint32_t stride;  // see above; offset depends on the kernel (CTA id, or (slice, part))
+    uint32_t shift;   // bin = (h >> shift) & mask
+    uint32_t mask;
+    uint32_t F, R;    // bins, staging-ring slots per bin
+};
+
+struct BinBasesParams {
+    TableGeom g;
+    const uint8_t *bases;
+    uint64_t n_valid, n_starts;
+    int n_tiles, tma_ok;
+    uint32_t cta_rot;
+    BinDst dst;
+    SideList side;
+    uint32_t *hll;
+};
+
+// Level 2 (and the owner side of the multi-GPU exchange): keys in, keys out.
+struct BinKeysParams {
+    TableGeom g;
+    // source A: a flat array of hashed keys, tiled over the grid (level 1 of received keys)
+    const uint64_t *in_keys;
+    uint64_t n_keys;
+    uint32_t cta_rot;
+    // source B: the level-1 segments of slice (first_slice + blockIdx.x / parts), share blockIdx.x % parts
+    const uint64_t *src_keys; // [slice][src_segs][src_cap]
+    const uint32_t *src_len;
+    uint32_t src_segs, src_cap, first_slice, parts;
+    uint32_t tile_keys;       // keys binned between two flushes
+    BinDst dst;
+    SideList side;
+    uint32_t *hll;            // source A only
+};
+
+struct TileParams {
+    TableGeom g;
+    const uint64_t *keys;  // [tile][parts][cap]
+    const uint32_t *len;
+    uint32_t cap, parts;
+    uint32_t first_tile;   // table tile of local tile 0
+    uint32_t n_tiles;
+    SideList side;
+};
+
+size_t bin_bases_smem(uint32_t F, uint32_t R);
+size_t bin_keys_smem(uint32_t F, uint32_t R);
+cudaError_t tile_configure(int *bps_bases, int *bps_tile);
+void launch_bin_bases(const BinBasesParams &P, int grid, cudaStream_t st);
+void launch_bin_keys(const BinKeysParams &P, int grid, cudaStream_t st);
+void launch_tile_insert(const TileParams &P, int grid, cudaStream_t st);
+// general insertion of every key of the listed (deferred) tiles' segments
+void launch_insert_deferred(const TileParams &P, const uint32_t *tiles, uint32_t n, cudaStream_t st);
+
+} // namespace katgpu

@@ -22,7 +22,7 @@ def workdir(tmp_path_factory):
     return d
 
 
-@pytest.mark.parametrize("path", ["direct", "partition"])
+@pytest.mark.parametrize("path", ["direct", "partition", "tiled"])
 @pytest.mark.parametrize("case", G.cases(), ids=lambda c: c["name"])
 def test_cli_output_files_byte_identical(case, path, workdir):
     out = os.path.join("expected", case["name"])  # same relative prefix as the reference run -> same headers
@@ -91,7 +91,7 @@ def test_cli_load_mode_files_byte_identical(case, jf_workdir):
         assert open(jf_workdir / out / f, "rb").read() == _jf_expected(case["name"], f), f"{case['name']}/{f}"
 
 
-@pytest.mark.parametrize("path", ["direct", "partition"])
+@pytest.mark.parametrize("path", ["direct", "partition", "tiled"])
 def test_cli_dump_hash_is_a_jellyfish_file(path, jf_workdir):
     """`kat hist -d` writes <prefix>-hash.jf<k>: the same (k-mer, count) records as the reference's
     own dump of the same input, readable by the unmodified jellyfish, and loadable again."""

@@ -11,10 +11,11 @@ from kat_b200 import binding as B
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True, params=["direct", "partition"])
+@pytest.fixture(autouse=True, params=["direct", "partition", "tiled"])
 def count_path(request, monkeypatch):
-    """Every case runs through both counting paths of libkatgpu: extract+insert in
-    read order ("direct") and partition-by-slice + L2-resident sweep ("partition")."""
+    """Every case runs through the three counting paths of libkatgpu: extract+insert in
+    read order ("direct"), partition-by-slice + L2-resident sweep ("partition"), and two binning
+    passes + shared-memory table tiles ("tiled"; tables too small for it fall back to "direct")."""
     monkeypatch.setenv("KATGPU_COUNT_PATH", request.param)
     return request.param
 
@@ -275,3 +276,19 @@ def test_add_pairs_is_hash_add(ctx, k):
     assert t.n_total == int(want.sum())
     _, bins = t.hist(1, 10000, 1)
     assert int(bins.sum()) == n
+
+
+@pytest.mark.parametrize("slots_log2,k", [(22, 27), (26, 21), (26, 32), (24, 15)])
+def test_larger_tables_many_tiles(ctx, slots_log2, k):
+    """Tables of 2^22..2^26 slots = 2^9..2^13 shared-memory tiles: both binning levels have real
+    fan-out, feeds arrive in several launches (unaligned segment tails), and a low-complexity
+    tail makes full home buckets, count-field carries (forced 6-bit field) and the side list real."""
+    s1 = seqgen.genome_reads(120_000, 9000, 150, seed=slots_log2 + k)
+    s2 = seqgen.random_stream(700_001, seed=k, n_rate=0.002)
+    s3 = np.concatenate([seqgen.low_complexity(400, 150, seed=3), seqgen.genome_reads(120_000, 5000, 150, seed=slots_log2 + k)])
+    B.lib().katgpu_debug_set_count_bits(6)
+    try:
+        gt = gpu_table(ctx, [s1, s2, s3], k, hash_size=1 << slots_log2, allow_grow=True)
+    finally:
+        B.lib().katgpu_debug_set_count_bits(0)
+    assert_same_multiset(gt, ora_table([s1, s2, s3], k))

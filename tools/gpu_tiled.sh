@@ -1,0 +1,12 @@
+#!/bin/bash
+# One gpurun call for the tiled path: its parity tests first, then benches (tiled vs partition).
+out=gpurun_out/${1:-tiled}; mkdir -p $out
+P='import json,sys; d=json.loads(sys.stdin.read()); r=d["roofline"]; e=d.get("e2e") or {}; print("value %.2f G/s ms/step %.1f  %s other %s launches %d e2e %.2f G/s" % (d["value"]/1e9, d["ms_per_step"], {k: round(v/d["steps"],2) for k,v in r["kernel_ms_by_family"].items()}, {k: round(v/d["steps"],2) for k,v in r["other_kernels_ms"].items() if v}, d["gpu_launches"], (e.get("value") or 0)/1e9))'
+(time timeout 900 python -m pytest tests -m gpu -q --maxfail=10 -k "tiled or add_pairs or load_mode or dump or larger") > $out/tests_tiled.log 2>&1; grep -E "passed|failed|^FAILED|^ERROR" $out/tests_tiled.log | head -30
+run() { name=$1; shift; echo -n "$name: "; timeout 500 env "$@" python bench.py --steps 2 --warmup 2 --no-cpu-baseline $BENCHFLAGS 2>$out/$name.err > $out/$name.json; python -c "$P" < $out/$name.json 2>/dev/null || tail -5 $out/$name.err; grep "katgpu\] sweep_tiled" $out/$name.err | sort | uniq -c | head -4; }
+BENCHFLAGS="--no-e2e --reads 8000000" run tiled_small KATGPU_COUNT_PATH=tiled KATGPU_TRACE=1
+BENCHFLAGS="--no-e2e" run tiled_full KATGPU_COUNT_PATH=tiled KATGPU_TRACE=1
+BENCHFLAGS="" run tiled_e2e KATGPU_COUNT_PATH=tiled
+BENCHFLAGS="--no-e2e --slots-log2 31" run tiled_slots31 KATGPU_COUNT_PATH=tiled KATGPU_TRACE=1
+BENCHFLAGS="--no-e2e" run partition_full A=1
+if [ "$2" = "full" ]; then (time timeout 1200 python -m pytest tests -m gpu -q --maxfail=10) > $out/tests_all.log 2>&1; grep -E "passed|failed|^FAILED|^ERROR" $out/tests_all.log | head -30; fi
