@@ -621,11 +621,11 @@ static bool want_tiled(const katgpu_table *t) {
 }
 
 // Staging-ring slots per bin for a binning pass of `tile_keys` keys over F bins: the leftover of
-// the previous flush (< 4) + mean + ~4 sigma, within `max_bytes` of shared memory (a ring that
+// the previous flush (< kBinGranule) + mean + ~4 sigma, within `max_bytes` of shared memory (a ring that
 // is too small only sends more keys the slow way).
 static uint32_t ring_slots(uint32_t F, uint32_t tile_keys, size_t max_bytes) {
     const double mean = (double)tile_keys / (double)F;
-    uint64_t R = 4 + (uint64_t)std::ceil(mean + 4.0 * std::sqrt(mean));
+    uint64_t R = kBinGranule + (uint64_t)std::ceil(mean + 4.0 * std::sqrt(mean));
     const uint64_t fit = max_bytes > (size_t)F * 8 + 16 ? (max_bytes - (size_t)F * 8 - 16) / ((size_t)F * 8) : 4;
     R = std::max<uint64_t>(4, std::min(R, fit));
     return (uint32_t)R;
@@ -694,8 +694,8 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     t->pend_bound = 0;
     t->tiled = tiled;
     if (tiled) {
-        // two CTAs of bin_bases_kernel per SM: ~104 KB each, 16.5 KB of it fixed
-        t->ring1 = ring_slots((uint32_t)nparts, kBinTile, (104u << 10) - 16896);
+        // bps_bin1 CTAs of bin_bases_kernel per SM (two: <= 111 KB each), 16.5 KB of it fixed
+        t->ring1 = ring_slots((uint32_t)nparts, kBinTile, ((c->bps_bin1 >= 3 ? 74u : 111u) << 10) - 16896);
         // side list: keys that leave the fast path (~1 % at load 0.3, ~5 % at 0.55)
         t->side_cap = std::min<uint64_t>(std::max<uint64_t>(hint / 8, 4u << 20), 512u << 20);
         t->side_bytes = t->side_cap * 8;
@@ -1141,7 +1141,10 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
     for (int b = 0; b < ring; b++) CU(cudaEventRecord(c->chunk_free[b], c->stream));
     // With the partitioned path and a long feed, insert the first half of the keys while the
     // second half is still crossing PCIe: the copy engine keeps filling the ring during the sweep.
-    const size_t mid_sweep_at = (n_chunks >= 16 && use_partition(t, n)) ? n_chunks / 2 : (size_t)-1;
+    // (KATGPU_MID_SWEEPS: how many; default 2 = after each third, measured best of 0..3)
+    int mid_sweeps = 2;
+    if (const char *e = getenv("KATGPU_MID_SWEEPS")) mid_sweeps = std::max(0, std::min(atoi(e), 8));
+    const bool mid_ok = n_chunks >= 16 && mid_sweeps > 0 && use_partition(t, n);
     size_t issued = 0;
     for (size_t i = 0; i < n_chunks; i++) {
         while (issued < n_chunks && issued < i + (size_t)ring) KT(issue_copy(issued++)); // run ahead of the kernels
@@ -1152,7 +1155,7 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
         CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
         KT(feed_device_range(t, c->chunk[b], len, starts, ctr, n));
         CU(cudaEventRecord(c->chunk_free[b], c->stream));
-        if (i + 1 == mid_sweep_at) KT(sweep_pending(t, ctr));
+        if (mid_ok && i + 1 < n_chunks && ((i + 1) * (size_t)(mid_sweeps + 1)) / n_chunks != (i * (size_t)(mid_sweeps + 1)) / n_chunks) KT(sweep_pending(t, ctr));
     }
     return KATGPU_OK;
 }

@@ -90,7 +90,8 @@ struct BinCore {
         if (pos < R) ring[(size_t)pos * F + d] = h;
         else side_push_or_insert(S, g, h, t); // ring full (sized so that this is rare)
     }
-    // Move staged keys to the segments as whole 32-byte sectors; `final` also writes the tails.
+    // Move staged keys to the segments in whole granules (kBinGranule keys, as 32-byte sector
+    // stores to consecutive addresses); `final` also writes the tails.
     // Collective: every thread of the CTA calls it.
     __device__ __forceinline__ void flush(bool final, const SideList &S, const TableGeom &g, SideTally &t) {
         __syncthreads();
@@ -106,7 +107,7 @@ struct BinCore {
                 continue;
             }
             uint64_t *seg = seg0 + (uint64_t)d * seg_stride;
-            const uint32_t aligned_end = (c + n) & ~3u;
+            const uint32_t aligned_end = (c + n) & ~(kBinGranule - 1);
             const uint32_t w = final ? n : (aligned_end > c ? aligned_end - c : 0u);
             uint32_t i = 0;
             for (; i < w && ((c + i) & 3u); i++) seg[c + i] = ring[(size_t)i * F + d]; // head of a segment a previous launch left unaligned
@@ -116,7 +117,7 @@ struct BinCore {
                 asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(seg + c + i), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
             }
             for (; i < w; i++) seg[c + i] = ring[(size_t)i * F + d]; // tail (final flush only)
-            const uint32_t r = n - w; // < 4 unless nothing could be written
+            const uint32_t r = n - w; // < kBinGranule
             for (uint32_t j = 0; j < r; j++) ring[(size_t)j * F + d] = ring[(size_t)(w + j) * F + d];
             cnt[d] = r;
             cur[d] = c + w;
@@ -152,7 +153,7 @@ struct __align__(128) BinBasesHead {
 };
 
 template <bool CANON, bool WIDE>
-__global__ void __launch_bounds__(kBin1Threads, 2) bin_bases_kernel(const __grid_constant__ BinBasesParams P) {
+__global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(const __grid_constant__ BinBasesParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     BinBasesHead &S = *reinterpret_cast<BinBasesHead *>(smem_raw);
     const TableGeom &g = P.g;
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_
         for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads) hll[i] = 0;
         __syncthreads();
         const uint32_t sshift = P.dst.shift - kTileHllSampleShift;
-        constexpr int kU = kBin2Unroll; // keys per thread per tile; host: P.tile_keys == kBin2Threads * kU
+        constexpr int kU = kBinTile / kBin2Threads; // keys per thread per tile; host: P.tile_keys == kBinTile (the level-1 ring is sized for it)
         const uint64_t n_tiles = (P.n_keys + P.tile_keys - 1) / P.tile_keys;
         for (uint64_t tile = (blockIdx.x + gridDim.x - P.cta_rot % gridDim.x) % gridDim.x; tile < n_tiles; tile += gridDim.x) {
             const uint64_t lo = tile * P.tile_keys;
@@ -295,12 +296,13 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_
                     kn[u] = i < len ? __ldg(src + i) : 0;
                 }
             };
-            if (len) fetch(0);
+            if (KATGPU_BIN2_PREFETCH && len) fetch(0);
             for (uint32_t base = 0; base < len; base += chunk) {
+                if (!KATGPU_BIN2_PREFETCH) fetch(base);
                 uint64_t kc[kBin2Unroll];
 #pragma unroll
                 for (int u = 0; u < kBin2Unroll; u++) kc[u] = kn[u];
-                if (base + chunk < len) fetch(base + chunk);
+                if (KATGPU_BIN2_PREFETCH && base + chunk < len) fetch(base + chunk);
 #pragma unroll
                 for (int u = 0; u < kBin2Unroll; u++)
                     if (base + u * kBin2Threads + tid < len) C.append(kc[u], P.side, g, tally);
@@ -328,7 +330,7 @@ __device__ __forceinline__ void tma_store_1d_and_wait(void *dst_gmem, const void
 }
 
 template <bool TAG32>
-__global__ void __launch_bounds__(kTileThreads, 2) tile_insert_kernel(const __grid_constant__ TileParams P) {
+__global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_insert_kernel(const __grid_constant__ TileParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     TileSmem &S = *reinterpret_cast<TileSmem *>(smem_raw);
     const TableGeom &g = P.g;
@@ -336,7 +338,7 @@ __global__ void __launch_bounds__(kTileThreads, 2) tile_insert_kernel(const __gr
     const uint64_t tagmask = g.tagmask, rmask = g.rmask, probe1 = 1ULL << g.rbits, one = 1ULL << g.cshift;
     const uint32_t rbits = g.rbits, cshift_hi = g.cshift - 32, inc_hi = 1u << (g.cshift - 32); // host: cshift >= 32
     const uint32_t slots_s = smem_u32(S.slots);
-    constexpr int kTileUnroll = 4;
+    constexpr int kTileUnroll = KATGPU_TILE_UNROLL;
     unsigned long long my_new = 0, my_total = 0;
     uint32_t parity = 0;
     if (tid == 0) {
@@ -548,7 +550,7 @@ cudaError_t tile_configure(int *bps_bases, int *bps_tile) {
     if ((e = cudaFuncSetAttribute(bin_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tile_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tile_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem))) != cudaSuccess) return e;
-    *bps_bases = 2; // the host sizes the staging ring so that two CTAs fit an SM
+    *bps_bases = kBin1MinCtas; // the host sizes the staging ring so that this many CTAs fit an SM
     int a = 0, b = 0;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, tile_insert_kernel<true>, kTileThreads, sizeof(TileSmem))) != cudaSuccess) return e;
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, tile_insert_kernel<false>, kTileThreads, sizeof(TileSmem));

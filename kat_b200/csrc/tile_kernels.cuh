@@ -9,9 +9,37 @@ namespace katgpu {
 constexpr int kBinTile = 4096;        // k-mer start positions per tile of the level-1 kernel (256 threads x 16)
 constexpr int kBinGroups = kBinTile / 16;
 constexpr int kBin1Threads = 256;
+#ifndef KATGPU_BIN1_MIN_CTAS
+#define KATGPU_BIN1_MIN_CTAS 2
+#endif
+constexpr int kBin1MinCtas = KATGPU_BIN1_MIN_CTAS;
 constexpr int kBin2Threads = 1024;    // one CTA per SM: 32 warps hide the key-load latency, one bin per thread in the flush
-constexpr int kBin2Unroll = 4;        // keys per thread between two flushes of bin_keys_kernel (4096 per CTA)
-constexpr int kTileThreads = 512;
+#ifndef KATGPU_BIN2_UNROLL
+#define KATGPU_BIN2_UNROLL 4
+#endif
+#ifndef KATGPU_BIN2_PREFETCH
+#define KATGPU_BIN2_PREFETCH 1
+#endif
+constexpr int kBin2Unroll = KATGPU_BIN2_UNROLL; // keys per thread between two flushes of bin_keys_kernel (level 2)
+#ifndef KATGPU_TILE_THREADS
+#define KATGPU_TILE_THREADS 384
+#endif
+#ifndef KATGPU_TILE_MIN_CTAS
+#define KATGPU_TILE_MIN_CTAS 3 // 3 x 64 KB tiles per SM: one CTA's tile load / write-back hides behind the others' key loops (measured 6 % over 512 x 2)
+#endif
+#ifndef KATGPU_TILE_UNROLL
+#define KATGPU_TILE_UNROLL 4
+#endif
+constexpr int kTileThreads = KATGPU_TILE_THREADS;
+// Keys leave the staging rings in granules of this many (x 8 bytes, aligned in the segment).
+// 4 keys = one 32-byte sector, the unit the L2 takes without a read-modify-write.  Measured:
+// 8-key granules (two adjacent sector stores) are 5 % SLOWER in both binning kernels — the
+// sectors of a 128-byte line already meet in L2 (a line lives there ~100 us) before it is
+// written back, and the bigger leftover costs ring slots.
+#ifndef KATGPU_BIN_GRANULE
+#define KATGPU_BIN_GRANULE 4
+#endif
+constexpr uint32_t kBinGranule = KATGPU_BIN_GRANULE; // 4, 8 or 16
 constexpr int kTileBucketsLog2 = 11;  // a table tile = 2048 buckets = 8192 slots = 64 KB
 constexpr int kTileBytes = (1 << kTileBucketsLog2) * 32;
 constexpr int kMaxBins = 1024;        // fan-out of one binning pass

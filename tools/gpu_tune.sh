@@ -1,0 +1,12 @@
+#!/bin/bash
+out=gpurun_out/${1:-tune}; mkdir -p $out
+P='import json,sys; d=json.loads(sys.stdin.read()); r=d["roofline"]; e=d.get("e2e") or {}; print("value %.2f G/s ms/step %.1f  %s other %s launches %d e2e %.2f G/s %.1f ms" % (d["value"]/1e9, d["ms_per_step"], {k: round(v/d["steps"],2) for k,v in r["kernel_ms_by_family"].items()}, {k: round(v/d["steps"],2) for k,v in r["other_kernels_ms"].items() if v}, d["gpu_launches"], (e.get("value") or 0)/1e9, e.get("ms_per_step") or 0))'
+run() { name=$1; shift; echo -n "$name: "; timeout 500 env "$@" python bench.py --steps 2 --warmup 2 --no-cpu-baseline $BENCHFLAGS 2>$out/$name.err > $out/$name.json; python -c "$P" < $out/$name.json 2>/dev/null || tail -5 $out/$name.err; }
+BENCHFLAGS="--no-e2e"
+run default A=1
+for v in b2u8 t384c3 tu8 b1c3; do run $v KATGPU_LIB=$PWD/kat_b200/lib/variants/libkatgpu_$v.so; done
+BENCHFLAGS=""
+run e2e_mid1 KATGPU_MID_SWEEPS=1
+run e2e_mid2 KATGPU_MID_SWEEPS=2
+run e2e_mid3 KATGPU_MID_SWEEPS=3
+run e2e_mid0 KATGPU_MID_SWEEPS=0
