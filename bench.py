@@ -51,6 +51,9 @@ B_ALG = READ_LEN / KMERS_PER_READ + 16.0
 # measured DRAM bytes per k-mer instance of K1 = partition_kernel + sweep_kernel, from the ncu --set full
 # captures summarised in profiles/r1_v2_partition_sweep_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum)
 TRAFFIC_B_PER_KMER_PARTITIONED = 26.0
+# ... and of K1 = bin_bases_kernel + bin_keys_kernel + tile_insert_kernel (profiles/r1_v3_tiled_ncu.txt):
+# 9.22 (stream read once + 8 B key written) + 15.85 (key read + written) + 16.4 (key read, 64 KB tile read + written)
+TRAFFIC_B_PER_KMER_TILED = 41.5
 
 
 def measured_peaks():
@@ -346,15 +349,19 @@ def main():
     else:
         fam, kname = ["count"], "extract_kernel<insert>"
     k_ms = sum(prof[f][0] for f in fam)
-    k_n = max(prof[f][1] for f in fam)
+    # K1 runs once per step; on the pending-key paths one run is several launches (binning passes, groups of tiles)
+    k_launches = sum(prof[f][1] for f in fam)
+    k_n = args.steps if fam != ["count"] else max(prof[f][1] for f in fam)
     k_inst = n_total * args.steps  # instances inserted on this rank's table
     achieved = (k_inst * B_ALG / 1e9) / (k_ms / 1e3) if k_ms > 0 else None  # GB/s; per launch: bytes/launch over ms/launch
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
-                "traffic": (TRAFFIC_B_PER_KMER_PARTITIONED * k_inst / max(k_n, 1)) if fam == ["partition", "sweep"] else None,
-                "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum of both kernels at 5 Gbp, scaled per k-mer (profiles/r1_v2_partition_sweep_ncu.txt)",
+                "traffic": (TRAFFIC_B_PER_KMER_PARTITIONED * k_inst / args.steps) if fam == ["partition", "sweep"] else
+                           (TRAFFIC_B_PER_KMER_TILED * k_inst / args.steps) if fam[:3] == ["bin1", "bin2", "tile"] else None,
+                "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum of the K1 kernels at 5 Gbp, scaled per k-mer to one step "
+                                  "(profiles/r1_v3_tiled_ncu.txt; r1_v2_partition_sweep_ncu.txt for the L2-sweep path)",
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_kmer": B_ALG, "kernel_ms_total": k_ms, "kernel_launches": k_n,
+                "algorithmic_bytes_per_kmer": B_ALG, "kernel_ms_total": k_ms, "kernel_launches": k_launches, "k1_passes": k_n,
                 "kernel_ms_by_family": {f: prof[f][0] for f in fam},
                 "kmers_per_launch": k_inst / k_n if k_n else None,
                 "input_only_GBps": (k_inst * (READ_LEN / KMERS_PER_READ) / 1e9) / (k_ms / 1e3) if k_ms > 0 else None,
