@@ -698,6 +698,7 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
         t->ring1 = ring_slots((uint32_t)nparts, kBinTile, ((c->bps_bin1 >= 3 ? 74u : 111u) << 10) - 16896);
         // side list: keys that leave the fast path (~1 % at load 0.3, ~5 % at 0.55)
         t->side_cap = std::min<uint64_t>(std::max<uint64_t>(hint / 8, 4u << 20), 512u << 20);
+        if (const char *e = getenv("KATGPU_SIDE_CAP")) t->side_cap = std::max<uint64_t>(16, strtoull(e, nullptr, 10)); // tests: force deferred tiles
         t->side_bytes = t->side_cap * 8;
         if (pool_alloc(c, t->side_bytes, &p) != cudaSuccess) {
             cudaGetLastError();
@@ -779,6 +780,51 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
     SideList side = side_list_of(t);
     bool general = Pb2 < 1 || Pb2 > 10; // (a table grown past 2^32 slots after binning started)
     if (const char *e = getenv("KATGPU_TILED_GENERAL")) general = general || atoi(e) != 0;
+    // sizes of the level-2 (per-tile) segments for one group of slices; smaller groups when the
+    // allocation fails, the general path when even one slice does not fit
+    uint32_t F2 = 0, spg = 0, parts = 1;
+    uint64_t cap2 = 0;
+    uint64_t *keys2 = nullptr;
+    uint32_t *len2 = nullptr;
+    size_t bytes2 = 0, len2_bytes = 0;
+    if (!general) {
+        F2 = 1u << Pb2;
+        // keys a slice can hold at most: sizing from the capacity (not from the current fill) gives
+        // every sweep of a job — and of the next job — the same buffer sizes, so the block cache hits
+        const double slice_keys = std::max(64.0, (double)t->pend_seg_cap * (double)n_segs);
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        double budget = std::min(0.80 * (double)(free_b + c->pooled_bytes), 24.0 * 1024 * 1024 * 1024);
+        if (const char *e = getenv("KATGPU_TILED_GROUP_MB")) budget = std::max(1.0, atof(e)) * 1024 * 1024;
+        const uint32_t want_ctas = (uint32_t)c->sm_count; // bin_keys_kernel: one 1024-thread CTA per SM
+        for (;;) {
+            spg = (uint32_t)std::max(1.0, std::min((double)F1, budget / (slice_keys * 8.0 * 1.3)));
+            parts = std::min<uint32_t>(std::max<uint32_t>(1, std::min<uint32_t>(8, (want_ctas + spg - 1) / spg)), n_segs);
+            for (;;) {
+                const double mean2 = slice_keys / ((double)F2 * parts);
+                cap2 = ((uint64_t)(mean2 + 6.0 * std::sqrt(mean2) + 32.0) + 15) / 16 * 16;
+                if ((double)spg * F2 * parts * cap2 * 8.0 <= budget || spg == 1) break;
+                spg = std::max<uint32_t>(1, spg * 3 / 4);
+            }
+            bytes2 = (size_t)spg * F2 * parts * cap2 * 8;
+            len2_bytes = (size_t)spg * F2 * parts * 4;
+            void *p = nullptr, *q = nullptr;
+            if (pool_alloc(c, bytes2, &p) == cudaSuccess) {
+                if (pool_alloc(c, len2_bytes, &q) == cudaSuccess) {
+                    keys2 = (uint64_t *)p;
+                    len2 = (uint32_t *)q;
+                    break;
+                }
+                pool_free(c, p, bytes2);
+            }
+            cudaGetLastError();
+            if (spg == 1) { // not even one slice's tile segments fit
+                general = true;
+                break;
+            }
+            budget *= 0.5;
+        }
+    }
     if (general) { // insert the level-1 segments as they are, the general way
         TileParams P{};
         P.g = gchk;
@@ -795,36 +841,6 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
         c->launches++;
         CU(cudaGetLastError());
     } else {
-        const uint32_t F2 = 1u << Pb2;
-        // keys a slice can hold at most: sizing from the capacity (not from the current fill) gives
-        // every sweep of a job — and of the next job — the same buffer sizes, so the block cache hits
-        const double slice_keys = std::max(64.0, (double)t->pend_seg_cap * (double)n_segs);
-        size_t free_b = 0, total_b = 0;
-        CU(cudaMemGetInfo(&free_b, &total_b));
-        double budget = std::min(0.80 * (double)(free_b + c->pooled_bytes), 24.0 * 1024 * 1024 * 1024);
-        if (const char *e = getenv("KATGPU_TILED_GROUP_MB")) budget = std::max(1.0, atof(e)) * 1024 * 1024;
-        uint32_t spg = (uint32_t)std::max(1.0, std::min((double)F1, budget / (slice_keys * 8.0 * 1.3)));
-        const uint32_t want_ctas = (uint32_t)c->sm_count; // bin_keys_kernel: one 1024-thread CTA per SM
-        uint32_t parts = std::max<uint32_t>(1, std::min<uint32_t>(8, (want_ctas + spg - 1) / spg));
-        parts = std::min(parts, n_segs);
-        uint64_t cap2 = 0;
-        for (;;) {
-            const double mean2 = slice_keys / ((double)F2 * parts);
-            cap2 = ((uint64_t)(mean2 + 6.0 * std::sqrt(mean2) + 32.0) + 15) / 16 * 16;
-            if ((double)spg * F2 * parts * cap2 * 8.0 <= budget || spg == 1) break;
-            spg = std::max<uint32_t>(1, spg * 3 / 4);
-        }
-        void *p = nullptr;
-        const size_t bytes2 = (size_t)spg * F2 * parts * cap2 * 8;
-        cudaError_t e2 = pool_alloc(c, bytes2, &p);
-        if (e2 != cudaSuccess) return fail(KATGPU_ERR_NOMEM, "sweep_tiled: cannot allocate %zu bytes for the tile segments", bytes2);
-        uint64_t *keys2 = (uint64_t *)p;
-        const size_t len2_bytes = (size_t)spg * F2 * parts * 4;
-        if (pool_alloc(c, len2_bytes, &p) != cudaSuccess) {
-            pool_free(c, keys2, bytes2);
-            return fail(KATGPU_ERR_NOMEM, "sweep_tiled: out of device memory");
-        }
-        uint32_t *len2 = (uint32_t *)p;
         // keys binned between two flushes of bin_keys_kernel and its ring (one CTA per SM, <= 200 KB)
         const uint32_t tile2 = kBin2Threads * kBin2Unroll; // bin_keys_kernel bins chunks of kBin2Unroll keys per thread
         const uint32_t ring2 = ring_slots(F2, tile2, (196u << 10) - kTileHllM * 4); // one CTA per SM

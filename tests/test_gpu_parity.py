@@ -292,3 +292,26 @@ def test_larger_tables_many_tiles(ctx, slots_log2, k):
     finally:
         B.lib().katgpu_debug_set_count_bits(0)
     assert_same_multiset(gt, ora_table([s1, s2, s3], k))
+
+
+@pytest.mark.parametrize("env", [{"KATGPU_TILED_GROUP_MB": "1"},      # many small groups of slices
+                                 {"KATGPU_TILED_GENERAL": "1"},        # level-1 segments inserted the general way
+                                 {"KATGPU_SIDE_CAP": "64"},            # side list too small: tiles deferred, rings spill to direct inserts
+                                 {"KATGPU_SIDE_CAP": "20000", "KATGPU_TILED_GROUP_MB": "2"}],
+                         ids=["small_groups", "general", "tiny_side_list", "small_side_list_and_groups"])
+def test_tiled_rare_paths(ctx, env, count_path, monkeypatch):
+    """The slow-but-exact exits of the tiled path (tile_kernels.cu): group-wise level-2 buffers,
+    the general fallback, deferred tiles and a full side list must all give the oracle's multiset."""
+    if count_path != "tiled":
+        pytest.skip("tiled path only")
+    for k_, v in env.items():
+        monkeypatch.setenv(k_, v)
+    k = 21
+    s1 = seqgen.genome_reads(150_000, 12000, 150, seed=5)
+    s2 = np.concatenate([seqgen.low_complexity(300, 150, seed=9), seqgen.random_stream(300_000, seed=2)])
+    B.lib().katgpu_debug_set_count_bits(5)
+    try:
+        gt = gpu_table(ctx, [s1, s2], k, hash_size=1 << 22, allow_grow=True)
+    finally:
+        B.lib().katgpu_debug_set_count_bits(0)
+    assert_same_multiset(gt, ora_table([s1, s2], k))

@@ -37,6 +37,32 @@ __global__ void __launch_bounds__(256) gmem_kernel(uint64_t *buf, uint64_t windo
     if (acc == 0x1234567) *sink = acc;
 }
 
+// Scattered writes of whole pieces: `lanes` adjacent lanes (1, 2, 4) write the consecutive 32-byte
+// sectors of one random 32/64/128-byte piece in ONE store instruction (coalesced by the LSU);
+// mode 1: one thread writes the 2 or 4 sectors of its piece in consecutive instructions instead.
+__global__ void __launch_bounds__(256) piece_kernel(uint64_t *buf, uint64_t window_words, int iters, int lanes, int mode, int hint) {
+    const uint32_t lane = threadIdx.x & 31, sub = lane % lanes;
+    uint64_t s = ((blockIdx.x * 256ull + threadIdx.x) / lanes) * 0x9E3779B97F4A7C15ULL + 999; // same stream for the lanes of a group
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    const uint64_t n_pieces = window_words / (4ull * (mode ? lanes : lanes));
+    for (int i = 0; i < iters; i++) {
+        const uint64_t r = rng(s);
+        uint64_t *p = buf + __umul64hi(r, n_pieces) * 4ull * lanes;
+        if (mode == 0) {
+            uint64_t *q = p + 4 * sub;
+            if (hint) asm volatile("st.global.L2::cache_hint.v4.u64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(q), "l"(r), "l"(r + 1), "l"(r + 2), "l"(r + 3), "l"(pol) : "memory");
+            else asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(q), "l"(r), "l"(r + 1), "l"(r + 2), "l"(r + 3) : "memory");
+        } else if (sub == 0) {
+            for (int j = 0; j < lanes; j++) {
+                uint64_t *q = p + 4 * j;
+                if (hint) asm volatile("st.global.L2::cache_hint.v4.u64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(q), "l"(r), "l"(r + 1), "l"(r + 2), "l"(r + 3), "l"(pol) : "memory");
+                else asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(q), "l"(r), "l"(r + 1), "l"(r + 2), "l"(r + 3) : "memory");
+            }
+        }
+    }
+}
+
 // shared-memory atomics: mode 0 atomicAdd u32 random, 1 atomicAdd u64 random, 2 ticket (st + ld + ld + st), 3 plain ld+st u32
 __global__ void __launch_bounds__(512) smem_kernel(int iters, int mode, int words, uint64_t *sink) {
     extern __shared__ uint32_t sm[];
@@ -80,6 +106,23 @@ int main() {
             printf("window %5llu MB  %-28s %8.2f G ops/s  (%.2f ms)\n", (unsigned long long)win_mb, names[mode], ops / ms / 1e6, ms);
         }
     }
+    for (int hint = 0; hint < 2; hint++)
+        for (int mode = 0; mode < 2; mode++)
+            for (int lanes : {1, 2, 4}) {
+                if (mode == 1 && lanes == 1) continue;
+                const uint64_t window_words = total_bytes / 8;
+                const int iters = 256;
+                piece_kernel<<<grid, 256>>>(buf, window_words, iters, lanes, mode, hint);
+                cudaEventRecord(a);
+                piece_kernel<<<grid, 256>>>(buf, window_words, iters, lanes, mode, hint);
+                cudaEventRecord(b); CK(cudaEventSynchronize(b));
+                float ms; cudaEventElapsedTime(&ms, a, b);
+                const double sectors = (double)grid * 256 * iters * (mode ? 1.0 : 1.0) * (mode ? (double)lanes / lanes : 1.0);
+                const double bytes = (mode == 0 ? (double)grid * 256 * iters * 32.0 : (double)grid * 256 / lanes * iters * 32.0 * lanes);
+                printf("scattered %3d-byte pieces over 8 GB, %s%s: %8.2f G sectors/s = %6.0f GB/s (%.2f ms)\n", 32 * lanes,
+                       mode ? "one thread, consecutive stores" : "one coalesced store by adjacent lanes", hint ? ", L2::evict_last" : "", bytes / 32.0 / ms / 1e6, bytes / ms / 1e6, ms);
+                (void)sectors;
+            }
     const char *sn[] = {"atomicAdd u32 smem", "atomicAdd u64 smem", "ticket st+ld+ld+st", "plain ld+st u32"};
     CK(cudaFuncSetAttribute(smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 << 10));
     for (int words : {1024, 24576}) for (int mode = 0; mode < 4; mode++) {
