@@ -787,9 +787,14 @@ int main(int argc, char **argv) {
             if (a.positional.size() != 1) throw KatError(1, "usage: kat _parse -m K [--5ptrim X] <file>");
             std::vector<unsigned char> raw;
             string err, bases;
+            Timer t0;
             if (!kat_host::read_file(a.positional[0], raw, err)) throw KatError(4, err);
+            const double t_read = t0.secs();
             const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), (int)to_u64(a.get("mer_len", "27"), "mer_len"),
                                                           (unsigned)to_u64(a.get("5ptrim", "0"), "5ptrim"), bases);
+            if (getenv("KAT_TRACE"))
+                fprintf(stderr, "[kat] read %.3f s, parse %.3f s (%zu -> %zu bytes), parser: %s\n", t_read, t0.secs() - t_read, raw.size(), bases.size(),
+                        kat_host::last_parse_was_fast() ? "fast" : "exact");
             fwrite(bases.data(), 1, bases.size(), stdout);
             return st == kat_host::ParseStatus::Ok ? 0 : st == kat_host::ParseStatus::UnsupportedFormat ? 2 : 3;
         }

@@ -12,5 +12,7 @@ bool read_file(const std::string &path, std::vector<unsigned char> &out, std::st
 
 // Append the base stream of one file image to `out` (records separated by 'N').
 ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out);
+// Which route the last parse_sequence_file call took: true = the validated regular-layout fast path.
+bool last_parse_was_fast();
 
 } // namespace kat_host

@@ -621,11 +621,11 @@ static bool want_tiled(const katgpu_table *t) {
 }
 
 // Staging-ring slots per bin for a binning pass of `tile_keys` keys over F bins: the leftover of
-// the previous flush (< kBinGranule) + mean + ~4 sigma, within `max_bytes` of shared memory (a ring that
+// the previous flush (< granule) + mean + ~4 sigma, within `max_bytes` of shared memory (a ring that
 // is too small only sends more keys the slow way).
-static uint32_t ring_slots(uint32_t F, uint32_t tile_keys, size_t max_bytes) {
+static uint32_t ring_slots(uint32_t F, uint32_t tile_keys, size_t max_bytes, uint32_t granule) {
     const double mean = (double)tile_keys / (double)F;
-    uint64_t R = kBinGranule + (uint64_t)std::ceil(mean + 4.0 * std::sqrt(mean));
+    uint64_t R = granule + (uint64_t)std::ceil(mean + 4.0 * std::sqrt(mean));
     const uint64_t fit = max_bytes > (size_t)F * 8 + 16 ? (max_bytes - (size_t)F * 8 - 16) / ((size_t)F * 8) : 4;
     R = std::max<uint64_t>(4, std::min(R, fit));
     return (uint32_t)R;
@@ -695,7 +695,7 @@ static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) 
     t->tiled = tiled;
     if (tiled) {
         // bps_bin1 CTAs of bin_bases_kernel per SM (two: <= 111 KB each), 16.5 KB of it fixed
-        t->ring1 = ring_slots((uint32_t)nparts, kBinTile, ((c->bps_bin1 >= 3 ? 74u : 111u) << 10) - 16896);
+        t->ring1 = ring_slots((uint32_t)nparts, kBinTile, ((c->bps_bin1 >= 3 ? 74u : 111u) << 10) - 16896, kBin1Granule);
         // side list: keys that leave the fast path (~1 % at load 0.3, ~5 % at 0.55)
         t->side_cap = std::min<uint64_t>(std::max<uint64_t>(hint / 8, 4u << 20), 512u << 20);
         if (const char *e = getenv("KATGPU_SIDE_CAP")) t->side_cap = std::max<uint64_t>(16, strtoull(e, nullptr, 10)); // tests: force deferred tiles
@@ -843,7 +843,7 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
     } else {
         // keys binned between two flushes of bin_keys_kernel and its ring (one CTA per SM, <= 200 KB)
         const uint32_t tile2 = kBin2Threads * kBin2Unroll; // bin_keys_kernel bins chunks of kBin2Unroll keys per thread
-        const uint32_t ring2 = ring_slots(F2, tile2, (196u << 10) - kTileHllM * 4); // one CTA per SM
+        const uint32_t ring2 = ring_slots(F2, tile2, (196u << 10) - kTileHllM * 4, kBin2Granule); // one CTA per SM
         if (getenv("KATGPU_TRACE"))
             fprintf(stderr, "[katgpu] sweep_tiled: F1=%u F2=%u slices/group=%u parts=%u cap2=%llu ring1=%u ring2=%u tile2=%u level-2 buffer %.1f MB side cap %llu\n",
                     F1, F2, spg, parts, (unsigned long long)cap2, t->ring1, ring2, tile2, bytes2 / 1048576.0, (unsigned long long)t->side_cap);

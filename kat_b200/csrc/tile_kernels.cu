@@ -59,6 +59,7 @@ __device__ __forceinline__ void tally_flush(const TableGeom &g, SideTally &t) {
 
 // ---- staging ring: F bins x R slots, slot-major so that the flush (one thread per bin) reads
 // consecutive words -------------------------------------------------------------------------------
+template <uint32_t G> // keys per granule written to a segment: 4 (one sector) or 8 (lane pairs write 64 bytes per request)
 struct BinCore {
     uint64_t *ring;  // [R][F]
     uint32_t *cnt;   // [F] keys staged (may run past R: those keys went to the side list)
@@ -90,37 +91,79 @@ struct BinCore {
         if (pos < R) ring[(size_t)pos * F + d] = h;
         else side_push_or_insert(S, g, h, t); // ring full (sized so that this is rare)
     }
-    // Move staged keys to the segments in whole granules (kBinGranule keys, as 32-byte sector
-    // stores to consecutive addresses); `final` also writes the tails.
-    // Collective: every thread of the CTA calls it.
+    // One bin, one thread, any state: unaligned segment head (a previous launch ended there),
+    // final flush (tails are written too), full segment (keys go to the side list).
+    __device__ __forceinline__ void flush_bin_serial(uint32_t d, uint32_t n, uint32_t c, bool final, const SideList &S, const TableGeom &g, SideTally &t) {
+        if (c + n > cap) { // segment full (sized by the host so that this is rare)
+            for (uint32_t i = 0; i < n; i++) side_push_or_insert(S, g, ring[(size_t)i * F + d], t);
+            cnt[d] = 0;
+            return;
+        }
+        uint64_t *seg = seg0 + (uint64_t)d * seg_stride;
+        const uint32_t aligned_end = (c + n) & ~(G - 1);
+        const uint32_t w = final ? n : (aligned_end > c ? aligned_end - c : 0u);
+        uint32_t i = 0;
+        for (; i < w && ((c + i) & 3u); i++) seg[c + i] = ring[(size_t)i * F + d]; // head of a segment a previous launch left unaligned
+        for (; i + 4 <= w; i += 4) {
+            const uint64_t k0 = ring[(size_t)i * F + d], k1 = ring[(size_t)(i + 1) * F + d], k2 = ring[(size_t)(i + 2) * F + d],
+                           k3 = ring[(size_t)(i + 3) * F + d];
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(seg + c + i), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
+        }
+        for (; i < w; i++) seg[c + i] = ring[(size_t)i * F + d]; // tail (final flush only)
+        const uint32_t r = n - w; // < G
+        for (uint32_t j = 0; j < r; j++) ring[(size_t)j * F + d] = ring[(size_t)(w + j) * F + d];
+        cnt[d] = r;
+        cur[d] = c + w;
+    }
+    // Move staged keys to the segments in whole granules of G keys (32-byte sector stores);
+    // `final` also writes the tails.  Collective: every thread of the CTA calls it.
+    // G == 8: the two sectors of a granule are written by ADJACENT LANES in one store instruction
+    // (lane 2j and 2j+1 first serve bin 2j, then bin 2j+1; the owner's fill state travels by
+    // shuffle), so that HBM sees one 64-byte request instead of two sector requests — it takes
+    // ~35 G scattered write requests per second whatever their size.
     __device__ __forceinline__ void flush(bool final, const SideList &S, const TableGeom &g, SideTally &t) {
         __syncthreads();
+        if (G == 8 && (F & 31u) == 0 && !final) {
+            const uint32_t lane = threadIdx.x & 31u, sub = lane & 1u;
+            for (uint32_t d = threadIdx.x; d < F; d += blockDim.x) { // warp-uniform trip count (F and blockDim are multiples of 32)
+                const uint32_t n = min(cnt[d], R), c = cur[d];
+                const bool simple = n > 0 && (c & 7u) == 0 && c + n <= cap;
+                const uint32_t w = simple ? (n & ~7u) : 0u;
+                if (!simple) {
+                    if (n) flush_bin_serial(d, n, c, false, S, g, t);
+                    else cnt[d] = 0;
+                }
+#pragma unroll
+                for (uint32_t phase = 0; phase < 2; phase++) {
+                    const uint32_t src = (lane & ~1u) | phase;
+                    const uint32_t wb = __shfl_sync(0xffffffffu, w, src), cb = __shfl_sync(0xffffffffu, c, src);
+                    const uint32_t db = (d & ~1u) | phase;
+                    const uint64_t *col = ring + db;
+                    uint64_t *dst = seg0 + (uint64_t)db * seg_stride + cb;
+                    for (uint32_t i = 4 * sub; i < wb; i += 8) {
+                        const uint64_t k0 = col[(size_t)i * F], k1 = col[(size_t)(i + 1) * F], k2 = col[(size_t)(i + 2) * F], k3 = col[(size_t)(i + 3) * F];
+                        asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
+                    }
+                }
+                __syncwarp(); // both lanes of a pair have read a bin's rows before its owner moves the leftover
+                if (simple) {
+                    const uint32_t r = n - w; // < 8
+                    if (w)
+                        for (uint32_t j = 0; j < r; j++) ring[(size_t)j * F + d] = ring[(size_t)(w + j) * F + d];
+                    cnt[d] = r;
+                    cur[d] = c + w;
+                }
+            }
+            __syncthreads();
+            return;
+        }
         for (uint32_t d = threadIdx.x; d < F; d += blockDim.x) {
             const uint32_t n = min(cnt[d], R), c = cur[d];
             if (n == 0) {
                 cnt[d] = 0;
                 continue;
             }
-            if (c + n > cap) { // segment full (sized by the host so that this is rare)
-                for (uint32_t i = 0; i < n; i++) side_push_or_insert(S, g, ring[(size_t)i * F + d], t);
-                cnt[d] = 0;
-                continue;
-            }
-            uint64_t *seg = seg0 + (uint64_t)d * seg_stride;
-            const uint32_t aligned_end = (c + n) & ~(kBinGranule - 1);
-            const uint32_t w = final ? n : (aligned_end > c ? aligned_end - c : 0u);
-            uint32_t i = 0;
-            for (; i < w && ((c + i) & 3u); i++) seg[c + i] = ring[(size_t)i * F + d]; // head of a segment a previous launch left unaligned
-            for (; i + 4 <= w; i += 4) {
-                const uint64_t k0 = ring[(size_t)i * F + d], k1 = ring[(size_t)(i + 1) * F + d], k2 = ring[(size_t)(i + 2) * F + d],
-                               k3 = ring[(size_t)(i + 3) * F + d];
-                asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(seg + c + i), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
-            }
-            for (; i < w; i++) seg[c + i] = ring[(size_t)i * F + d]; // tail (final flush only)
-            const uint32_t r = n - w; // < kBinGranule
-            for (uint32_t j = 0; j < r; j++) ring[(size_t)j * F + d] = ring[(size_t)(w + j) * F + d];
-            cnt[d] = r;
-            cur[d] = c + w;
+            flush_bin_serial(d, n, c, final, S, g, t);
         }
         __syncthreads();
     }
@@ -161,7 +204,7 @@ __global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(c
     const uint32_t k = g.k, sh = g.sh;
     const uint32_t kmask_lo = (uint32_t)g.kmask, kmask_hi = (uint32_t)(g.kmask >> 32);
     const uint32_t sshift = P.dst.shift - kTileHllSampleShift; // host: dst.shift >= 10
-    BinCore C;
+    BinCore<kBin1Granule> C;
     C.init(P.dst, blockIdx.x, smem_raw + sizeof(BinBasesHead));
     for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin1Threads) S.hll[i] = 0;
     SideTally tally;
@@ -247,9 +290,10 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_
     const TableGeom &g = P.g;
     const uint32_t tid = threadIdx.x;
     SideTally tally;
-    BinCore C;
+    BinCore<kBin1Granule> C1; // a flat source fills level-1 segments (ring sized like bin_bases_kernel's)
+    BinCore<kBin2Granule> C;
     if (P.in_keys) { // source A: flat array, tiles strided over the grid, per-CTA destination segments
-        C.init(P.dst, blockIdx.x, smem_raw + kTileHllM * 4);
+        C1.init(P.dst, blockIdx.x, smem_raw + kTileHllM * 4);
         for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads) hll[i] = 0;
         __syncthreads();
         const uint32_t sshift = P.dst.shift - kTileHllSampleShift;
@@ -266,14 +310,14 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_
 #pragma unroll
             for (int u = 0; u < kU; u++) {
                 if (lo + (uint64_t)u * kBin2Threads + tid < P.n_keys) {
-                    C.append(kc[u], P.side, g, tally);
+                    C1.append(kc[u], P.side, g, tally);
                     hll_sample(hll, kc[u], sshift);
                 }
             }
-            C.flush(false, P.side, g, tally);
+            C1.flush(false, P.side, g, tally);
         }
-        C.flush(true, P.side, g, tally);
-        C.store_lengths();
+        C1.flush(true, P.side, g, tally);
+        C1.store_lengths();
         for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads)
             if (hll[i]) atomicMax(P.hll + i, hll[i]);
     } else { // source B: the level-1 segments of one slice, one share of them per CTA

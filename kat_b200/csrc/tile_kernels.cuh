@@ -31,15 +31,16 @@ constexpr int kBin2Unroll = KATGPU_BIN2_UNROLL; // keys per thread between two f
 #define KATGPU_TILE_UNROLL 4
 #endif
 constexpr int kTileThreads = KATGPU_TILE_THREADS;
-// Keys leave the staging rings in granules of this many (x 8 bytes, aligned in the segment).
-// 4 keys = one 32-byte sector, the unit the L2 takes without a read-modify-write.  Measured:
-// 8-key granules (two adjacent sector stores) are 5 % SLOWER in both binning kernels — the
-// sectors of a 128-byte line already meet in L2 (a line lives there ~100 us) before it is
-// written back, and the bigger leftover costs ring slots.
-#ifndef KATGPU_BIN_GRANULE
-#define KATGPU_BIN_GRANULE 4
+// Keys leave the staging rings in granules of this many (x 8 bytes, aligned in the segment):
+// 4 = one 32-byte sector per request; 8 = lane pairs write 64 bytes per request (BinCore::flush).
+#ifndef KATGPU_BIN1_GRANULE
+#define KATGPU_BIN1_GRANULE 4
 #endif
-constexpr uint32_t kBinGranule = KATGPU_BIN_GRANULE; // 4, 8 or 16
+#ifndef KATGPU_BIN2_GRANULE
+#define KATGPU_BIN2_GRANULE 4
+#endif
+constexpr uint32_t kBin1Granule = KATGPU_BIN1_GRANULE; // level-1 segments (bin_bases_kernel; bin_keys_kernel on a flat source)
+constexpr uint32_t kBin2Granule = KATGPU_BIN2_GRANULE; // level-2 (per-tile) segments
 constexpr int kTileBucketsLog2 = 11;  // a table tile = 2048 buckets = 8192 slots = 64 KB
 constexpr int kTileBytes = (1 << kTileBucketsLog2) * 32;
 constexpr int kMaxBins = 1024;        // fan-out of one binning pass

@@ -53,8 +53,10 @@ def test_product_does_not_reference_the_oracle():
     assert "oracle" not in out
 
 
-def _kat_parse(path, k, trim=0):
-    r = subprocess.run([KAT, "_parse", "-m", str(k), "--5ptrim", str(trim), path], capture_output=True)
+def _kat_parse(path, k, trim=0, want_route=None):
+    r = subprocess.run([KAT, "_parse", "-m", str(k), "--5ptrim", str(trim), path], capture_output=True, env=dict(os.environ, KAT_TRACE="1"))
+    if want_route is not None:
+        assert b"parser: " + want_route in r.stderr, r.stderr
     return r.stdout, {0: 0, 2: -1, 3: -2}[r.returncode]
 
 
@@ -101,3 +103,87 @@ def test_host_parser_matches_oracle_on_random_files(seed, tmp_path):
     p.write_bytes(data)
     for k, trim in [(5, 0), (27, 0), (21, int(rng.integers(1, 12)))]:
         assert _kat_parse(str(p), k, trim) == O.parse_file(data, k, trim), (seed, k, trim)
+
+
+# ---- the parser's fast paths (regular 4-line FASTQ / FASTA layouts, parsed piece-wise in parallel)
+def _regular_file(rng, fastq, n_records, crlf=False, tricky_quals=True, no_final_newline=False, wrap=0):
+    nl = b"\r\n" if crlf else b"\n"
+    out = bytearray()
+    for i in range(n_records):
+        n = int(rng.integers(12, 400)) if rng.random() < 0.97 else int(rng.integers(4000, 9000))
+        seq = bytes(rng.choice(np.frombuffer(b"ACGTacgtNRY-", dtype=np.uint8), n, p=[.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .01, .01]))
+        if fastq:
+            q = bytes(rng.choice(np.frombuffer(b"I@+>#5" if tricky_quals else b"IJK#5", dtype=np.uint8), n))
+            plus = b"+" if rng.random() < 0.7 else b"+r%d again" % i
+            out += b"@r%d/1 x@y+z" % i + nl + seq + nl + plus + nl + q + nl
+        else:
+            w = wrap or n
+            out += b">ctg%d len=%d" % (i, n) + nl + nl.join(seq[j:j + w] for j in range(0, n, w)) + nl
+    if no_final_newline:
+        out = out[:-len(nl)]
+    return bytes(out)
+
+
+@pytest.mark.parametrize("fastq,kw", [(True, {}), (True, {"crlf": True}), (True, {"no_final_newline": True}),
+                                      (False, {}), (False, {"wrap": 70}), (False, {"wrap": 61, "no_final_newline": True}),
+                                      (False, {"wrap": 70, "crlf": True})],
+                         ids=["fq", "fq_crlf", "fq_no_final_nl", "fa", "fa_wrapped", "fa_wrapped_no_final_nl", "fa_crlf"])
+@pytest.mark.parametrize("piece,threads", [(700, 3), (5000, 1), (1 << 24, 4)])
+def test_host_parser_fast_paths_equal_the_emulation(fastq, kw, piece, threads, tmp_path, monkeypatch):
+    """Regular layouts go through the memchr fast path, cut in pieces and parsed by several
+    threads; the result must be the byte stream of the character-level emulation of the
+    reference parser (forced with KAT_PARSE_EXACT_ONLY) and of the oracle."""
+    rng = np.random.default_rng(piece + threads + len(kw) + fastq)
+    data = _regular_file(rng, fastq, 600, **kw)
+    p = tmp_path / ("r.fq" if fastq else "r.fa")
+    p.write_bytes(data)
+    for k, trim in [(27, 0), (21, 5), (5, 11)]:
+        monkeypatch.setenv("KAT_PARSE_PIECE_BYTES", str(piece))
+        monkeypatch.setenv("KAT_PARSE_THREADS", str(threads))
+        monkeypatch.delenv("KAT_PARSE_EXACT_ONLY", raising=False)
+        # FASTA with --5ptrim keeps the reference's per-buffer quirk: emulation only; a FASTQ whose
+        # last line lacks its newline is "Invalid fastq" territory: emulation only
+        expect_fast = not (not fastq and trim) and not (fastq and kw.get("no_final_newline"))
+        fast = _kat_parse(str(p), k, trim, b"fast" if expect_fast else b"exact")
+        monkeypatch.setenv("KAT_PARSE_EXACT_ONLY", "1")
+        exact = _kat_parse(str(p), k, trim, b"exact")
+        assert fast == exact == O.parse_file(data, k, trim), (k, trim)
+
+
+@pytest.mark.parametrize("mutate", ["blank_line", "multi_line_seq", "plus_in_seq", "short_qual", "seq_shorter_than_trim",
+                                    "gt_in_fasta_seq", "at_seq", "trailing_garbage"])
+def test_host_parser_irregular_inputs_fall_back(mutate, tmp_path, monkeypatch):
+    """Anything outside the regular layouts must come out exactly as the emulation gives it."""
+    rng = np.random.default_rng(len(mutate))
+    fastq = mutate != "gt_in_fasta_seq"
+    recs = _regular_file(rng, fastq, 40, tricky_quals=False).split(b"\n")
+    i = 4 * 17 + 1 if fastq else 2 * 17 + 1  # the sequence line of record 17
+    if mutate == "blank_line":
+        recs.insert(i - 1, b"")
+    elif mutate == "multi_line_seq":
+        s = recs[i]
+        recs[i:i + 1] = [s[:5], s[5:]]
+        q = recs[i + 3]
+        recs[i + 3:i + 4] = [q[:7], q[7:]]
+    elif mutate == "plus_in_seq":
+        recs[i] = recs[i][:3] + b"+" + recs[i][4:]
+    elif mutate == "short_qual":
+        recs[i + 2] = recs[i + 2][:-2]
+    elif mutate == "seq_shorter_than_trim":
+        recs[i] = recs[i][:3]
+        recs[i + 2] = recs[i + 2][:3]
+    elif mutate == "gt_in_fasta_seq":
+        recs[i] = recs[i][:6] + b">" + recs[i][7:]
+    elif mutate == "at_seq":
+        recs[i] = b"@" + recs[i][1:]
+    elif mutate == "trailing_garbage":
+        recs.append(b"garbage without newline")
+    data = b"\n".join(recs)
+    p = tmp_path / ("m.fq" if fastq else "m.fa")
+    p.write_bytes(data)
+    monkeypatch.setenv("KAT_PARSE_PIECE_BYTES", "900")
+    for k, trim in [(21, 0), (21, 6)]:
+        monkeypatch.delenv("KAT_PARSE_EXACT_ONLY", raising=False)
+        fast = _kat_parse(str(p), k, trim, b"exact")  # the fast path must have refused the file
+        monkeypatch.setenv("KAT_PARSE_EXACT_ONLY", "1")
+        assert fast == _kat_parse(str(p), k, trim) == O.parse_file(data, k, trim), (mutate, k, trim)
