@@ -157,7 +157,7 @@ def run_reference_hist(fastq, threads, slots, workdir):
     return wall, phases, out
 
 
-def cpu_reference_sample(ctx_or_none, sample_reads, threads, workdir, stream=None):
+def cpu_reference_sample(ctx_or_none, sample_reads, threads, workdir, stream=None, keep_fastq=False):
     """Time the reference on `sample_reads` reads of the workload (reads
     [0, sample_reads) of rank 0's shard).  Returns dict + the reference's bins."""
     import numpy as np
@@ -171,8 +171,24 @@ def cpu_reference_sample(ctx_or_none, sample_reads, threads, workdir, stream=Non
     slots = 1 << max(20, (n_kmers_nominal - 1).bit_length())  # no doubling for this sample
     wall, phases, hist = run_reference_hist(fq, threads, slots, workdir)
     _, bins = O.read_hist(hist)
-    os.unlink(fq)
+    if not keep_fastq:
+        os.unlink(fq)
     return wall, phases, bins, slots
+
+
+def run_product_cli_hist(fastq, slots, workdir):
+    """The product's own `kat hist` binary (C++ front-end over libkatgpu) on the same FASTQ file
+    with the same options: file open -> parse -> count -> bin -> output file written.
+    Returns (wall seconds, output path)."""
+    kat = os.path.join(ROOT, "kat_b200", "bin", "kat")
+    out = os.path.join(workdir, "ours.hist")
+    t0 = time.perf_counter()
+    r = subprocess.run([kat, "hist", f"-m{K}", f"-H{slots}", "-o", out, fastq], cwd=workdir, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=1800)
+    wall = time.perf_counter() - t0
+    if r.returncode != 0:
+        raise RuntimeError("kat_b200/bin/kat failed: " + r.stdout[-400:])
+    return wall, out
 
 
 def main():
@@ -407,12 +423,33 @@ def main():
             try:
                 stream = np.empty(sample * (READ_LEN + 1), dtype=np.uint8)
                 ctx.d2h(stream, d_bases)
-                wall, phases, ref_bins, slots = cpu_reference_sample(ctx, sample, threads, work, stream)
+                wall, phases, ref_bins, slots = cpu_reference_sample(ctx, sample, threads, work, stream, keep_fastq=True)
+                # R2 of SURVEY.md §8(d): the same FILE through the product's CLI, output FILE compared byte for byte
+                try:
+                    fq = os.path.join(work, "sample.fastq")
+                    run_product_cli_hist(fq, slots, work)  # first run pays the CUDA context + module load of a new process
+                    cli_wall, ours = run_product_cli_hist(fq, slots, work)
+                    a_, b_ = open(ours, "rb").read(), open(os.path.join(work, "ref.hist"), "rb").read()
+                    same = a_ == b_
+                    line["cli_file"] = {"wall_s": cli_wall, "reference_wall_s": wall, "output_file_identical": bool(same),
+                                        "what": f"kat_b200/bin/kat hist -m27 -H{slots} on the sample FASTQ ({os.path.getsize(fq)} bytes, in /dev/shm): "
+                                                "process start, file read, host parse, H2D, count, bin, hist file written"}
+                    if not same:
+                        for la, lb in zip(a_.splitlines(), b_.splitlines()):
+                            if la != lb:
+                                line["cli_file"]["first_difference"] = [la[:120].decode(errors="replace"), lb[:120].decode(errors="replace")]
+                                break
+                    os.unlink(fq)
+                except Exception as ex:  # never lose the bench line over the extra measurement
+                    line["cli_file"] = {"error": str(ex)[:300]}
                 t = ctx.count_begin(K, True, slots, True)
                 t.feed(stream).end()
                 _, gbins = t.hist(1, 10000, 1)
                 n_inst = t.n_total
                 t.free()
+                if "wall_s" in line.get("cli_file", {}):
+                    line["cli_file"]["value"] = n_inst / line["cli_file"]["wall_s"]
+                    line["cli_file"]["unit"] = "k-mers/s"
                 line["cpu_baseline"] = {
                     "value": n_inst / wall, "unit": "k-mers/s", "cores": threads, "kind": "reference",
                     "sample": f"first {sample} reads ({n_inst} k-mer instances) of the workload written as FASTQ; "

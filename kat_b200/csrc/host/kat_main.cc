@@ -157,9 +157,13 @@ string leaf(const string &p) {
     const size_t s = p.find_last_of('/');
     return s == string::npos ? p : p.substr(s + 1);
 }
-string join(const vector<string> &v, bool leaves) {
+// JellyfishHelper::isPipe (lib/src/jellyfish_helper.cc:258-260): anything under /proc or /dev —
+// including regular files in /dev/shm — is "a pipe": printed as <pipe>, assumed to be a sequence
+// file, exempt from the existence check.
+bool is_pipe(const string &p) { return p.rfind("/proc", 0) == 0 || p.rfind("/dev", 0) == 0; }
+string join(const vector<string> &v, bool leaves) { // leaves: InputHandler::fileName, else InputHandler::pathString
     string s;
-    for (auto &p : v) s += (leaves ? leaf(p) : p) + " ";
+    for (auto &p : v) s += (leaves ? leaf(p) : is_pipe(p) ? string("<pipe>") : p) + " ";
     while (!s.empty() && s.back() == ' ') s.pop_back(); // boost::trim_right_copy
     return s;
 }
@@ -178,6 +182,7 @@ string ext_of(const string &p) {
 }
 // JellyfishHelper::isSequenceFile (lib/src/jellyfish_helper.cc:270-307): by extension, else by first byte
 bool is_sequence_file(const string &path) {
+    if (is_pipe(path)) return true; // lib/src/jellyfish_helper.cc:273
     string e = lower(ext_of(path));
     string stem = path;
     if (e == ".gz") {
@@ -233,7 +238,7 @@ struct Input {
     }
     void validate() { // InputHandler::validateInput (lib/src/input_handler.cc:99-136)
         for (auto &p : files) {
-            if (!exists(p)) throw KatError(4, "Could not find input file at: " + p + "; please check the path and try again.");
+            if (!is_pipe(p) && !exists(p)) throw KatError(4, "Could not find input file at: " + p + "; please check the path and try again.");
             // `start` is never cleared in the reference, so the mode is simply that of the last
             // file and the "Cannot mix sequence files and jellyfish hashes" check cannot fire
             load_mode = !is_sequence_file(p);

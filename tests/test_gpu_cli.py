@@ -123,3 +123,19 @@ def test_cli_comp_dump_hashes_and_symlink(jf_workdir):
     d = subprocess.run([KAT, "_jfdump", "cd/c-hash2.jf21"], cwd=jf_workdir, capture_output=True, text=True)
     assert d.returncode == 0 and "k=21 canonical=1" in d.stdout.splitlines()[0]
     assert open(jf_workdir / "cd" / "c-main.mx", "rb").read() == _jf_expected("load_comp_hash_vs_reads_k21", "c-main.mx")
+
+
+@pytest.mark.skipif(not os.path.isdir("/dev/shm"), reason="no /dev/shm")
+def test_cli_dev_paths_are_pipes(workdir):
+    """JellyfishHelper::isPipe: every path under /dev or /proc — a regular file in /dev/shm too —
+    is printed as <pipe> in the output headers (InputHandler::pathString, lib/src/input_handler.cc:160-170)."""
+    import tempfile
+    d = tempfile.mkdtemp(prefix="katcli_", dir="/dev/shm")
+    try:
+        shutil.copy(workdir / "inputs" / "synth_c.fa", os.path.join(d, "c.fa"))
+        r = subprocess.run([KAT, "hist", "-m21", "-o", os.path.join(d, "h"), os.path.join(d, "c.fa")], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        head = open(os.path.join(d, "h")).read().splitlines()[:5]
+        assert head[0] == "# Title:21-mer spectra for: c.fa" and head[4] == "# Input 1:<pipe>"
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
