@@ -13,10 +13,14 @@ resident base stream, walk the table into the histogram bins.
 `value`  : k-mer instances / s with the base stream already resident in HBM.
 `e2e`    : same job through katgpu_count_feed with the base stream in pinned
            HOST memory (H2D inside the timed region) and the bins read back.
-`roofline`: dominant kernel (extract+insert) — algorithmic bytes / CUDA-event time.
+`roofline`: K1 = extract + canonicalise + insert (bin_bases + bin_keys + tile_insert kernels on the
+           default path) — algorithmic bytes / CUDA-event time of those kernels; `traffic` = their
+           DRAM bytes from the committed ncu capture.
 `cpu_baseline`: the unmodified reference binary (oracle/_ref/kat, built by
            oracle/ref.mk) timed on this box's host cores on a bounded sample of
            the same reads, its histogram compared bit-for-bit with the GPU's.
+`cli_file`: the same sample FILE through the product's own `kat hist` binary (process start to
+           histogram file written) next to the reference's wall time, output files compared byte for byte.
 
 At N > 1 (torchrun, one rank per GPU) reads are sharded by record, every k-mer
 is routed to its owner rank (hash partition), exchanged, inserted by the owner,
