@@ -1,4 +1,4 @@
-// partition_kernels.cu — the L2-resident counting path.
+// partition_kernels.cu — the L2-resident counting path (selectable with KATGPU_COUNT_PATH=partition).
 //
 // Measured on B200: inserting k-mers in read order makes every probe a random
 // HBM line fetch and tops out at ~15.6 G inserts/s whatever the occupancy
