@@ -257,16 +257,46 @@ void phase_done(const Timer &t) {
     cout.flush();
 }
 
+// Files at least this large (KAT_STREAM_BYTES) are read, parsed and counted block by block
+// (KAT_STREAM_BLOCK bytes at a time) when they are in a regular layout: host memory stays at a
+// few blocks instead of file + base stream.
+size_t env_size(const char *name, size_t dflt) {
+    const char *e = getenv(name);
+    return e ? (size_t)strtoull(e, nullptr, 10) : dflt;
+}
+size_t file_size_or_zero(const string &p) {
+    struct stat st;
+    return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode) ? (size_t)st.st_size : 0;
+}
+
 // InputHandler::count (lib/src/input_handler.cc:180-202) on the GPU
-void count_input(katgpu_ctx *ctx, Input &in, int k, bool allow_grow) {
+void count_input(katgpu_ctx *ctx, Input &in, int k, bool allow_grow, bool allow_streaming = true) {
     Timer t;
-    cout << "Input " << in.index << " is a sequence file.  Counting kmers for input " << in.index << " (" << join(in.files, false) << ") ...";
-    cout.flush();
+    if (allow_streaming) {
+        cout << "Input " << in.index << " is a sequence file.  Counting kmers for input " << in.index << " (" << join(in.files, false) << ") ...";
+        cout.flush();
+    }
     gpu_check(katgpu_count_begin(ctx, k, in.canonical ? 1 : 0, in.hash_size, allow_grow ? 1 : 0, &in.table));
+    const size_t stream_from = env_size("KAT_STREAM_BYTES", (size_t)2 << 30), block = env_size("KAT_STREAM_BLOCK", (size_t)512 << 20);
     std::vector<unsigned char> raw;
     std::string bases;
     for (size_t i = 0; i < in.files.size(); i++) {
         string err;
+        if (allow_streaming && file_size_or_zero(in.files[i]) >= stream_from) {
+            katgpu_status bad = KATGPU_OK;
+            const int r = kat_host::stream_regular_file(in.files[i], in.trim5p[i], block, [&](const char *b, size_t n) {
+                bad = katgpu_count_feed(in.table, b, n);
+                return bad == KATGPU_OK;
+            }, err);
+            gpu_check(bad);
+            if (r == 1) continue;
+            if (r < 0) { // irregular after some blocks were counted: start this input over, whole files at a time
+                katgpu_table_free(in.table);
+                in.table = nullptr;
+                count_input(ctx, in, k, allow_grow, false);
+                return;
+            }
+        }
         if (!kat_host::read_file(in.files[i], raw, err)) throw KatError(4, err);
         bases.clear();
         const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), k, in.trim5p[i], bases);
@@ -793,6 +823,21 @@ int main(int argc, char **argv) {
             std::vector<unsigned char> raw;
             string err, bases;
             Timer t0;
+            if (file_size_or_zero(a.positional[0]) >= env_size("KAT_STREAM_BYTES", (size_t)2 << 30)) { // the streaming route, blocks joined by 'N'
+                size_t n_blocks = 0;
+                const int r = kat_host::stream_regular_file(a.positional[0], (unsigned)to_u64(a.get("5ptrim", "0"), "5ptrim"),
+                                                            env_size("KAT_STREAM_BLOCK", (size_t)512 << 20), [&](const char *b, size_t n) {
+                                                                if (n_blocks++) bases += 'N';
+                                                                bases.append(b, n);
+                                                                return true;
+                                                            }, err);
+                if (getenv("KAT_TRACE")) fprintf(stderr, "[kat] stream route: rc %d, %zu blocks, %.3f s\n", r, n_blocks, t0.secs());
+                if (r == 1) {
+                    fwrite(bases.data(), 1, bases.size(), stdout);
+                    return 0;
+                }
+                bases.clear();
+            }
             if (!kat_host::read_file(a.positional[0], raw, err)) throw KatError(4, err);
             const double t_read = t0.secs();
             const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), (int)to_u64(a.get("mer_len", "27"), "mer_len"),

@@ -399,4 +399,102 @@ ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsi
     return parse_sequence_file_exact(data, n, k, trim5p, out);
 }
 
+int stream_regular_file(const std::string &path, unsigned trim5p, size_t block_bytes,
+                        const std::function<bool(const char *, size_t)> &sink, std::string &err) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return 0;
+    struct stat st;
+    unsigned char magic[2] = {0, 0};
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || pread(fd, magic, 2, 0) < 1 || (magic[0] == 0x1f && magic[1] == 0x8b) ||
+        (magic[0] != '@' && magic[0] != '>')) {
+        close(fd);
+        return 0;
+    }
+    const bool fastq = magic[0] == '@';
+    if (!fastq && trim5p != 0) { // per-buffer trim quirk: emulation only
+        close(fd);
+        return 0;
+    }
+    block_bytes = std::max<size_t>(block_bytes, 256);
+    std::vector<unsigned char> buf;
+    std::string bases;
+    size_t file_off = 0, emitted = 0;
+    const size_t file_size = (size_t)st.st_size;
+    int rc = 1;
+    while (file_off < file_size || !buf.empty()) {
+        // top the buffer up by one block
+        const size_t have = buf.size(), want = std::min(block_bytes, file_size - file_off);
+        buf.resize(have + want);
+        size_t got = 0;
+        while (got < want) {
+            const ssize_t r = pread(fd, buf.data() + have + got, want - got, (off_t)(file_off + got));
+            if (r <= 0) break;
+            got += (size_t)r;
+        }
+        if (got != want) {
+            err = "Read error on input file: " + path;
+            rc = emitted ? -1 : 0;
+            break;
+        }
+        file_off += want;
+        const bool last = file_off >= file_size;
+        // the records that are complete in the buffer end where the last record START in it begins
+        size_t boundary = buf.size();
+        if (!last) {
+            boundary = 0;
+            const unsigned char *b = buf.data(), *e = b + buf.size();
+            size_t p = buf.size();
+            if (!fastq) { // the last header line: '>' is only allowed as the first byte of a line
+                for (const void *q = memrchr(b, '>', buf.size()); q != nullptr;) {
+                    const size_t at = (size_t)(static_cast<const unsigned char *>(q) - b);
+                    if (at > 0 && b[at - 1] == '\n') {
+                        boundary = at;
+                        break;
+                    }
+                    q = at > 0 ? memrchr(b, '>', at) : nullptr;
+                }
+            } else {
+                for (int lines = 0; p > 0 && lines < 64; lines++) { // walk line starts backwards: a record start is at most 4 lines away
+                    const void *nl = p >= 2 ? memrchr(b, '\n', p - 1) : nullptr; // newline before the line that ends at p
+                    const size_t ls = nl ? (size_t)(static_cast<const unsigned char *>(nl) - b) + 1 : 0;
+                    const unsigned char *c = b + ls;
+                    if (ls > 0 && *c == '@') {
+                        const unsigned char *l1 = find_nl(c, e);
+                        const unsigned char *l2 = l1 ? find_nl(l1 + 1, e) : nullptr;
+                        if (l1 && l2 && l2 + 1 < e && l2[1] == '+' && l1[1] != '@' && l1[1] != '+') { boundary = ls; break; }
+                    }
+                    if (ls == 0) break;
+                    p = ls;
+                }
+            }
+            if (boundary == 0) { // no record start in a whole block (a giant record, or not the regular layout)
+                if (buf.size() > 8 * block_bytes + (64u << 20)) {
+                    rc = emitted ? -1 : 0;
+                    break;
+                }
+                continue; // read more
+            }
+        }
+        bases.clear();
+        if (boundary > 0 && !parse_regular_layout(buf.data(), boundary, fastq, trim5p, bases)) {
+            rc = emitted ? -1 : 0;
+            break;
+        }
+        if (!bases.empty()) {
+            if (!sink(bases.data(), bases.size())) {
+                rc = -1;
+                break;
+            }
+            emitted++;
+        }
+        buf.erase(buf.begin(), buf.begin() + (std::ptrdiff_t)boundary);
+        if (last) {
+            if (!buf.empty()) rc = emitted ? -1 : 0; // (cannot happen: the last block is parsed to its end)
+            break;
+        }
+    }
+    close(fd);
+    return rc;
+}
+
 } // namespace kat_host

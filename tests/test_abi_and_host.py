@@ -187,3 +187,41 @@ def test_host_parser_irregular_inputs_fall_back(mutate, tmp_path, monkeypatch):
         fast = _kat_parse(str(p), k, trim, b"exact")  # the fast path must have refused the file
         monkeypatch.setenv("KAT_PARSE_EXACT_ONLY", "1")
         assert fast == _kat_parse(str(p), k, trim) == O.parse_file(data, k, trim), (mutate, k, trim)
+
+
+@pytest.mark.parametrize("fastq,kw", [(True, {}), (True, {"crlf": True}), (False, {}), (False, {"wrap": 70}), (False, {"wrap": 61, "no_final_newline": True})],
+                         ids=["fq", "fq_crlf", "fa", "fa_wrapped", "fa_wrapped_no_final_nl"])
+@pytest.mark.parametrize("block", [300, 4096, 70000])
+def test_host_streaming_route_equals_whole_file(fastq, kw, block, tmp_path, monkeypatch):
+    """Large regular files are read, parsed and fed block by block (stream_regular_file); the blocks,
+    joined by the 'N' that separates records, are the whole-file base stream."""
+    rng = np.random.default_rng(block + fastq)
+    data = _regular_file(rng, fastq, 500, **kw)
+    p = tmp_path / ("s.fq" if fastq else "s.fa")
+    p.write_bytes(data)
+    monkeypatch.setenv("KAT_STREAM_BYTES", "1")
+    monkeypatch.setenv("KAT_STREAM_BLOCK", str(block))
+    for k, trim in [(27, 0), (21, 4)]:
+        r = subprocess.run([KAT, "_parse", "-m", str(k), "--5ptrim", str(trim), str(p)], capture_output=True, env=dict(os.environ, KAT_TRACE="1"))
+        if fastq or trim == 0:
+            assert b"stream route: rc 1" in r.stderr, r.stderr
+        assert (r.stdout, r.returncode) == (O.parse_file(data, k, trim)[0], 0), (k, trim)
+
+
+@pytest.mark.parametrize("mutate_at", [3, 250, 499])
+def test_host_streaming_route_gives_up_on_irregular_files(mutate_at, tmp_path, monkeypatch):
+    """An irregular record anywhere makes the streaming route report it (0 = nothing emitted yet,
+    -1 = start over); the hook then takes the whole-file route and the stream is the emulation's."""
+    rng = np.random.default_rng(mutate_at)
+    recs = _regular_file(rng, True, 500, tricky_quals=False).split(b"\n")
+    s = recs[4 * mutate_at + 1]
+    recs[4 * mutate_at + 1:4 * mutate_at + 2] = [s[:6], s[6:]]  # a two-line sequence
+    data = b"\n".join(recs)
+    p = tmp_path / "m.fq"
+    p.write_bytes(data)
+    monkeypatch.setenv("KAT_STREAM_BYTES", "1")
+    monkeypatch.setenv("KAT_STREAM_BLOCK", "5000")
+    r = subprocess.run([KAT, "_parse", "-m", "21", str(p)], capture_output=True, env=dict(os.environ, KAT_TRACE="1"))
+    assert b"stream route: rc 1" not in r.stderr
+    want, st = O.parse_file(data, 21, 0)
+    assert r.stdout == want
