@@ -387,11 +387,24 @@ def main():
                 "input_only_GBps": (k_inst * (READ_LEN / KMERS_PER_READ) / 1e9) / (k_ms / 1e3) if k_ms > 0 else None,
                 "other_kernels_ms": {f: prof[f][0] for f in prof if f not in fam}}
 
+    # K2 (hist walk): 8 B per slot read once; one histogram update per distinct k-mer
+    # (warp-aggregated shared-memory atomics, flushed with 64-bit global atomics)
+    reduction = None
+    try:
+        h_ms, h_n = prof["hist"]
+        if h_n:
+            per = h_ms / h_n / 1e3
+            table_gb = (1 << args.slots_log2) * 8 / 1e9
+            reduction = {"kernel": "hist_kernel", "ms_per_launch": h_ms / h_n, "bound": "hbm",
+                         "achieved": table_gb / per, "peak": hbm_peak, "unit": "GB/s", "frac": table_gb / per / hbm_peak,
+                         "histogram_updates_per_s": n_distinct / per, "slots_per_s": (1 << args.slots_log2) / per}
+    except Exception as ex:  # an extra, never worth the bench line
+        reduction = {"error": str(ex)[:200]}
     line = {"metric": "canonical k-mers/sec (k=27) into hist", "value": value, "unit": "k-mers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "kmer_instances_per_step": n_total_all, "distinct_kmers_rank0": n_distinct,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "reduction": reduction}
 
     # ------------------------------------------------------------ end to end
     if not args.no_e2e and world == 1:
