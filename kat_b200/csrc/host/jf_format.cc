@@ -13,6 +13,10 @@
 #include <numeric>
 #include <ostream>
 #include <sstream>
+#include <atomic>
+#include <cstdlib>
+#include <thread>
+#include <utility>
 
 namespace kat_host {
 namespace {
@@ -295,6 +299,38 @@ bool jf_read_records(std::istream &is, const JfHeader &h, size_t batch,
     return true;
 }
 
+// Sort (key, count) records by key.  Large tables (a 10 Gbp data set dumps 1.2 G records) are
+// split by the top key bits into 4096 buckets in one counting pass, and the buckets are sorted
+// by all host threads; small ones go through one std::sort.
+static void sort_by_key(std::vector<uint64_t> &keys, std::vector<uint64_t> &counts, unsigned k) {
+    const size_t n = keys.size();
+    size_t parallel_from = (size_t)1 << 20;
+    if (const char *e = getenv("KAT_SORT_PARALLEL_MIN")) parallel_from = (size_t)strtoull(e, nullptr, 10);
+    std::vector<std::pair<uint64_t, uint64_t>> rec(n);
+    if (n < parallel_from) {
+        for (size_t i = 0; i < n; i++) rec[i] = {keys[i], counts[i]};
+        std::sort(rec.begin(), rec.end());
+    } else {
+        const unsigned key_bits = 2 * k, bb = std::min(12u, key_bits), shift = key_bits - bb;
+        const size_t nb = (size_t)1 << bb;
+        std::vector<size_t> start(nb + 1, 0);
+        for (size_t i = 0; i < n; i++) start[(keys[i] >> shift) + 1]++;
+        for (size_t b = 0; b < nb; b++) start[b + 1] += start[b];
+        std::vector<size_t> at(start.begin(), start.end() - 1);
+        for (size_t i = 0; i < n; i++) rec[at[keys[i] >> shift]++] = {keys[i], counts[i]};
+        unsigned nt = std::max(1u, std::min(std::thread::hardware_concurrency(), 64u));
+        std::vector<std::thread> th;
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t b; (b = next.fetch_add(1)) < nb;) std::sort(rec.begin() + (std::ptrdiff_t)start[b], rec.begin() + (std::ptrdiff_t)start[b + 1]);
+        };
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto &x : th) x.join();
+    }
+    for (size_t i = 0; i < n; i++) keys[i] = rec[i].first, counts[i] = rec[i].second;
+}
+
 void jf_prepare_dump(JfHeader &h, unsigned k, bool canonical, uint64_t n, std::vector<uint64_t> &keys, std::vector<uint64_t> &counts) {
     h.format = "binary/sorted";
     h.key_len = 2 * k;
@@ -314,13 +350,7 @@ void jf_prepare_dump(JfHeader &h, unsigned k, bool canonical, uint64_t n, std::v
     h.reprobes.resize(h.max_reprobe + 1);
     for (unsigned i = 0; i <= h.max_reprobe; i++) h.reprobes[i] = i == 0 ? 1 : (uint64_t)i * (i + 1) / 2; // JF/lib/storage.cc quadratic_reprobes
     // ascending (position, key) == ascending key under this matrix
-    std::vector<uint64_t> idx(keys.size());
-    std::iota(idx.begin(), idx.end(), (uint64_t)0);
-    std::sort(idx.begin(), idx.end(), [&](uint64_t a, uint64_t b) { return keys[a] < keys[b]; });
-    std::vector<uint64_t> k2(keys.size()), c2(keys.size());
-    for (size_t i = 0; i < idx.size(); i++) k2[i] = keys[idx[i]], c2[i] = counts[idx[i]];
-    keys.swap(k2);
-    counts.swap(c2);
+    sort_by_key(keys, counts, k);
 }
 
 void jf_write_file(std::ostream &os, JfHeader &h, const std::vector<uint64_t> &keys, const std::vector<uint64_t> &counts) {
