@@ -35,8 +35,13 @@ HASHES = [
     # canonical 21-mers counted by jellyfish from the assembly-like FASTA
     ("synthc_k21_jf", ["kat_jellyfish", "count", "-C", "-m", "21", "-s", "50000", "-o", "OUT/y.jf", "inputs/synth_c.fa"], "OUT/y.jf"),
 ]
+# the reference's OWN hash fixture (tests/data/ecoli.header.jf27, 22 KB, written by jellyfish with a
+# random hash matrix): its tests expect 1889 records and four named counts (tests/check_jellyfish.cc:38-116)
+REF_FIXTURE = ("/root/reference/tests/data/ecoli.header.jf27", "ref_ecoli_header_k27")
+
 # reference KAT runs that take a hash as input (LOAD mode); paths relative to tests/golden
 CASES = [
+    ("load_hist_ref_fixture_k27", ["hist", "-o", "OUT/h", "jf/ref_ecoli_header_k27.jf"]),
     ("load_hist_k13", ["hist", "-o", "OUT/h", "jf/long_k13_kat.jf"]),
     ("load_hist_k5_lowhigh", ["hist", "-l", "2", "-h", "40000", "-i", "7", "-o", "OUT/h", "jf/polyA_edge_k5_jf.jf"]),
     ("load_gcp_k21", ["gcp", "-y", "30", "-o", "OUT/g", "jf/synthc_k21_jf.jf"]),
@@ -61,6 +66,10 @@ def main():
             f.write(run([os.path.join(REF, "kat_jellyfish"), "dump", "-c", "jf/" + name + ".jf"]).encode())
         manifest["hashes"].append({"name": name, "cmd": cmd})
         print(name, os.path.getsize(dst), "bytes")
+    shutil.copy(REF_FIXTURE[0], os.path.join(JF, REF_FIXTURE[1] + ".jf"))
+    with gzip.GzipFile(os.path.join(JF, REF_FIXTURE[1] + ".dump.txt.gz"), "wb", mtime=0) as f:
+        f.write(run([os.path.join(REF, "kat_jellyfish"), "dump", "-c", "jf/" + REF_FIXTURE[1] + ".jf"]).encode())
+    manifest["hashes"].append({"name": REF_FIXTURE[1], "cmd": ["copy of the reference's tests/data/ecoli.header.jf27"]})
     for name, args in CASES:
         out = os.path.join("jf", "expected", name)
         os.makedirs(os.path.join(HERE, out))

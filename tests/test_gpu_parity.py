@@ -315,3 +315,23 @@ def test_tiled_rare_paths(ctx, env, count_path, monkeypatch):
     finally:
         B.lib().katgpu_debug_set_count_bits(0)
     assert_same_multiset(gt, ora_table([s1, s2], k))
+
+
+def test_reference_hash_fixture_queries(ctx):
+    """tests/check_jellyfish.cc:62-116 on the GPU: load the reference's own hash fixture
+    (ecoli.header.jf27: 1889 records) record by record — HashLoader::loadHash — and query the four
+    named 27-mers: 3/1/1/1 as stored, 3/1/0/0 with the probe canonicalised (JellyfishHelper::getCount)."""
+    import gzip
+    import os
+    import golden_util as G
+    recs = [l.split() for l in gzip.open(os.path.join(G.GOLDEN, "jf", "ref_ecoli_header_k27.dump.txt.gz"), "rt").read().splitlines()]
+    assert len(recs) == 1889
+    keys = np.array([seqgen.encode_kmer(a) for a, _ in recs], dtype=np.uint64)
+    counts = np.array([int(c) for _, c in recs], dtype=np.uint64)
+    t = ctx.count_begin(27, False, 2 * len(recs), True)
+    t.add_pairs(keys, counts).end()
+    assert t.n_distinct == 1889 and t.n_total == int(counts.sum())
+    named = ["AGCTTTTCATTCTGACTGCAACGGGCA", "GCATAGCGCACAGACAGATAAAAATTA", "AATGAAAAAGGCGAACTGGTGGTGCTT", "CTCACCAATGTACATGGCCTTAATCTG"]
+    probe = np.array([seqgen.encode_kmer(s) for s in named], dtype=np.uint64)
+    assert list(t.lookup(probe, False)) == [3, 1, 1, 1]
+    assert list(t.lookup(probe, True)) == [3, 1, 0, 0]
