@@ -127,57 +127,72 @@ class ClockSampler:
             self.proc.terminate()
 
 
-def write_fastq_sample(stream, n_reads, path):
-    """stream: uint8 [n_reads*(L+1)] base stream (read,'N',...).  Writes 4-line FASTQ."""
+class ReferenceFailed(RuntimeError):
+    pass
+
+
+def run_reference_hist(fastq, threads, slots, workdir, expect_instances, max_attempts=6):
+    """`kat hist -m27 -t<threads> [-H<slots>]` with the UNMODIFIED reference binary (oracle/_ref/kat).
+
+    The reference has a data race of its own in the binning phase — T threads `push_back` into one
+    std::vector without a lock (src/histogram.cc:198) — which at 16-32 threads regularly ends in
+    `double free or corruption` and can also silently lose one thread's bins.  Neither is a result:
+    a run counts only if it exits 0 AND its histogram accounts for every k-mer instance of the
+    sample (sum(label*bins) == instances when the open last bin is empty).  Anything else is
+    retried (same binary, same options); after `max_attempts` failures the thread count is halved.
+    Returns dict(wall, phases, hist, attempts, threads, rejected)."""
     import numpy as np
-    L = READ_LEN
-    reads = stream.reshape(n_reads, L + 1)[:, :L]
-    hdr = np.frombuffer(b"@r\n", dtype=np.uint8)
-    mid = np.frombuffer(b"\n+\n", dtype=np.uint8)
-    rec = np.empty((n_reads, len(hdr) + L + len(mid) + L + 1), dtype=np.uint8)
-    rec[:, :3] = hdr
-    rec[:, 3:3 + L] = reads
-    rec[:, 3 + L:6 + L] = mid
-    rec[:, 6 + L:6 + 2 * L] = ord("I")
-    rec[:, -1] = ord("\n")
-    rec.tofile(path)
-
-
-def run_reference_hist(fastq, threads, slots, workdir):
-    """`kat hist -m27 -t<threads> -H<slots>` with the unmodified reference binary.
-    Returns (wall seconds, phase dict, hist path)."""
     import oracle as O
     out = os.path.join(workdir, "ref.hist")
-    t0 = time.perf_counter()
-    r = O.run_ref(["hist", f"-m{K}", f"-t{threads}", f"-H{slots}", "-o", out, fastq], cwd=workdir, timeout=3600)
-    wall = time.perf_counter() - t0
-    if r.returncode != 0:
-        raise RuntimeError("reference kat failed: " + r.stdout[-500:])
-    phases = {}
-    for name, pat in (("count", r"Counting kmers.*?Time taken: ([0-9.]+)s"), ("bin", r"Bining kmers.*?Time taken: ([0-9.]+)s")):
-        m = re.search(pat, r.stdout, re.S)
-        if m:
-            phases[name] = float(m.group(1))
-    return wall, phases, out
+    attempts, rejected, t = 0, [], max(1, threads)
+    while True:
+        for _ in range(max_attempts):
+            attempts += 1
+            if os.path.exists(out):
+                os.unlink(out)
+            t0 = time.perf_counter()
+            args = ["hist", f"-m{K}", f"-t{t}"] + ([f"-H{slots}"] if slots else []) + ["-o", out, fastq]
+            try:
+                r = O.run_ref(args, cwd=workdir, timeout=1800)
+            except subprocess.TimeoutExpired:
+                rejected.append(f"-t{t}: timeout")
+                continue
+            wall = time.perf_counter() - t0
+            if r.returncode != 0:
+                rejected.append(f"-t{t}: rc {r.returncode} ({(r.stdout or '').strip().splitlines()[-1][:80] if (r.stdout or '').strip() else 'no output'})")
+                continue
+            try:
+                lab, bins = O.read_hist(out)
+            except Exception as ex:
+                rejected.append(f"-t{t}: unreadable output ({ex})")
+                continue
+            if len(bins) == 0 or (bins[-1] == 0 and int((lab * bins).sum()) != expect_instances):
+                rejected.append(f"-t{t}: histogram accounts for {int((lab * bins).sum()) if len(bins) else 0} of {expect_instances} k-mer instances")
+                continue
+            phases = {}
+            for name, pat in (("count", r"Counting kmers.*?Time taken: ([0-9.]+)s"), ("bin", r"Bining kmers.*?Time taken: ([0-9.]+)s")):
+                m = re.search(pat, r.stdout, re.S)
+                if m:
+                    phases[name] = float(m.group(1))
+            return {"wall": wall, "phases": phases, "hist": out, "bins": bins, "attempts": attempts, "threads": t, "rejected": rejected}
+        if t == 1:
+            raise ReferenceFailed("reference kat hist failed %d times: %s" % (attempts, "; ".join(rejected[-3:])))
+        t = max(1, t // 2)
 
 
-def cpu_reference_sample(ctx_or_none, sample_reads, threads, workdir, stream=None, keep_fastq=False):
-    """Time the reference on `sample_reads` reads of the workload (reads
-    [0, sample_reads) of rank 0's shard).  Returns dict + the reference's bins."""
-    import numpy as np
-    from kat_b200 import binding as B
+def reference_sample(sample_reads, workdir):
+    """The first `sample_reads` reads of rank 0's shard of the workload, generated on the CPU by
+    oracle/synth_ref.c (no product library involved), written as 4-line FASTQ.
+    Returns (fastq path, k-mer instances in it, base stream)."""
     import oracle as O
-    if stream is None:
-        stream = B.synth_reads_host(GENOME_PER_GPU, SEED_G, SEED_R, 0, sample_reads, READ_LEN, SUB_RATE, N_RATE)
+    stream = O.synth_reads(GENOME_PER_GPU, SEED_G, SEED_R, 0, sample_reads, READ_LEN, SUB_RATE, N_RATE)
     fq = os.path.join(workdir, "sample.fastq")
-    write_fastq_sample(stream, sample_reads, fq)
-    n_kmers_nominal = sample_reads * KMERS_PER_READ
-    slots = 1 << max(20, (n_kmers_nominal - 1).bit_length())  # no doubling for this sample
-    wall, phases, hist = run_reference_hist(fq, threads, slots, workdir)
-    _, bins = O.read_hist(hist)
-    if not keep_fastq:
-        os.unlink(fq)
-    return wall, phases, bins, slots
+    O.write_fastq(stream, sample_reads, READ_LEN, fq)
+    return fq, O.count_instances(stream, K), stream
+
+
+def sample_slots(sample_reads):
+    return 1 << max(20, (sample_reads * KMERS_PER_READ - 1).bit_length())  # no doubling for this sample
 
 
 def run_product_cli_hist(fastq, slots, workdir):
@@ -193,6 +208,72 @@ def run_product_cli_hist(fastq, slots, workdir):
     if r.returncode != 0:
         raise RuntimeError("kat_b200/bin/kat failed: " + r.stdout[-400:])
     return wall, out
+
+
+def cpu_baseline_leg(ctx, d_bases, n_reads, threads, args, line):
+    """The unmodified reference timed on this box's host cores on a bounded sample of the workload
+    (the first reads of the resident stream), its histogram compared bit for bit with the GPU's; the
+    same FILE through the product's `kat hist` binary (cli_file); a second reference run with the
+    default -H (1e8: the table doubles on the way).  Never raises: a failure is
+    reported inside the object, the bench line is kept."""
+    import numpy as np
+    import oracle as O
+    out = {"value": None, "unit": "k-mers/s", "cores": threads, "kind": "reference"}
+    if not O.have_ref():
+        out["sample"] = "oracle/_ref/kat not present"
+        return out
+    sample = min(args.cpu_sample_reads, n_reads)
+    work = tempfile.mkdtemp(prefix="katref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        stream = np.empty(sample * (READ_LEN + 1), dtype=np.uint8)
+        ctx.d2h(stream, d_bases)
+        fq = os.path.join(work, "sample.fastq")
+        O.write_fastq(stream, sample, READ_LEN, fq)
+        n_inst = O.count_instances(stream, K)
+        slots = sample_slots(sample)
+        out["sample"] = f"first {sample} reads ({n_inst} k-mer instances) of the workload written as 4-line FASTQ in /dev/shm"
+        # the GPU's histogram of the same sample (through the host-feed path)
+        t = ctx.count_begin(K, True, slots, True)
+        t.feed(stream).end()
+        _, gbins = t.hist(1, 10000, 1)
+        assert t.n_total == n_inst, "GPU k-mer instances differ from the CPU count of the sample"
+        t.free()
+        r = run_reference_hist(fq, threads, slots, work, n_inst)
+        out.update({"value": n_inst / r["wall"], "cores": r["threads"], "host_cores": threads,
+                    "sample": out["sample"] + f"; unmodified reference `kat hist -m27 -t{r['threads']} -H{slots}` wall {r['wall']:.2f}s (phases {r['phases']})",
+                    "attempts": r["attempts"], "rejected_runs": r["rejected"][:6],
+                    "parity_on_sample": bool(np.array_equal(gbins, r["bins"]))})
+        ref_hist_bytes = open(r["hist"], "rb").read()
+        # R2 of SURVEY.md §8(d): the same FILE through the product's CLI, output FILE compared byte for byte
+        try:
+            run_product_cli_hist(fq, slots, work)  # first run pays the page-in of a new binary
+            cli_wall, ours = run_product_cli_hist(fq, slots, work)
+            a_ = open(ours, "rb").read()
+            same = a_ == ref_hist_bytes
+            line["cli_file"] = {"wall_s": cli_wall, "reference_wall_s": r["wall"], "output_file_identical": bool(same),
+                                "value": n_inst / cli_wall, "unit": "k-mers/s",
+                                "what": f"kat_b200/bin/kat hist -m27 -H{slots} on the sample FASTQ ({os.path.getsize(fq)} bytes, in /dev/shm): "
+                                        "process start, file read, parse, H2D, count, bin, hist file written"}
+            if not same:
+                for la, lb in zip(a_.splitlines(), ref_hist_bytes.splitlines()):
+                    if la != lb:
+                        line["cli_file"]["first_difference"] = [la[:120].decode(errors="replace"), lb[:120].decode(errors="replace")]
+                        break
+        except Exception as ex:  # never lose the bench line over the extra measurement
+            line["cli_file"] = {"error": str(ex)[:300]}
+        # out-of-the-box behaviour: default -H 1e8, the hash doubles while counting
+        try:
+            r2 = run_reference_hist(fq, r["threads"], 0, work, n_inst, max_attempts=3)
+            out["default_hash_size"] = {"value": n_inst / r2["wall"], "unit": "k-mers/s", "wall_s": r2["wall"], "phases": r2["phases"],
+                                        "what": "same sample, reference run with its default -H 100000000 (table doubles during counting)",
+                                        "attempts": r2["attempts"]}
+        except Exception as ex:
+            out["default_hash_size"] = {"error": str(ex)[:200]}
+    except Exception as ex:
+        out["error"] = (type(ex).__name__ + ": " + str(ex))[:300]
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    return out
 
 
 def main():
@@ -240,32 +321,50 @@ def main():
         if not O.have_ref():
             emit({"impl": "reference", "unavailable": "oracle/_ref/kat not built (run oracle/ref.mk where /root/reference exists)"})
             return 0
-        from kat_b200 import binding as B
         sample = min(args.cpu_sample_reads, n_reads)
         work = tempfile.mkdtemp(prefix="katref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        base = {"impl": "reference", "metric": "canonical k-mers/sec (k=27) into hist", "unit": "k-mers/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "u64", "data": "synthetic"}
         try:
-            stream = B.synth_reads_host(GENOME_PER_GPU, SEED_G, SEED_R, 0, sample, READ_LEN, SUB_RATE, N_RATE)
-            import numpy as np
-            n_inst = None
-            times = []
+            fq, n_inst, _ = reference_sample(sample, work)
+            slots = sample_slots(sample)
+            # one probing run sizes the sample so that warmup+steps runs end within a few minutes
+            probe = run_reference_hist(fq, threads, slots, work, n_inst)
+            budget_s = 200.0
+            if probe["wall"] * (args.warmup + args.steps) > budget_s and sample > 500_000:
+                sample = max(500_000, int(sample * budget_s / (probe["wall"] * (args.warmup + args.steps))) // 100_000 * 100_000)
+                fq, n_inst, _ = reference_sample(sample, work)
+                slots = sample_slots(sample)
+            times, attempts, rejected, used_threads = [], 0, [], threads
             for i in range(args.warmup + args.steps):
-                wall, phases, bins, slots = cpu_reference_sample(None, sample, threads, work, stream)
-                lab = np.arange(1, len(bins) + 1, dtype=np.uint64)
-                n_inst = int((bins[:-1] * lab[:-1]).sum()) if bins[-1] == 0 else None
+                r = run_reference_hist(fq, used_threads, slots, work, n_inst)
+                attempts += r["attempts"]
+                rejected += r["rejected"]
+                used_threads = r["threads"]
                 if i >= args.warmup:
-                    times.append((wall, phases))
+                    times.append((r["wall"], r["phases"]))
             total = sum(t[0] for t in times)
-            n_inst = n_inst or sample * KMERS_PER_READ
             val = n_inst * len(times) / total
-            line = {"impl": "reference", "metric": "canonical k-mers/sec (k=27) into hist", "value": val, "unit": "k-mers/s",
-                    "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-                    "config": config,
-                    "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": threads, "kind": "reference",
-                                     "sample": f"first {sample} reads ({n_inst} k-mer instances) of the workload as FASTQ; "
-                                               f"`kat hist -m27 -t{threads} -H{slots}` wall time incl. parse; phases {times[-1][1]}"},
-                    "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-            emit(line)
+            cfg = dict(config)
+            cfg["workload"] = (f"kat hist -m{K} (unmodified reference, oracle/_ref/kat) on a bounded sample of the workload: the first {sample} reads "
+                               f"({sample * READ_LEN / 1e9:.2f} Gbp, {n_inst} k-mer instances) of the {n_reads}-read / {n_reads * READ_LEN / 1e9:.2f} Gbp set, "
+                               f"as 4-line FASTQ in /dev/shm; -t{used_threads} -H{slots}")
+            cfg["sample_reads"] = sample
+            cfg["table_slots_per_gpu"] = slots
+            cfg["parallelism"] = f"{used_threads} host threads"
+            base.update({"value": val, "ms_per_step": 1e3 * total / len(times), "config": cfg,
+                         "cpu_baseline": {"value": val, "unit": "k-mers/s", "cores": used_threads, "kind": "reference",
+                                          "sample": f"first {sample} reads ({n_inst} k-mer instances) of the workload as FASTQ; "
+                                                    f"`kat hist -m27 -t{used_threads} -H{slots}` wall time per run incl. process start, parse, count, bin, write; "
+                                                    f"last run phases {times[-1][1]}",
+                                          "runs": args.warmup + args.steps, "attempts": attempts, "rejected_runs": rejected[:8],
+                                          "host_cores": threads},
+                         "e2e": {"value": val, "unit": "k-mers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+            emit(base)
+        except Exception as ex:  # the reference could not be made to produce a valid run: say so, exit 0
+            base.update({"unavailable": ("reference run failed: " + str(ex))[:300]})
+            emit(base)
         finally:
             shutil.rmtree(work, ignore_errors=True)
         return 0
@@ -433,50 +532,7 @@ def main():
 
     # ------------------------------------------------------------ CPU baseline (rank 0, N=1)
     if not args.no_cpu_baseline and world == 1 and rank == 0:
-        import oracle as O
-        if O.have_ref():
-            sample = min(args.cpu_sample_reads, n_reads)
-            work = tempfile.mkdtemp(prefix="katref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-            try:
-                stream = np.empty(sample * (READ_LEN + 1), dtype=np.uint8)
-                ctx.d2h(stream, d_bases)
-                wall, phases, ref_bins, slots = cpu_reference_sample(ctx, sample, threads, work, stream, keep_fastq=True)
-                # R2 of SURVEY.md §8(d): the same FILE through the product's CLI, output FILE compared byte for byte
-                try:
-                    fq = os.path.join(work, "sample.fastq")
-                    run_product_cli_hist(fq, slots, work)  # first run pays the CUDA context + module load of a new process
-                    cli_wall, ours = run_product_cli_hist(fq, slots, work)
-                    a_, b_ = open(ours, "rb").read(), open(os.path.join(work, "ref.hist"), "rb").read()
-                    same = a_ == b_
-                    line["cli_file"] = {"wall_s": cli_wall, "reference_wall_s": wall, "output_file_identical": bool(same),
-                                        "what": f"kat_b200/bin/kat hist -m27 -H{slots} on the sample FASTQ ({os.path.getsize(fq)} bytes, in /dev/shm): "
-                                                "process start, file read, host parse, H2D, count, bin, hist file written"}
-                    if not same:
-                        for la, lb in zip(a_.splitlines(), b_.splitlines()):
-                            if la != lb:
-                                line["cli_file"]["first_difference"] = [la[:120].decode(errors="replace"), lb[:120].decode(errors="replace")]
-                                break
-                    os.unlink(fq)
-                except Exception as ex:  # never lose the bench line over the extra measurement
-                    line["cli_file"] = {"error": str(ex)[:300]}
-                t = ctx.count_begin(K, True, slots, True)
-                t.feed(stream).end()
-                _, gbins = t.hist(1, 10000, 1)
-                n_inst = t.n_total
-                t.free()
-                if "wall_s" in line.get("cli_file", {}):
-                    line["cli_file"]["value"] = n_inst / line["cli_file"]["wall_s"]
-                    line["cli_file"]["unit"] = "k-mers/s"
-                line["cpu_baseline"] = {
-                    "value": n_inst / wall, "unit": "k-mers/s", "cores": threads, "kind": "reference",
-                    "sample": f"first {sample} reads ({n_inst} k-mer instances) of the workload written as FASTQ; "
-                              f"unmodified reference `kat hist -m27 -t{threads} -H{slots}` wall {wall:.2f}s (phases {phases})",
-                    "parity_on_sample": bool(np.array_equal(gbins, ref_bins))}
-            finally:
-                shutil.rmtree(work, ignore_errors=True)
-        else:
-            line["cpu_baseline"] = {"value": None, "unit": "k-mers/s", "cores": threads, "kind": "reference",
-                                    "sample": "oracle/_ref/kat not present"}
+        line["cpu_baseline"] = cpu_baseline_leg(ctx, d_bases, n_reads, threads, args, line)
 
     ctx.device_free(d_bases)
     sampler.stop()

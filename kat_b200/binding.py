@@ -251,13 +251,15 @@ class Table:
         _check(lib().katgpu_lookup(self.h, _ptr(keys), keys.size, int(canonicalise), _ptr(out)))
         return out
 
-    def export(self):
+    def export(self, sort=True):
         n = C.c_uint64()
         cap = int(self.n_distinct if self.n_distinct is not None else self.info()["n_distinct"])
         keys = np.zeros(max(cap, 1), dtype=np.uint64)
         counts = np.zeros(max(cap, 1), dtype=np.uint64)
         _check(lib().katgpu_table_export(self.h, _ptr(keys), _ptr(counts), cap, C.byref(n)))
         m = min(cap, n.value)
+        if not sort:
+            return keys[:m], counts[:m], n.value
         order = np.argsort(keys[:m], kind="stable")
         return keys[:m][order], counts[:m][order], n.value
 

@@ -944,8 +944,10 @@ static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
     if (t->tiled) return sweep_tiled(t, ctr);
     SweepParams P{};
     P.g = t->g;
-    const double per_part = t->pend_fill * (double)t->pend_segs; // keys that can target one slot
-    set_add_bound(P.g, per_part < 1.8e19 ? (uint64_t)per_part + 1 : ~0ULL);
+    // Keys that can target one slot in this sweep: a slice never holds more than its segments'
+    // capacity, and no more than were fed.  (pend_fill is a fill MODEL for uniform hashes — on
+    // skewed input one slice really fills its segments, so it is not a bound.)
+    set_add_bound(P.g, std::min<uint64_t>(t->pend_bound, (uint64_t)t->pend_seg_cap * t->pend_segs));
     P.keys = t->pend_keys;
     P.seglen = t->pend_seglen;
     P.seg_cap = t->pend_seg_cap;
@@ -1173,6 +1175,9 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
         CU(cudaEventRecord(c->chunk_free[b], c->stream));
         if (mid_ok && i + 1 < n_chunks && ((i + 1) * (size_t)(mid_sweeps + 1)) / n_chunks != (i * (size_t)(mid_sweeps + 1)) / n_chunks) KT(sweep_pending(t, ctr));
     }
+    // `bases` belongs to the caller again when this returns: every host->device copy has completed
+    // (the kernels consuming the staged chunks may still be running — they only touch device memory).
+    CU(cudaStreamSynchronize(c->copy_stream));
     return KATGPU_OK;
 }
 

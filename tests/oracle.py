@@ -232,3 +232,48 @@ def read_mx(path):
             if line.strip():
                 rows.append(np.array(line.split(), dtype=np.uint64))
     return hdr, np.vstack(rows) if rows else np.zeros((0, 0), dtype=np.uint64)
+
+
+# ---- bench tooling beside the oracle (oracle/synth_ref.c): no product library involved ----
+_synth = None
+
+
+def synth_lib():
+    global _synth
+    if _synth is not None:
+        return _synth
+    so = os.path.join(ORACLE_DIR, "libsynthref.so")
+    src = os.path.join(ORACLE_DIR, "synth_ref.c")
+    if not os.path.exists(so) or (os.path.exists(src) and os.path.getmtime(so) < os.path.getmtime(src)):
+        subprocess.check_call(["make", "-C", ORACLE_DIR, "libsynthref.so"], stdout=subprocess.DEVNULL)
+    L = C.CDLL(so)
+    L.synthref_reads.restype = C.c_int
+    L.synthref_reads.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32,
+                                 C.c_double, C.c_double, C.c_int, C.c_void_p]
+    L.synthref_instances.restype = C.c_uint64
+    L.synthref_instances.argtypes = [C.c_void_p, C.c_uint64, C.c_int]
+    L.synthref_write_fastq.restype = C.c_int
+    L.synthref_write_fastq.argtypes = [C.c_void_p, C.c_uint64, C.c_uint32, C.c_char_p]
+    _synth = L
+    return L
+
+
+def synth_reads(genome_len, seed_g, seed_r, first_read, n_reads, read_len=150, sub_rate=0.005, n_rate=0.0001, threads=None):
+    """SURVEY.md §8(d) synthetic reads as a base stream (read,'N',...), generated on the CPU
+    without libkatgpu; byte-equal to katgpu_synth_reads_host (tests/test_abi_and_host.py)."""
+    out = np.empty(n_reads * (read_len + 1), dtype=np.uint8)
+    rc = synth_lib().synthref_reads(genome_len, seed_g, seed_r, first_read, n_reads, read_len, sub_rate, n_rate,
+                                    threads or (os.cpu_count() or 1), _ptr(out))
+    if rc != 0:
+        raise ValueError("synth_reads: bad parameters")
+    return out
+
+
+def count_instances(stream, k):
+    a = np.frombuffer(stream, dtype=np.uint8) if not isinstance(stream, np.ndarray) else stream
+    return int(synth_lib().synthref_instances(_ptr(a), a.size, k)) if a.size else 0
+
+
+def write_fastq(stream, n_reads, read_len, path):
+    if synth_lib().synthref_write_fastq(_ptr(stream), n_reads, read_len, os.fsencode(path)) != 0:
+        raise OSError("write_fastq failed: " + str(path))

@@ -40,6 +40,29 @@ def test_cli_output_files_byte_identical(case, path, workdir):
         assert got == want, f"{case['name']}/{f} differs from the reference's file"
 
 
+@pytest.mark.parametrize("path", ["auto", "tiled"])
+def test_cli_c1_ecoli_k27(path, tmp_path):
+    """BASELINE configs[0] through the PRODUCT on a GPU: `kat hist -m27` on the reference's own test
+    genome (tests/golden/c1/EcoliK12.fasta.gz) writes the reference's file byte for byte (bins sum to
+    4,550,880 distinct / 4,641,626 instances, tests/check_jellyfish.cc:118-135), and
+    `kat comp -m13 reads genome` writes its matrix and .stats byte for byte."""
+    import gzip
+    shutil.copytree(os.path.join(G.GOLDEN, "c1"), tmp_path / "c1", ignore=shutil.ignore_patterns("out"))
+    os.makedirs(tmp_path / "c1" / "out")
+    env = dict(os.environ)
+    if path != "auto":
+        env["KATGPU_COUNT_PATH"] = path
+    for args in (["hist", "-m27", "-t1", "-o", "c1/out/ecoli.hist", "c1/EcoliK12.fasta.gz"],
+                 ["comp", "-m13", "-t1", "-o", "c1/out/r1_vs_k12", "c1/ecoli_r1.1K.fastq.gz", "c1/EcoliK12.fasta.gz"]):
+        r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, env=env, timeout=300)
+        assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    for f in ("ecoli.hist", "r1_vs_k12-main.mx", "r1_vs_k12.stats"):
+        want = gzip.open(os.path.join(G.GOLDEN, "c1", "out", f + ".gz"), "rb").read()
+        assert open(tmp_path / "c1" / "out" / f, "rb").read() == want, f + " differs from the reference's file"
+    lab, val = G.parse_hist_text(open(tmp_path / "c1" / "out" / "ecoli.hist", "rb").read())
+    assert int(val.sum()) == 4550880 and int((lab * val).sum()) == 4641626
+
+
 def test_cli_hash_full_exit_code(workdir):
     """--disable_hash_grow + a table that is too small: the reference throws
     std::runtime_error("Hash full") -> "Error: Hash full", exit code 5 (src/kat.cc:292-294)."""

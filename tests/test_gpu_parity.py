@@ -335,3 +335,60 @@ def test_reference_hash_fixture_queries(ctx):
     probe = np.array([seqgen.encode_kmer(s) for s in named], dtype=np.uint64)
     assert list(t.lookup(probe, False)) == [3, 1, 1, 1]
     assert list(t.lookup(probe, True)) == [3, 1, 0, 0]
+
+
+def test_c1_named_kmer_on_gpu(ctx):
+    """tests/check_jellyfish.cc:118-135 through the C-ABI: count EcoliK12 (committed fixture) at
+    k=27 canonical, query AGCTTTTCATTCTGACTGCAACGGGCA -> 1; totals 4,641,626 / 4,550,880."""
+    import os
+    import golden_util as G
+    chunks = O.parse_files([os.path.join(G.GOLDEN, "c1", "EcoliK12.fasta.gz")], 27)
+    t = ctx.count([np.frombuffer(c, dtype=np.uint8) for c in chunks], 27, True, 1 << 24)
+    assert (t.n_total, t.n_distinct) == (4641626, 4550880)
+    assert list(t.lookup(np.array([seqgen.encode_kmer("AGCTTTTCATTCTGACTGCAACGGGCA")], dtype=np.uint64), True)) == [1]
+
+
+def _multiset_checksums(keys, counts):
+    """Order-independent fingerprints of a (key, count) multiset (uint64 arithmetic wraps)."""
+    keys, counts = keys.astype(np.uint64), counts.astype(np.uint64)
+    m = np.uint64(0x9E3779B97F4A7C15)
+    mixed = (keys ^ (keys >> np.uint64(29))) * m
+    return (int(len(keys)), int(counts.sum(dtype=np.uint64)), int((mixed * counts).sum(dtype=np.uint64)),
+            int(np.bitwise_xor.reduce(mixed + counts * m)) if len(keys) else 0)
+
+
+@pytest.mark.parametrize("slots_log2", [32, 30])
+def test_tiled_path_at_benchmark_geometry(ctx, slots_log2, monkeypatch):
+    """The benchmarked path at the benchmark's table geometry (bench.py: 2^32 slots -> 512 level-1
+    slices, 1024 tiles per slice, several level-2 groups; 2^30 for the 2-GPU setting): 2 M synthetic
+    150 bp reads generated ON THE DEVICE (the bench's generator, ~250 M 27-mers), counted through the
+    tiled kernels, against the oracle on the same bytes: totals, hist, gcp, order-independent
+    checksums of the full exported multiset, and 200k point lookups."""
+    monkeypatch.setenv("KATGPU_COUNT_PATH", "tiled")
+    n_reads, L, k = 2_000_000, 150, 27
+    n_bytes = n_reads * (L + 1)
+    d = ctx.device_alloc(n_bytes + 64)
+    try:
+        ctx.synth_reads_device(d, 200_000_000, 1, 2, 0, n_reads, L, 0.005, 0.0001)
+        host = np.empty(n_bytes, dtype=np.uint8)
+        ctx.d2h(host, d)
+        t = ctx.count_begin(k, True, 1 << slots_log2, True)
+        t.feed_device(d, n_bytes).end()
+    finally:
+        ctx.device_free(d)
+    assert np.array_equal(host[: 3 * (L + 1)], O.synth_reads(200_000_000, 1, 2, 0, 3, L))  # same generator as the reference arm's
+    ot = O.Table.from_chunks([host], k, True)
+    assert (t.n_total, t.n_distinct) == (ot.total, ot.distinct)
+    assert t.info()["slots"] == 1 << slots_log2
+    assert np.array_equal(t.hist()[1], ot.hist()[1])
+    assert np.array_equal(t.gcp(), ot.gcp())
+    okeys, ocounts = ot.export()
+    keys, counts, n = t.export(sort=False)
+    assert n == len(okeys)
+    assert _multiset_checksums(keys, counts) == _multiset_checksums(okeys, ocounts)
+    rng = np.random.default_rng(7)
+    pick = rng.integers(0, len(okeys), 200_000)
+    probe = np.concatenate([okeys[pick], rng.integers(0, 1 << 54, 1000, dtype=np.uint64)])
+    want = np.concatenate([ocounts[pick], np.array([ot.lookup(int(x)) for x in probe[-1000:]], dtype=np.uint64)])
+    assert np.array_equal(t.lookup(probe, False), want)
+    t.free()
