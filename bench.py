@@ -210,6 +210,42 @@ def run_product_cli_hist(fastq, slots, workdir):
     return wall, out
 
 
+def multi_gpu_parity(ctx, dist, rank, world, local_rank, reads_per_rank=150_000):
+    """A bounded job through the same multi-GPU engine, checked against the ORACLE (not just
+    sum invariants): every rank feeds `reads_per_rank` reads of its shard of a small read set, rank 0
+    compares the all-reduced hist and gcp with the oracle's single table over all the reads."""
+    import numpy as np
+    import torch
+    from kat_b200 import binding as B
+    out = {"reads": reads_per_rank * world}
+    try:
+        mine = B.synth_reads_host(3_000_000, 11, 12, rank * reads_per_rank, reads_per_rank, READ_LEN, SUB_RATE, N_RATE)
+        d = ctx.device_alloc(mine.size + 64)
+        ctx.h2d(d, mine)
+        t = ctx.count_begin(K, True, 1 << 24, True)
+        t.feed_device(d, mine.size).end()
+        _, gb = t.hist(1, 10000, 1)
+        gm = t.gcp()
+        nt, nd = t.n_total, t.n_distinct
+        t.free()
+        ctx.device_free(d)
+        ok = torch.zeros(1, dtype=torch.int64, device="cuda")
+        if rank == 0:
+            import oracle as O
+            full = O.synth_reads(3_000_000, 11, 12, 0, reads_per_rank * world, READ_LEN, SUB_RATE, N_RATE)
+            ot = O.Table.from_chunks([full], K, True)
+            same = (nt, nd) == (ot.total, ot.distinct) and np.array_equal(gb, ot.hist()[1]) and np.array_equal(gm, ot.gcp())
+            out.update({"kmer_instances": nt, "distinct": nd, "hist_and_gcp_equal_oracle": bool(same)})
+            ok[0] = 1 if same else 0
+        dist.broadcast(ok, src=0)
+        assert int(ok.item()) == 1, "multi-GPU result differs from the oracle"
+    except AssertionError:
+        raise
+    except Exception as ex:
+        out["error"] = (type(ex).__name__ + ": " + str(ex))[:300]
+    return out
+
+
 def cpu_baseline_leg(ctx, d_bases, n_reads, threads, args, line):
     """The unmodified reference timed on this box's host cores on a bounded sample of the workload
     (the first reads of the resident stream), its histogram compared bit for bit with the GPU's; the
@@ -394,20 +430,19 @@ def main():
     ctx.synth_reads_device(d_bases, genome_len, SEED_G, SEED_R, first_read, n_reads, READ_LEN, SUB_RATE, N_RATE)
     base, ceil_, nb = B.hist_geometry(1, 10000)
 
-    if world > 1:
-        from kat_b200.multigpu import DistributedCounter
-        dc = DistributedCounter(ctx, dist, K, True, 1 << args.slots_log2)
+    if world > 1:  # this context becomes one rank of the job; every table call below is then collective
+        from kat_b200.multigpu import join_job
+        join_job(ctx, dist, device=torch.device("cuda", local_rank))
 
     def job_resident():
-        """One whole `kat hist` job, base stream resident in HBM.  Returns (bins, n_total)."""
-        if world == 1:
-            t = ctx.count_begin(K, True, 1 << args.slots_log2, True)
-            t.feed_device(d_bases, n_bytes).end()
-            _, bins = t.hist(1, 10000, 1)
-            nt, nd = t.n_total, t.n_distinct
-            t.free()
-            return bins, nt, nd
-        return dc.hist_job(d_bases, n_bytes, 1, 10000, 1, READ_LEN + 1)
+        """One whole `kat hist` job, base stream resident in HBM.  Returns (bins, n_total, n_distinct[, local n_total])."""
+        t = ctx.count_begin(K, True, 1 << args.slots_log2, True)
+        t.feed_device(d_bases, n_bytes).end()
+        _, bins = t.hist(1, 10000, 1)
+        nt, nd = t.n_total, t.n_distinct  # on a job: the job's totals
+        local = t.info()["n_total"]        # k-mer instances inserted into THIS rank's table
+        t.free()
+        return bins, nt, nd, local
 
     def barrier():
         ctx.synchronize()
@@ -439,27 +474,22 @@ def main():
             dt = float(tt.item())
         return dt, out, ctx.launch_count() - l0, clocks, prof
 
-    dt, (bins, n_total, n_distinct), launches, clocks, prof = timed(job_resident, args.steps, args.warmup)
-    if dist is not None:
-        tt = torch.tensor([n_total], device="cuda", dtype=torch.int64)
-        dist.all_reduce(tt)
-        n_total_all = int(tt.item())
-    else:
-        n_total_all = n_total
+    dt, (bins, n_total_all, n_distinct, n_total), launches, clocks, prof = timed(job_resident, args.steps, args.warmup)
     value = n_total_all * args.steps / dt
     # size-independent checks of the full-size result
     labels = np.arange(base, base + nb, dtype=np.uint64)
     # KATGPU_SWEEP_EXPERIMENT runs (measurement aids with deliberately wrong results) skip the checks
     nocheck = bool(os.environ.get("KATGPU_SWEEP_EXPERIMENT"))
-    assert nocheck or int(bins.sum()) == (n_distinct if dist is None else int(bins.sum()))
+    assert nocheck or int(bins.sum()) == n_distinct, "sum(bins) != distinct k-mers"
     if bins[-1] == 0:
         assert nocheck or int((bins * labels).sum()) == n_total_all, "sum(label*bins) != k-mer instances"
 
     # K1 (extract + canonicalise + insert) is either one kernel (extract_kernel<insert>,
     # family "count") or the pair partition_kernel + sweep_kernel; its algorithmic bytes are B_ALG per k-mer.
     if world > 1:
-        fam = [f for f in ("route", "partition", "sweep", "bin1", "bin2", "tile", "insert") if prof[f][1] > 0]
-        kname = "extract_kernel<route> + owner-side binning + insertion kernels (K1 + K5; NCCL exchange between route and binning not included)"
+        fam = [f for f in ("route", "bin1", "bin2", "tile", "insert") if prof[f][1] > 0]
+        kname = ("route_bases_kernel (extract + hash + peer stores of every key into its owner's HBM over NVLink) + bin_hashed_kernel + bin_keys_kernel + "
+                 "tile_insert_kernel on the owner: K1 + K5 of this rank")
     elif prof["bin1"][1] > 0:
         fam = [f for f in ("bin1", "bin2", "tile", "insert") if prof[f][1] > 0]
         kname = "bin_bases_kernel + bin_keys_kernel + tile_insert_kernel (+ general insert of the side list): K1 as two binning passes and shared-memory table tiles"
@@ -476,7 +506,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": kname,
                 "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak if achieved else None,
                 "traffic": (TRAFFIC_B_PER_KMER_PARTITIONED * k_inst / args.steps) if fam == ["partition", "sweep"] else
-                           (TRAFFIC_B_PER_KMER_TILED * k_inst / args.steps) if fam[:3] == ["bin1", "bin2", "tile"] else None,
+                           (TRAFFIC_B_PER_KMER_TILED * k_inst / args.steps) if fam[:3] == ["bin1", "bin2", "tile"] and world == 1 else None,
                 "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum of the K1 kernels at 5 Gbp, scaled per k-mer to one step "
                                   "(profiles/r1_v3_tiled_ncu.txt; r1_v2_partition_sweep_ncu.txt for the L2-sweep path)",
                 "peak_source": peak_src,
@@ -502,11 +532,11 @@ def main():
     line = {"metric": "canonical k-mers/sec (k=27) into hist", "value": value, "unit": "k-mers/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
-            "kmer_instances_per_step": n_total_all, "distinct_kmers_rank0": n_distinct,
+            "kmer_instances_per_step": n_total_all, "distinct_kmers": n_distinct, "kmer_instances_rank0_table": n_total,
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "reduction": reduction}
 
     # ------------------------------------------------------------ end to end
-    if not args.no_e2e and world == 1:
+    if not args.no_e2e:
         hp = C_void_p_host(n_bytes)
         try:
             B._check(B.lib().katgpu_memcpy_d2h(ctx.h, hp, d_bases, n_bytes))
@@ -517,18 +547,32 @@ def main():
                 _, b2 = t.hist(1, 10000, 1)
                 nt = t.n_total
                 t.free()
-                return b2, nt, None
-            dt2, (bins2, nt2, _), _, _, _ = timed(job_e2e, args.steps, min(args.warmup, 3))
-            assert np.array_equal(bins2, bins) and nt2 == n_total
+                return b2, nt, None, None
+            dt2, (bins2, nt2, _, _), _, _, _ = timed(job_e2e, args.steps, min(args.warmup, 3))
+            assert np.array_equal(bins2, bins) and nt2 == n_total_all
             chunks = (n_bytes + (128 << 20) - 1) // (128 << 20)
             line["e2e"] = {"value": nt2 * args.steps / dt2, "unit": "k-mers/s",
-                           "h2d_bytes_per_step": n_bytes + 32 * (chunks - 1), "d2h_bytes_per_step": nb * 8,
+                           "h2d_bytes_per_step": (n_bytes + 32 * (chunks - 1)) * world, "d2h_bytes_per_step": nb * 8 * world,
                            "ms_per_step": 1e3 * dt2 / args.steps,
-                           "path": "katgpu_count_begin -> katgpu_count_feed(pinned host base stream) -> katgpu_count_end -> katgpu_hist"}
+                           "path": "katgpu_count_begin -> katgpu_count_feed(pinned host base stream, one shard per rank) -> katgpu_count_end -> katgpu_hist"}
         finally:
             B.lib().katgpu_host_free(hp)
-    elif world > 1:
-        line["e2e"] = None
+
+    # ------------------------------------------------------------ multi-GPU: exchange figures + parity against the oracle
+    if world > 1:
+        try:
+            st = ctx.dist_stats()
+            r_ms = prof["route"][0]
+            runs = args.steps  # profiled jobs (the resident ones)
+            recv_bytes = n_total * 8.0 * (world - 1) / world  # hashed keys that reached this rank from the others, per job
+            line["nvlink"] = {"key_bytes_in_per_job_rank0": recv_bytes, "route_kernel_ms_per_job": r_ms / max(runs, 1),
+                              "GBps_in_during_route": recv_bytes * runs / 1e9 / (r_ms / 1e3) if r_ms else None,
+                              "peak_GBps_per_direction": 900.0, "rounds_total": st["rounds"],
+                              "what": "8-byte hashed keys stored by the other ranks' route_bases_kernel straight into this rank's receive area (peer-mapped HBM); "
+                                      "an equal amount leaves this rank in the same kernel time"}
+        except Exception as ex:
+            line["nvlink"] = {"error": str(ex)[:200]}
+        line["parity_multi_gpu"] = multi_gpu_parity(ctx, dist, rank, world, local_rank)
 
     # ------------------------------------------------------------ CPU baseline (rank 0, N=1)
     if not args.no_cpu_baseline and world == 1 and rank == 0:

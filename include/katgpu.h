@@ -170,7 +170,42 @@ katgpu_status katgpu_table_get_info(katgpu_table *t, katgpu_table_info *out);
  * afterwards, to exercise the exact-overflow side table at small sizes.  0 = auto. */
 void katgpu_debug_set_count_bits(int bits);
 
-/* Multi-GPU (one process per GPU).  Every distinct k-mer must be owned by
+/* ---- multi-GPU jobs ---------------------------------------------
+ * One context per GPU; N contexts (N host threads of one process, or N processes —
+ * one per GPU, e.g. under torchrun) form a job.  A count histogram is not additive
+ * over read shards, so every distinct k-mer is counted by exactly one owner rank:
+ * reads are sharded by record, each rank feeds ITS shard, and inside
+ * katgpu_count_feed* the extraction kernel stores every k-mer's hashed key straight
+ * into the owner's memory over NVLink (peer-mapped receive areas, no NCCL in the data
+ * path, no host staging); the owner bins and inserts it with the single-GPU kernels.
+ *
+ *   katgpu_dist_unique_id   128-byte job id (ncclGetUniqueId); rank 0 makes it, the
+ *                           caller hands it to every rank (a broadcast, a file, argv).
+ *   katgpu_dist_init        joins the job: NCCL communicator (NCCL is called directly,
+ *                           dlopen'ed on first use), receive areas, peer mappings.
+ *                           2 <= n_ranks <= 8 (one NVSwitch box).
+ *
+ * On a job context the calls below are COLLECTIVE — every rank makes them in the same
+ * order: katgpu_count_begin, katgpu_count_feed / _feed_device (each rank its own
+ * bytes, sizes may differ, 0 is fine), katgpu_count_end (returns the job's totals),
+ * katgpu_hist / katgpu_gcp / katgpu_comp / katgpu_lookup (every rank receives the
+ * complete result: the local walk is followed by ONE ncclAllReduce(sum, uint64) of
+ * the bins / matrix / counters, replacing the reference's merge of per-thread
+ * results, src/histogram.cc:146-160, src/gcp.cc:158-177, src/comp.cc:308-326).
+ * katgpu_comp needs every input counted canonically (the default); katgpu_table_export
+ * returns the rank's own part; katgpu_count_add_pairs is single-GPU only. */
+katgpu_status katgpu_dist_unique_id(void *id128);
+katgpu_status katgpu_dist_init(katgpu_ctx *ctx, int rank, int n_ranks, const void *id128);
+int katgpu_dist_rank(katgpu_ctx *ctx);    /* 0 on a single-GPU context */
+int katgpu_dist_n_ranks(katgpu_ctx *ctx); /* 1 on a single-GPU context */
+katgpu_status katgpu_dist_barrier(katgpu_ctx *ctx);
+/* k-mer starts routed and hashed keys received by this rank since katgpu_dist_init, and
+ * route rounds taken part in (8 bytes per key cross NVLink for (N-1)/N of them). */
+katgpu_status katgpu_dist_stats(katgpu_ctx *ctx, uint64_t *starts_routed, uint64_t *keys_received,
+                                uint64_t *rounds);
+
+/* Building blocks of the round-1 exchange (route into caller-provided buckets, insert
+ * received keys); kept for callers that move the keys themselves.  Every distinct k-mer must be owned by
  * exactly one rank before histograms become additive:
  *   1. katgpu_route_device: extract + canonicalise + hash this rank's base
  *      stream and write each k-mer's 64-bit hashed key into the bucket of its

@@ -67,6 +67,12 @@ SIGNATURES = {
     "katgpu_ipc_import": (_i, [_vp, C.POINTER(_vp)]),
     "katgpu_ipc_close": (None, [_vp]),
     "katgpu_synchronize": (_i, [_vp]),
+    "katgpu_dist_unique_id": (_i, [_vp]),
+    "katgpu_dist_init": (_i, [_vp, _i, _i, _vp]),
+    "katgpu_dist_rank": (_i, [_vp]),
+    "katgpu_dist_n_ranks": (_i, [_vp]),
+    "katgpu_dist_barrier": (_i, [_vp]),
+    "katgpu_dist_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "katgpu_launch_count": (_u64, [_vp]),
     "katgpu_profile_enable": (_i, [_vp, _i]),
     "katgpu_profile_get": (_i, [_vp, C.c_char_p, C.POINTER(_d), C.POINTER(_u64)]),
@@ -161,6 +167,29 @@ class Context:
     def synchronize(self):
         _check(lib().katgpu_synchronize(self.h))
 
+    # --- multi-GPU job (one context per GPU) ------------------------------------
+    def dist_init(self, rank, n_ranks, unique_id: bytes):
+        """Join a job of n_ranks contexts; unique_id = dist_unique_id() of rank 0, handed to everybody."""
+        assert len(unique_id) == 128
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        _check(lib().katgpu_dist_init(self.h, rank, n_ranks, buf))
+
+    @property
+    def rank(self):
+        return int(lib().katgpu_dist_rank(self.h))
+
+    @property
+    def n_ranks(self):
+        return int(lib().katgpu_dist_n_ranks(self.h))
+
+    def dist_barrier(self):
+        _check(lib().katgpu_dist_barrier(self.h))
+
+    def dist_stats(self):
+        a, b, r = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().katgpu_dist_stats(self.h, C.byref(a), C.byref(b), C.byref(r)))
+        return {"starts_routed": a.value, "keys_received": b.value, "rounds": r.value}
+
     def launch_count(self):
         return int(lib().katgpu_launch_count(self.h))
 
@@ -176,6 +205,12 @@ class Context:
                            sub_rate=0.005, n_rate=0.0001):
         _check(lib().katgpu_synth_reads_device(self.h, genome_len, seed_g, seed_r, first_read, n_reads, read_len,
                                                sub_rate, n_rate, out_dev))
+
+
+def dist_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    _check(lib().katgpu_dist_unique_id(buf))
+    return buf.raw
 
 
 def synth_reads_host(genome_len, seed_g, seed_r, first_read, n_reads, read_len=150, sub_rate=0.005, n_rate=0.0001):

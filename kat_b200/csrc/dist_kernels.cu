@@ -1,0 +1,182 @@
+// dist_kernels.cu — route_bases_kernel: extraction + the multi-GPU exchange in one kernel.
+//
+// Why k-mers must move at all: a count histogram is not additive over read shards, so every
+// distinct k-mer has to be counted on exactly one rank.  Reads are sharded by
+// record; this kernel does for rank q what bin_bases_kernel does on one GPU up to the hash —
+// TMA bulk copies of 4 KiB base tiles, SIMD-in-register 2-bit packing, 16 k-mers per thread cut
+// with constant funnel shifts (extract.cuh: Cut16), canonical strand, mix_words — and then, instead
+// of binning by table slice, sorts the tile's keys BY OWNER RANK in shared memory (one warp-
+// aggregated shared atomic per owner per warp instruction hands out the ranks) and copies each
+// owner's run with coalesced stores into this CTA's private segment of the receive area in the
+// OWNER's HBM.  The segment pointers are peer-mapped device memory: the stores of the (N-1)/N
+// remote keys travel over NVLink / NVSwitch as whole 128-byte lines while the next tile is being
+// hashed.  A segment holds every k-mer start its CTA processes in one launch (host: cap), so there
+// is no overflow path.  What follows on the owner is bin_keys_kernel (segment source) -> level-2
+// binning -> tile_insert_kernel: the single-GPU pipeline, unchanged.
+//
+// Replaces, for N > 1, the same reference loop as bin_bases_kernel (lib/src/jellyfish_helper.cc:
+// 202-211, JFI/mer_iterator.hpp:59-89) plus the exchange the reference never needs (one host).
+#include "dist_kernels.cuh"
+#include "extract.cuh"
+
+namespace katgpu {
+
+struct __align__(128) RouteSmem {
+    uint8_t ascii[kBinTile + kHalo];
+    uint32_t W[2][kBinGroups + 2];
+    uint32_t B[2][kBinGroups + 2];
+    uint64_t mbar;
+    uint32_t cnt[kMaxRanks];     // keys of the current tile per owner
+    uint32_t off[kMaxRanks + 1]; // exclusive prefix of cnt
+    uint32_t cur[kMaxRanks];     // keys this CTA has already written to each owner's segment
+    uint64_t pool[kBinTile];     // the tile's keys, sorted by owner
+};
+
+template <bool CANON, bool WIDE>
+__global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __grid_constant__ RouteParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    RouteSmem &S = *reinterpret_cast<RouteSmem *>(smem_raw);
+    const TableGeom &g = P.g;
+    const int tid = threadIdx.x;
+    const uint32_t lane = tid & 31u, lt_mask = (1u << lane) - 1u;
+    const uint32_t k = g.k, sh = g.sh, n_ranks = P.n_ranks;
+    const uint32_t kmask_lo = (uint32_t)g.kmask, kmask_hi = (uint32_t)(g.kmask >> 32);
+
+    auto tile_tma = [&](int t) { return P.tma_ok && ((uint64_t)(t + 1) * kBinTile + kHalo <= P.n_valid); };
+    int tile = (int)blockIdx.x; // static striding: CTA j owns tiles j, j + grid, ... (the host sizes `cap` from that)
+    if (tid < kMaxRanks) {
+        S.cnt[tid] = 0;
+        S.cur[tid] = 0;
+    }
+    if (tid == 0) {
+        mbar_init(&S.mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        if (tile < P.n_tiles && tile_tma(tile)) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            mbar_expect_tx(&S.mbar, kBinTile + kHalo);
+            tma_load_1d(S.ascii, P.bases + (uint64_t)tile * kBinTile, kBinTile + kHalo, &S.mbar);
+        }
+    }
+    __syncthreads();
+    uint32_t parity = 0, buf = 0;
+
+    for (; tile < P.n_tiles; tile += gridDim.x, buf ^= 1) {
+        const uint64_t tile_base = (uint64_t)tile * kBinTile;
+        if (tile_tma(tile)) {
+            while (!mbar_try_wait(&S.mbar, parity)) {
+            }
+            parity ^= 1;
+        } else { // ragged tail / unaligned input: guarded loads, bytes past n_valid read as 0 (= not a base)
+            for (int i = tid; i < (kBinTile + kHalo); i += kRouteThreads) {
+                const uint64_t p = tile_base + i;
+                S.ascii[i] = p < P.n_valid ? P.bases[p] : (uint8_t)0;
+            }
+            __syncthreads();
+        }
+        uint32_t *Wb = S.W[buf], *Bb = S.B[buf];
+        for (int gi = tid; gi < kBinGroups + 2; gi += kRouteThreads) {
+            const uint4 v = reinterpret_cast<const uint4 *>(S.ascii)[gi];
+            uint32_t c0, c1, c2, c3, b0, b1, b2, b3;
+            pack4(v.x, c0, b0);
+            pack4(v.y, c1, b1);
+            pack4(v.z, c2, b2);
+            pack4(v.w, c3, b3);
+            Wb[gi] = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+            Bb[gi] = (b0 << 12) | (b1 << 8) | (b2 << 4) | b3;
+        }
+        __syncthreads();
+        if (tid == 0) { // ascii is free again: fetch the next tile while this one is hashed
+            const int nt = tile + gridDim.x;
+            if (nt < P.n_tiles && tile_tma(nt)) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_expect_tx(&S.mbar, kBinTile + kHalo);
+                tma_load_1d(S.ascii, P.bases + (uint64_t)nt * kBinTile, kBinTile + kHalo, &S.mbar);
+            }
+        }
+        // 16 k-mers per thread, kept in registers until every key of the tile has its place
+        const uint64_t p0 = tile_base + (uint64_t)tid * 16;
+        const uint64_t bad48 = ((uint64_t)Bb[tid] << 32) | ((uint64_t)Bb[tid + 1] << 16) | Bb[tid + 2];
+        const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
+        Cut16 cut;
+        cut.init(Wb[tid], Wb[tid + 1], Wb[tid + 2], bad48, k, nst);
+        uint64_t hk[16];
+        uint32_t meta[8]; // two keys per word: bit 15 valid, bits 12-14 owner, bits 0-11 rank inside the owner's run
+#pragma unroll
+        for (uint32_t r = 0; r < 8; r++) meta[r] = 0;
+#pragma unroll
+        for (uint32_t r = 0; r < 16; r++) {
+            uint32_t lo, hi;
+            cut.key<CANON, WIDE>(r, kmask_lo, kmask_hi, lo, hi);
+            const uint64_t h = mix_words<WIDE>(lo, hi, sh, kmask_lo, kmask_hi);
+            const bool ok = cut.ok(r);
+            const uint32_t o = ok ? owner_of(h, n_ranks) : 0xFFu;
+            const uint32_t peers = __match_any_sync(0xffffffffu, o); // lanes whose key goes to the same owner
+            const int leader = __ffs(peers) - 1;
+            uint32_t base = 0;
+            if (ok && (int)lane == leader) base = atomicAdd(&S.cnt[o], (uint32_t)__popc(peers));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            hk[r] = h;
+            if (ok) meta[r >> 1] |= (0x8000u | (o << 12) | (base + (uint32_t)__popc(peers & lt_mask))) << (16 * (r & 1));
+        }
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t a = 0;
+            for (uint32_t d = 0; d < n_ranks; d++) {
+                S.off[d] = a;
+                a += S.cnt[d];
+            }
+            S.off[n_ranks] = a;
+        }
+        __syncthreads();
+#pragma unroll
+        for (uint32_t r = 0; r < 16; r++) {
+            const uint32_t m = (meta[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
+            if (m & 0x8000u) S.pool[S.off[(m >> 12) & 7u] + (m & 0xFFFu)] = hk[r];
+        }
+        __syncthreads();
+        // copy-out: consecutive threads store consecutive keys of a run -> whole lines per warp store,
+        // local HBM for the own rank, NVLink for the others
+        const uint32_t total = S.off[n_ranks];
+        for (uint32_t i = tid; i < total; i += kRouteThreads) {
+            uint32_t d = 0;
+#pragma unroll
+            for (uint32_t j = 1; j < (uint32_t)kMaxRanks; j++) d += (j < n_ranks && i >= S.off[j]) ? 1u : 0u;
+            uint64_t *dst = P.seg[d] + (size_t)blockIdx.x * P.cap + S.cur[d] + (i - S.off[d]);
+            *dst = S.pool[i];
+        }
+        __syncthreads();
+        if (tid < (int)n_ranks) {
+            S.cur[tid] += S.cnt[tid];
+            S.cnt[tid] = 0;
+        }
+        // (the pack phase of the next iteration ends with a barrier before cnt is touched again)
+    }
+    __syncthreads();
+    if (tid < (int)n_ranks) P.len[tid][blockIdx.x] = S.cur[tid];
+}
+
+size_t route_smem_bytes() { return sizeof(RouteSmem); }
+
+cudaError_t route_configure(int *blocks_per_sm) {
+    cudaError_t e;
+    const int smem = (int)sizeof(RouteSmem);
+    if ((e = cudaFuncSetAttribute(route_bases_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(route_bases_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(route_bases_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(route_bases_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    int a = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, route_bases_kernel<true, true>, kRouteThreads, sizeof(RouteSmem));
+    *blocks_per_sm = a < 2 ? a : 2;
+    return e;
+}
+
+void launch_route_bases(const RouteParams &P, int grid, cudaStream_t st) {
+    const bool canon = P.g.canonical != 0, wide = P.g.b >= 32;
+    const size_t smem = sizeof(RouteSmem);
+    if (canon && wide) route_bases_kernel<true, true><<<grid, kRouteThreads, smem, st>>>(P);
+    else if (canon) route_bases_kernel<true, false><<<grid, kRouteThreads, smem, st>>>(P);
+    else if (wide) route_bases_kernel<false, true><<<grid, kRouteThreads, smem, st>>>(P);
+    else route_bases_kernel<false, false><<<grid, kRouteThreads, smem, st>>>(P);
+}
+
+} // namespace katgpu

@@ -25,9 +25,11 @@
 #include <fstream>
 #include <iostream>
 #include <map>
+#include <mutex>
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "katgpu.h"
@@ -227,7 +229,8 @@ struct Input {
     uint64_t hash_size = 100000000ULL; // DEFAULT_HASH_SIZE, lib/include/kat/jellyfish_helper.hpp:76
     int index = 1;
     bool load_mode = false; // InputMode::LOAD: the (first) input is a jellyfish hash
-    katgpu_table *table = nullptr;
+    katgpu_table *table = nullptr;        // rank 0's (the only one on a single GPU)
+    vector<katgpu_table *> tables;        // one per GPU of the job
     uint64_t n_distinct = 0, n_total = 0;
 
     void set_trim(const vector<unsigned> &t) { // InputHandler::set5pTrim
@@ -269,14 +272,97 @@ size_t file_size_or_zero(const string &p) {
     return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode) ? (size_t)st.st_size : 0;
 }
 
+// ---- GPUs -------------------------------------------------------------------------
+// `--gpus N` (or KATGPU_GPUS): one libkatgpu context and one host thread per GPU in this process.
+// The contexts form a job (katgpu_dist_init: NCCL communicator + peer-mapped receive areas); every
+// libkatgpu call on a job is collective, so run_on_all() makes the same call from N threads.
+// Reads are sharded by position in the parsed base stream; k-mers travel to their owner GPU
+// inside libkatgpu; every GPU receives the all-reduced result and rank 0's copy is written out.
+[[noreturn]] void die(const KatError &e) {
+    cout.flush();
+    cerr << (e.code == 5 ? "Error: " : "") << e.what() << endl;
+    _exit(e.code); // other GPU threads may be parked in a collective: no orderly unwinding
+}
+template <class F>
+void run_on_all(int n, F f) { // f(rank)
+    if (n == 1) {
+        f(0);
+        return;
+    }
+    vector<std::thread> th;
+    for (int r = 0; r < n; r++)
+        th.emplace_back([&f, r] {
+            try {
+                f(r);
+            } catch (const KatError &e) {
+                static std::mutex m;
+                std::lock_guard<std::mutex> g(m);
+                die(e);
+            }
+        });
+    for (auto &t : th) t.join();
+}
+struct Ctx {
+    vector<katgpu_ctx *> all;
+    katgpu_ctx *c = nullptr; // rank 0
+    explicit Ctx(int gpus) {
+        int dev0 = 0;
+        if (const char *e = getenv("KATGPU_DEVICE")) dev0 = atoi(e);
+        if (gpus < 1 || gpus > 8) throw KatError(4, "--gpus must be 1..8");
+        if (gpus > 1 && katgpu_device_count() < dev0 + gpus)
+            throw KatError(4, "--gpus " + std::to_string(gpus) + ": only " + std::to_string(katgpu_device_count()) + " CUDA devices visible");
+        all.assign(gpus, nullptr);
+        for (int r = 0; r < gpus; r++) gpu_check(katgpu_init(dev0 + r, &all[r]));
+        c = all[0];
+        if (gpus > 1) {
+            unsigned char id[128];
+            gpu_check(katgpu_dist_unique_id(id));
+            run_on_all(gpus, [&](int r) { gpu_check(katgpu_dist_init(all[r], r, gpus, id)); });
+        }
+    }
+    int n() const { return (int)all.size(); }
+    ~Ctx() {
+        run_on_all(n(), [&](int r) { katgpu_shutdown(all[r]); });
+    }
+};
+int gpus_option(const Parsed &a) {
+    const char *e = getenv("KATGPU_GPUS");
+    return (int)to_u64(a.get("gpus", e ? e : "1"), "gpus");
+}
+void free_tables(Ctx &ctx, Input &in) {
+    run_on_all(ctx.n(), [&](int r) {
+        if (r < (int)in.tables.size()) katgpu_table_free(in.tables[r]);
+    });
+    in.tables.clear();
+    in.table = nullptr;
+}
+// Feed one parsed base stream: on a job, GPU r takes the r-th share of the k-mer START positions;
+// its bytes run k-1 past the share's end so that every k-mer is complete on exactly one GPU (a
+// start inside that tail has fewer than k bases left and yields nothing).
+void feed_all(Ctx &ctx, Input &in, int k, const char *b, size_t n) {
+    if (ctx.n() == 1) {
+        gpu_check(katgpu_count_feed(in.table, b, n));
+        return;
+    }
+    run_on_all(ctx.n(), [&](int r) {
+        const size_t lo = n * (size_t)r / ctx.n(), hi = n * (size_t)(r + 1) / ctx.n();
+        const size_t end = std::min(n, hi + (size_t)k - 1);
+        gpu_check(katgpu_count_feed(in.tables[r], b + lo, hi > lo ? end - lo : 0));
+    });
+}
+
 // InputHandler::count (lib/src/input_handler.cc:180-202) on the GPU
-void count_input(katgpu_ctx *ctx, Input &in, int k, bool allow_grow, bool allow_streaming = true) {
+void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_streaming = true) {
     Timer t;
     if (allow_streaming) {
         cout << "Input " << in.index << " is a sequence file.  Counting kmers for input " << in.index << " (" << join(in.files, false) << ") ...";
         cout.flush();
     }
-    gpu_check(katgpu_count_begin(ctx, k, in.canonical ? 1 : 0, in.hash_size, allow_grow ? 1 : 0, &in.table));
+    in.tables.assign(ctx.n(), nullptr);
+    // a job shares the k-mers out: every GPU's table needs room for its 1/N of the distinct ones
+    const uint64_t per_gpu_slots = ctx.n() > 1 ? std::max<uint64_t>(in.hash_size / ctx.n(), 1024) : in.hash_size;
+    run_on_all(ctx.n(), [&](int r) { gpu_check(katgpu_count_begin(ctx.all[r], k, in.canonical ? 1 : 0, per_gpu_slots, allow_grow ? 1 : 0, &in.tables[r])); });
+    in.table = in.tables[0];
     const size_t stream_from = env_size("KAT_STREAM_BYTES", (size_t)2 << 30), block = env_size("KAT_STREAM_BLOCK", (size_t)512 << 20);
     std::vector<unsigned char> raw;
     std::string bases;
@@ -285,14 +371,13 @@ void count_input(katgpu_ctx *ctx, Input &in, int k, bool allow_grow, bool allow_
         if (allow_streaming && file_size_or_zero(in.files[i]) >= stream_from) {
             katgpu_status bad = KATGPU_OK;
             const int r = kat_host::stream_regular_file(in.files[i], in.trim5p[i], block, [&](const char *b, size_t n) {
-                bad = katgpu_count_feed(in.table, b, n);
-                return bad == KATGPU_OK;
+                feed_all(ctx, in, k, b, n);
+                return true;
             }, err);
             gpu_check(bad);
             if (r == 1) continue;
             if (r < 0) { // irregular after some blocks were counted: start this input over, whole files at a time
-                katgpu_table_free(in.table);
-                in.table = nullptr;
+                free_tables(ctx, in);
                 count_input(ctx, in, k, allow_grow, false);
                 return;
             }
@@ -304,13 +389,17 @@ void count_input(katgpu_ctx *ctx, Input &in, int k, bool allow_grow, bool allow_
             cerr << "warning: " << in.files[i] << ": Unsupported format (the reference silently stops reading this input here)" << endl;
             break;
         }
-        if (!bases.empty()) gpu_check(katgpu_count_feed(in.table, bases.data(), bases.size()));
+        if (!bases.empty()) feed_all(ctx, in, k, bases.data(), bases.size());
         if (st == kat_host::ParseStatus::InvalidFastq) {
             cerr << "warning: " << in.files[i] << ": Invalid fastq sequence; like the reference, the rest of this input is ignored" << endl;
             break;
         }
     }
-    gpu_check(katgpu_count_end(in.table, &in.n_distinct, &in.n_total));
+    run_on_all(ctx.n(), [&](int r) {
+        uint64_t nd = 0, nt = 0;
+        gpu_check(katgpu_count_end(in.tables[r], &nd, &nt)); // on a job: the job's totals, on every rank
+        if (r == 0) in.n_distinct = nd, in.n_total = nt;
+    });
     phase_done(t);
 }
 
@@ -355,13 +444,16 @@ int load_input(katgpu_ctx *ctx, Input &in) {
     gpu_check(katgpu_count_end(in.table, &in.n_distinct, &in.n_total));
     return k;
 }
-void load_inputs_phase(katgpu_ctx *ctx, Input *ins, int n_in, int &k) { // the "Loading hashes into memory..." phase
+void load_inputs_phase(Ctx &gpus, Input *ins, int n_in, int &k) { // the "Loading hashes into memory..." phase
+    if (gpus.n() > 1) throw KatError(4, "jellyfish hash inputs are loaded on one GPU: run without --gpus");
+    katgpu_ctx *ctx = gpus.c;
     Timer t;
     cout << "Loading hashes into memory...";
     cout.flush();
     for (int i = 0; i < n_in; i++)
         if (ins[i].load_mode) {
             const int kk = load_input(ctx, ins[i]);
+            ins[i].tables.assign(1, ins[i].table);
             if (n_in == 1) k = kk; // hist / gcp take merLen from the loaded hash (InputHandler::loadHash)
         }
     phase_done(t);
@@ -479,22 +571,13 @@ void print_distances(std::ostream &out, const vector<uint64_t> &a, const vector<
     out << " - Jaccard distance: " << jaccard(a, b) << endl;
 }
 
-struct Ctx {
-    katgpu_ctx *c = nullptr;
-    Ctx() {
-        int dev = 0;
-        if (const char *e = getenv("KATGPU_DEVICE")) dev = atoi(e);
-        gpu_check(katgpu_init(dev, &c));
-    }
-    ~Ctx() { katgpu_shutdown(c); }
-};
 
 // =============================== kat hist ========================================
 int hist_main(int argc, char **argv) {
     const vector<OptSpec> specs = {{'o', "output_prefix", true}, {'t', "threads", true}, {'l', "low", true}, {'h', "high", true},
                                    {'i', "inc", true}, {0, "5ptrim", true}, {'N', "non_canonical", false}, {'m', "mer_len", true},
                                    {'H', "hash_size", true}, {'d', "dump_hash", false}, {'p', "output_type", true},
-                                   {'v', "verbose", false}, {0, "help", false}};
+                                   {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat hist [options] (<input>)+\n\nCreate an histogram of k-mer occurrences from the input.\n\n"
@@ -518,15 +601,20 @@ int hist_main(int argc, char **argv) {
     if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
     in.validate();
     ensure_parent_dir(prefix);
-    Ctx ctx;
-    if (in.load_mode) load_inputs_phase(ctx.c, &in, 1, k);
-    else count_input(ctx.c, in, k, true);
+    Ctx ctx(gpus_option(a));
+    if (a.has("dump_hash") && ctx.n() > 1) throw KatError(4, "--dump_hash writes one GPU's table: run without --gpus");
+    if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
+    else count_input(ctx, in, k, true);
     vector<uint64_t> bins(nb);
     {
         Timer t;
         cout << "Bining kmers ...";
         cout.flush();
-        gpu_check(katgpu_hist(in.table, base, ceil, inc, nb, bins.data()));
+        vector<vector<uint64_t>> other(ctx.n()); // every GPU of a job receives the all-reduced bins
+        run_on_all(ctx.n(), [&](int r) {
+            if (r) other[r].resize(nb);
+            gpu_check(katgpu_hist(in.tables[r], base, ceil, inc, nb, r ? other[r].data() : bins.data()));
+        });
         phase_done(t);
     }
     if (a.has("dump_hash")) dump_input(in, k, prefix + "-hash.jf" + std::to_string(k));
@@ -546,7 +634,7 @@ int hist_main(int argc, char **argv) {
         out.close();
         phase_done(t);
     }
-    katgpu_table_free(in.table);
+    free_tables(ctx, in);
     char b[96];
     snprintf(b, sizeof b, "KAT HIST completed.\nTotal runtime: %.1fs\n\n", total.secs());
     cout << b;
@@ -557,7 +645,7 @@ int hist_main(int argc, char **argv) {
 int gcp_main(int argc, char **argv) {
     const vector<OptSpec> specs = {{'o', "output_prefix", true}, {'t', "threads", true}, {'x', "cvg_scale", true}, {'y', "cvg_bins", true},
                                    {0, "5ptrim", true}, {'N', "non_canonical", false}, {'m', "mer_len", true}, {'H', "hash_size", true},
-                                   {'d', "dump_hash", false}, {'p', "output_type", true}, {'v', "verbose", false}, {0, "help", false}};
+                                   {'d', "dump_hash", false}, {'p', "output_type", true}, {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat gcp [options] (<input>)+\n\nCompares GC content and K-mer coverage from the input.\n\n"
@@ -578,15 +666,20 @@ int gcp_main(int argc, char **argv) {
     if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
     in.validate();
     ensure_parent_dir(prefix);
-    Ctx ctx;
-    if (in.load_mode) load_inputs_phase(ctx.c, &in, 1, k);
-    else count_input(ctx.c, in, k, true);
+    Ctx ctx(gpus_option(a));
+    if (a.has("dump_hash") && ctx.n() > 1) throw KatError(4, "--dump_hash writes one GPU's table: run without --gpus");
+    if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
+    else count_input(ctx, in, k, true);
     vector<uint64_t> mx((size_t)k * (bins + 1));
     {
         Timer t;
         cout << "Analysing kmers in hash ...";
         cout.flush();
-        gpu_check(katgpu_gcp(in.table, scale, bins, mx.data()));
+        vector<vector<uint64_t>> other(ctx.n());
+        run_on_all(ctx.n(), [&](int r) {
+            if (r) other[r].resize(mx.size());
+            gpu_check(katgpu_gcp(in.tables[r], scale, bins, r ? other[r].data() : mx.data()));
+        });
         phase_done(t);
         if (a.has("dump_hash")) dump_input(in, k, prefix + "-hash.jf" + std::to_string(k));
     }
@@ -610,7 +703,7 @@ int gcp_main(int argc, char **argv) {
         out.close();
         phase_done(t);
     }
-    katgpu_table_free(in.table);
+    free_tables(ctx, in);
     char b[96];
     snprintf(b, sizeof b, "KAT GCP completed.\nTotal runtime: %.1fs\n\n", total.secs());
     cout << b;
@@ -661,7 +754,7 @@ int comp_main(int argc, char **argv) {
                                    {'N', "non_canonical_1", false}, {'O', "non_canonical_2", false}, {'P', "non_canonical_3", false},
                                    {'m', "mer_len", true}, {'H', "hash_size_1", true}, {'I', "hash_size_2", true}, {'J', "hash_size_3", true},
                                    {'d', "dump_hashes", false}, {'g', "disable_hash_grow", false}, {'n', "density_plot", false},
-                                   {'p', "output_type", true}, {'h', "output_hists", false}, {'v', "verbose", false}, {0, "help", false}};
+                                   {'p', "output_type", true}, {'h', "output_hists", false}, {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat comp [options] <input_1> <input_2> [<input_3>]\n\nCompares jellyfish K-mer count hashes.\n\n"
@@ -694,13 +787,17 @@ int comp_main(int argc, char **argv) {
     const string prefix = a.get("output_prefix", "kat-comp");
     for (int i = 0; i < (three ? 3 : 2); i++) in[i].validate();
     ensure_parent_dir(prefix);
-    Ctx ctx;
+    Ctx ctx(gpus_option(a));
+    if (a.has("dump_hashes") && ctx.n() > 1) throw KatError(4, "--dump_hashes writes one GPU's table: run without --gpus");
+    if (ctx.n() > 1)
+        for (int i = 0; i < (three ? 3 : 2); i++)
+            if (!in[i].canonical) throw KatError(4, "with --gpus every input must be counted canonically (no -N/-O/-P): the shared-k-mer walk is local to the GPU that owns a k-mer");
     const int n_in = three ? 3 : 2;
     // Comp::execute (src/comp.cc:140-167): count the sequence inputs, then read the headers of
     // the hash inputs; when every input is a hash the mer length comes from the first header;
     // every hash must hold k-mers of the mer length in use (InputHandler::validateMerLen).
     for (int i = 0; i < n_in; i++)
-        if (!in[i].load_mode) count_input(ctx.c, in[i], k, !a.has("disable_hash_grow"));
+        if (!in[i].load_mode) count_input(ctx, in[i], k, !a.has("disable_hash_grow"));
     bool any_load = false, all_load = true;
     vector<unsigned> hash_k(n_in, 0);
     for (int i = 0; i < n_in; i++) {
@@ -718,7 +815,7 @@ int comp_main(int argc, char **argv) {
                                   ".  Key length was " + std::to_string(hash_k[i]) + " for : " + in[i].files[0]);
     if (any_load) {
         int k_unused = k;
-        load_inputs_phase(ctx.c, in, n_in, k_unused);
+        load_inputs_phase(ctx, in, n_in, k_unused);
     }
     const size_t cells = (size_t)d1b * d2b, len = std::min(d1b, d2b);
     vector<uint64_t> main_mx(cells), ends, middle, mixed, spectra(4 * len);
@@ -732,9 +829,19 @@ int comp_main(int argc, char **argv) {
         Timer t;
         cout << "Comparing hashes ...";
         cout.flush();
-        gpu_check(katgpu_comp(in[0].table, in[1].table, three ? in[2].table : nullptr, d1s, d2s, d1b, d2b, main_mx.data(),
-                              three ? ends.data() : nullptr, three ? middle.data() : nullptr, three ? mixed.data() : nullptr, &cc,
-                              spectra.data()));
+        run_on_all(ctx.n(), [&](int r) {
+            if (r == 0) {
+                gpu_check(katgpu_comp(in[0].tables[0], in[1].tables[0], three ? in[2].tables[0] : nullptr, d1s, d2s, d1b, d2b, main_mx.data(),
+                                      three ? ends.data() : nullptr, three ? middle.data() : nullptr, three ? mixed.data() : nullptr, &cc,
+                                      spectra.data()));
+                return;
+            }
+            vector<uint64_t> m(cells), e, mi, mx2, sp(4 * len); // the other GPUs' copies of the all-reduced result
+            if (three) e.resize(cells), mi.resize(cells), mx2.resize(cells);
+            katgpu_comp_counters c2;
+            gpu_check(katgpu_comp(in[0].tables[r], in[1].tables[r], three ? in[2].tables[r] : nullptr, d1s, d2s, d1b, d2b, m.data(),
+                                  three ? e.data() : nullptr, three ? mi.data() : nullptr, three ? mx2.data() : nullptr, &c2, sp.data()));
+        });
         phase_done(t);
     }
     if (a.has("dump_hashes")) // src/comp.cc:174-179
@@ -795,7 +902,7 @@ int comp_main(int argc, char **argv) {
     }
     cout << endl << "Summary statistics" << endl << "------------------" << endl << endl;
     print_comp_counts(cout, cc, p1, p2, p3, sp1, sp2, ssp1, ssp2);
-    for (int i = 0; i < (three ? 3 : 2); i++) katgpu_table_free(in[i].table);
+    for (int i = 0; i < (three ? 3 : 2); i++) free_tables(ctx, in[i]);
     char b[96];
     snprintf(b, sizeof b, "KAT COMP completed.\nTotal runtime: %.1fs\n\n", total.secs());
     cout << b;

@@ -1,130 +1,35 @@
 // katgpu_api.cu — C-ABI of libkatgpu (include/katgpu.h): contexts, table
 // lifetime (allocation, admission control, doubling), the host->device feed
 // pipeline and the launch glue around the kernels.
-#include "../../include/katgpu.h"
-#include "count_kernels.cuh"
-#include "partition_kernels.cuh"
-#include "tile_kernels.cuh"
-#include "reduce_kernels.cuh"
+#include "katgpu_internal.cuh"
 #include "synth.cuh"
 
 #include <algorithm>
-#include <chrono>
 #include <cstdarg>
-#include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <cmath>
-#include <map>
 #include <new>
-#include <string>
-#include <vector>
 
 using namespace katgpu;
 
 static thread_local char g_err[512] = "";
 static int g_debug_count_bits = 0;
 
-static katgpu_status fail(katgpu_status st, const char *fmt, ...) {
+katgpu_status katgpu_fail(katgpu_status st, const char *fmt, ...) {
     va_list ap;
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof g_err, fmt, ap);
     va_end(ap);
     return st;
 }
-#define CU(call)                                                                                              \
-    do {                                                                                                      \
-        cudaError_t e__ = (call);                                                                             \
-        if (e__ != cudaSuccess)                                                                               \
-            return fail(e__ == cudaErrorMemoryAllocation ? KATGPU_ERR_NOMEM : KATGPU_ERR_CUDA, "%s: %s (%s:%d)", \
-                        #call, cudaGetErrorString(e__), __FILE__, __LINE__);                                  \
-    } while (0)
-#define KT(call)                          \
-    do {                                  \
-        katgpu_status s__ = (call);       \
-        if (s__ != KATGPU_OK) return s__; \
-    } while (0)
-
-struct ProfSpan {
-    std::string family;
-    cudaEvent_t a, b;
-};
-
-static const int kRing = 24; // host-feed staging ring: lets the copy engine run ahead of a mid-feed sweep
-
-struct katgpu_ctx {
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t stream = nullptr, copy_stream = nullptr;
-    int bps[2] = {1, 1}; // resident CTAs per SM of the extract kernels
-    int bps_part = 1;    // ... of the partition kernel
-    int bps_sweep = 1;   // ... of the sweep kernel
-    int bps_bin1 = 2, bps_tile = 1; // ... of the tiled path's bin_bases / tile_insert kernels
-    unsigned int *tile_counter = nullptr; // device
-    unsigned long long *route_cursors = nullptr; // device [kMaxRanks] + overflow flag after
-    // host feed staging
-    uint8_t *chunk[kRing] = {};
-    size_t chunk_cap = 0;
-    int chunk_n = 0;          // staging buffers currently allocated (2 .. kRing)
-    cudaEvent_t chunk_free[kRing] = {}, chunk_ready[kRing] = {};
-    TableCounters *h_ctr = nullptr; // pinned mirror
-    uint64_t launches = 0;
-    bool profiling = false;
-    std::vector<ProfSpan> spans;
-    std::map<std::string, std::pair<double, uint64_t>> prof;
-    // freed device blocks kept for reuse: a `kat hist` job after the first one does not pay
-    // cudaMalloc/cudaFree of tens of GB again (the reference likewise keeps its mmap'd arena)
-    std::multimap<size_t, void *> pool;
-    size_t pooled_bytes = 0;
-};
-
-struct katgpu_table {
-    katgpu_ctx *ctx = nullptr;
-    TableGeom g{};
-    uint64_t n_slots = 0;
-    bool allow_grow = true, ended = false;
-    uint32_t grow_events = 0;
-    int count_bits_cap = 0;
-    // keys partitioned by table slice, waiting for the next sweep (partitioned path)
-    uint64_t *pend_keys = nullptr;
-    uint32_t *pend_seglen = nullptr, *pend_hll = nullptr, *pend_done = nullptr;
-    uint32_t pend_Pb = 0, pend_segs = 0, pend_seg_cap = 0;
-    double pend_fill = 0;      // conservative estimate of the fullest segment (keys)
-    uint64_t pend_tiles = 0;   // tiles the busiest CTA has partitioned since the last sweep
-    uint64_t pend_total_tiles = 0; // all tiles since the last sweep (also the CTA rotation)
-    uint64_t pend_bound = 0;   // upper bound on pending k-mer instances
-    size_t pend_bytes = 0, pend_seglen_bytes = 0;
-    // tiled path (tile_kernels.cu): the pending keys are level-1 segments of the same layout
-    bool tiled = false;
-    uint32_t ring1 = 0;           // staging-ring slots per bin of the level-1 kernels
-    uint64_t *side_keys = nullptr; // side list + its counters {n, reserved} and the deferred-tile list
-    unsigned long long *side_ctr = nullptr;
-    uint32_t *side_deferred = nullptr;
-    uint64_t side_cap = 0;
-    size_t side_bytes = 0;
-};
-
-static const size_t kChunkBytes = 128u << 20; // host feed granularity
-static const uint64_t kSpillCap = 1u << 20;   // (hashed key, count) pairs
-
-// KATGPU_TRACE=1: wall-clock of every host-side phase to stderr (debugging aid).
-struct TraceScope {
-    const char *name;
-    std::chrono::steady_clock::time_point t0;
-    bool on;
-    explicit TraceScope(const char *n) : name(n), t0(std::chrono::steady_clock::now()), on(getenv("KATGPU_TRACE") != nullptr) {}
-    ~TraceScope() {
-        if (on) fprintf(stderr, "[katgpu] %-28s %8.3f ms\n", name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
-    }
-};
 
 // ---- device block cache ----
-static void pool_flush(katgpu_ctx *c) {
+void pool_flush(katgpu_ctx *c) {
     for (auto &kv : c->pool) cudaFree(kv.second);
     c->pool.clear();
     c->pooled_bytes = 0;
 }
-static cudaError_t pool_alloc(katgpu_ctx *c, size_t bytes, void **out) {
+cudaError_t pool_alloc(katgpu_ctx *c, size_t bytes, void **out) {
     bytes = std::max<size_t>(bytes, 256);
     auto it = c->pool.find(bytes);
     if (it != c->pool.end()) {
@@ -141,34 +46,13 @@ static cudaError_t pool_alloc(katgpu_ctx *c, size_t bytes, void **out) {
     }
     return e;
 }
-static void pool_free(katgpu_ctx *c, void *p, size_t bytes) {
+void pool_free(katgpu_ctx *c, void *p, size_t bytes) {
     if (!p) return;
     bytes = std::max<size_t>(bytes, 256);
     c->pool.emplace(bytes, p);
     c->pooled_bytes += bytes;
 }
 
-// ---- profiling helpers ----
-struct ProfScope {
-    katgpu_ctx *c;
-    cudaStream_t st;
-    ProfSpan sp;
-    bool on;
-    ProfScope(katgpu_ctx *ctx, const char *family, cudaStream_t s) : c(ctx), st(s), on(ctx->profiling) {
-        if (on) {
-            sp.family = family;
-            cudaEventCreate(&sp.a);
-            cudaEventCreate(&sp.b);
-            cudaEventRecord(sp.a, st);
-        }
-    }
-    ~ProfScope() {
-        if (on) {
-            cudaEventRecord(sp.b, st);
-            c->spans.push_back(sp);
-        }
-    }
-};
 static void prof_collect(katgpu_ctx *c) {
     for (auto &sp : c->spans) {
         cudaEventSynchronize(sp.b);
@@ -248,6 +132,7 @@ extern "C" void katgpu_shutdown(katgpu_ctx *c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->copy_stream);
+    dist_shutdown(c);
     prof_collect(c);
     for (int i = 0; i < kRing; i++) {
         if (c->chunk[i]) cudaFree(c->chunk[i]);
@@ -341,7 +226,7 @@ extern "C" katgpu_status katgpu_profile_get(katgpu_ctx *c, const char *family, d
 }
 
 // Per-launch bound on the increments one slot can receive -> when RED is provably safe.
-static void set_add_bound(TableGeom &g, uint64_t bound) {
+void set_add_bound(TableGeom &g, uint64_t bound) {
     g.add_bound = bound;
     g.red_below = bound <= g.cmax ? g.cmax - bound + 1 : 0;
 }
@@ -482,7 +367,7 @@ extern "C" void katgpu_table_free(katgpu_table *t) {
 }
 
 // Read the device counter block (synchronises the compute stream).
-static katgpu_status read_counters(katgpu_table *t, TableCounters &out) {
+katgpu_status read_counters(katgpu_table *t, TableCounters &out) {
     katgpu_ctx *c = t->ctx;
     CU(cudaMemcpyAsync(c->h_ctr, t->g.ctr, sizeof(TableCounters), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -529,7 +414,7 @@ static const double kMaxLoad = 0.80;  // grow beyond this
 static const double kHardLoad = 0.90; // never admit more k-mers than this could hold
 
 // After a launch: replay spills (growing), check the overflow side table.
-static katgpu_status settle(katgpu_table *t, TableCounters &ctr) {
+katgpu_status settle(katgpu_table *t, TableCounters &ctr) {
     KT(read_counters(t, ctr));
     if (ctr.ovf_full) return fail(KATGPU_ERR_OVERFLOW, "count-overflow side table exhausted (%u keys)", kOvfCap);
     while (ctr.spill_n > 0) {
@@ -606,7 +491,7 @@ static int count_path_mode() { // 0 auto, 1 direct, 2 partition (L2 sweep), 3 ti
 }
 static const int kAutoPendingPath = 3; // which pending-key path "auto" picks for large jobs (2 = L2 sweep, 3 = tiled)
 static bool tiled_possible(const katgpu_table *t) { return (int)t->g.Lb >= kTileBucketsLog2 + 2; }
-static bool use_partition(const katgpu_table *t, uint64_t kmers_hint) {
+bool use_partition(const katgpu_table *t, uint64_t kmers_hint) {
     if (t->pend_keys) return true; // keep the path the pending buffer was built for
     const int m = count_path_mode();
     if (m == 1 || t->g.Lb < 6) return false;
@@ -631,7 +516,7 @@ static uint32_t ring_slots(uint32_t F, uint32_t tile_keys, size_t max_bytes, uin
     return (uint32_t)R;
 }
 
-static katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) {
+katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) {
     TraceScope trace__("  pend_alloc");
     ok = true;
     if (t->pend_keys) return KATGPU_OK;
@@ -729,9 +614,7 @@ static double hll_estimate(const uint32_t *reg, int m) {
     return e;
 }
 
-static katgpu_status settle(katgpu_table *t, TableCounters &ctr);
 static katgpu_status admit(katgpu_table *t, TableCounters &ctr, uint64_t want, uint64_t &granted);
-static void set_add_bound(TableGeom &g, uint64_t bound);
 
 // Insert `n` hashed keys held in device memory with the general random-access kernel.
 static katgpu_status insert_hashed_direct(katgpu_table *t, TableCounters &ctr, const uint64_t *hs, uint64_t n) {
@@ -755,7 +638,7 @@ static katgpu_status insert_hashed_direct(katgpu_table *t, TableCounters &ctr, c
     return KATGPU_OK;
 }
 
-static SideList side_list_of(const katgpu_table *t) {
+SideList side_list_of(const katgpu_table *t) {
     SideList S{};
     S.keys = t->side_keys;
     S.n = t->side_ctr;
@@ -921,7 +804,7 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
 
 // Insert every pending key, slice by slice (sweep_kernel), after sizing the table
 // for the estimated number of new distinct keys.
-static katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
+katgpu_status sweep_pending(katgpu_table *t, TableCounters &ctr) {
     TraceScope trace__("  sweep_pending");
     if (!t->pend_keys || t->pend_bound == 0) return KATGPU_OK;
     katgpu_ctx *c = t->ctx;
@@ -1082,7 +965,7 @@ static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint6
 }
 
 // Count a device-resident stream, in admission-controlled sub-launches.
-static katgpu_status feed_device_range(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
+katgpu_status feed_device_range(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
                                        TableCounters &ctr, uint64_t kmers_hint) {
     // a k-mer start needs k bases
     if (n_valid < (uint64_t)t->g.k) return KATGPU_OK;
@@ -1111,9 +994,31 @@ extern "C" katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *b
     if (!t || (!bases_dev && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_feed_device: NULL argument");
     if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_feed_device: table already finished");
     CU(cudaSetDevice(t->ctx->device));
+    if (t->ctx->dist) return dist_feed_device(t, (const uint8_t *)bases_dev, n);
     TableCounters ctr;
     KT(read_counters(t, ctr));
     return feed_device_range(t, (const uint8_t *)bases_dev, n, n, ctr, n);
+}
+
+// Device staging buffers of the host feed: `ring` buffers of at least `chunk` + halo bytes.
+katgpu_status ensure_feed_staging(katgpu_ctx *c, size_t chunk, int ring) {
+    if (c->chunk_cap >= chunk + kHalo && c->chunk_n >= ring) return KATGPU_OK;
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    for (int i = 0; i < kRing; i++) {
+        if (c->chunk[i]) cudaFree(c->chunk[i]);
+        c->chunk[i] = nullptr;
+    }
+    const size_t cap = std::max(c->chunk_cap, chunk + kHalo);
+    ring = std::max(ring, c->chunk_n);
+    for (int i = 0; i < ring; i++) {
+        void *p = nullptr;
+        CU(cudaMalloc(&p, cap + 64));
+        c->chunk[i] = (uint8_t *)p;
+    }
+    c->chunk_cap = cap;
+    c->chunk_n = ring;
+    return KATGPU_OK;
 }
 
 extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n) {
@@ -1123,25 +1028,11 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));
     if (n == 0) return KATGPU_OK;
+    if (c->dist) return dist_feed_host(t, bases, n);
     const size_t chunk = std::min(kChunkBytes, (n + 4095) / 4096 * 4096);
     const size_t n_chunks = (n + chunk - 1) / chunk;
     const int ring = (int)std::min<size_t>(kRing, std::max<size_t>(2, n_chunks));
-    if (c->chunk_cap < chunk + kHalo || c->chunk_n < ring) {
-        CU(cudaStreamSynchronize(c->stream));
-        CU(cudaStreamSynchronize(c->copy_stream));
-        for (int i = 0; i < kRing; i++) {
-            if (c->chunk[i]) cudaFree(c->chunk[i]);
-            c->chunk[i] = nullptr;
-        }
-        const size_t cap = std::max(c->chunk_cap, chunk + kHalo);
-        for (int i = 0; i < ring; i++) {
-            void *p = nullptr;
-            CU(cudaMalloc(&p, cap + 64));
-            c->chunk[i] = (uint8_t *)p;
-        }
-        c->chunk_cap = cap;
-        c->chunk_n = ring;
-    }
+    KT(ensure_feed_staging(c, chunk, ring));
     TableCounters ctr;
     KT(read_counters(t, ctr));
     // chunk i holds host bytes [i*chunk, (i+1)*chunk + halo): k-mers starting in
@@ -1198,12 +1089,31 @@ extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct,
     CU(cudaSetDevice(t->ctx->device));
     TableCounters ctr;
     KT(read_counters(t, ctr));
+    if (t->ctx->dist && !t->ended) KT(dist_count_end(t, ctr)); // every rank's last route round has been binned here
     KT(sweep_pending(t, ctr));
     KT(settle(t, ctr));
-    t->ended = true;
     pend_release(t); // the pending-key buffers are only needed while counting
-    if (n_distinct) *n_distinct = ctr.n_distinct;
-    if (n_total) *n_total = ctr.n_total;
+    uint64_t tot[2] = {ctr.n_distinct, ctr.n_total};
+    if (t->ctx->dist) { // every k-mer lives on exactly one rank: the job's totals are the sums
+        if (!t->ended) {
+            katgpu_ctx *c = t->ctx;
+            void *d = nullptr;
+            CU(pool_alloc(c, 256, &d));
+            CU(cudaMemcpyAsync(d, tot, 16, cudaMemcpyHostToDevice, c->stream));
+            katgpu_status st = dist_allreduce_u64(c, d, 2);
+            if (st == KATGPU_OK && cudaMemcpyAsync(tot, d, 16, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess) st = fail(KATGPU_ERR_CUDA, "katgpu_count_end: copy failed");
+            cudaStreamSynchronize(c->stream);
+            pool_free(c, d, 256);
+            KT(st);
+            t->dist_global_distinct = tot[0];
+            t->dist_global_total = tot[1];
+        }
+        tot[0] = t->dist_global_distinct;
+        tot[1] = t->dist_global_total;
+    }
+    t->ended = true;
+    if (n_distinct) *n_distinct = tot[0];
+    if (n_total) *n_total = tot[1];
     return KATGPU_OK;
 }
 
@@ -1268,6 +1178,7 @@ extern "C" katgpu_status katgpu_count_add_pairs(katgpu_table *t, const uint64_t 
     if (!t || ((!keys || !counts) && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_add_pairs: NULL argument");
     if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_add_pairs: table already finished");
     katgpu_ctx *c = t->ctx;
+    if (c->dist) return fail(KATGPU_ERR_STATE, "katgpu_count_add_pairs: not available on a multi-GPU context (load hashes on one GPU)");
     CU(cudaSetDevice(c->device));
     TableCounters ctr;
     KT(read_counters(t, ctr));
@@ -1372,6 +1283,7 @@ extern "C" katgpu_status katgpu_hist(katgpu_table *t, uint64_t base, uint64_t ce
     }
     c->launches++;
     CU(cudaGetLastError());
+    if (c->dist) KT(dist_allreduce_u64(c, d.p, nb)); // ranks own disjoint k-mers: bins add up
     CU(cudaMemcpyAsync(bins_out, d.p, nb * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return KATGPU_OK;
@@ -1392,6 +1304,7 @@ extern "C" katgpu_status katgpu_gcp(katgpu_table *t, double cvg_scale, uint32_t 
     }
     c->launches++;
     CU(cudaGetLastError());
+    if (c->dist) KT(dist_allreduce_u64(c, d.p, cells));
     CU(cudaMemcpyAsync(mx_out, d.p, cells * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return KATGPU_OK;
@@ -1409,6 +1322,11 @@ extern "C" katgpu_status katgpu_comp(katgpu_table *t1, katgpu_table *t2, katgpu_
     if (t1->g.k != t2->g.k || (t3 && t3->g.k != t1->g.k)) return fail(KATGPU_ERR_INVALID, "katgpu_comp: tables were counted with different k");
     if (t1->ctx != t2->ctx || (t3 && t3->ctx != t1->ctx)) return fail(KATGPU_ERR_INVALID, "katgpu_comp: tables live on different contexts");
     katgpu_ctx *c = t1->ctx;
+    // Multi-GPU: the dual-hash walk is local because both inputs place a k-mer on the same owner rank.
+    // That holds for the stored k-mer; a probe that re-canonicalises a non-canonical stored k-mer
+    // (src/comp.cc:400,447) may belong to another rank.
+    if (c->dist && !(t1->g.canonical && t2->g.canonical && (!t3 || t3->g.canonical)))
+        return fail(KATGPU_ERR_INVALID, "katgpu_comp: on a multi-GPU context every input must be counted canonically");
     CU(cudaSetDevice(c->device));
     const uint32_t len = std::min(d1_bins, d2_bins);
     const size_t cells = (size_t)d1_bins * d2_bins;
@@ -1467,6 +1385,7 @@ extern "C" katgpu_status katgpu_comp(katgpu_table *t1, katgpu_table *t2, katgpu_
         }
     }
     CU(cudaGetLastError());
+    if (c->dist) KT(dist_allreduce_u64(c, d.p, words)); // matrices, counters and spectra in one all-reduce
     CU(cudaMemcpyAsync(main_mx, P.main_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
     if (t3) {
         CU(cudaMemcpyAsync(ends_mx, P.ends_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -1495,6 +1414,7 @@ extern "C" katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, si
     launch_lookup(t->g, (const uint64_t *)dk.p, n, canonicalise, (uint64_t *)dc.p, grid, c->stream);
     c->launches++;
     CU(cudaGetLastError());
+    if (c->dist) KT(dist_allreduce_u64(c, dc.p, n)); // the owner rank answers, everybody else holds 0
     CU(cudaMemcpyAsync(counts_out, dc.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return KATGPU_OK;

@@ -283,95 +283,104 @@ __global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(c
     tally_flush(g, tally);
 }
 
-// ---- B2 (and level 1 of already hashed keys): keys -> segments ---------------------------------
-__global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_constant__ BinKeysParams P) {
+// ---- level 1 of keys that are already hashed (received from other ranks): keys -> level-1 segments ---
+__global__ void __launch_bounds__(kBin2Threads, 1) bin_hashed_kernel(const __grid_constant__ BinKeysParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    uint32_t *hll = reinterpret_cast<uint32_t *>(smem_raw); // source A only; [kTileHllM]
+    uint32_t *hll = reinterpret_cast<uint32_t *>(smem_raw); // [kTileHllM]
     const TableGeom &g = P.g;
     const uint32_t tid = threadIdx.x;
     SideTally tally;
-    BinCore<kBin1Granule> C1; // a flat source fills level-1 segments (ring sized like bin_bases_kernel's)
-    BinCore<kBin2Granule> C;
-    if (P.in_keys) { // source A: flat array, tiles strided over the grid, per-CTA destination segments
-        C1.init(P.dst, blockIdx.x, smem_raw + kTileHllM * 4);
-        for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads) hll[i] = 0;
-        __syncthreads();
-        const uint32_t sshift = P.dst.shift - kTileHllSampleShift;
-        constexpr int kU = kBinTile / kBin2Threads; // keys per thread per tile; host: P.tile_keys == kBinTile (the level-1 ring is sized for it)
-        const uint64_t n_tiles = (P.n_keys + P.tile_keys - 1) / P.tile_keys;
-        for (uint64_t tile = (blockIdx.x + gridDim.x - P.cta_rot % gridDim.x) % gridDim.x; tile < n_tiles; tile += gridDim.x) {
+    BinCore<kBin1Granule> C1; // per-CTA destination segments, ring sized like bin_bases_kernel's
+    C1.init(P.dst, blockIdx.x, smem_raw + kTileHllM * 4);
+    for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads) hll[i] = 0;
+    __syncthreads();
+    const uint32_t sshift = P.dst.shift - kTileHllSampleShift;
+    constexpr int kU = kBinTile / kBin2Threads; // keys per thread per tile; host: P.tile_keys == kBinTile (the level-1 ring is sized for it)
+    // tiles first, first + step, ... of `n` keys at `keys`
+    auto bin_tiles = [&](const uint64_t *keys, uint64_t n, uint64_t first, uint64_t step) {
+        const uint64_t n_tiles = (n + P.tile_keys - 1) / P.tile_keys;
+        for (uint64_t tile = first; tile < n_tiles; tile += step) {
             const uint64_t lo = tile * P.tile_keys;
             uint64_t kc[kU];
 #pragma unroll
             for (int u = 0; u < kU; u++) { // every load in flight before the first key is binned
                 const uint64_t i = lo + (uint64_t)u * kBin2Threads + tid;
-                kc[u] = i < P.n_keys ? __ldg(P.in_keys + i) : 0;
+                kc[u] = i < n ? __ldg(keys + i) : 0;
             }
 #pragma unroll
             for (int u = 0; u < kU; u++) {
-                if (lo + (uint64_t)u * kBin2Threads + tid < P.n_keys) {
+                if (lo + (uint64_t)u * kBin2Threads + tid < n) {
                     C1.append(kc[u], P.side, g, tally);
                     hll_sample(hll, kc[u], sshift);
                 }
             }
             C1.flush(false, P.side, g, tally);
         }
-        C1.flush(true, P.side, g, tally);
-        C1.store_lengths();
-        for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads)
-            if (hll[i]) atomicMax(P.hll + i, hll[i]);
-    } else { // source B: the level-1 segments of one slice, one share of them per CTA
-        const uint32_t s_local = blockIdx.x / P.parts, q = blockIdx.x % P.parts;
-        C.init(P.dst, (s_local * P.dst.F) * P.parts + q, smem_raw + kTileHllM * 4);
-        __syncthreads();
-        const uint32_t seg_lo = (uint32_t)(((uint64_t)P.src_segs * q) / P.parts), seg_hi = (uint32_t)(((uint64_t)P.src_segs * (q + 1)) / P.parts);
-        // Chunks of kBin2Unroll keys per thread: every load of a chunk is in flight before the
-        // first key is binned, and the next chunk is requested before this one is flushed.
-        const uint32_t chunk = kBin2Threads * kBin2Unroll; // == P.tile_keys (host)
-        uint64_t kn[kBin2Unroll];
-        for (uint32_t s = seg_lo; s < seg_hi; s++) {
-            const size_t sidx = (size_t)(P.first_slice + s_local) * P.src_segs + s;
-            const uint32_t len = P.src_len[sidx];
-            const uint64_t *src = P.src_keys + sidx * P.src_cap;
-            auto fetch = [&](uint32_t base) {
+    };
+    if (P.in_keys) // source A: one flat array, tiles strided over the grid
+        bin_tiles(P.in_keys, P.n_keys, (blockIdx.x + gridDim.x - P.cta_rot % gridDim.x) % gridDim.x, gridDim.x);
+    else // source C: the dense segments other ranks' route_bases_kernel wrote here, whole segments per CTA
+        for (uint32_t sgm = blockIdx.x; sgm < P.n_src; sgm += gridDim.x) bin_tiles(P.seg_keys + (size_t)sgm * P.seg_cap, P.seg_len[sgm], 0, 1);
+    C1.flush(true, P.side, g, tally);
+    C1.store_lengths();
+    for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads)
+        if (hll[i]) atomicMax(P.hll + i, hll[i]);
+    tally_flush(g, tally);
+}
+
+// ---- B2: the level-1 segments of one slice, one share of them per CTA -> per-tile segments --------
+__global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_constant__ BinKeysParams P) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const TableGeom &g = P.g;
+    const uint32_t tid = threadIdx.x;
+    SideTally tally;
+    BinCore<kBin2Granule> C;
+    const uint32_t s_local = blockIdx.x / P.parts, q = blockIdx.x % P.parts;
+    C.init(P.dst, (s_local * P.dst.F) * P.parts + q, smem_raw + kTileHllM * 4);
+    __syncthreads();
+    const uint32_t seg_lo = (uint32_t)(((uint64_t)P.src_segs * q) / P.parts), seg_hi = (uint32_t)(((uint64_t)P.src_segs * (q + 1)) / P.parts);
+    // Chunks of kBin2Unroll keys per thread: every load of a chunk is in flight before the
+    // first key is binned, and the next chunk is requested before this one is flushed.
+    const uint32_t chunk = kBin2Threads * kBin2Unroll; // == P.tile_keys (host)
+    uint64_t kn[kBin2Unroll];
+    for (uint32_t s = seg_lo; s < seg_hi; s++) {
+        const size_t sidx = (size_t)(P.first_slice + s_local) * P.src_segs + s;
+        const uint32_t len = P.src_len[sidx];
+        const uint64_t *src = P.src_keys + sidx * P.src_cap;
+        auto fetch = [&](uint32_t base) {
 #pragma unroll
-                for (int u = 0; u < kBin2Unroll; u++) {
-                    const uint32_t i = base + u * kBin2Threads + tid;
-                    kn[u] = i < len ? __ldg(src + i) : 0;
-                }
-            };
-            if (KATGPU_BIN2_PREFETCH && len) fetch(0);
-            for (uint32_t base = 0; base < len; base += chunk) {
-                if (!KATGPU_BIN2_PREFETCH) fetch(base);
-                uint64_t kc[kBin2Unroll];
-#pragma unroll
-                for (int u = 0; u < kBin2Unroll; u++) kc[u] = kn[u];
-                if (KATGPU_BIN2_PREFETCH && base + chunk < len) fetch(base + chunk);
-#pragma unroll
-                for (int u = 0; u < kBin2Unroll; u++)
-                    if (base + u * kBin2Threads + tid < len) C.append(kc[u], P.side, g, tally);
-                C.flush(false, P.side, g, tally);
+            for (int u = 0; u < kBin2Unroll; u++) {
+                const uint32_t i = base + u * kBin2Threads + tid;
+                kn[u] = i < len ? __ldg(src + i) : 0;
             }
+        };
+        if (KATGPU_BIN2_PREFETCH && len) fetch(0);
+        for (uint32_t base = 0; base < len; base += chunk) {
+            if (!KATGPU_BIN2_PREFETCH) fetch(base);
+            uint64_t kc[kBin2Unroll];
+#pragma unroll
+            for (int u = 0; u < kBin2Unroll; u++) kc[u] = kn[u];
+            if (KATGPU_BIN2_PREFETCH && base + chunk < len) fetch(base + chunk);
+#pragma unroll
+            for (int u = 0; u < kBin2Unroll; u++)
+                if (base + u * kBin2Threads + tid < len) C.append(kc[u], P.side, g, tally);
+            C.flush(false, P.side, g, tally);
         }
-        C.flush(true, P.side, g, tally);
-        C.store_lengths();
     }
+    C.flush(true, P.side, g, tally);
+    C.store_lengths();
     tally_flush(g, tally);
 }
 
 // ---- T: apply a tile's keys in shared memory ---------------------------------------------------
+constexpr uint32_t kParkCap = 1024; // parked keys a CTA collects per tile before it touches the global side list
 struct __align__(128) TileSmem {
     uint64_t slots[kTileBytes / 8];
+    uint64_t park[kParkCap];
     uint64_t mbar;
-    uint32_t total, go, pushed;
+    unsigned long long park_base;
+    uint32_t total, go, pushed, park_n;
 };
-
-// 1-D TMA bulk store shared -> global (SASS: UBLKCP), then wait until the source has been read.
-__device__ __forceinline__ void tma_store_1d_and_wait(void *dst_gmem, const void *src_smem, uint32_t bytes) {
-    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-}
 
 template <bool TAG32>
 __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_insert_kernel(const __grid_constant__ TileParams P) {
@@ -389,6 +398,7 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
         mbar_init(&S.mbar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         S.pushed = 0;
+        S.park_n = 0;
     }
     __syncthreads();
     for (uint32_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x) {
@@ -447,8 +457,16 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
         // word (the count field starts at bit cshift >= 32).  Miss: CAS into the first free slot
         // (slots fill in order and never empty, so the key is not further along its probe
         // sequence).  Full bucket, or a count that could carry: side list.
+        // Parked keys are collected in shared memory and appended to the global side list with ONE
+        // atomic per tile: at table load 0.56 almost 1 % of the keys park, and 66 M increments of
+        // one global word serialise (measured: tile kernel 43 -> 77 ms with per-key pushes).
         auto park_key = [&](uint64_t h) {
-            const unsigned long long idx = atomicAdd(P.side.n, 1ULL); // below cap: this tile's keys are reserved
+            const uint32_t at = atomicAdd(&S.park_n, 1u);
+            if (at < kParkCap) {
+                S.park[at] = h;
+                return;
+            }
+            const unsigned long long idx = atomicAdd(P.side.n, 1ULL); // buffer full; below cap: this tile's keys are reserved
             P.side.keys[idx] = h;
             atomicAdd(&S.pushed, 1u);
         };
@@ -528,11 +546,23 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
             }
         }
         __syncthreads();
+        const uint32_t parked = min(S.park_n, kParkCap);
         if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            tma_store_1d_and_wait(gtile, S.slots, kTileBytes);
-            const uint32_t pushed = S.pushed;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gtile), "r"(smem_u32(S.slots)), "r"((uint32_t)kTileBytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (parked) S.park_base = atomicAdd(P.side.n, (unsigned long long)parked);
+        }
+        __syncthreads();
+        if (parked) { // the tile travels back to HBM while the parked keys are appended to the side list
+            const unsigned long long base = S.park_base;
+            for (uint32_t i = tid; i < parked; i += kTileThreads) P.side.keys[base + i] = S.park[i];
+        }
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the tile has been read out of shared memory
+            const uint32_t pushed = S.pushed + parked;
             S.pushed = 0;
+            S.park_n = 0;
             my_total += total - pushed;
             if (total > pushed) atomicAdd(P.side.reserved, ~(unsigned long long)(total - pushed) + 1ULL); // release the unused reservation
         }
@@ -592,6 +622,7 @@ cudaError_t tile_configure(int *bps_bases, int *bps_tile) {
     if ((e = cudaFuncSetAttribute(bin_bases_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(bin_bases_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(bin_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(bin_hashed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tile_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tile_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem))) != cudaSuccess) return e;
     *bps_bases = kBin1MinCtas; // the host sizes the staging ring so that this many CTAs fit an SM
@@ -610,7 +641,8 @@ void launch_bin_bases(const BinBasesParams &P, int grid, cudaStream_t st) {
     else bin_bases_kernel<false, false><<<grid, kBin1Threads, smem, st>>>(P);
 }
 void launch_bin_keys(const BinKeysParams &P, int grid, cudaStream_t st) {
-    bin_keys_kernel<<<grid, kBin2Threads, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
+    if (P.in_keys || P.seg_keys) bin_hashed_kernel<<<grid, kBin2Threads, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
+    else bin_keys_kernel<<<grid, kBin2Threads, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
 }
 void launch_tile_insert(const TileParams &P, int grid, cudaStream_t st) {
     if (P.g.tagmask <= 0xFFFFFFFFULL) tile_insert_kernel<true><<<grid, kTileThreads, sizeof(TileSmem), st>>>(P);

@@ -91,6 +91,11 @@ struct BinKeysParams {
     const uint64_t *in_keys;
     uint64_t n_keys;
     uint32_t cta_rot;
+    // source C (multi-GPU): dense segments [n_src][seg_cap] with seg_len[n_src] keys each, written by the
+    // route_bases_kernel of every rank (dist_kernels.cu); CTA j bins segments j, j + grid, ...
+    const uint64_t *seg_keys;
+    const uint32_t *seg_len;
+    uint32_t n_src, seg_cap;
     // source B: the level-1 segments of slice (first_slice + blockIdx.x / parts), share blockIdx.x % parts
     const uint64_t *src_keys; // [slice][src_segs][src_cap]
     const uint32_t *src_len;

@@ -1,169 +1,95 @@
-"""Multi-GPU counting: one process per GPU, reads sharded by record, k-mers
-hash-partitioned to owner ranks.
+"""Multi-GPU jobs, one process per GPU (torchrun): the plumbing around libkatgpu's own
+multi-GPU engine (kat_b200/csrc/katgpu_dist.cu, dist_kernels.cu).
 
-A count histogram is not additive over read shards (a k-mer seen 3x on GPU0 and
-2x on GPU1 belongs in bin 5), so before any reduction every distinct k-mer must
-live on exactly one rank:
+A count histogram is not additive over read shards (a k-mer seen 3x on GPU0 and 2x on GPU1
+belongs in bin 5), so every distinct k-mer is counted by exactly one owner rank.  The engine
+does that inside the library: reads are sharded by record, each rank feeds its shard, the
+extraction kernel stores every hashed key straight into the owner's HBM over NVLink, the owner
+inserts, and hist / gcp / comp end with ONE ncclAllReduce of the result.  What is left for Python:
 
-  route    katgpu_route_device: extract + canonicalise + hash the local base
-           stream, bucket the 64-bit hashed keys by owner = f(hash) % world
-  exchange all-to-all of the buckets over NVLink (NCCL through torch.distributed)
-  insert   katgpu_insert_hashed_device on the owner
-  reduce   local hist/gcp walk, then ONE all-reduce(sum) of the bins / matrix
+  shard_records()        which records a rank feeds (contiguous, balanced)
+  broadcast_unique_id()  rank 0's 128-byte job id to every rank through torch.distributed
+  join_job()             ctx.dist_init(...) with it
+  DistributedJob         `kat hist|gcp|comp` as collective calls, mirroring the C++ front-end
 
-The orchestration is engine-agnostic so that the host logic can be exercised
-with gloo on CPU (tests/test_multigpu_gloo.py passes a numpy engine); the
-product engine below drives libkatgpu and has no CPU path."""
-import math
-
+torch.distributed is only the rendezvous here (gloo or nccl, both work) — tests/test_multigpu_gloo.py
+drives the same functions with world_size 2 and 3 on CPU.  There is no CPU engine."""
 import numpy as np
 
 from . import binding as B
-from .routing import KMERS_SLACK
 
 
-class GpuEngine:
-    """libkatgpu + torch tensors for the exchange buffers."""
+def shard_records(n_records, rank, world):
+    """(first, count) of the contiguous block of records rank `rank` feeds: blocks differ by at most one
+    record and cover [0, n_records) exactly once."""
+    base, extra = divmod(n_records, world)
+    first = rank * base + min(rank, extra)
+    return first, base + (1 if rank < extra else 0)
 
-    def __init__(self, ctx, k, canonical, slots):
-        import torch
-        self.torch = torch
+
+def broadcast_unique_id(dist, make_id=B.dist_unique_id, device=None):
+    """Rank 0 creates the job id (katgpu_dist_unique_id -> ncclGetUniqueId), everybody receives it."""
+    import torch
+    rank = dist.get_rank()
+    raw = make_id() if rank == 0 else bytes(128)
+    t = torch.tensor(list(raw), dtype=torch.uint8, device=device)
+    dist.broadcast(t, src=0)
+    return bytes(t.cpu().tolist())
+
+
+def join_job(ctx, dist, device=None):
+    """Make `ctx` rank dist.get_rank() of a dist.get_world_size()-GPU job.  world 1: nothing to do."""
+    world = dist.get_world_size()
+    if world > 1:
+        ctx.dist_init(dist.get_rank(), world, broadcast_unique_id(dist, device=device))
+    return ctx
+
+
+class DistributedJob:
+    """Collective `kat` jobs on a joined context: every rank calls the same methods in the same
+    order with ITS shard of the input; every rank gets the complete result."""
+
+    def __init__(self, ctx, k, canonical=True, slots=1 << 31):
         self.ctx, self.k, self.canonical, self.slots = ctx, k, canonical, slots
-        self.table = None
-        self.device = torch.device("cuda", torch.cuda.current_device())
 
-    def begin(self, expected_kmers=0):
-        self.table = self.ctx.count_begin(self.k, self.canonical, self.slots, True)
+    def count(self, bases_ptr, n_bytes, device=True, expected_kmers=0):
+        t = self.ctx.count_begin(self.k, self.canonical, self.slots, True)
         if expected_kmers:
-            self.table.reserve(expected_kmers)
+            t.reserve(expected_kmers)
+        if device:
+            t.feed_device(bases_ptr, n_bytes)
+        else:
+            t.feed_ptr(bases_ptr, n_bytes)
+        return t.end()
 
-    def alloc_keys(self, n):
-        return self.torch.empty(max(n, 1), dtype=self.torch.int64, device=self.device)
-
-    def route(self, bases_ptr, n_bytes, out_tensors, cap):
-        return self.table.route_device(bases_ptr, n_bytes, [t.data_ptr() for t in out_tensors], cap)
-
-    def insert(self, keys_tensor, n):
-        if n:
-            self.table.insert_hashed_device(keys_tensor.data_ptr(), n)
-
-    def sync_exchange(self):
-        self.torch.cuda.current_stream().synchronize()
-
-    def end(self):
-        self.table.end()
-        return self.table.n_distinct, self.table.n_total
-
-    def hist(self, low, high, inc):
-        return self.table.hist(low, high, inc)[1]
-
-    def gcp(self, scale, bins):
-        return self.table.gcp(scale, bins)
-
-    def to_tensor(self, arr):
-        return self.torch.from_numpy(arr.astype(np.int64)).to(self.device)
-
-    def from_tensor(self, t):
-        return t.cpu().numpy().astype(np.uint64)
-
-    def free(self):
-        if self.table is not None:
-            self.table.free()
-            self.table = None
-
-
-class DistributedCounter:
-    def __init__(self, ctx, dist, k, canonical=True, slots=1 << 31, batch_bytes=1 << 29, engine=None):
-        self.dist = dist
-        self.rank, self.world = dist.get_rank(), dist.get_world_size()
-        self.k = k
-        self.batch_bytes = batch_bytes
-        self.engine = engine if engine is not None else GpuEngine(ctx, k, canonical, slots)
-        self._send = self._recv = None
-        self._cap = 0
-
-    def _buffers(self, cap):
-        """Two send and two receive bucket sets: batch b+1 is routed and batch b-1 is
-        inserted while batch b is on the wire."""
-        if cap > self._cap:
-            self._send = [[self.engine.alloc_keys(cap) for _ in range(self.world)] for _ in range(2)]
-            self._recv = [[self.engine.alloc_keys(cap) for _ in range(self.world)] for _ in range(2)]
-            self._cap = cap
-        return self._send, self._recv
-
-    def count(self, bases_ptr, n_bytes, record_len=None):
-        """Route / exchange / insert the local base stream in batches, software-pipelined:
-        route(b+1) and insert(b-1) overlap the exchange of batch b.  Batches end on record
-        boundaries when record_len is given (no k-mer is cut)."""
-        e, dist, W = self.engine, self.dist, self.world
-        # with a uniform owner hash every rank receives about what it routes
-        e.begin(n_bytes)
-        step = self.batch_bytes
-        if record_len:  # whole records per batch, and 16-byte aligned batch starts (TMA path)
-            unit = record_len * 16
-            step = max(unit, step // unit * unit)
-        # every rank must take part in the same number of collectives
-        nb_local = max(1, math.ceil(n_bytes / step))
-        nbt = e.to_tensor(np.array([nb_local]))
-        dist.all_reduce(nbt, op=dist.ReduceOp.MAX)
-        n_batches = int(e.from_tensor(nbt)[0])
-        cap = int(step / W * 1.25) + KMERS_SLACK
-        send, recv = self._buffers(cap)
-
-        def route(b):
-            off = min(n_bytes, b * step)
-            n = max(0, min(step, n_bytes - off))
-            counts = e.route(bases_ptr + off, n, send[b & 1], cap) if n else [0] * W
-            sc = e.to_tensor(np.array(counts))
-            rc = e.to_tensor(np.zeros(W))
-            dist.all_to_all_single(rc, sc)
-            rcounts = [int(x) for x in e.from_tensor(rc)]
-            if max(rcounts) > cap:
-                raise B.KatGpuError(-1, "receive bucket too small for this batch")
-            return counts, rcounts
-
-        cnt = route(0)
-        works = self._exchange_start(send[0], cnt[0], recv[0], cnt[1])
-        for b in range(n_batches):
-            nxt = route(b + 1) if b + 1 < n_batches else None  # overlaps exchange b
-            for w in works:
-                w.wait()
-            e.sync_exchange()
-            if nxt is not None:
-                works = self._exchange_start(send[(b + 1) & 1], nxt[0], recv[(b + 1) & 1], nxt[1])
-            for r in range(W):  # overlaps exchange b+1
-                e.insert(recv[b & 1][r], cnt[1][r])
-            cnt = nxt
-        return e.end()
-
-    def _exchange_start(self, send, counts, recv, rcounts):
-        """Ragged all-to-all as grouped point-to-point (what NCCL's all-to-all is
-        underneath); works on NCCL and gloo alike.  Returns the pending work handles."""
-        dist, W, me = self.dist, self.world, self.rank
-        ops = []
-        for d in range(1, W):
-            to, frm = (me + d) % W, (me - d) % W
-            if counts[to]:
-                ops.append(dist.P2POp(dist.isend, send[to][: counts[to]], to))
-            if rcounts[frm]:
-                ops.append(dist.P2POp(dist.irecv, recv[frm][: rcounts[frm]], frm))
-        if rcounts[me]:
-            recv[me][: rcounts[me]].copy_(send[me][: counts[me]])
-        return dist.batch_isend_irecv(ops) if ops else []
-
-    def _allreduce_u64(self, arr):
-        t = self.engine.to_tensor(arr.reshape(-1))
-        self.dist.all_reduce(t)
-        return self.engine.from_tensor(t).reshape(arr.shape)
-
-    def hist_job(self, bases_ptr, n_bytes, low=1, high=10000, inc=1, record_len=None):
-        nd, nt = self.count(bases_ptr, n_bytes, record_len)
-        bins = self._allreduce_u64(self.engine.hist(low, high, inc))
-        self.engine.free()
+    def hist_job(self, bases_ptr, n_bytes, low=1, high=10000, inc=1, device=True):
+        t = self.count(bases_ptr, n_bytes, device)
+        _, bins = t.hist(low, high, inc)
+        nt, nd = t.n_total, t.n_distinct
+        t.free()
         return bins, nt, nd
 
-    def gcp_job(self, bases_ptr, n_bytes, scale=1.0, cvg_bins=1000, record_len=None):
-        nd, nt = self.count(bases_ptr, n_bytes, record_len)
-        mx = self._allreduce_u64(self.engine.gcp(scale, cvg_bins))
-        self.engine.free()
+    def gcp_job(self, bases_ptr, n_bytes, scale=1.0, cvg_bins=1000, device=True):
+        t = self.count(bases_ptr, n_bytes, device)
+        mx = t.gcp(scale, cvg_bins)
+        nt, nd = t.n_total, t.n_distinct
+        t.free()
         return mx, nt, nd
+
+    def comp_job(self, ptr1, n1, ptr2, n2, device=True, **kw):
+        t1 = self.count(ptr1, n1, device)
+        t2 = self.count(ptr2, n2, device)
+        r = B.comp(t1, t2, **kw)
+        r["n_total"] = (t1.n_total, t2.n_total)
+        t1.free()
+        t2.free()
+        return r
+
+
+def simulate_partitioned_counts(keys, world, k):
+    """What the engine does, restated on the host for one rank's canonical k-mer instances `keys`
+    (uint64): the hashed keys and their owner ranks (kat_b200/routing.py = table.cuh).  Used by the CPU
+    tests to check that owner-partitioned counting followed by a sum reproduces the single table."""
+    from .routing import mix_key, owner_of
+    h = mix_key(np.asarray(keys, dtype=np.uint64), k)
+    return h, owner_of(h, world)

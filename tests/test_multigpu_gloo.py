@@ -1,8 +1,8 @@
-"""world_size-2 (and 3) gloo tests of the multi-GPU host logic on CPU: read
-sharding, owner routing, all-to-all exchange with ragged counts, batching, and
-the final all-reduce.  The CUDA engine is replaced by a numpy engine built on
-the oracle (checker), so this runs without a GPU; the same orchestration class
-drives libkatgpu on the B200 box (tests/test_gpu_multi.py, bench.py --gpus N)."""
+"""world_size-2 (and 3) gloo tests of the multi-GPU host logic on CPU: record sharding, the job-id
+broadcast, and the algorithm the engine implements — owner routing of every k-mer instance
+(kat_b200/routing.py restates table.cuh), a ragged all-to-all, per-owner counting, one all-reduce of
+the bins — against the oracle's single table.  The CUDA engine itself (route_bases_kernel + peer
+stores) is covered on GPUs by tests/test_gpu_multi.py and bench.py --gpus N."""
 import os
 import socket
 
@@ -14,76 +14,45 @@ import torch.multiprocessing as mp
 
 import oracle as O
 import seqgen
-from kat_b200.multigpu import DistributedCounter
+from kat_b200.multigpu import broadcast_unique_id, shard_records, simulate_partitioned_counts
 from kat_b200.routing import mix_key, owner_of
-
-
-class NumpyEngine:
-    def __init__(self, bases, k, canonical):
-        self.bases, self.k, self.canonical = bases, k, canonical
-
-    def begin(self, expected_kmers=0):
-        self.h = []
-
-    def alloc_keys(self, n):
-        return torch.empty(max(n, 1), dtype=torch.int64)
-
-    def route(self, ptr, n, outs, cap):
-        t = O.Table.from_chunks([self.bases[ptr:ptr + n].tobytes()], self.k, self.canonical)
-        keys, counts = t.export()
-        inst = np.repeat(keys, counts.astype(np.int64))
-        h = mix_key(inst, self.k)
-        own = owner_of(h, len(outs))
-        res = []
-        for r, o in enumerate(outs):
-            sel = h[own == r]
-            assert len(sel) <= cap
-            o[: len(sel)] = torch.from_numpy(sel.view(np.int64))
-            res.append(len(sel))
-        return res
-
-    def insert(self, keys, n):
-        self.h.append(keys[:n].numpy().view(np.uint64).copy())
-
-    def sync_exchange(self):
-        pass
-
-    def end(self):
-        allh = np.concatenate(self.h) if self.h else np.zeros(0, np.uint64)
-        self.uniq, self.counts = np.unique(allh, return_counts=True)
-        return len(self.uniq), len(allh)
-
-    def hist(self, low, high, inc):
-        assert (low, high, inc) == (1, 10000, 1)
-        bins = np.zeros(10001, dtype=np.uint64)
-        np.add.at(bins, np.minimum(self.counts, 10001) - 1, 1)
-        return bins
-
-    def to_tensor(self, arr):
-        return torch.from_numpy(np.asarray(arr).astype(np.int64))
-
-    def from_tensor(self, t):
-        return t.numpy().astype(np.uint64)
-
-    def free(self):
-        pass
 
 
 def _worker(rank, world, port, k, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        full = seqgen.genome_reads(20_000, 1500, 100, seed=5)
-        rec = 101
-        per = (1500 + world - 1) // world
-        mine = full[rank * per * rec: min(1500, (rank + 1) * per) * rec]
-        eng = NumpyEngine(mine, k, True)
-        dc = DistributedCounter(None, dist, k, True, 0, batch_bytes=rec * 16 * 9, engine=eng)
-        bins, nt, nd = dc.hist_job(0, len(mine), record_len=rec)
-        tot = torch.tensor([nt, nd])
+        # the rendezvous the GPU job uses: rank 0's 128-byte id reaches everybody unchanged
+        uid = broadcast_unique_id(dist, make_id=lambda: bytes(range(128)))
+        assert uid == bytes(range(128))
+        n_records, rec = 1500, 101
+        full = seqgen.genome_reads(20_000, n_records, 100, seed=5)
+        first, cnt = shard_records(n_records, rank, world)
+        mine = full[first * rec:(first + cnt) * rec]
+        # this rank's canonical k-mer instances (the oracle stands in for the extraction kernel)
+        t = O.Table.from_chunks([mine.tobytes()], k, True)
+        keys, counts = t.export()
+        inst = np.repeat(keys, counts.astype(np.int64))
+        h, own = simulate_partitioned_counts(inst, world, k)
+        # ragged all-to-all of the hashed keys to their owners
+        send = [h[own == r] for r in range(world)]
+        sc = torch.tensor([len(s) for s in send])
+        rc = torch.zeros(world, dtype=torch.int64)
+        dist.all_to_all_single(rc, sc)
+        recv = torch.empty(int(rc.sum()), dtype=torch.int64)
+        dist.all_to_all_single(recv, torch.from_numpy(np.concatenate(send).view(np.int64).copy()),
+                               output_split_sizes=[int(n) for n in rc], input_split_sizes=[int(n) for n in sc])
+        got = recv.numpy().view(np.uint64)
+        assert np.all(owner_of(got, world) == rank)  # every received key is mine
+        uniq, cts = np.unique(got, return_counts=True)
+        bins = np.zeros(10001, dtype=np.int64)
+        np.add.at(bins, np.minimum(cts, 10001) - 1, 1)
+        tb = torch.from_numpy(bins)
+        dist.all_reduce(tb)  # the one all-reduce of the result
+        tot = torch.tensor([len(got), len(uniq)])
         dist.all_reduce(tot)
         if rank == 0:
-            np.savez(q, bins=bins, tot=tot.numpy())
+            np.savez(q, bins=tb.numpy().astype(np.uint64), tot=tot.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -107,6 +76,16 @@ def test_partitioned_hist_equals_single_table(world, tmp_path):
     ot = O.Table.from_chunks([full.tobytes()], k, True)
     assert n_total == ot.total and n_distinct == ot.distinct
     assert np.array_equal(bins, ot.hist()[1])
+
+
+def test_shard_records_covers_everything_once():
+    for n in (0, 1, 7, 1500, 66_666_667):
+        for world in (1, 2, 3, 4, 8):
+            blocks = [shard_records(n, r, world) for r in range(world)]
+            assert blocks[0][0] == 0 and sum(c for _, c in blocks) == n
+            for (f0, c0), (f1, _) in zip(blocks, blocks[1:]):
+                assert f0 + c0 == f1
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
 
 
 def test_routing_restatement_properties():
