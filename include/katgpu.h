@@ -89,6 +89,19 @@ katgpu_status katgpu_count_begin(katgpu_ctx *ctx, int k, int canonical, uint64_t
 katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n);
 /* Same, for a stream already resident in device memory (16-byte aligned). */
 katgpu_status katgpu_count_feed_device(katgpu_table *t, const void *bases_dev, size_t n);
+/* Feed RAW FILE BYTES: `n` bytes (at most 1 GiB per call, HOST memory, pageable is fine) holding
+ * WHOLE records of a 4-line FASTQ file.  The bytes are copied to the GPU and parsed THERE
+ * (JFI/mer_overlap_sequence_parser.hpp:218-289 read_fastq / read_sequence / skip_quals for the
+ * regular layout): newline index, per-record validation ('@' header, sequence longer than trim5p
+ * that neither starts with '@'/'+' nor contains '+', '+' line, quality of the same length, every
+ * line '\n'-terminated), then every non-sequence byte and the first trim5p bases of every read are
+ * blanked in place and the result is counted like katgpu_count_feed_device.
+ *   *regular = 1  the bytes were in the regular layout and have been counted;
+ *   *regular = 0  they were not: NOTHING was counted — parse them on the host with the exact
+ *                 emulation of the reference parser and use katgpu_count_feed.
+ * No k-mer spans two calls (records are whole).  On a multi-GPU context the call is collective. */
+katgpu_status katgpu_count_feed_fastq(katgpu_table *t, const char *bytes, size_t n, unsigned trim5p,
+                                      int *regular);
 /* Optional hint: about `expected_kmers` k-mer instances will be fed before
  * katgpu_count_end.  Lets the library size its pending-key buffer once (the
  * partitioned counting path inserts slice by slice; fewer, larger sweeps are

@@ -48,6 +48,7 @@ SIGNATURES = {
     "katgpu_count_begin": (_i, [_vp, _i, _i, _u64, _i, C.POINTER(_vp)]),
     "katgpu_count_feed": (_i, [_vp, _vp, _sz]),
     "katgpu_count_feed_device": (_i, [_vp, _vp, _sz]),
+    "katgpu_count_feed_fastq": (_i, [_vp, _vp, _sz, C.c_uint, C.POINTER(_i)]),
     "katgpu_count_reserve": (_i, [_vp, _u64]),
     "katgpu_count_add_pairs": (_i, [_vp, _vp, _vp, _sz]),
     "katgpu_count_end": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
@@ -236,6 +237,14 @@ class Table:
         if a.size:
             _check(lib().katgpu_count_feed(self.h, _ptr(a), a.size))
         return self
+
+    def feed_fastq(self, raw, trim5p=0):
+        """raw: bytes / numpy uint8 of WHOLE 4-line FASTQ records in host memory; parsed on the GPU.
+        Returns True when the bytes were regular and have been counted, False when nothing was counted."""
+        a = np.frombuffer(raw, dtype=np.uint8) if isinstance(raw, (bytes, bytearray, memoryview)) else raw
+        reg = C.c_int(0)
+        _check(lib().katgpu_count_feed_fastq(self.h, _ptr(a) if a.size else None, a.size, trim5p, C.byref(reg)))
+        return bool(reg.value)
 
     def feed_ptr(self, host_ptr, n):
         _check(lib().katgpu_count_feed(self.h, host_ptr, n))

@@ -21,15 +21,23 @@
 
 namespace katgpu {
 
+// Keys leave the SM in whole, aligned 128-byte lines (16 keys): NVLink takes ~6.5 G write requests
+// per second whatever their size (tools/p2p_bench.cu: 32 B pieces 215 GB/s, 128 B pieces 710 GB/s),
+// so each owner's run is stored from its line-aligned position and the < 16 keys that do not fill
+// a line wait in shared memory for the next tile.
+constexpr uint32_t kRouteLine = 16;
 struct __align__(128) RouteSmem {
     uint8_t ascii[kBinTile + kHalo];
     uint32_t W[2][kBinGroups + 2];
     uint32_t B[2][kBinGroups + 2];
     uint64_t mbar;
     uint32_t cnt[kMaxRanks];     // keys of the current tile per owner
-    uint32_t off[kMaxRanks + 1]; // exclusive prefix of cnt
-    uint32_t cur[kMaxRanks];     // keys this CTA has already written to each owner's segment
-    uint64_t pool[kBinTile];     // the tile's keys, sorted by owner
+    uint32_t nc[kMaxRanks];      // keys carried over from the previous tile per owner (< kRouteLine)
+    uint32_t off[kMaxRanks + 1]; // start of each owner's run in `pool` (carried keys first, then this tile's)
+    uint32_t goff[kMaxRanks + 1];// exclusive prefix of the 4-key groups each owner's run stores in this tile
+    uint32_t cur[kMaxRanks];     // keys this CTA has already written to each owner's segment (multiple of kRouteLine)
+    uint64_t carry[kMaxRanks][kRouteLine];
+    uint64_t pool[kBinTile + kMaxRanks * kRouteLine]; // the tile's keys, sorted by owner
 };
 
 template <bool CANON, bool WIDE>
@@ -47,6 +55,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
     if (tid < kMaxRanks) {
         S.cnt[tid] = 0;
         S.cur[tid] = 0;
+        S.nc[tid] = 0;
     }
     if (tid == 0) {
         mbar_init(&S.mbar, 1);
@@ -120,39 +129,62 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
         }
         __syncthreads();
         if (tid == 0) {
-            uint32_t a = 0;
+            uint32_t a = 0, ga = 0;
             for (uint32_t d = 0; d < n_ranks; d++) {
                 S.off[d] = a;
-                a += S.cnt[d];
+                S.goff[d] = ga;
+                const uint32_t m = S.nc[d] + S.cnt[d];
+                a += m;
+                ga += m / kRouteLine * (kRouteLine / 4);
             }
             S.off[n_ranks] = a;
+            S.goff[n_ranks] = ga;
         }
         __syncthreads();
+        if (tid < (int)(n_ranks * kRouteLine)) { // carried keys open each run
+            const uint32_t d = tid / kRouteLine, j = tid % kRouteLine;
+            if (j < S.nc[d]) S.pool[S.off[d] + j] = S.carry[d][j];
+        }
 #pragma unroll
         for (uint32_t r = 0; r < 16; r++) {
             const uint32_t m = (meta[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
-            if (m & 0x8000u) S.pool[S.off[(m >> 12) & 7u] + (m & 0xFFFu)] = hk[r];
+            const uint32_t d = (m >> 12) & 7u;
+            if (m & 0x8000u) S.pool[S.off[d] + S.nc[d] + (m & 0xFFFu)] = hk[r];
         }
         __syncthreads();
-        // copy-out: consecutive threads store consecutive keys of a run -> whole lines per warp store,
-        // local HBM for the own rank, NVLink for the others
-        const uint32_t total = S.off[n_ranks];
-        for (uint32_t i = tid; i < total; i += kRouteThreads) {
+        // copy-out: every thread stores 32 bytes, a warp 1 KiB of consecutive lines — local HBM for
+        // the own rank, NVLink for the others
+        const uint32_t groups = S.goff[n_ranks];
+        for (uint32_t gi = tid; gi < groups; gi += kRouteThreads) {
             uint32_t d = 0;
 #pragma unroll
-            for (uint32_t j = 1; j < (uint32_t)kMaxRanks; j++) d += (j < n_ranks && i >= S.off[j]) ? 1u : 0u;
-            uint64_t *dst = P.seg[d] + (size_t)blockIdx.x * P.cap + S.cur[d] + (i - S.off[d]);
-            *dst = S.pool[i];
+            for (uint32_t j = 1; j < (uint32_t)kMaxRanks; j++) d += (j < n_ranks && gi >= S.goff[j]) ? 1u : 0u;
+            const uint32_t q = (gi - S.goff[d]) * 4;
+            const uint64_t *src = S.pool + S.off[d] + q;
+            uint64_t *dst = P.seg[d] + (size_t)blockIdx.x * P.cap + S.cur[d] + q;
+            asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(src[0]), "l"(src[1]), "l"(src[2]), "l"(src[3]) : "memory");
+        }
+        __syncthreads();
+        if (tid < (int)(n_ranks * kRouteLine)) { // what did not fill a line waits for the next tile
+            const uint32_t d = tid / kRouteLine, j = tid % kRouteLine;
+            const uint32_t m = S.nc[d] + S.cnt[d], w = m / kRouteLine * kRouteLine;
+            if (j < m - w) S.carry[d][j] = S.pool[S.off[d] + w + j];
         }
         __syncthreads();
         if (tid < (int)n_ranks) {
-            S.cur[tid] += S.cnt[tid];
+            const uint32_t m = S.nc[tid] + S.cnt[tid], w = m / kRouteLine * kRouteLine;
+            S.cur[tid] += w;
+            S.nc[tid] = m - w;
             S.cnt[tid] = 0;
         }
-        // (the pack phase of the next iteration ends with a barrier before cnt is touched again)
+        // (the pack phase of the next iteration ends with a barrier before cnt / nc are touched again)
     }
     __syncthreads();
-    if (tid < (int)n_ranks) P.len[tid][blockIdx.x] = S.cur[tid];
+    if (tid < (int)(n_ranks * kRouteLine)) { // the last, partial line of every run
+        const uint32_t d = tid / kRouteLine, j = tid % kRouteLine;
+        if (j < S.nc[d]) P.seg[d][(size_t)blockIdx.x * P.cap + S.cur[d] + j] = S.carry[d][j];
+    }
+    if (tid < (int)n_ranks) P.len[tid][blockIdx.x] = S.cur[tid] + S.nc[tid];
 }
 
 size_t route_smem_bytes() { return sizeof(RouteSmem); }

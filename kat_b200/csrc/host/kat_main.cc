@@ -366,8 +366,29 @@ void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_streami
     const size_t stream_from = env_size("KAT_STREAM_BYTES", (size_t)2 << 30), block = env_size("KAT_STREAM_BLOCK", (size_t)512 << 20);
     std::vector<unsigned char> raw;
     std::string bases;
+    // KAT_GPU_PARSE=0 keeps FASTQ parsing on the host
+    const bool gpu_parse = allow_streaming && env_size("KAT_GPU_PARSE", 1) != 0;
     for (size_t i = 0; i < in.files.size(); i++) {
         string err;
+        if (gpu_parse) { // plain 4-line FASTQ: the raw bytes go to the GPU(s) and are parsed there
+            const int r = kat_host::stream_fastq_raw(in.files[i], env_size("KAT_RAW_BLOCK", (size_t)256 << 20) * (size_t)ctx.n(), ctx.n(),
+                                                     [&](const char *const *parts, const size_t *lens) {
+                                                         vector<int> regular(ctx.n(), 0);
+                                                         run_on_all(ctx.n(), [&](int rk) {
+                                                             gpu_check(katgpu_count_feed_fastq(in.tables[rk], parts[rk], lens[rk], in.trim5p[i], &regular[rk]));
+                                                         });
+                                                         int n_reg = 0;
+                                                         for (int rk = 0; rk < ctx.n(); rk++) n_reg += regular[rk] != 0;
+                                                         // some GPUs counted their share, others refused theirs: start over
+                                                         return n_reg == ctx.n() ? 1 : n_reg == 0 ? 0 : -1;
+                                                     }, err);
+            if (r == 1) continue;
+            if (r < 0) { // irregular after some blocks were counted: start this input over with host parsing
+                free_tables(ctx, in);
+                count_input(ctx, in, k, allow_grow, false);
+                return;
+            }
+        }
         if (allow_streaming && file_size_or_zero(in.files[i]) >= stream_from) {
             katgpu_status bad = KATGPU_OK;
             const int r = kat_host::stream_regular_file(in.files[i], in.trim5p[i], block, [&](const char *b, size_t n) {

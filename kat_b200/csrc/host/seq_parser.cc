@@ -21,6 +21,7 @@
 #include "seq_parser.hpp"
 
 #include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <zlib.h>
@@ -494,6 +495,76 @@ int stream_regular_file(const std::string &path, unsigned trim5p, size_t block_b
         }
     }
     close(fd);
+    return rc;
+}
+
+// First FASTQ record start at or after `from` (the line after a '\n' that starts with '@', whose
+// next line starts with neither '@' nor '+' and whose line after that starts with '+'); `n` if none.
+static size_t next_fastq_record(const unsigned char *data, size_t n, size_t from) {
+    if (from == 0) return 0;
+    const unsigned char *e = data + n;
+    const unsigned char *nl = find_nl(data + from - 1, e);
+    for (int tries = 0; nl && tries < 64; tries++) {
+        const unsigned char *c = nl + 1;
+        if (c >= e) break;
+        if (*c == '@') {
+            const unsigned char *l1 = find_nl(c, e);
+            const unsigned char *l2 = l1 ? find_nl(l1 + 1, e) : nullptr;
+            if (l1 && l2 && l2 + 1 < e && l2[1] == '+' && l1[1] != '@' && l1[1] != '+') return (size_t)(c - data);
+        }
+        nl = find_nl(c, e);
+    }
+    return n;
+}
+
+int stream_fastq_raw(const std::string &path, size_t block_bytes, int n_parts,
+                     const std::function<int(const char *const *parts, const size_t *lens)> &sink, std::string &err) {
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) return 0;
+    struct stat st;
+    unsigned char magic[2] = {0, 0};
+    if (fstat(fd, &st) != 0 || !S_ISREG(st.st_mode) || st.st_size < 8 || pread(fd, magic, 2, 0) < 1 || magic[0] != '@') {
+        close(fd);
+        return 0;
+    }
+    const size_t n = (size_t)st.st_size;
+    void *map = mmap(nullptr, n, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (map == MAP_FAILED) return 0;
+    const unsigned char *data = static_cast<const unsigned char *>(map);
+    int rc = 1;
+    if (data[n - 1] != '\n') rc = 0; // the regular layout ends every line with '\n'
+    block_bytes = std::max<size_t>(std::min<size_t>(block_bytes, (size_t)768 << 20), 4096);
+    n_parts = std::max(1, std::min(n_parts, 8));
+    size_t at = 0, taken = 0;
+    while (rc == 1 && at < n) {
+        const size_t want = at + block_bytes;
+        const size_t end = want >= n ? n : next_fastq_record(data, n, want);
+        if (end - at > ((size_t)1 << 30) * (size_t)n_parts) { // no record start for a long stretch: not this layout
+            rc = taken ? -1 : 0;
+            break;
+        }
+        madvise(const_cast<unsigned char *>(data) + (end & ~(size_t)4095), std::min(block_bytes, n - (end & ~(size_t)4095)), MADV_WILLNEED);
+        const char *parts[8];
+        size_t lens[8], lo = at;
+        for (int p = 0; p < n_parts; p++) {
+            size_t hi = p + 1 == n_parts ? end : next_fastq_record(data, end, at + (end - at) * (size_t)(p + 1) / (size_t)n_parts);
+            hi = std::max(std::min(hi, end), lo);
+            parts[p] = reinterpret_cast<const char *>(data + lo);
+            lens[p] = hi - lo;
+            lo = hi;
+        }
+        const int r = sink(parts, lens);
+        if (r < 0) {
+            err = "raw FASTQ feed failed for " + path;
+            rc = -1;
+        } else if (r == 0)
+            rc = taken ? -1 : 0;
+        else
+            taken++;
+        at = end;
+    }
+    munmap(map, n);
     return rc;
 }
 

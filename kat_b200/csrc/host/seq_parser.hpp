@@ -24,6 +24,16 @@ ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsi
 int stream_regular_file(const std::string &path, unsigned trim5p, size_t block_bytes,
                         const std::function<bool(const char *, size_t)> &sink, std::string &err);
 
+// Plain 4-line FASTQ files WITHOUT host parsing: the file is memory-mapped and handed out in blocks
+// of whole records, each block cut into `n_parts` shares of whole records (one per GPU); `sink`
+// gets the raw bytes (libkatgpu parses them on the device, katgpu_count_feed_fastq) and returns
+// 1 = taken, 0 = not in the regular layout (nothing counted), < 0 = error.  Record starts are found
+// with the same test as the host fast path; a wrong guess shows up as an irregular block.
+//   returns 1 whole file taken, 0 not applicable / first block irregular (nothing was counted),
+//          -1 irregular (or error) after blocks were counted: the caller must start over on the host route
+int stream_fastq_raw(const std::string &path, size_t block_bytes, int n_parts,
+                     const std::function<int(const char *const *parts, const size_t *lens)> &sink, std::string &err);
+
 // Which route the last parse_sequence_file call took: true = the validated regular-layout fast path.
 bool last_parse_was_fast();
 

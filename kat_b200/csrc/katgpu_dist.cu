@@ -291,7 +291,7 @@ static katgpu_status allreduce_max_host(katgpu_ctx *c, uint64_t &v) {
 //   ready_ev   the route kernel waits for it (the H2D copy of a staged chunk), may be null
 //   consumed_ev recorded when the route kernel has read its input, may be null
 static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts, TableCounters &ctr,
-                                 cudaEvent_t ready_ev, cudaEvent_t consumed_ev) {
+                                 cudaEvent_t ready_ev, cudaEvent_t consumed_ev, uint64_t kmers_hint) {
     katgpu_ctx *c = t->ctx;
     DistState *d = c->dist;
     const int b = (int)(d->round & 1);
@@ -338,49 +338,76 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
     d->keys_received += received;
     d->keys_sent += n_starts; // upper bound (every start a k-mer); the exact figure is the job's n_total
     if (received) {
-        bool ok = false;
-        KT(pend_alloc(t, std::max<uint64_t>(received, t->n_slots / 4), ok));
-        if (!ok || !t->tiled) return fail(KATGPU_ERR_NOMEM, "multi-GPU counting needs the tiled path's pending buffer (table too small or out of memory)");
-        // segments s = j, j + G, ... go to level-1 CTA j: the fullest CTA bounds every (slice, CTA) segment
-        const uint32_t G = t->pend_segs;
-        std::vector<uint64_t> per_cta(G, 0);
-        for (size_t s = 0; s < n_src; s++) per_cta[s % G] += d->h_len[s];
-        const uint64_t worst = *std::max_element(per_cta.begin(), per_cta.end());
-        const double F = (double)(1u << t->pend_Pb);
-        auto fill_of = [&](uint64_t keys) { return (double)keys / F + 4.5 * std::sqrt((double)keys / F) + 16.0; };
-        if (t->dist_cta_keys && fill_of(t->dist_cta_keys + worst) > (double)t->pend_seg_cap) {
-            KT(sweep_pending(t, ctr)); // local: level-2 binning + tile insertion of what is pending
-            t->dist_cta_keys = 0;
+        // The pending-key (tiled) path when the table is large enough for it; its buffers are sized once,
+        // for the whole feed (with a uniform owner hash a rank receives about what it routes).
+        bool tiled = t->pend_keys != nullptr && t->tiled;
+        if (!t->pend_keys && dist_can_tile(t)) {
+            bool ok = false;
+            KT(pend_alloc(t, std::max<uint64_t>(std::max(received, kmers_hint), t->n_slots / 4), ok));
+            tiled = ok && t->tiled;
         }
-        BinDst D{};
-        D.keys = t->pend_keys;
-        D.len = t->pend_seglen;
-        D.cap = t->pend_seg_cap;
-        D.stride = t->pend_segs;
-        D.shift = t->g.b - t->pend_Pb;
-        D.mask = (1u << t->pend_Pb) - 1;
-        D.F = 1u << t->pend_Pb;
-        D.R = t->ring1;
-        BinKeysParams B{};
-        B.g = t->g;
-        set_add_bound(B.g, ~0ULL);
-        B.seg_keys = reinterpret_cast<const uint64_t *>(d->block + d->keys_off(b));
-        B.seg_len = len_dev;
-        B.n_src = (uint32_t)n_src;
-        B.seg_cap = d->cap;
-        B.tile_keys = kBinTile;
-        B.dst = D;
-        B.side = side_list_of(t);
-        B.hll = t->pend_hll;
-        {
-            ProfScope ps(c, "bin1", c->stream);
-            launch_bin_keys(B, (int)G, c->stream);
+        if (tiled) {
+            // segments s = j, j + G, ... go to level-1 CTA j: the fullest CTA bounds every (slice, CTA) segment
+            const uint32_t G = t->pend_segs;
+            std::vector<uint64_t> per_cta(G, 0);
+            for (size_t s = 0; s < n_src; s++) per_cta[s % G] += d->h_len[s];
+            const uint64_t worst = *std::max_element(per_cta.begin(), per_cta.end());
+            const double F = (double)(1u << t->pend_Pb);
+            auto fill_of = [&](uint64_t keys) { return (double)keys / F + 4.5 * std::sqrt((double)keys / F) + 16.0; };
+            if (t->dist_cta_keys && fill_of(t->dist_cta_keys + worst) > (double)t->pend_seg_cap) {
+                KT(sweep_pending(t, ctr)); // local: level-2 binning + tile insertion of what is pending
+                t->dist_cta_keys = 0;
+            }
+            BinDst D{};
+            D.keys = t->pend_keys;
+            D.len = t->pend_seglen;
+            D.cap = t->pend_seg_cap;
+            D.stride = t->pend_segs;
+            D.shift = t->g.b - t->pend_Pb;
+            D.mask = (1u << t->pend_Pb) - 1;
+            D.F = 1u << t->pend_Pb;
+            D.R = t->ring1;
+            BinKeysParams B{};
+            B.g = t->g;
+            set_add_bound(B.g, ~0ULL);
+            B.seg_keys = reinterpret_cast<const uint64_t *>(d->block + d->keys_off(b));
+            B.seg_len = len_dev;
+            B.n_src = (uint32_t)n_src;
+            B.seg_cap = d->cap;
+            B.tile_keys = kBinTile;
+            B.dst = D;
+            B.side = side_list_of(t);
+            B.hll = t->pend_hll;
+            {
+                ProfScope ps(c, "bin1", c->stream);
+                launch_bin_keys(B, (int)G, c->stream);
+            }
+            c->launches++;
+            CU(cudaGetLastError());
+            t->dist_cta_keys += worst;
+            t->pend_bound += received;
+            t->pend_total_tiles += (received + kBinTile - 1) / kBinTile;
+        } else {
+            // small tables (small k, small -H): the received segments go through the general
+            // random-access insertion; the table is grown first so that they fit in any case
+            KT(sweep_pending(t, ctr));
+            KT(dist_make_room(t, ctr, received));
+            TileParams P{};
+            P.g = t->g;
+            set_add_bound(P.g, ~0ULL);
+            P.keys = reinterpret_cast<const uint64_t *>(d->block + d->keys_off(b));
+            P.len = len_dev;
+            P.cap = d->cap;
+            P.parts = 1;
+            P.n_tiles = (uint32_t)n_src;
+            {
+                ProfScope ps(c, "insert", c->stream);
+                launch_insert_deferred(P, nullptr, P.n_tiles, c->stream);
+            }
+            c->launches++;
+            CU(cudaGetLastError());
+            KT(settle(t, ctr));
         }
-        c->launches++;
-        CU(cudaGetLastError());
-        t->dist_cta_keys += worst;
-        t->pend_bound += received;
-        t->pend_total_tiles += (received + kBinTile - 1) / kBinTile;
     }
     CU(cudaEventRecord(d->ev_binned[b], c->stream));
     // barrier Y: every owner has consumed receive area `b`
@@ -401,7 +428,7 @@ katgpu_status dist_feed_device(katgpu_table *t, const uint8_t *dev, uint64_t n) 
     KT(allreduce_max_host(c, rounds));
     for (uint64_t r = 0; r < rounds; r++) {
         const uint64_t off = std::min<uint64_t>(n, r * R);
-        KT(route_round(t, dev + off, n - off, std::min<uint64_t>(n - off, R), ctr, nullptr, nullptr));
+        KT(route_round(t, dev + off, n - off, std::min<uint64_t>(n - off, R), ctr, nullptr, nullptr, n));
     }
     return KATGPU_OK;
 }
@@ -433,11 +460,20 @@ katgpu_status dist_feed_host(katgpu_table *t, const char *bases, size_t n) {
             while (issued < n_chunks && issued < i + (size_t)ring) KT(issue_copy(issued++));
             const int b = (int)(i % ring);
             const size_t off = i * chunk;
-            KT(route_round(t, c->chunk[b], std::min(n - off, chunk + kHalo), std::min(n - off, chunk), ctr, c->chunk_ready[b], c->chunk_free[b]));
+            KT(route_round(t, c->chunk[b], std::min(n - off, chunk + kHalo), std::min(n - off, chunk), ctr, c->chunk_ready[b], c->chunk_free[b], n));
         } else
-            KT(route_round(t, nullptr, 0, 0, ctr, nullptr, nullptr));
+            KT(route_round(t, nullptr, 0, 0, ctr, nullptr, nullptr, n));
     }
     CU(cudaStreamSynchronize(c->copy_stream)); // `bases` belongs to the caller again
+    return KATGPU_OK;
+}
+
+katgpu_status record_feed_consumed(katgpu_ctx *c, cudaEvent_t ev) {
+    if (c->dist) { // the route kernel reads the input on its own stream
+        CU(cudaEventRecord(c->dist->ev_tmp, c->dist->route_stream));
+        CU(cudaStreamWaitEvent(c->stream, c->dist->ev_tmp, 0));
+    }
+    CU(cudaEventRecord(ev, c->stream));
     return KATGPU_OK;
 }
 

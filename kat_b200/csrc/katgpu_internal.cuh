@@ -8,6 +8,7 @@
 #include "partition_kernels.cuh"
 #include "tile_kernels.cuh"
 #include "reduce_kernels.cuh"
+#include "parse_kernels.cuh"
 
 #include <chrono>
 #include <cstdio>
@@ -64,6 +65,17 @@ struct katgpu_ctx {
     std::multimap<size_t, void *> pool;
     size_t pooled_bytes = 0;
     DistState *dist = nullptr; // set by katgpu_dist_init: this context is one rank of a multi-GPU job
+    // raw-file feed (katgpu_count_feed_fastq): two device buffers for file bytes, pinned bounce
+    // buffers filled by several host threads, newline index scratch
+    uint8_t *raw[2] = {};
+    size_t raw_cap = 0;
+    cudaEvent_t raw_free[2] = {};
+    int raw_next = 0;
+    uint32_t *nl_buf = nullptr, *nl_tiles_buf = nullptr, *parse_flags = nullptr; // device
+    size_t nl_cap = 0, nl_tiles_cap = 0;
+    uint8_t *bounce[8] = {};
+    cudaEvent_t bounce_free[8] = {};
+    size_t bounce_bytes = 0;
 };
 
 struct katgpu_table {
@@ -151,6 +163,10 @@ void set_add_bound(katgpu::TableGeom &g, uint64_t bound);
 katgpu_status feed_device_range(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
                                 katgpu::TableCounters &ctr, uint64_t kmers_hint);
 katgpu_status ensure_feed_staging(katgpu_ctx *c, size_t chunk, int ring);
+bool dist_can_tile(const katgpu_table *t);                                              // the tiled pending-key path is possible for this table
+katgpu_status dist_make_room(katgpu_table *t, katgpu::TableCounters &ctr, uint64_t n); // grow until n more distinct keys fit
+// record `ev` once everything queued so far that reads feed input has run (compute stream and, on a job, the route stream)
+katgpu_status record_feed_consumed(katgpu_ctx *c, cudaEvent_t ev);
 
 // ---- multi-GPU hooks (katgpu_dist.cu); all are no-ops / never called when ctx->dist is null ----
 void dist_shutdown(katgpu_ctx *c);

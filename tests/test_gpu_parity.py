@@ -358,13 +358,14 @@ def _multiset_checksums(keys, counts):
 
 
 @pytest.mark.parametrize("slots_log2", [32, 30])
-def test_tiled_path_at_benchmark_geometry(ctx, slots_log2, monkeypatch):
+def test_tiled_path_at_benchmark_geometry(ctx, slots_log2, count_path):
     """The benchmarked path at the benchmark's table geometry (bench.py: 2^32 slots -> 512 level-1
     slices, 1024 tiles per slice, several level-2 groups; 2^30 for the 2-GPU setting): 2 M synthetic
     150 bp reads generated ON THE DEVICE (the bench's generator, ~250 M 27-mers), counted through the
     tiled kernels, against the oracle on the same bytes: totals, hist, gcp, order-independent
     checksums of the full exported multiset, and 200k point lookups."""
-    monkeypatch.setenv("KATGPU_COUNT_PATH", "tiled")
+    if count_path != "tiled":
+        pytest.skip("the benchmarked (tiled) path only")
     n_reads, L, k = 2_000_000, 150, 27
     n_bytes = n_reads * (L + 1)
     d = ctx.device_alloc(n_bytes + 64)
@@ -392,3 +393,70 @@ def test_tiled_path_at_benchmark_geometry(ctx, slots_log2, monkeypatch):
     want = np.concatenate([ocounts[pick], np.array([ot.lookup(int(x)) for x in probe[-1000:]], dtype=np.uint64)])
     assert np.array_equal(t.lookup(probe, False), want)
     t.free()
+
+
+# ---- FASTQ records parsed on the device (katgpu_count_feed_fastq, parse_kernels.cu) ---------------
+def _regular_fastq(rng, n_records, crlf=False):
+    """4-line FASTQ in the regular layout, with everything that layout allows: ragged read lengths
+    (1..300), long and empty-ish headers, '@' and '+' opening quality lines, 'N'/IUPAC/lower-case
+    bases, repeated header on the '+' line."""
+    out = bytearray()
+    alpha = np.frombuffer(b"ACGTACGTACGTNacgtRY", dtype=np.uint8)
+    qual = np.frombuffer(b"@+I#5?!~", dtype=np.uint8)
+    for i in range(n_records):
+        L = int(rng.integers(1, 301)) if i % 7 else int(rng.integers(1, 6))
+        seq = alpha[rng.integers(0, len(alpha), L)].tobytes()
+        if seq[:1] in (b"@", b"+"):
+            seq = b"A" + seq[1:]
+        hdr = b"@r%d %s" % (i, b"x" * int(rng.integers(0, 70))) if i % 11 else b"@"
+        q = qual[rng.integers(0, len(qual), L)].tobytes()
+        plus = b"+" + (hdr[1:] if i % 3 == 0 else b"")
+        eol = b"\r\n" if crlf else b"\n"
+        if crlf:  # '\r' is part of the line: the quality line must match the sequence line's length including it
+            out += hdr + eol + seq + eol + plus + eol + q + eol
+        else:
+            out += hdr + eol + seq + eol + plus + eol + q + eol
+    return bytes(out)
+
+
+@pytest.mark.parametrize("k,trim,crlf", [(27, 0, False), (5, 0, False), (21, 3, False), (31, 0, True), (17, 7, True)])
+def test_feed_fastq_device_parse_matches_reference_parser(ctx, k, trim, crlf, count_path):
+    """Raw 4-line FASTQ bytes parsed on the GPU give exactly the k-mers of the oracle's emulation of
+    the reference parser (JFI/mer_overlap_sequence_parser.hpp:218-289), with and without 5' trim."""
+    rng = np.random.default_rng(100 * k + trim)
+    raw = _regular_fastq(rng, 20000, crlf)
+    stream, st = O.parse_file(raw, k, trim)
+    assert st == 0
+    t = ctx.count_begin(k, True, 1 << 22, True)
+    assert t.feed_fastq(raw, trim) is True
+    # second call: another block of whole records (no k-mer spans calls), different size -> buffers regrow
+    raw2 = _regular_fastq(rng, 45000, crlf)
+    assert t.feed_fastq(raw2, trim) is True
+    t.end()
+    stream2, st2 = O.parse_file(raw2, k, trim)
+    assert st2 == 0
+    assert_same_multiset(t, ora_table([stream, stream2], k))
+
+
+@pytest.mark.parametrize("what", ["multi_line", "no_final_newline", "length_mismatch", "plus_in_sequence", "missing_plus",
+                                  "three_lines", "empty_sequence", "trim_too_long", "fasta", "sequence_starts_with_at"])
+def test_feed_fastq_refuses_irregular_input_and_counts_nothing(ctx, what):
+    """Every precondition of the regular layout is checked on the device; a violation anywhere means
+    regular = 0 and an untouched table, and the host route (exact emulation) then gives the result."""
+    good = b"@a\nACGTACGTAC\n+\nIIIIIIIIII\n" * 50
+    bad = {"multi_line": b"@r\nACGTA\nCGTAC\n+\nIIIII\nIIIII\n", "no_final_newline": b"@r\nACGTACGTAC\n+\nIIIIIIIIII",
+           "length_mismatch": b"@r\nACGTACGTAC\n+\nIIIIIIIII\n", "plus_in_sequence": b"@r\nACGT+CGTAC\n+\nIIIIIIIIII\n",
+           "missing_plus": b"@r\nACGTACGTAC\n-\nIIIIIIIIII\n", "three_lines": b"@r\nACGTACGTAC\n+\n",
+           "empty_sequence": b"@r\n\n+\n\n", "trim_too_long": b"@r\nACG\n+\nIII\n", "fasta": b">r\nACGTACGTAC\n>s\nACGTACGTAC\n",
+           "sequence_starts_with_at": b"@r\n@CGTACGTAC\n+\nIIIIIIIIII\n"}[what]
+    raw = good + bad if what != "fasta" else bad * 2
+    trim = 3 if what == "trim_too_long" else 0
+    t = ctx.count_begin(5, True, 1 << 16, True)
+    assert t.feed_fastq(raw, trim) is False
+    assert t.info()["n_total"] == 0 and t.info()["n_distinct"] == 0
+    stream, st = O.parse_file(raw, 5, trim)
+    if st != -1:
+        t.feed(stream)
+    t.end()
+    assert_same_multiset(t, ora_table([stream] if st != -1 else [], 5))
+    assert ctx.count_begin(5, True, 1 << 16, True).feed_fastq(b"") is True  # nothing to do is fine
