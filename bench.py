@@ -312,6 +312,199 @@ def cpu_baseline_leg(ctx, d_bases, n_reads, threads, args, line):
     return out
 
 
+# ---------------------------------------------------------------------------------------------------
+# The other two tools of the path (BASELINE.json configs[2] and, per GPU, configs[3]); the default run
+# (the driver's) is `hist` above.  Same contract: one JSON line, value = k-mer instances / s resident,
+# roofline for the WALK kernel of the tool (K3 gcp_kernel / K4 comp_kernel), the
+# reference timed beside it on a bounded sample with its output compared bit for bit.
+WORKLOADS = {
+    # C4 per GPU: 50 Gbp / 8 = 6.25 Gbp of 150 bp reads from 1 Gbp / 8 of genome, k = 21
+    "gcp": {"k": 21, "reads": 41_666_667, "genome": 125_000_000, "seeds": [(4, 5)], "slots_log2": 31,
+            "what": "kat gcp -m21 (BASELINE configs[3] per GPU: 50 Gbp / 8)"},
+    # C3: two read sets of 10 Gbp from the same 200 Mbp genome, k = 27
+    "comp": {"k": 27, "reads": 66_666_667, "genome": 200_000_000, "seeds": [(1, 2), (1, 3)], "slots_log2": 31,
+             "what": "kat comp -m27 reads-vs-reads (BASELINE configs[2])"},
+}
+
+
+def run_reference_tool(tool, k, fastqs, threads, slots, workdir, max_attempts=4):
+    """`kat gcp|comp` with the unmodified reference.  Returns dict(wall, out prefix, attempts)."""
+    import oracle as O
+    prefix = os.path.join(workdir, "ref_" + tool)
+    attempts, last = 0, ""
+    t = max(1, threads)
+    while True:
+        for _ in range(max_attempts):
+            attempts += 1
+            if tool == "gcp":
+                args = ["gcp", f"-m{k}", f"-t{t}", f"-H{slots}", "-o", prefix] + fastqs
+            else:
+                args = ["comp", f"-m{k}", f"-t{t}", f"-H{slots}", f"-I{slots}", "-o", prefix] + fastqs
+            t0 = time.perf_counter()
+            try:
+                r = O.run_ref(args, cwd=workdir, timeout=3600)
+            except subprocess.TimeoutExpired:
+                last = "timeout"
+                continue
+            wall = time.perf_counter() - t0
+            ok = r.returncode == 0 and os.path.exists(prefix + (".mx" if tool == "gcp" else "-main.mx"))
+            if ok:
+                return {"wall": wall, "prefix": prefix, "attempts": attempts, "threads": t}
+            last = f"rc {r.returncode}"
+        if t == 1:
+            raise ReferenceFailed(f"reference kat {tool} failed {attempts} times ({last})")
+        t = max(1, t // 2)
+
+
+def spectra_workload(args, ctx, dist, rank, world, local_rank, sampler, emit):
+    import numpy as np
+    import torch
+    from kat_b200 import binding as B
+    wl = WORKLOADS[args.workload]
+    k, L = wl["k"], READ_LEN
+    n_reads = args.reads if args.reads != READS_PER_GPU else wl["reads"]
+    slots_log2 = args.slots_log2 or wl["slots_log2"]
+    n_bytes = n_reads * (L + 1)
+    hbm_peak, peak_src = measured_peaks()
+    genome_len = wl["genome"] * world
+    d_bases = [ctx.device_alloc(n_bytes + 64) for _ in wl["seeds"]]
+    for d, (sg, sr) in zip(d_bases, wl["seeds"]):
+        ctx.synth_reads_device(d, genome_len, sg, sr, rank * n_reads, n_reads, L, SUB_RATE, N_RATE)
+
+    def count(d):
+        t = ctx.count_begin(k, True, 1 << slots_log2, True)
+        t.feed_device(d, n_bytes).end()
+        return t
+
+    def job():
+        tabs = [count(d) for d in d_bases]
+        if args.workload == "gcp":
+            res = tabs[0].gcp()
+        else:
+            res = B.comp(tabs[0], tabs[1])
+        tot = sum(t.n_total for t in tabs)
+        dis = [t.n_distinct for t in tabs]
+        loc = [t.info()["n_distinct"] for t in tabs]
+        for t in tabs:
+            t.free()
+        return res, tot, dis, loc
+
+    def barrier():
+        ctx.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        job()
+    barrier()
+    l0 = ctx.launch_count()
+    ctx.profile_enable(True)
+    sampler.mark_begin()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        res, n_total, n_distinct, local_distinct = job()
+    barrier()
+    dt = time.perf_counter() - t0
+    sampler.mark_end()
+    fams = ("route", "bin1", "bin2", "tile", "insert", "memset", "gcp", "comp", "hist")
+    prof = {f: ctx.profile_get(f) for f in fams}
+    ctx.profile_enable(False)
+    if dist is not None:
+        tt = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    table_bytes = (1 << slots_log2) * 8.0
+    walk = args.workload
+    w_ms, w_n = prof[walk]
+    per_job_ms = w_ms / max(args.steps, 1)
+    if walk == "gcp":
+        mx = res
+        assert int(mx.sum()) <= n_distinct[0]
+        alg_bytes = table_bytes  # 8 B per slot of THIS rank's table, read once (our slot is 8 B; SURVEY assumed 12)
+        updates = local_distinct[0]
+        kernel = "gcp_kernel: one pass over the table, GC count of the reconstructed k-mer, k x 1001 matrix in shared memory (warp-aggregated atomics), one flush per CTA"
+    else:
+        c = res["counters"]
+        assert c["hash1_total"] + c["hash2_total"] == n_total and c["hash1_distinct"] == n_distinct[0] and c["hash2_distinct"] == n_distinct[1]
+        assert int(res["main"].sum()) == c["hash1_distinct"] + c["hash2_only_distinct"]
+        # SURVEY.md §8(d): per distinct k-mer of the walked table 12 B sequential + 12 B random probe, both passes
+        alg_bytes = 24.0 * (local_distinct[0] + local_distinct[1])
+        updates = local_distinct[0] + local_distinct[1]
+        kernel = ("comp_kernel x2: walk hash1 probing hash2, walk hash2 probing hash1 (one 32-byte bucket per probe); matrix corner + spectra in "
+                  "shared memory, the rest global atomics")
+    achieved = alg_bytes / 1e9 / (per_job_ms / 1e3) if per_job_ms else None
+    traffic = (sum(table_bytes for _ in d_bases) + (32.0 * updates if walk == "comp" else 0.0))
+    line = {"metric": f"canonical k-mers/sec (k={k}) into {walk}", "value": n_total * args.steps / dt, "unit": "k-mers/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": f"{wl['what']}: {len(d_bases)} x {n_reads * L / 1e9:.2f} Gbp synthetic {L} bp reads per GPU ({n_reads} reads, genome {wl['genome'] / 1e6:.0f} Mbp/GPU, "
+                                   f"sub {SUB_RATE}, N {N_RATE}, seeds {wl['seeds']})", "k": k, "canonical": True, "read_len": L, "reads_per_gpu": n_reads,
+                       "table_slots_per_gpu": 1 << slots_log2, "parallelism": f"read-sharded x{world}, k-mers stored on their owner GPU over NVLink" if world > 1 else "1 GPU",
+                       "l2": "tables (17 GB each) and base streams far larger than the 126 MB L2; no explicit flush"},
+            "kmer_instances_per_step": n_total, "distinct_kmers": n_distinct, "gpu_launches": ctx.launch_count() - l0, "clocks": sampler.summary(),
+            "roofline": {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak if achieved else None, "traffic": None,
+                         "traffic_model_bytes": traffic, "peak_source": peak_src, "algorithmic_bytes": alg_bytes,
+                         "kernel_ms_per_job": per_job_ms, "kernel_launches": w_n,
+                         "matrix_updates_per_s": updates / (per_job_ms / 1e3) if per_job_ms else None,
+                         "what_updates_are": "one matrix (+ spectra / counter) update per distinct k-mer walked: shared-memory atomics, warp-aggregated (match.any); "
+                                             "cells outside the shared corner and the final flush are 64-bit global atomics",
+                         "counting_kernels_ms_per_job": {f: prof[f][0] / max(args.steps, 1) for f in ("route", "bin1", "bin2", "tile", "insert", "memset") if prof[f][1]}}}
+    # ---- the reference beside it: bounded sample, output compared bit for bit
+    if not args.no_cpu_baseline and world == 1 and rank == 0:
+        line["cpu_baseline"] = spectra_cpu_baseline(args, ctx, d_bases, wl, k, n_reads)
+    for d in d_bases:
+        ctx.device_free(d)
+    if rank == 0:
+        emit(line)
+
+
+def spectra_cpu_baseline(args, ctx, d_bases, wl, k, n_reads):
+    import numpy as np
+    import oracle as O
+    from kat_b200 import binding as B
+    import golden_util as G
+    threads = os.cpu_count() or 1
+    out = {"value": None, "unit": "k-mers/s", "cores": threads, "kind": "reference"}
+    if not O.have_ref():
+        out["sample"] = "oracle/_ref/kat not present"
+        return out
+    sample = min(args.cpu_sample_reads // len(d_bases), n_reads)
+    work = tempfile.mkdtemp(prefix="katref_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        fqs, streams, n_inst = [], [], 0
+        for i, d in enumerate(d_bases):
+            s = np.empty(sample * (READ_LEN + 1), dtype=np.uint8)
+            ctx.d2h(s, d)
+            fq = os.path.join(work, f"sample{i + 1}.fastq")
+            O.write_fastq(s, sample, READ_LEN, fq)
+            fqs.append(fq)
+            streams.append(s)
+            n_inst += O.count_instances(s, k)
+        slots = 1 << max(20, (sample * (READ_LEN - k + 1) - 1).bit_length())
+        tabs = [ctx.count([s], k, True, slots) for s in streams]
+        r = run_reference_tool(args.workload, k, fqs, threads, slots, work)
+        out.update({"value": n_inst / r["wall"], "cores": r["threads"], "attempts": r["attempts"],
+                    "sample": f"first {sample} reads of each set ({n_inst} k-mer instances) as FASTQ in /dev/shm; unmodified reference `kat {args.workload} -m{k} -t{r['threads']} -H{slots}` wall {r['wall']:.2f}s"})
+        if args.workload == "gcp":
+            _, ref_mx = G.parse_mx_text(open(r["prefix"] + ".mx", "rb").read())
+            out["parity_on_sample"] = bool(np.array_equal(tabs[0].gcp(), ref_mx))
+        else:
+            g = B.comp(tabs[0], tabs[1])
+            _, ref_mx = G.parse_mx_text(open(r["prefix"] + "-main.mx", "rb").read())
+            want, _ = G.parse_stats_text(open(r["prefix"] + ".stats", "rb").read())
+            out["parity_on_sample"] = bool(np.array_equal(g["main"], ref_mx) and g["counters"] == want)
+        for t in tabs:
+            t.free()
+    except Exception as ex:
+        out["error"] = (type(ex).__name__ + ": " + str(ex))[:300]
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    return out
+
+
 def main():
     # stdout carries exactly ONE JSON line: libraries that print to fd 1 (NCCL's version banner)
     # are sent to stderr, the result goes to the saved descriptor.
@@ -327,6 +520,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="katgpu", choices=["katgpu", "reference"])
+    ap.add_argument("--workload", default="hist", choices=["hist", "gcp", "comp"],
+                    help="hist = BASELINE configs[1] (the default, what the driver runs); gcp / comp = the other two tools of the path")
     ap.add_argument("--reads", type=int, default=READS_PER_GPU, help="reads per GPU (default: the 10 Gbp workload)")
     ap.add_argument("--slots-log2", type=int, default=0, help="table slots per GPU (log2)")
     ap.add_argument("--cpu-sample-reads", type=int, default=4_000_000)
@@ -336,8 +531,8 @@ def main():
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.slots_log2 == 0:  # load ~0.28 on one GPU; 2^31 when the exchange buffers also need HBM
-        args.slots_log2 = 32 if world == 1 else 31
+    if args.slots_log2 == 0 and args.workload == "hist":  # 1.2 G distinct 27-mers per GPU: load 0.56
+        args.slots_log2 = 31
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     n_reads = args.reads
     n_kmers_nominal = n_reads * KMERS_PER_READ
@@ -422,6 +617,16 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     hbm_peak, peak_src = measured_peaks()
+    if world > 1:  # this context becomes one rank of the job; every table call below is then collective
+        from kat_b200.multigpu import join_job
+        join_job(ctx, dist, device=torch.device("cuda", local_rank))
+    if args.workload != "hist":
+        spectra_workload(args, ctx, dist, rank, world, local_rank, sampler, emit)
+        sampler.stop()
+        ctx.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     n_bytes = n_reads * (READ_LEN + 1)
     genome_len = GENOME_PER_GPU * world
@@ -430,9 +635,6 @@ def main():
     ctx.synth_reads_device(d_bases, genome_len, SEED_G, SEED_R, first_read, n_reads, READ_LEN, SUB_RATE, N_RATE)
     base, ceil_, nb = B.hist_geometry(1, 10000)
 
-    if world > 1:  # this context becomes one rank of the job; every table call below is then collective
-        from kat_b200.multigpu import join_job
-        join_job(ctx, dist, device=torch.device("cuda", local_rank))
 
     def job_resident():
         """One whole `kat hist` job, base stream resident in HBM.  Returns (bins, n_total, n_distinct[, local n_total])."""

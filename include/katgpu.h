@@ -217,6 +217,11 @@ katgpu_status katgpu_dist_barrier(katgpu_ctx *ctx);
 katgpu_status katgpu_dist_stats(katgpu_ctx *ctx, uint64_t *starts_routed, uint64_t *keys_received,
                                 uint64_t *rounds);
 
+/* Measurement aid: the multi-GPU extraction kernel on ONE GPU with n_ranks local receive areas
+ * (its cost without NVLink); keys are discarded.  tools/route_probe.py, ncu captures. */
+katgpu_status katgpu_debug_route_local(katgpu_table *t, const void *bases_dev, size_t n, int n_ranks,
+                                       double *ms, uint64_t *keys);
+
 /* Building blocks of the round-1 exchange (route into caller-provided buckets, insert
  * received keys); kept for callers that move the keys themselves.  Every distinct k-mer must be owned by
  * exactly one rank before histograms become additive:

@@ -73,6 +73,7 @@ SIGNATURES = {
     "katgpu_dist_rank": (_i, [_vp]),
     "katgpu_dist_n_ranks": (_i, [_vp]),
     "katgpu_dist_barrier": (_i, [_vp]),
+    "katgpu_debug_route_local": (_i, [_vp, _vp, _sz, _i, C.POINTER(_d), C.POINTER(_u64)]),
     "katgpu_dist_stats": (_i, [_vp, C.POINTER(_u64), C.POINTER(_u64), C.POINTER(_u64)]),
     "katgpu_launch_count": (_u64, [_vp]),
     "katgpu_profile_enable": (_i, [_vp, _i]),

@@ -363,6 +363,11 @@ void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_streami
     const uint64_t per_gpu_slots = ctx.n() > 1 ? std::max<uint64_t>(in.hash_size / ctx.n(), 1024) : in.hash_size;
     run_on_all(ctx.n(), [&](int r) { gpu_check(katgpu_count_begin(ctx.all[r], k, in.canonical ? 1 : 0, per_gpu_slots, allow_grow ? 1 : 0, &in.tables[r])); });
     in.table = in.tables[0];
+    { // size the library's pending-key buffers once, for the whole input (about one k-mer per two file bytes of FASTQ)
+        uint64_t bytes = 0;
+        for (auto &f : in.files) bytes += file_size_or_zero(f);
+        if (bytes >= ((uint64_t)64 << 20)) run_on_all(ctx.n(), [&](int r) { gpu_check(katgpu_count_reserve(in.tables[r], bytes / 2 / (uint64_t)ctx.n())); });
+    }
     const size_t stream_from = env_size("KAT_STREAM_BYTES", (size_t)2 << 30), block = env_size("KAT_STREAM_BLOCK", (size_t)512 << 20);
     std::vector<unsigned char> raw;
     std::string bases;

@@ -83,6 +83,7 @@ extern "C" int katgpu_device_count(void) {
 extern "C" void katgpu_debug_set_count_bits(int bits) { g_debug_count_bits = bits; }
 
 extern "C" katgpu_status katgpu_init(int device, katgpu_ctx **out) {
+    TraceScope trace__("katgpu_init");
     if (!out) return fail(KATGPU_ERR_INVALID, "katgpu_init: out is NULL");
     *out = nullptr;
     int n = katgpu_device_count();

@@ -468,6 +468,65 @@ katgpu_status dist_feed_host(katgpu_table *t, const char *bases, size_t n) {
     return KATGPU_OK;
 }
 
+// Measurement aid (tools/route_probe.py, ncu captures): route_bases_kernel on ONE GPU with `n_ranks`
+// owners whose receive areas are all local memory — the kernel's own cost without NVLink.  The keys
+// are written and thrown away; *ms = kernel time (CUDA events on the compute stream), *keys = keys written.
+extern "C" katgpu_status katgpu_debug_route_local(katgpu_table *t, const void *bases_dev, size_t n, int n_ranks, double *ms, uint64_t *keys) {
+    if (!t || !bases_dev || !ms || n_ranks < 1 || n_ranks > kMaxRanks) return fail(KATGPU_ERR_INVALID, "katgpu_debug_route_local: bad arguments");
+    katgpu_ctx *c = t->ctx;
+    CU(cudaSetDevice(c->device));
+    int bps = 2;
+    CU(route_configure(&bps));
+    const uint32_t grid = (uint32_t)(c->sm_count * std::max(1, bps));
+    const uint64_t n_starts = n >= (size_t)t->g.k ? n - t->g.k + 1 : 0;
+    const uint64_t tiles = (n_starts + kBinTile - 1) / kBinTile, tiles_per_cta = (tiles + grid - 1) / grid;
+    const uint32_t cap = (uint32_t)std::max<uint64_t>(kBinTile, tiles_per_cta * kBinTile);
+    // each owner's share is ~1/n_ranks of a CTA's keys: size the areas for 2x that (uniform hashes; this is a probe)
+    const uint64_t per_owner = (uint64_t)grid * cap;
+    uint64_t *keys_buf = nullptr;
+    uint32_t *len_buf = nullptr;
+    CU(cudaMalloc((void **)&keys_buf, (size_t)n_ranks * per_owner * 8));
+    CU(cudaMalloc((void **)&len_buf, (size_t)n_ranks * grid * 4));
+    RouteParams P{};
+    P.g = t->g;
+    P.bases = (const uint8_t *)bases_dev;
+    P.n_valid = n;
+    P.n_starts = n_starts;
+    P.n_tiles = (int)tiles;
+    P.tma_ok = (reinterpret_cast<uintptr_t>(bases_dev) & 15) == 0;
+    P.n_ranks = (uint32_t)n_ranks;
+    for (int o = 0; o < n_ranks; o++) {
+        P.seg[o] = keys_buf + (size_t)o * per_owner;
+        P.len[o] = len_buf + (size_t)o * grid;
+    }
+    P.cap = cap;
+    cudaEvent_t a, b;
+    CU(cudaEventCreate(&a));
+    CU(cudaEventCreate(&b));
+    launch_route_bases(P, (int)grid, c->stream); // warm
+    CU(cudaEventRecord(a, c->stream));
+    launch_route_bases(P, (int)grid, c->stream);
+    CU(cudaEventRecord(b, c->stream));
+    CU(cudaEventSynchronize(b));
+    c->launches += 2;
+    float f = 0;
+    CU(cudaEventElapsedTime(&f, a, b));
+    *ms = f;
+    if (keys) {
+        std::vector<uint32_t> h((size_t)n_ranks * grid);
+        CU(cudaMemcpy(h.data(), len_buf, h.size() * 4, cudaMemcpyDeviceToHost));
+        uint64_t tot = 0;
+        for (uint32_t v : h) tot += v;
+        *keys = tot;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(keys_buf);
+    cudaFree(len_buf);
+    CU(cudaGetLastError());
+    return KATGPU_OK;
+}
+
 katgpu_status record_feed_consumed(katgpu_ctx *c, cudaEvent_t ev) {
     if (c->dist) { // the route kernel reads the input on its own stream
         CU(cudaEventRecord(c->dist->ev_tmp, c->dist->route_stream));

@@ -10,6 +10,8 @@
 // match.any so the hot cells (count 1) cost one shared atomic per warp.
 #include "reduce_kernels.cuh"
 
+#include <algorithm>
+
 namespace katgpu {
 
 // Add 1 to cells[cell] for every active lane, one atomic per distinct cell of the warp.
@@ -30,6 +32,8 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
     return v;
 }
 
+constexpr int kWalkUnroll = 4; // 16-byte loads a walking thread keeps in flight
+
 // scaleCounter (src/comp.hpp:303-306) / the cvg_pos expression of src/gcp.cc:188
 __device__ __forceinline__ uint64_t scale_count(uint64_t c, double scale, bool unit) {
     if (unit || c == 0) return c;
@@ -48,31 +52,39 @@ __global__ void __launch_bounds__(512) hist_kernel(const __grid_constant__ Table
     }
     const uint64_t n_pairs = n_slots >> 1;
     const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(g.slots);
-    // whole warps iterate together (match.any needs the full warp)
+    // whole warps iterate together (match.any needs the full warp); kWalkUnroll 16-byte loads of a
+    // thread are in flight before the first slot is looked at: the walk is a pure HBM stream
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (n_pairs + stride - 1) / stride;
+    const uint64_t rounds = (n_pairs + stride * kWalkUnroll - 1) / (stride * kWalkUnroll);
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t it = 0; it < rounds; it++, i += stride) {
-        ulonglong2 w = make_ulonglong2(0, 0);
-        if (i < n_pairs) w = __ldg(src + i);
+    for (uint64_t it = 0; it < rounds; it++, i += stride * kWalkUnroll) {
+        ulonglong2 w[kWalkUnroll];
 #pragma unroll
-        for (int s = 0; s < 2; s++) {
-            const uint64_t word = s ? w.y : w.x;
-            const bool occ = word != 0;
-            uint32_t bin = 0;
-            if (occ) {
-                uint64_t v = word >> g.cshift;
-                if (word & (1ULL << (g.rbits + kProbeBits))) {
-                    uint64_t h, c;
-                    decode_slot(g, 2 * i + s, word, h, c);
-                    v = c;
+        for (int u = 0; u < kWalkUnroll; u++) {
+            const uint64_t j = i + (uint64_t)u * stride;
+            w[u] = j < n_pairs ? __ldcs(src + j) : make_ulonglong2(0, 0);
+        }
+#pragma unroll
+        for (int u = 0; u < kWalkUnroll; u++) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const uint64_t word = s ? w[u].y : w[u].x;
+                const bool occ = word != 0;
+                uint32_t bin = 0;
+                if (occ) {
+                    uint64_t v = word >> g.cshift;
+                    if (word & (1ULL << (g.rbits + kProbeBits))) {
+                        uint64_t h, c;
+                        decode_slot(g, 2 * (i + (uint64_t)u * stride) + s, word, h, c);
+                        v = c;
+                    }
+                    if (v < base) bin = 0;
+                    else if (v > ceil_) bin = nb - 1;
+                    else bin = (uint32_t)(inc == 1 ? (v - base) : (v - base) / inc);
                 }
-                if (v < base) bin = 0;
-                else if (v > ceil_) bin = nb - 1;
-                else bin = (uint32_t)(inc == 1 ? (v - base) : (v - base) / inc);
+                if (SMEM) warp_agg_inc_u32(sbins, bin, occ);
+                else warp_agg_inc_u64(out, bin, occ);
             }
-            if (SMEM) warp_agg_inc_u32(sbins, bin, occ);
-            else warp_agg_inc_u64(out, bin, occ);
         }
     }
     if (SMEM) {
@@ -84,7 +96,7 @@ __global__ void __launch_bounds__(512) hist_kernel(const __grid_constant__ Table
 
 // ------------------------------------------------------------------- K3 gcp --
 template <bool SMEM>
-__global__ void __launch_bounds__(512) gcp_kernel(const __grid_constant__ TableGeom g, uint64_t n_slots,
+__global__ void __launch_bounds__(512, 2) gcp_kernel(const __grid_constant__ TableGeom g, uint64_t n_slots,
                                                   double scale, uint32_t cvg_bins,
                                                   unsigned long long *__restrict__ out) {
     extern __shared__ uint32_t scell[];
@@ -95,26 +107,40 @@ __global__ void __launch_bounds__(512) gcp_kernel(const __grid_constant__ TableG
         for (uint32_t i = threadIdx.x; i < cells; i += blockDim.x) scell[i] = 0;
         __syncthreads();
     }
+    const uint64_t n_pairs = n_slots >> 1;
+    const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(g.slots);
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (n_slots + stride - 1) / stride;
+    const uint64_t rounds = (n_pairs + stride * kWalkUnroll - 1) / (stride * kWalkUnroll);
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t it = 0; it < rounds; it++, i += stride) {
-        const uint64_t word = i < n_slots ? __ldg(g.slots + i) : 0;
-        bool act = word != 0;
-        uint32_t cell = 0;
-        if (act) {
-            uint64_t h, cnt;
-            decode_slot(g, i, word, h, cnt);
-            const uint64_t key = unmix_key(g, h);
-            // gcCount (lib/include/kat/str_utils.hpp:151-161): C = 01, G = 10 -> the two bits differ
-            const uint32_t gc = (uint32_t)__popcll((key ^ (key >> 1)) & 0x5555555555555555ULL);
-            uint64_t cvg = scale_count(cnt, scale, unit);
-            if (cvg > cvg_bins) cvg = cvg_bins;
-            act = gc < g.k; // rows 0..k-1 only: all-G/C k-mers are dropped like the reference
-            cell = gc * cols + (uint32_t)cvg;
+    for (uint64_t it = 0; it < rounds; it++, i += stride * kWalkUnroll) {
+        ulonglong2 w[kWalkUnroll];
+#pragma unroll
+        for (int u = 0; u < kWalkUnroll; u++) {
+            const uint64_t j = i + (uint64_t)u * stride;
+            w[u] = j < n_pairs ? __ldcs(src + j) : make_ulonglong2(0, 0);
         }
-        if (SMEM) warp_agg_inc_u32(scell, cell, act);
-        else warp_agg_inc_u64(out, cell, act);
+#pragma unroll
+        for (int u = 0; u < kWalkUnroll; u++) {
+#pragma unroll
+            for (int s = 0; s < 2; s++) {
+                const uint64_t word = s ? w[u].y : w[u].x;
+                bool act = word != 0;
+                uint32_t cell = 0;
+                if (act) {
+                    uint64_t h, cnt;
+                    decode_slot(g, 2 * (i + (uint64_t)u * stride) + s, word, h, cnt);
+                    const uint64_t key = unmix_key(g, h);
+                    // gcCount (lib/include/kat/str_utils.hpp:151-161): C = 01, G = 10 -> the two bits differ
+                    const uint32_t gc = (uint32_t)__popcll((key ^ (key >> 1)) & 0x5555555555555555ULL);
+                    uint64_t cvg = scale_count(cnt, scale, unit);
+                    if (cvg > cvg_bins) cvg = cvg_bins;
+                    act = gc < g.k; // rows 0..k-1 only: all-G/C k-mers are dropped like the reference
+                    cell = gc * cols + (uint32_t)cvg;
+                }
+                if (SMEM) warp_agg_inc_u32(scell, cell, act);
+                else warp_agg_inc_u64(out, cell, act);
+            }
+        }
     }
     if (SMEM) {
         __syncthreads();
@@ -308,7 +334,9 @@ void launch_gcp(const TableGeom &g, uint64_t n_slots, double scale, uint32_t cvg
     const size_t smem = (size_t)g.k * (cvg_bins + 1) * 4;
     if (smem <= kMaxReduceSmem) {
         cudaFuncSetAttribute(gcp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxReduceSmem);
-        gcp_kernel<true><<<grid, 512, smem, st>>>(g, n_slots, scale, cvg_bins, out);
+        // `grid` = SM count: as many CTAs per SM as their matrices fit in shared memory (at most 4)
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, ((size_t)220 << 10) / (smem + 1024)));
+        gcp_kernel<true><<<grid * per_sm, 512, smem, st>>>(g, n_slots, scale, cvg_bins, out);
     } else
         gcp_kernel<false><<<grid, 512, 0, st>>>(g, n_slots, scale, cvg_bins, out);
 }

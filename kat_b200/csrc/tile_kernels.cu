@@ -65,6 +65,7 @@ struct BinCore {
     uint32_t *cnt;   // [F] keys staged (may run past R: those keys went to the side list)
     uint32_t *cur;   // [F] keys already in the destination segment
     uint32_t F, R, shift, mask;
+    uint32_t cnt_s, ring_s; // the same arrays as 32-bit shared-window addresses (append: no generic-address arithmetic per key)
     uint64_t *seg0;  // destination segment of bin 0
     uint64_t seg_stride; // keys between the segments of consecutive bins
     uint32_t cap;
@@ -76,6 +77,8 @@ struct BinCore {
         cnt = reinterpret_cast<uint32_t *>(smem);
         cur = cnt + F;
         ring = reinterpret_cast<uint64_t *>(smem + (((size_t)F * 8 + 15) & ~(size_t)15));
+        cnt_s = smem_u32(cnt);
+        ring_s = smem_u32(ring);
         seg0 = d.keys + (uint64_t)offset * d.cap;
         seg_stride = (uint64_t)d.stride * d.cap;
         len0 = d.len + offset;
@@ -87,8 +90,9 @@ struct BinCore {
     }
     __device__ __forceinline__ void append(uint64_t h, const SideList &S, const TableGeom &g, SideTally &t) {
         const uint32_t d = (uint32_t)(h >> shift) & mask;
-        const uint32_t pos = atomicAdd(&cnt[d], 1u);
-        if (pos < R) ring[(size_t)pos * F + d] = h;
+        uint32_t pos;
+        asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(cnt_s + d * 4u) : "memory");
+        if (pos < R) asm volatile("st.shared.u64 [%0], %1;" ::"r"(ring_s + (pos * F + d) * 8u), "l"(h) : "memory");
         else side_push_or_insert(S, g, h, t); // ring full (sized so that this is rare)
     }
     // One bin, one thread, any state: unaligned segment head (a previous launch ended there),

@@ -396,7 +396,7 @@ def test_tiled_path_at_benchmark_geometry(ctx, slots_log2, count_path):
 
 
 # ---- FASTQ records parsed on the device (katgpu_count_feed_fastq, parse_kernels.cu) ---------------
-def _regular_fastq(rng, n_records, crlf=False):
+def _regular_fastq(rng, n_records, crlf=False, min_len=1):
     """4-line FASTQ in the regular layout, with everything that layout allows: ragged read lengths
     (1..300), long and empty-ish headers, '@' and '+' opening quality lines, 'N'/IUPAC/lower-case
     bases, repeated header on the '+' line."""
@@ -404,7 +404,7 @@ def _regular_fastq(rng, n_records, crlf=False):
     alpha = np.frombuffer(b"ACGTACGTACGTNacgtRY", dtype=np.uint8)
     qual = np.frombuffer(b"@+I#5?!~", dtype=np.uint8)
     for i in range(n_records):
-        L = int(rng.integers(1, 301)) if i % 7 else int(rng.integers(1, 6))
+        L = int(rng.integers(min_len, 301)) if i % 7 else int(rng.integers(min_len, min_len + 5))
         seq = alpha[rng.integers(0, len(alpha), L)].tobytes()
         if seq[:1] in (b"@", b"+"):
             seq = b"A" + seq[1:]
@@ -424,13 +424,14 @@ def test_feed_fastq_device_parse_matches_reference_parser(ctx, k, trim, crlf, co
     """Raw 4-line FASTQ bytes parsed on the GPU give exactly the k-mers of the oracle's emulation of
     the reference parser (JFI/mer_overlap_sequence_parser.hpp:218-289), with and without 5' trim."""
     rng = np.random.default_rng(100 * k + trim)
-    raw = _regular_fastq(rng, 20000, crlf)
+    # (a read no longer than the trim is outside the regular layout: the reference's ignore(trim) would eat its newline)
+    raw = _regular_fastq(rng, 20000, crlf, trim + 1 + (1 if crlf else 0))
     stream, st = O.parse_file(raw, k, trim)
     assert st == 0
     t = ctx.count_begin(k, True, 1 << 22, True)
     assert t.feed_fastq(raw, trim) is True
     # second call: another block of whole records (no k-mer spans calls), different size -> buffers regrow
-    raw2 = _regular_fastq(rng, 45000, crlf)
+    raw2 = _regular_fastq(rng, 45000, crlf, trim + 1 + (1 if crlf else 0))
     assert t.feed_fastq(raw2, trim) is True
     t.end()
     stream2, st2 = O.parse_file(raw2, k, trim)

@@ -10,10 +10,11 @@ O.write_fastq(s,$reads,150,'/dev/shm/sample.fastq')
 P
 ls -la /dev/shm/sample.fastq
 cd /dev/shm
-for i in 1 2 3; do /usr/bin/time -f "wall %e s  user %U  sys %S  maxrss %M KB" $OLDPWD/kat_b200/bin/kat hist -m27 -H536870912 -o ours.hist sample.fastq > ours.log 2> ours.err; tail -1 ours.err; done
-KATGPU_TRACE=1 $OLDPWD/kat_b200/bin/kat hist -m27 -H536870912 -o ours.hist sample.fastq 2>&1 | grep -E "katgpu|Time taken|Total" | head -60
+TIMEFORMAT="wall %R s  user %U  sys %S"
+for i in 1 2 3; do time $OLDPWD/kat_b200/bin/kat hist -m27 -H536870912 -o ours.hist sample.fastq > ours.log 2> ours.err; done
+KATGPU_TRACE=1 $OLDPWD/kat_b200/bin/kat hist -m27 -H536870912 -o ours.hist sample.fastq 2>&1 | grep -E "katgpu_init|count_begin|alloc_table|pend_alloc|feed_fastq|count_end|katgpu_hist|Time taken|Total" | head -40
 echo "--- host parse route (KAT_GPU_PARSE=0)"
-for i in 1 2; do KAT_GPU_PARSE=0 /usr/bin/time -f "wall %e s  user %U  sys %S" $OLDPWD/kat_b200/bin/kat hist -m27 -H536870912 -o ours0.hist sample.fastq > /dev/null 2> ours0.err; tail -1 ours0.err; done
+for i in 1 2; do time KAT_GPU_PARSE=0 $OLDPWD/kat_b200/bin/kat hist -m27 -H536870912 -o ours0.hist sample.fastq > /dev/null 2> ours0.err; done
 cmp ours.hist ours0.hist && echo "gpu-parse and host-parse outputs identical"
-if [ -x $OLDPWD/oracle/_ref/kat ]; then /usr/bin/time -f "reference wall %e s" $OLDPWD/oracle/_ref/kat hist -m27 -t$(nproc) -H536870912 -o ref.hist sample.fastq > /dev/null 2> ref.err; tail -1 ref.err; cmp ours.hist ref.hist && echo "identical to the reference's file"; fi
+if [ -x $OLDPWD/oracle/_ref/kat ]; then echo -n "reference: "; time $OLDPWD/oracle/_ref/kat hist -m27 -t$(nproc) -H536870912 -o ref.hist sample.fastq > /dev/null 2> ref.err; cmp ours.hist ref.hist && echo "identical to the reference's file"; fi
 rm -f /dev/shm/sample.fastq /dev/shm/*.hist
