@@ -31,12 +31,16 @@ void pool_flush(katgpu_ctx *c) {
     c->pool.clear();
     c->pooled_bytes = 0;
 }
+// Cached blocks are handed out best-fit: the smallest one that holds the request and is at most
+// 25 % larger (buffer sizes follow the free memory of the moment, so the second table of a job asks
+// for a little less than the first got; cudaMalloc / cudaFree of tens of GB cost tens of ms each).
 cudaError_t pool_alloc(katgpu_ctx *c, size_t bytes, void **out) {
     bytes = std::max<size_t>(bytes, 256);
-    auto it = c->pool.find(bytes);
-    if (it != c->pool.end()) {
+    auto it = c->pool.lower_bound(bytes);
+    if (it != c->pool.end() && it->first <= bytes + bytes / 4) {
         *out = it->second;
-        c->pooled_bytes -= bytes;
+        c->pooled_bytes -= it->first;
+        c->block_size[it->second] = it->first;
         c->pool.erase(it);
         return cudaSuccess;
     }
@@ -46,11 +50,17 @@ cudaError_t pool_alloc(katgpu_ctx *c, size_t bytes, void **out) {
         pool_flush(c);
         e = cudaMalloc(out, bytes);
     }
+    if (e == cudaSuccess) c->block_size[*out] = bytes;
     return e;
 }
 void pool_free(katgpu_ctx *c, void *p, size_t bytes) {
     if (!p) return;
     bytes = std::max<size_t>(bytes, 256);
+    auto it = c->block_size.find(p); // the block's true size (it may have been handed out for a smaller request)
+    if (it != c->block_size.end()) {
+        bytes = it->second;
+        c->block_size.erase(it);
+    }
     c->pool.emplace(bytes, p);
     c->pooled_bytes += bytes;
 }
@@ -522,7 +532,7 @@ static bool want_tiled(const katgpu_table *t) {
 // Staging-ring slots per bin for a binning pass of `tile_keys` keys over F bins: the leftover of
 // the previous flush (< granule) + mean + ~4 sigma, within `max_bytes` of shared memory (a ring that
 // is too small only sends more keys the slow way).
-static uint32_t ring_slots(uint32_t F, uint32_t tile_keys, size_t max_bytes, uint32_t granule) {
+uint32_t ring_slots(uint32_t F, uint32_t tile_keys, size_t max_bytes, uint32_t granule) {
     const double mean = (double)tile_keys / (double)F;
     uint64_t R = granule + (uint64_t)std::ceil(mean + 4.0 * std::sqrt(mean));
     const uint64_t fit = max_bytes > (size_t)F * 8 + 16 ? (max_bytes - (size_t)F * 8 - 16) / ((size_t)F * 8) : 4;
@@ -545,7 +555,9 @@ katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) {
     if (tiled) // level 1 of two: leave at least one bit for level 2 (slice -> 64 KB tile)
         Pb = std::max(1, std::min(9, (int)t->g.Lb - kTileBucketsLog2 - 1));
     const uint64_t tile_pos = tiled ? kBinTile : kTile; // positions one CTA bins between two flushes
-    const uint64_t nparts = 1ull << Pb, n_segs = (uint64_t)c->sm_count * (tiled ? c->bps_bin1 : c->bps_part);
+    // level-1 segment columns = CTAs of the kernel that fills them: bin_bases_kernel (bps_bin1 per SM), or on a
+    // multi-GPU job bin_hashed_kernel (one per SM)
+    const uint64_t nparts = 1ull << Pb, n_segs = (uint64_t)c->sm_count * (c->dist ? 1 : tiled ? c->bps_bin1 : c->bps_part);
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
     const uint64_t budget_keys = (uint64_t)((double)(free_b + c->pooled_bytes) * (tiled ? 0.60 : 0.70) / 8.0);
@@ -670,6 +682,7 @@ SideList side_list_of(const katgpu_table *t) {
 // (bin_keys_kernel), then update every tile in shared memory (tile_insert_kernel); finally the
 // side list goes through the general kernel.  Called with the table already sized.
 static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
+    TraceScope trace__("    sweep_tiled");
     katgpu_ctx *c = t->ctx;
     const uint32_t F1 = 1u << t->pend_Pb, n_segs = t->pend_segs;
     const int total_bits = (int)t->g.Lb - kTileBucketsLog2; // table tiles = 2^total_bits
@@ -747,6 +760,7 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
             fprintf(stderr, "[katgpu] sweep_tiled: F1=%u F2=%u slices/group=%u parts=%u cap2=%llu ring1=%u ring2=%u tile2=%u level-2 buffer %.1f MB side cap %llu\n",
                     F1, F2, spg, parts, (unsigned long long)cap2, t->ring1, ring2, tile2, bytes2 / 1048576.0, (unsigned long long)t->side_cap);
         katgpu_status st = KATGPU_OK;
+        TraceScope trace_k("      level-2 binning + tiles");
         for (uint32_t s0 = 0; s0 < F1 && st == KATGPU_OK; s0 += spg) {
             const uint32_t ns = std::min(spg, F1 - s0);
             cudaMemsetAsync(len2, 0, (size_t)ns * F2 * parts * 4, c->stream);
@@ -802,6 +816,7 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
         KT(st);
     }
     // keys that left the fast path: general insertion (may grow the table)
+    TraceScope trace_s("      side list");
     unsigned long long side_n = 0;
     CU(cudaMemcpyAsync(&side_n, t->side_ctr, 8, cudaMemcpyDeviceToHost, c->stream));
     KT(settle(t, ctr)); // synchronises; spills of the general inserts above

@@ -94,7 +94,6 @@ struct DistState {
     bool peer_ipc[kMaxRanks] = {};
     uint32_t grid = 0, cap = 0;          // CTAs of route_bases_kernel, keys per (sender, CTA) segment
     uint64_t round_positions = 0;        // k-mer starts a rank routes per round
-    uint32_t *h_len = nullptr;           // pinned [n][grid]
     cudaEvent_t ev_routed[2] = {}, ev_x[2] = {}, ev_binned[2] = {}, ev_y[2] = {}, ev_tmp = nullptr;
     uint64_t round = 0;
     uint64_t keys_sent = 0, keys_received = 0; // totals, for the NVLink line of the bench
@@ -143,8 +142,8 @@ extern "C" katgpu_status katgpu_dist_init(katgpu_ctx *c, int rank, int n_ranks, 
     c->dist = d;
     CU(cudaStreamCreateWithFlags(&d->comm_stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&d->route_stream, cudaStreamNonBlocking));
-    CU(cudaMalloc((void **)&d->d_token, 256));
-    CU(cudaMemset(d->d_token, 0, 256));
+    CU(cudaMalloc((void **)&d->d_token, 512));
+    CU(cudaMemset(d->d_token, 0, 512));
     for (int i = 0; i < 2; i++) {
         CU(cudaEventCreateWithFlags(&d->ev_routed[i], cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&d->ev_x[i], cudaEventDisableTiming));
@@ -176,7 +175,6 @@ extern "C" katgpu_status katgpu_dist_init(katgpu_ctx *c, int rank, int n_ranks, 
         d->block = (uint8_t *)p;
         CU(cudaMemset(d->block + d->len_off(0), 0, 2 * (size_t)n_ranks * d->grid * 4));
     }
-    CU(cudaMallocHost((void **)&d->h_len, (size_t)n_ranks * d->grid * 4));
 
     // tell everybody where it is; map everybody else's
     PeerInfo mine{};
@@ -225,7 +223,6 @@ void dist_shutdown(katgpu_ctx *c) {
         if (d->peer_ipc[o] && d->peer_block[o]) cudaIpcCloseMemHandle(d->peer_block[o]);
     if (d->comm) g_nccl.CommDestroy(d->comm);
     if (d->block) cudaFree(d->block);
-    if (d->h_len) cudaFreeHost(d->h_len);
     if (d->d_token) cudaFree(d->d_token);
     for (int i = 0; i < 2; i++) {
         cudaEventDestroy(d->ev_routed[i]);
@@ -274,24 +271,29 @@ katgpu_status dist_allreduce_u64(katgpu_ctx *c, void *dev_buf, size_t count) {
     return KATGPU_OK;
 }
 
-// max over the job of one host value (host-synchronous; used once per feed call)
-static katgpu_status allreduce_max_host(katgpu_ctx *c, uint64_t &v) {
+// Every rank's feed size, gathered once per feed call (host-synchronous): from it each rank knows
+// how many rounds the job needs and about how many keys every round will bring — no host
+// synchronisation is needed inside the rounds.
+static katgpu_status allgather_sizes(katgpu_ctx *c, uint64_t mine, uint64_t *all) {
     DistState *d = c->dist;
-    unsigned long long *buf = reinterpret_cast<unsigned long long *>(d->d_token + 16);
-    CU(cudaMemcpyAsync(buf, &v, 8, cudaMemcpyHostToDevice, d->comm_stream));
-    NC(g_nccl.AllReduce(buf, buf, 1, ncclUint64, ncclMax, d->comm, d->comm_stream));
-    CU(cudaMemcpyAsync(&v, buf, 8, cudaMemcpyDeviceToHost, d->comm_stream));
+    unsigned long long *buf = reinterpret_cast<unsigned long long *>(d->d_token + 16); // [kMaxRanks]
+    CU(cudaMemcpyAsync(buf + d->rank, &mine, 8, cudaMemcpyHostToDevice, d->comm_stream));
+    NC(g_nccl.AllGather(buf + d->rank, buf, 1, ncclUint64, d->comm, d->comm_stream));
+    CU(cudaMemcpyAsync(all, buf, 8 * (size_t)d->n, cudaMemcpyDeviceToHost, d->comm_stream));
     CU(cudaStreamSynchronize(d->comm_stream));
     return KATGPU_OK;
 }
 
 // ---- one round -------------------------------------------------------------------------------------
 // Route [dev, dev + n_valid) (k-mers starting in the first n_starts positions; 0 = this rank has
-// nothing left but must still take part), then bin what this rank received.
-//   ready_ev   the route kernel waits for it (the H2D copy of a staged chunk), may be null
-//   consumed_ev recorded when the route kernel has read its input, may be null
+// nothing left but must still take part), then bin what this rank received.  Everything is queued
+// on streams — the host does not wait for the GPU here, so route(r+1) follows route(r) immediately
+// and overlaps the owner-side binning of round r.
+//   ready_ev     the route kernel waits for it (the H2D copy of a staged chunk), may be null
+//   consumed_ev  recorded when the route kernel has read its input, may be null
+//   job_starts   k-mer starts all ranks route in this round (an upper bound on the keys this rank receives)
 static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts, TableCounters &ctr,
-                                 cudaEvent_t ready_ev, cudaEvent_t consumed_ev, uint64_t kmers_hint) {
+                                 cudaEvent_t ready_ev, cudaEvent_t consumed_ev, uint64_t kmers_hint, uint64_t job_starts) {
     katgpu_ctx *c = t->ctx;
     DistState *d = c->dist;
     const int b = (int)(d->round & 1);
@@ -330,31 +332,27 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
     CU(cudaStreamWaitEvent(c->stream, d->ev_x[b], 0));
     const size_t n_src = (size_t)d->n * d->grid;
     const uint32_t *len_dev = reinterpret_cast<const uint32_t *>(d->block + d->len_off(b));
-    CU(cudaMemcpyAsync(d->h_len, len_dev, n_src * 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    uint64_t received = 0, sent = 0;
-    for (size_t s = 0; s < n_src; s++) received += d->h_len[s];
-    (void)sent;
-    d->keys_received += received;
-    d->keys_sent += n_starts; // upper bound (every start a k-mer); the exact figure is the job's n_total
-    if (received) {
+    // with a uniform owner hash this rank receives its 1/N of the round; the binning kernels cope
+    // with any excess exactly (full segments spill to the side list), so an estimate is enough here
+    const uint64_t expected = job_starts / (uint64_t)d->n + (job_starts ? 1 : 0);
+    d->keys_received += expected;
+    d->keys_sent += n_starts;
+    if (job_starts) {
         // The pending-key (tiled) path when the table is large enough for it; its buffers are sized once,
-        // for the whole feed (with a uniform owner hash a rank receives about what it routes).
+        // for the whole feed.
         bool tiled = t->pend_keys != nullptr && t->tiled;
         if (!t->pend_keys && dist_can_tile(t)) {
             bool ok = false;
-            KT(pend_alloc(t, std::max<uint64_t>(std::max(received, kmers_hint), t->n_slots / 4), ok));
+            KT(pend_alloc(t, std::max<uint64_t>(std::max(expected, kmers_hint), t->n_slots / 4), ok));
             tiled = ok && t->tiled;
         }
         if (tiled) {
-            // segments s = j, j + G, ... go to level-1 CTA j: the fullest CTA bounds every (slice, CTA) segment
+            // segments s = j, j + G, ... go to level-1 CTA j
             const uint32_t G = t->pend_segs;
-            std::vector<uint64_t> per_cta(G, 0);
-            for (size_t s = 0; s < n_src; s++) per_cta[s % G] += d->h_len[s];
-            const uint64_t worst = *std::max_element(per_cta.begin(), per_cta.end());
+            const uint64_t per_cta = (uint64_t)((double)expected / G * 1.05) + kBinTile;
             const double F = (double)(1u << t->pend_Pb);
             auto fill_of = [&](uint64_t keys) { return (double)keys / F + 4.5 * std::sqrt((double)keys / F) + 16.0; };
-            if (t->dist_cta_keys && fill_of(t->dist_cta_keys + worst) > (double)t->pend_seg_cap) {
+            if (t->dist_cta_keys && fill_of(t->dist_cta_keys + per_cta) > (double)t->pend_seg_cap) {
                 KT(sweep_pending(t, ctr)); // local: level-2 binning + tile insertion of what is pending
                 t->dist_cta_keys = 0;
             }
@@ -366,7 +364,8 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
             D.shift = t->g.b - t->pend_Pb;
             D.mask = (1u << t->pend_Pb) - 1;
             D.F = 1u << t->pend_Pb;
-            D.R = t->ring1;
+            // bin_hashed_kernel runs one 1024-thread CTA per SM: its staging ring may take most of the shared memory
+            D.R = ring_slots(D.F, kBinTile, ((size_t)190 << 10) - kTileHllM * 4, kBinHGranule);
             BinKeysParams B{};
             B.g = t->g;
             set_add_bound(B.g, ~0ULL);
@@ -384,25 +383,25 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
             }
             c->launches++;
             CU(cudaGetLastError());
-            t->dist_cta_keys += worst;
-            t->pend_bound += received;
-            t->pend_total_tiles += (received + kBinTile - 1) / kBinTile;
+            t->dist_cta_keys += per_cta;
+            t->pend_bound += job_starts; // upper bound: every key of the round could have come here
+            t->pend_total_tiles += (expected + kBinTile - 1) / kBinTile;
         } else {
             // small tables (small k, small -H): the received segments go through the general
             // random-access insertion; the table is grown first so that they fit in any case
             KT(sweep_pending(t, ctr));
-            KT(dist_make_room(t, ctr, received));
-            TileParams P{};
-            P.g = t->g;
-            set_add_bound(P.g, ~0ULL);
-            P.keys = reinterpret_cast<const uint64_t *>(d->block + d->keys_off(b));
-            P.len = len_dev;
-            P.cap = d->cap;
-            P.parts = 1;
-            P.n_tiles = (uint32_t)n_src;
+            KT(dist_make_room(t, ctr, job_starts));
+            TileParams P2{};
+            P2.g = t->g;
+            set_add_bound(P2.g, ~0ULL);
+            P2.keys = reinterpret_cast<const uint64_t *>(d->block + d->keys_off(b));
+            P2.len = len_dev;
+            P2.cap = d->cap;
+            P2.parts = 1;
+            P2.n_tiles = (uint32_t)n_src;
             {
                 ProfScope ps(c, "insert", c->stream);
-                launch_insert_deferred(P, nullptr, P.n_tiles, c->stream);
+                launch_insert_deferred(P2, nullptr, P2.n_tiles, c->stream);
             }
             c->launches++;
             CU(cudaGetLastError());
@@ -418,17 +417,26 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
     return KATGPU_OK;
 }
 
+// k-mer starts all ranks route in round r when rank q feeds sizes[q] bytes in pieces of `piece`
+static uint64_t job_starts_of_round(const uint64_t *sizes, int n, uint64_t piece, uint64_t r) {
+    uint64_t tot = 0;
+    for (int q = 0; q < n; q++) tot += sizes[q] > r * piece ? std::min(piece, sizes[q] - r * piece) : 0;
+    return tot;
+}
+
 katgpu_status dist_feed_device(katgpu_table *t, const uint8_t *dev, uint64_t n) {
     katgpu_ctx *c = t->ctx;
     DistState *d = c->dist;
     TableCounters ctr;
     KT(read_counters(t, ctr));
     const uint64_t R = d->round_positions;
-    uint64_t rounds = (n + R - 1) / R;
-    KT(allreduce_max_host(c, rounds));
+    uint64_t sizes[kMaxRanks];
+    KT(allgather_sizes(c, n, sizes));
+    uint64_t rounds = 0;
+    for (int q = 0; q < d->n; q++) rounds = std::max(rounds, (sizes[q] + R - 1) / R);
     for (uint64_t r = 0; r < rounds; r++) {
         const uint64_t off = std::min<uint64_t>(n, r * R);
-        KT(route_round(t, dev + off, n - off, std::min<uint64_t>(n - off, R), ctr, nullptr, nullptr, n));
+        KT(route_round(t, dev + off, n - off, std::min<uint64_t>(n - off, R), ctr, nullptr, nullptr, n, job_starts_of_round(sizes, d->n, R, r)));
     }
     return KATGPU_OK;
 }
@@ -439,9 +447,11 @@ katgpu_status dist_feed_host(katgpu_table *t, const char *bases, size_t n) {
     TableCounters ctr;
     KT(read_counters(t, ctr));
     const size_t chunk = (size_t)std::min<uint64_t>(kChunkBytes, d->round_positions);
-    size_t n_chunks = (n + chunk - 1) / chunk;
-    uint64_t rounds = n_chunks;
-    KT(allreduce_max_host(c, rounds));
+    const size_t n_chunks = (n + chunk - 1) / chunk;
+    uint64_t sizes[kMaxRanks];
+    KT(allgather_sizes(c, n, sizes));
+    uint64_t rounds = 0;
+    for (int q = 0; q < d->n; q++) rounds = std::max<uint64_t>(rounds, (sizes[q] + chunk - 1) / chunk);
     const int ring = (int)std::min<size_t>(kRing, std::max<size_t>(2, n_chunks));
     if (n_chunks) KT(ensure_feed_staging(c, chunk, ring));
     auto issue_copy = [&](size_t i) -> katgpu_status {
@@ -456,16 +466,29 @@ katgpu_status dist_feed_host(katgpu_table *t, const char *bases, size_t n) {
     for (int b = 0; b < ring && n_chunks; b++) CU(cudaEventRecord(c->chunk_free[b], d->route_stream));
     size_t issued = 0;
     for (uint64_t i = 0; i < rounds; i++) {
+        const uint64_t js = job_starts_of_round(sizes, d->n, chunk, i);
         if (i < n_chunks) {
             while (issued < n_chunks && issued < i + (size_t)ring) KT(issue_copy(issued++));
             const int b = (int)(i % ring);
             const size_t off = i * chunk;
-            KT(route_round(t, c->chunk[b], std::min(n - off, chunk + kHalo), std::min(n - off, chunk), ctr, c->chunk_ready[b], c->chunk_free[b], n));
+            KT(route_round(t, c->chunk[b], std::min(n - off, chunk + kHalo), std::min(n - off, chunk), ctr, c->chunk_ready[b], c->chunk_free[b], n, js));
         } else
-            KT(route_round(t, nullptr, 0, 0, ctr, nullptr, nullptr, n));
+            KT(route_round(t, nullptr, 0, 0, ctr, nullptr, nullptr, n, js));
     }
     CU(cudaStreamSynchronize(c->copy_stream)); // `bases` belongs to the caller again
     return KATGPU_OK;
+}
+
+// Called by katgpu_count_end before the local sweep: all rounds of every feed have completed their
+// barriers already; drain the streams so that the sweep sees every binned key.
+katgpu_status dist_count_end(katgpu_table *t, TableCounters &ctr) {
+    katgpu_ctx *c = t->ctx;
+    DistState *d = c->dist;
+    CU(cudaStreamSynchronize(d->route_stream));
+    CU(cudaStreamSynchronize(d->comm_stream));
+    CU(cudaStreamSynchronize(c->stream));
+    t->dist_cta_keys = 0;
+    return read_counters(t, ctr);
 }
 
 // Measurement aid (tools/route_probe.py, ncu captures): route_bases_kernel on ONE GPU with `n_ranks`
@@ -534,16 +557,4 @@ katgpu_status record_feed_consumed(katgpu_ctx *c, cudaEvent_t ev) {
     }
     CU(cudaEventRecord(ev, c->stream));
     return KATGPU_OK;
-}
-
-// Called by katgpu_count_end before the local sweep: all rounds of every feed have completed their
-// barriers already; drain the streams so that the sweep sees every binned key.
-katgpu_status dist_count_end(katgpu_table *t, TableCounters &ctr) {
-    katgpu_ctx *c = t->ctx;
-    DistState *d = c->dist;
-    CU(cudaStreamSynchronize(d->route_stream));
-    CU(cudaStreamSynchronize(d->comm_stream));
-    CU(cudaStreamSynchronize(c->stream));
-    t->dist_cta_keys = 0;
-    return read_counters(t, ctr);
 }

@@ -63,6 +63,7 @@ struct katgpu_ctx {
     // freed device blocks kept for reuse: a `kat hist` job after the first one does not pay
     // cudaMalloc/cudaFree of tens of GB again (the reference likewise keeps its mmap'd arena)
     std::multimap<size_t, void *> pool;
+    std::map<void *, size_t> block_size; // true size of every block handed out by pool_alloc
     size_t pooled_bytes = 0;
     DistState *dist = nullptr; // set by katgpu_dist_init: this context is one rank of a multi-GPU job
     // raw-file feed (katgpu_count_feed_fastq): two device buffers for file bytes, pinned bounce
@@ -163,6 +164,7 @@ void set_add_bound(katgpu::TableGeom &g, uint64_t bound);
 katgpu_status feed_device_range(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
                                 katgpu::TableCounters &ctr, uint64_t kmers_hint);
 katgpu_status ensure_feed_staging(katgpu_ctx *c, size_t chunk, int ring);
+uint32_t ring_slots(uint32_t F, uint32_t tile_keys, size_t max_bytes, uint32_t granule);
 bool dist_can_tile(const katgpu_table *t);                                              // the tiled pending-key path is possible for this table
 katgpu_status dist_make_room(katgpu_table *t, katgpu::TableCounters &ctr, uint64_t n); // grow until n more distinct keys fit
 // record `ev` once everything queued so far that reads feed input has run (compute stream and, on a job, the route stream)

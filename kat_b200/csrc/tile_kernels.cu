@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_hashed_kernel(const __gri
     const TableGeom &g = P.g;
     const uint32_t tid = threadIdx.x;
     SideTally tally;
-    BinCore<kBin1Granule> C1; // per-CTA destination segments, ring sized like bin_bases_kernel's
+    BinCore<kBinHGranule> C1; // per-CTA destination segments; one CTA per SM, so its ring may use most of the shared memory
     C1.init(P.dst, blockIdx.x, smem_raw + kTileHllM * 4);
     for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads) hll[i] = 0;
     __syncthreads();

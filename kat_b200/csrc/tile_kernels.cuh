@@ -39,7 +39,11 @@ constexpr int kTileThreads = KATGPU_TILE_THREADS;
 #ifndef KATGPU_BIN2_GRANULE
 #define KATGPU_BIN2_GRANULE 4
 #endif
-constexpr uint32_t kBin1Granule = KATGPU_BIN1_GRANULE; // level-1 segments (bin_bases_kernel; bin_keys_kernel on a flat source)
+#ifndef KATGPU_BINH_GRANULE
+#define KATGPU_BINH_GRANULE 4
+#endif
+constexpr uint32_t kBin1Granule = KATGPU_BIN1_GRANULE; // level-1 segments written by bin_bases_kernel
+constexpr uint32_t kBinHGranule = KATGPU_BINH_GRANULE; // level-1 segments written by bin_hashed_kernel (keys received from other ranks)
 constexpr uint32_t kBin2Granule = KATGPU_BIN2_GRANULE; // level-2 (per-tile) segments
 constexpr int kTileBucketsLog2 = 11;  // a table tile = 2048 buckets = 8192 slots = 64 KB
 constexpr int kTileBytes = (1 << kTileBucketsLog2) * 32;
