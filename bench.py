@@ -636,14 +636,23 @@ def main():
     base, ceil_, nb = B.hist_geometry(1, 10000)
 
 
+    call_ms = {}  # host wall time per C-ABI call of the job, summed over the timed steps (where a step's time goes)
+
+    def timed_call(name, fn, *a):
+        t0 = time.perf_counter()
+        r = fn(*a)
+        call_ms[name] = call_ms.get(name, 0.0) + 1e3 * (time.perf_counter() - t0)
+        return r
+
     def job_resident():
         """One whole `kat hist` job, base stream resident in HBM.  Returns (bins, n_total, n_distinct[, local n_total])."""
-        t = ctx.count_begin(K, True, 1 << args.slots_log2, True)
-        t.feed_device(d_bases, n_bytes).end()
-        _, bins = t.hist(1, 10000, 1)
+        t = timed_call("count_begin", ctx.count_begin, K, True, 1 << args.slots_log2, True)
+        timed_call("count_feed_device", t.feed_device, d_bases, n_bytes)
+        timed_call("count_end", t.end)
+        _, bins = timed_call("hist", t.hist, 1, 10000, 1)
         nt, nd = t.n_total, t.n_distinct  # on a job: the job's totals
-        local = t.info()["n_total"]        # k-mer instances inserted into THIS rank's table
-        t.free()
+        local = timed_call("table_get_info", t.info)["n_total"]  # k-mer instances inserted into THIS rank's table
+        timed_call("table_free", t.free)
         return bins, nt, nd, local
 
     def barrier():
@@ -653,6 +662,8 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
+    step_ms = []
+
     def timed(fn, steps, warmup):
         out = None
         for _ in range(warmup):
@@ -660,10 +671,14 @@ def main():
         barrier()
         l0 = ctx.launch_count()
         ctx.profile_enable(True)
+        call_ms.clear()
+        step_ms.clear()
         sampler.mark_begin()
         t0 = time.perf_counter()
         for _ in range(steps):
+            t1 = time.perf_counter()
             out = fn()
+            step_ms.append(round(1e3 * (time.perf_counter() - t1), 2))
         barrier()
         dt = time.perf_counter() - t0
         sampler.mark_end()
@@ -677,6 +692,8 @@ def main():
         return dt, out, ctx.launch_count() - l0, clocks, prof
 
     dt, (bins, n_total_all, n_distinct, n_total), launches, clocks, prof = timed(job_resident, args.steps, args.warmup)
+    resident_calls = {k_: round(v / args.steps, 2) for k_, v in call_ms.items()}
+    resident_steps = list(step_ms)
     value = n_total_all * args.steps / dt
     # size-independent checks of the full-size result
     labels = np.arange(base, base + nb, dtype=np.uint64)
@@ -735,7 +752,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic", "config": config,
             "kmer_instances_per_step": n_total_all, "distinct_kmers": n_distinct, "kmer_instances_rank0_table": n_total,
-            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "reduction": reduction}
+            "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "reduction": reduction,
+            "host_ms_per_step_by_call": resident_calls, "step_ms": resident_steps[:32]}
 
     # ------------------------------------------------------------ end to end
     if not args.no_e2e:

@@ -44,13 +44,16 @@ cudaError_t pool_alloc(katgpu_ctx *c, size_t bytes, void **out) {
         c->pool.erase(it);
         return cudaSuccess;
     }
+    TraceScope trace__("      cudaMalloc (block cache miss)");
     cudaError_t e = cudaMalloc(out, bytes);
     if (e == cudaErrorMemoryAllocation && !c->pool.empty()) {
         cudaGetLastError();
+        if (getenv("KATGPU_TRACE")) fprintf(stderr, "[katgpu]       out of memory for %.2f GB: releasing %.2f GB of cached blocks\n", bytes / 1073741824.0, c->pooled_bytes / 1073741824.0);
         pool_flush(c);
         e = cudaMalloc(out, bytes);
     }
     if (e == cudaSuccess) c->block_size[*out] = bytes;
+    if (getenv("KATGPU_TRACE")) fprintf(stderr, "[katgpu]       new block of %.3f GB (%zu cached blocks, %.2f GB)\n", bytes / 1073741824.0, c->pool.size(), c->pooled_bytes / 1073741824.0);
     return e;
 }
 void pool_free(katgpu_ctx *c, void *p, size_t bytes) {
@@ -754,8 +757,16 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
         CU(cudaGetLastError());
     } else {
         // keys binned between two flushes of bin_keys_kernel and its ring (one CTA per SM, <= 200 KB)
-        const uint32_t tile2 = kBin2Threads * kBin2Unroll; // bin_keys_kernel bins chunks of kBin2Unroll keys per thread
-        const uint32_t ring2 = ring_slots(F2, tile2, (196u << 10) - kTileHllM * 4, kBin2Granule); // one CTA per SM
+        // keys bin_keys_kernel bins between two flushes: as many chunks as its ring (one CTA per SM) can take
+        // without cutting into the 4-sigma head room
+        const size_t ring2_bytes = (196u << 10) - kTileHllM * 4;
+        uint32_t cpf = (uint32_t)kBin2MaxCpf;
+        for (; cpf > 1; cpf--) {
+            const double mean = (double)(kBin2Threads * kBin2Unroll * cpf) / F2;
+            if (((double)kBin2Granule + mean + 3.5 * std::sqrt(mean) + 1.0) * F2 * 8.0 + F2 * 8.0 + 16.0 <= (double)ring2_bytes) break; // (ring_slots then takes what fits: >= 3.5 sigma)
+        }
+        const uint32_t tile2 = kBin2Threads * kBin2Unroll * cpf;
+        const uint32_t ring2 = ring_slots(F2, tile2, ring2_bytes, kBin2Granule);
         if (getenv("KATGPU_TRACE"))
             fprintf(stderr, "[katgpu] sweep_tiled: F1=%u F2=%u slices/group=%u parts=%u cap2=%llu ring1=%u ring2=%u tile2=%u level-2 buffer %.1f MB side cap %llu\n",
                     F1, F2, spg, parts, (unsigned long long)cap2, t->ring1, ring2, tile2, bytes2 / 1048576.0, (unsigned long long)t->side_cap);
@@ -773,6 +784,7 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
             B.first_slice = s0;
             B.parts = parts;
             B.tile_keys = tile2;
+            B.cpf = cpf;
             B.dst.keys = keys2;
             B.dst.len = len2;
             B.dst.cap = (uint32_t)cap2;

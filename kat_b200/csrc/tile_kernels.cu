@@ -345,7 +345,8 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_
     const uint32_t seg_lo = (uint32_t)(((uint64_t)P.src_segs * q) / P.parts), seg_hi = (uint32_t)(((uint64_t)P.src_segs * (q + 1)) / P.parts);
     // Chunks of kBin2Unroll keys per thread: every load of a chunk is in flight before the
     // first key is binned, and the next chunk is requested before this one is flushed.
-    const uint32_t chunk = kBin2Threads * kBin2Unroll; // == P.tile_keys (host)
+    const uint32_t chunk = kBin2Threads * kBin2Unroll; // x P.cpf == P.tile_keys (host)
+    uint32_t since_flush = 0;                          // chunks in the ring since the last flush
     uint64_t kn[kBin2Unroll];
     for (uint32_t s = seg_lo; s < seg_hi; s++) {
         const size_t sidx = (size_t)(P.first_slice + s_local) * P.src_segs + s;
@@ -368,7 +369,10 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_
 #pragma unroll
             for (int u = 0; u < kBin2Unroll; u++)
                 if (base + u * kBin2Threads + tid < len) C.append(kc[u], P.side, g, tally);
-            C.flush(false, P.side, g, tally);
+            if (++since_flush >= P.cpf) { // (uniform: every thread counts the same chunks)
+                C.flush(false, P.side, g, tally);
+                since_flush = 0;
+            }
         }
     }
     C.flush(true, P.side, g, tally);

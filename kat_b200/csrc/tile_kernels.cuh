@@ -20,7 +20,14 @@ constexpr int kBin2Threads = 1024;    // one CTA per SM: 32 warps hide the key-l
 #ifndef KATGPU_BIN2_PREFETCH
 #define KATGPU_BIN2_PREFETCH 1
 #endif
-constexpr int kBin2Unroll = KATGPU_BIN2_UNROLL; // keys per thread between two flushes of bin_keys_kernel (level 2)
+#ifndef KATGPU_BIN2_CPF
+#define KATGPU_BIN2_CPF 3
+#endif
+constexpr int kBin2Unroll = KATGPU_BIN2_UNROLL; // keys per thread and chunk of bin_keys_kernel (level 2)
+// Chunks bin_keys_kernel bins between two flushes of its staging ring, at most: a flush is two CTA-wide
+// barriers and a pass over all bins, so fewer, fuller flushes are cheaper (measured 70.9 / 59.1 / 57.6 ms
+// for 1 / 2 / 3 at 512 bins); the host picks the largest count whose ring still fits shared memory.
+constexpr int kBin2MaxCpf = KATGPU_BIN2_CPF;
 #ifndef KATGPU_TILE_THREADS
 #define KATGPU_TILE_THREADS 384
 #endif
@@ -105,6 +112,7 @@ struct BinKeysParams {
     const uint32_t *src_len;
     uint32_t src_segs, src_cap, first_slice, parts;
     uint32_t tile_keys;       // keys binned between two flushes
+    uint32_t cpf;             // source B: chunks (of kBin2Threads * kBin2Unroll keys) between two flushes
     BinDst dst;
     SideList side;
     uint32_t *hll;            // source A only
