@@ -155,7 +155,10 @@ extern "C" katgpu_status katgpu_dist_init(katgpu_ctx *c, int rank, int n_ranks, 
     if (d->bps_route < 1) return fail(KATGPU_ERR_CUDA, "katgpu_dist_init: route kernel does not fit on an SM");
 
     // receive block: sized once, for rounds of KATGPU_DIST_ROUND_MB megabytes of base stream per rank
-    uint64_t round_mb = 128;
+    // A round is two kernels per rank (route, owner-side binning) and two barriers: long rounds amortise
+    // their tails.  The receive block is 2 areas x N senders x 8 bytes per k-mer start of a round: 1 GiB / N
+    // of base stream per round keeps it at 16 GiB whatever N.
+    uint64_t round_mb = std::max(128, std::min(512, 1024 / n_ranks));
     if (const char *e = getenv("KATGPU_DIST_ROUND_MB")) round_mb = std::max(1, atoi(e));
     d->grid = (uint32_t)(c->sm_count * d->bps_route);
     const uint64_t tiles = ((round_mb << 20) + kBinTile - 1) / kBinTile;
@@ -365,7 +368,13 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
             D.mask = (1u << t->pend_Pb) - 1;
             D.F = 1u << t->pend_Pb;
             // bin_hashed_kernel runs one 1024-thread CTA per SM: its staging ring may take most of the shared memory
-            D.R = ring_slots(D.F, kBinTile, ((size_t)190 << 10) - kTileHllM * 4, kBinHGranule);
+            const size_t ringh_bytes = ((size_t)190 << 10) - kTileHllM * 4;
+            uint32_t cpf = 3; // tiles between two flushes: as many as the ring takes with 3.5 sigma of head room (as sweep_tiled does for level 2)
+            for (; cpf > 1; cpf--) {
+                const double mean = (double)(kBinTile * cpf) / D.F;
+                if (((double)kBinHGranule + mean + 3.5 * std::sqrt(mean) + 1.0) * D.F * 8.0 + D.F * 8.0 + 16.0 <= (double)ringh_bytes) break;
+            }
+            D.R = ring_slots(D.F, kBinTile * cpf, ringh_bytes, kBinHGranule);
             BinKeysParams B{};
             B.g = t->g;
             set_add_bound(B.g, ~0ULL);
@@ -373,7 +382,8 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
             B.seg_len = len_dev;
             B.n_src = (uint32_t)n_src;
             B.seg_cap = d->cap;
-            B.tile_keys = kBinTile;
+            B.tile_keys = kBinTile * cpf;
+            B.cpf = cpf;
             B.dst = D;
             B.side = side_list_of(t);
             B.hll = t->pend_hll;

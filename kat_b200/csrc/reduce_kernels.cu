@@ -52,39 +52,32 @@ __global__ void __launch_bounds__(512) hist_kernel(const __grid_constant__ Table
     }
     const uint64_t n_pairs = n_slots >> 1;
     const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(g.slots);
-    // whole warps iterate together (match.any needs the full warp); kWalkUnroll 16-byte loads of a
-    // thread are in flight before the first slot is looked at: the walk is a pure HBM stream
+    // whole warps iterate together (match.any needs the full warp); one 16-byte load per thread and
+    // round at full occupancy (a 4-deep unrolled variant measured 14 % slower: 5.78 vs 5.08 ms for 17 GB)
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-    const uint64_t rounds = (n_pairs + stride * kWalkUnroll - 1) / (stride * kWalkUnroll);
+    const uint64_t rounds = (n_pairs + stride - 1) / stride;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    for (uint64_t it = 0; it < rounds; it++, i += stride * kWalkUnroll) {
-        ulonglong2 w[kWalkUnroll];
+    for (uint64_t it = 0; it < rounds; it++, i += stride) {
+        ulonglong2 w = make_ulonglong2(0, 0);
+        if (i < n_pairs) w = __ldg(src + i);
 #pragma unroll
-        for (int u = 0; u < kWalkUnroll; u++) {
-            const uint64_t j = i + (uint64_t)u * stride;
-            w[u] = j < n_pairs ? __ldcs(src + j) : make_ulonglong2(0, 0);
-        }
-#pragma unroll
-        for (int u = 0; u < kWalkUnroll; u++) {
-#pragma unroll
-            for (int s = 0; s < 2; s++) {
-                const uint64_t word = s ? w[u].y : w[u].x;
-                const bool occ = word != 0;
-                uint32_t bin = 0;
-                if (occ) {
-                    uint64_t v = word >> g.cshift;
-                    if (word & (1ULL << (g.rbits + kProbeBits))) {
-                        uint64_t h, c;
-                        decode_slot(g, 2 * (i + (uint64_t)u * stride) + s, word, h, c);
-                        v = c;
-                    }
-                    if (v < base) bin = 0;
-                    else if (v > ceil_) bin = nb - 1;
-                    else bin = (uint32_t)(inc == 1 ? (v - base) : (v - base) / inc);
+        for (int s = 0; s < 2; s++) {
+            const uint64_t word = s ? w.y : w.x;
+            const bool occ = word != 0;
+            uint32_t bin = 0;
+            if (occ) {
+                uint64_t v = word >> g.cshift;
+                if (word & (1ULL << (g.rbits + kProbeBits))) {
+                    uint64_t h, c;
+                    decode_slot(g, 2 * i + s, word, h, c);
+                    v = c;
                 }
-                if (SMEM) warp_agg_inc_u32(sbins, bin, occ);
-                else warp_agg_inc_u64(out, bin, occ);
+                if (v < base) bin = 0;
+                else if (v > ceil_) bin = nb - 1;
+                else bin = (uint32_t)(inc == 1 ? (v - base) : (v - base) / inc);
             }
+            if (SMEM) warp_agg_inc_u32(sbins, bin, occ);
+            else warp_agg_inc_u64(out, bin, occ);
         }
     }
     if (SMEM) {

@@ -299,12 +299,14 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_hashed_kernel(const __gri
     for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads) hll[i] = 0;
     __syncthreads();
     const uint32_t sshift = P.dst.shift - kTileHllSampleShift;
-    constexpr int kU = kBinTile / kBin2Threads; // keys per thread per tile; host: P.tile_keys == kBinTile (the level-1 ring is sized for it)
+    constexpr int kU = kBinTile / kBin2Threads; // keys per thread per tile of kBinTile keys; host: P.tile_keys == kBinTile * P.cpf sizes the ring
     // tiles first, first + step, ... of `n` keys at `keys`
+    const uint32_t cpf = P.cpf ? P.cpf : 1u; // tiles binned between two flushes (the ring is sized for them)
+    uint32_t since_flush = 0;
     auto bin_tiles = [&](const uint64_t *keys, uint64_t n, uint64_t first, uint64_t step) {
-        const uint64_t n_tiles = (n + P.tile_keys - 1) / P.tile_keys;
+        const uint64_t n_tiles = (n + kBinTile - 1) / kBinTile;
         for (uint64_t tile = first; tile < n_tiles; tile += step) {
-            const uint64_t lo = tile * P.tile_keys;
+            const uint64_t lo = tile * kBinTile;
             uint64_t kc[kU];
 #pragma unroll
             for (int u = 0; u < kU; u++) { // every load in flight before the first key is binned
@@ -318,7 +320,10 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_hashed_kernel(const __gri
                     hll_sample(hll, kc[u], sshift);
                 }
             }
-            C1.flush(false, P.side, g, tally);
+            if (++since_flush >= cpf) {
+                C1.flush(false, P.side, g, tally);
+                since_flush = 0;
+            }
         }
     };
     if (P.in_keys) // source A: one flat array, tiles strided over the grid

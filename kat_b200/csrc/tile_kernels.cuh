@@ -112,7 +112,7 @@ struct BinKeysParams {
     const uint32_t *src_len;
     uint32_t src_segs, src_cap, first_slice, parts;
     uint32_t tile_keys;       // keys binned between two flushes
-    uint32_t cpf;             // source B: chunks (of kBin2Threads * kBin2Unroll keys) between two flushes
+    uint32_t cpf;             // chunks (source B: of kBin2Threads * kBin2Unroll keys; sources A, C: of kBinTile keys) between two flushes
     BinDst dst;
     SideList side;
     uint32_t *hll;            // source A only
