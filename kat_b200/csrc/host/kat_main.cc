@@ -1,4 +1,5 @@
-// kat_main.cc — `kat hist | gcp | comp` front-end over libkatgpu.
+// kat_main.cc — entry point of the `kat hist | gcp | comp | sect` front-end over libkatgpu (tools: kat_hist.cc,
+// kat_gcp.cc, kat_comp.cc, kat_sect.cc; shared helpers: kat_front.hpp).
 //
 // Mirrors the reference's CLI surface and output files for the three spectra
 // tools (src/kat.cc:178-305, src/histogram.cc:257-369, src/gcp.cc:255-370,
@@ -11,938 +12,22 @@
 // as the reference does.  Jellyfish-hash inputs (LOAD mode, InputHandler::loadHash) and
 // -d/--dump_hash (InputHandler::dump) read and write the reference's "binary/sorted" files
 // (jf_format.cc).  Not supported (outside the hot path): plotting.
-#include <glob.h>
-#include <sys/stat.h>
-#include <unistd.h>
+#include "kat_front.hpp"
 
-#include <algorithm>
-#include <chrono>
-#include <cmath>
-#include <cstdint>
-#include <cstdio>
-#include <cstdlib>
-#include <cstring>
-#include <fstream>
-#include <iostream>
-#include <map>
-#include <mutex>
-#include <sstream>
-#include <stdexcept>
-#include <string>
-#include <thread>
-#include <vector>
-
-#include "katgpu.h"
-#include "jf_format.hpp"
-#include "seq_parser.hpp"
-
-using std::cerr;
-using std::cout;
-using std::endl;
-using std::string;
-using std::vector;
-
-namespace {
-
-const char *kVersion = "2.4.2-katgpu0.1";
-
-struct KatError : std::runtime_error {
-    int code;
-    KatError(int c, const string &m) : std::runtime_error(m), code(c) {}
-};
-void gpu_check(katgpu_status st) {
-    if (st == KATGPU_ERR_HASH_FULL) throw KatError(5, "Hash full"); // std::runtime_error("Hash full") -> exit 5 (src/kat.cc:292)
-    if (st != KATGPU_OK) throw KatError(4, string("katgpu: ") + katgpu_last_error());
-}
-
-// ---- tiny option parser (boost::program_options stand-in) ----------------------
-struct OptSpec {
-    char shortname;     // 0 = none
-    const char *longname;
-    bool takes_value;
-};
-struct Parsed {
-    std::map<string, string> val;
-    vector<string> positional;
-    bool has(const string &k) const { return val.count(k) != 0; }
-    string get(const string &k, const string &dflt) const {
-        auto it = val.find(k);
-        return it == val.end() ? dflt : it->second;
-    }
-};
-Parsed parse_args(int argc, char **argv, const vector<OptSpec> &specs) {
-    Parsed p;
-    for (int i = 1; i < argc; i++) {
-        const string a = argv[i];
-        const OptSpec *sp = nullptr;
-        string value;
-        bool have_value = false;
-        if (a.size() > 2 && a[0] == '-' && a[1] == '-') {
-            string name = a.substr(2);
-            const size_t eq = name.find('=');
-            if (eq != string::npos) {
-                value = name.substr(eq + 1);
-                name = name.substr(0, eq);
-                have_value = true;
-            }
-            for (auto &s : specs)
-                if (name == s.longname) sp = &s;
-            if (!sp) throw KatError(1, "Error: Parsing Command Line: unrecognised option '--" + name + "'");
-        } else if (a.size() >= 2 && a[0] == '-' && a != "-") {
-            for (auto &s : specs)
-                if (s.shortname && a[1] == s.shortname) sp = &s;
-            if (!sp) throw KatError(1, "Error: Parsing Command Line: unrecognised option '" + a + "'");
-            if (a.size() > 2) {
-                if (sp->takes_value) {
-                    value = a.substr(2);
-                    have_value = true;
-                } else { // bundled switches: -nv
-                    for (size_t j = 1; j < a.size(); j++) {
-                        const OptSpec *q = nullptr;
-                        for (auto &s : specs)
-                            if (s.shortname && a[j] == s.shortname) q = &s;
-                        if (!q || q->takes_value) throw KatError(1, "Error: Parsing Command Line: bad option bundle '" + a + "'");
-                        p.val[q->longname] = "1";
-                    }
-                    continue;
-                }
-            }
-        } else {
-            p.positional.push_back(a);
-            continue;
-        }
-        if (sp->takes_value) {
-            if (!have_value) {
-                if (i + 1 >= argc) throw KatError(1, string("Error: Parsing Command Line: the required argument for option '--") + sp->longname + "' is missing");
-                value = argv[++i];
-            }
-            p.val[sp->longname] = value;
-        } else
-            p.val[sp->longname] = "1";
-    }
-    return p;
-}
-uint64_t to_u64(const string &s, const char *what) {
-    try {
-        size_t pos = 0;
-        if (s.empty() || s[0] == '-') throw std::invalid_argument(s);
-        // boost::lexical_cast-like: accept plain integers and 1e8-style values
-        const double d = std::stod(s, &pos);
-        if (pos != s.size() || d < 0) throw std::invalid_argument(s);
-        if (s.find_first_of(".eE") == string::npos) return std::stoull(s);
-        return (uint64_t)d;
-    } catch (...) {
-        throw KatError(1, string("Error: Parsing Command Line: the argument ('") + s + "') for option '--" + what + "' is invalid");
-    }
-}
-double to_double(const string &s, const char *what) {
-    try {
-        size_t pos = 0;
-        const double d = std::stod(s, &pos);
-        if (pos != s.size()) throw std::invalid_argument(s);
-        return d;
-    } catch (...) {
-        throw KatError(1, string("Error: Parsing Command Line: the argument ('") + s + "') for option '--" + what + "' is invalid");
-    }
-}
-vector<unsigned> parse_trim(const string &s) {
-    vector<unsigned> v;
-    std::stringstream ss(s);
-    string item;
-    while (std::getline(ss, item, ',')) v.push_back((unsigned)to_u64(item, "5ptrim"));
-    if (v.empty()) v.push_back(0);
-    return v;
-}
-
-// ---- InputHandler (lib/src/input_handler.cc) ------------------------------------
-string leaf(const string &p) {
-    const size_t s = p.find_last_of('/');
-    return s == string::npos ? p : p.substr(s + 1);
-}
-// JellyfishHelper::isPipe (lib/src/jellyfish_helper.cc:258-260): anything under /proc or /dev —
-// including regular files in /dev/shm — is "a pipe": printed as <pipe>, assumed to be a sequence
-// file, exempt from the existence check.
-bool is_pipe(const string &p) { return p.rfind("/proc", 0) == 0 || p.rfind("/dev", 0) == 0; }
-string join(const vector<string> &v, bool leaves) { // leaves: InputHandler::fileName, else InputHandler::pathString
-    string s;
-    for (auto &p : v) s += (leaves ? leaf(p) : is_pipe(p) ? string("<pipe>") : p) + " ";
-    while (!s.empty() && s.back() == ' ') s.pop_back(); // boost::trim_right_copy
-    return s;
-}
-bool exists(const string &p) {
-    struct stat st;
-    return stat(p.c_str(), &st) == 0;
-}
-string lower(string s) {
-    for (auto &c : s) c = (char)tolower((unsigned char)c);
-    return s;
-}
-string ext_of(const string &p) {
-    const string l = leaf(p);
-    const size_t d = l.find_last_of('.');
-    return d == string::npos || d == 0 ? "" : l.substr(d);
-}
-// JellyfishHelper::isSequenceFile (lib/src/jellyfish_helper.cc:270-307): by extension, else by first byte
-bool is_sequence_file(const string &path) {
-    if (is_pipe(path)) return true; // lib/src/jellyfish_helper.cc:273
-    string e = lower(ext_of(path));
-    string stem = path;
-    if (e == ".gz") {
-        stem = path.substr(0, path.size() - 3);
-        e = lower(ext_of(stem));
-    }
-    static const char *kExt[] = {".fastq", ".fq", ".fasta", ".fa", ".fna", ".fas", ".scafseq"};
-    for (auto x : kExt)
-        if (e == x) return true;
-    std::ifstream f(path);
-    char ch = 0;
-    f >> ch;
-    return ch == '>' || ch == '@';
-}
-// InputHandler::globFiles (lib/src/input_handler.cc:245-316): space-separated patterns, brace + tilde expansion
-vector<string> glob_group(const string &group) {
-    vector<string> pats;
-    std::stringstream ss(group);
-    string item;
-    while (std::getline(ss, item, ' '))
-        pats.push_back(item);
-    if (pats.empty()) throw KatError(4, "No input provided for this input group");
-    glob_t g;
-    memset(&g, 0, sizeof g);
-    int i = 0;
-    for (auto &p : pats) {
-        int flags = GLOB_TILDE | GLOB_NOCHECK | GLOB_BRACE;
-        if (i++ > 0) flags |= GLOB_APPEND;
-        if (glob(p.c_str(), flags, nullptr, &g) != 0) throw KatError(4, "Problem globbing input pattern: " + p);
-    }
-    vector<string> out;
-    for (size_t j = 0; j < g.gl_pathc; j++) out.push_back(g.gl_pathv[j]);
-    if (g.gl_pathc) globfree(&g);
-    if (out.empty()) out.push_back(pats[0]);
-    return out;
-}
-
-struct Input {
-    vector<string> files;
-    vector<unsigned> trim5p;
-    bool canonical = true;
-    uint64_t hash_size = 100000000ULL; // DEFAULT_HASH_SIZE, lib/include/kat/jellyfish_helper.hpp:76
-    int index = 1;
-    bool load_mode = false; // InputMode::LOAD: the (first) input is a jellyfish hash
-    katgpu_table *table = nullptr;        // rank 0's (the only one on a single GPU)
-    vector<katgpu_table *> tables;        // one per GPU of the job
-    uint64_t n_distinct = 0, n_total = 0;
-
-    void set_trim(const vector<unsigned> &t) { // InputHandler::set5pTrim
-        if (t.empty()) trim5p.assign(files.size(), 0);
-        else if (t.size() == 1) trim5p.assign(files.size(), t[0]);
-        else if (t.size() == files.size()) trim5p = t;
-        else throw KatError(4, "Inconsistent number of inputs and trimming settings.  Please establish your inputs before trying to set trimming vector.  Also ensure you have the same number of input files to trimming settings.");
-    }
-    void validate() { // InputHandler::validateInput (lib/src/input_handler.cc:99-136)
-        for (auto &p : files) {
-            if (!is_pipe(p) && !exists(p)) throw KatError(4, "Could not find input file at: " + p + "; please check the path and try again.");
-            // `start` is never cleared in the reference, so the mode is simply that of the last
-            // file and the "Cannot mix sequence files and jellyfish hashes" check cannot fire
-            load_mode = !is_sequence_file(p);
-        }
-    }
-};
-
-struct Timer {
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-    double secs() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
-};
-void phase_done(const Timer &t) {
-    char b[64];
-    snprintf(b, sizeof b, "  Time taken: %.1fs\n\n", t.secs()); // auto_cpu_timer(1, "  Time taken: %ws\n\n")
-    cout << " done." << b;
-    cout.flush();
-}
-
-// Files at least this large (KAT_STREAM_BYTES) are read, parsed and counted block by block
-// (KAT_STREAM_BLOCK bytes at a time) when they are in a regular layout: host memory stays at a
-// few blocks instead of file + base stream.
-size_t env_size(const char *name, size_t dflt) {
-    const char *e = getenv(name);
-    return e ? (size_t)strtoull(e, nullptr, 10) : dflt;
-}
-size_t file_size_or_zero(const string &p) {
-    struct stat st;
-    return stat(p.c_str(), &st) == 0 && S_ISREG(st.st_mode) ? (size_t)st.st_size : 0;
-}
-
-// ---- GPUs -------------------------------------------------------------------------
-// `--gpus N` (or KATGPU_GPUS): one libkatgpu context and one host thread per GPU in this process.
-// The contexts form a job (katgpu_dist_init: NCCL communicator + peer-mapped receive areas); every
-// libkatgpu call on a job is collective, so run_on_all() makes the same call from N threads.
-// Reads are sharded by position in the parsed base stream; k-mers travel to their owner GPU
-// inside libkatgpu; every GPU receives the all-reduced result and rank 0's copy is written out.
-[[noreturn]] void die(const KatError &e) {
-    cout.flush();
-    cerr << (e.code == 5 ? "Error: " : "") << e.what() << endl;
-    _exit(e.code); // other GPU threads may be parked in a collective: no orderly unwinding
-}
-template <class F>
-void run_on_all(int n, F f) { // f(rank)
-    if (n == 1) {
-        f(0);
-        return;
-    }
-    vector<std::thread> th;
-    for (int r = 0; r < n; r++)
-        th.emplace_back([&f, r] {
-            try {
-                f(r);
-            } catch (const KatError &e) {
-                static std::mutex m;
-                std::lock_guard<std::mutex> g(m);
-                die(e);
-            }
-        });
-    for (auto &t : th) t.join();
-}
-struct Ctx {
-    vector<katgpu_ctx *> all;
-    katgpu_ctx *c = nullptr; // rank 0
-    explicit Ctx(int gpus) {
-        int dev0 = 0;
-        if (const char *e = getenv("KATGPU_DEVICE")) dev0 = atoi(e);
-        if (gpus < 1 || gpus > 8) throw KatError(4, "--gpus must be 1..8");
-        if (gpus > 1 && katgpu_device_count() < dev0 + gpus)
-            throw KatError(4, "--gpus " + std::to_string(gpus) + ": only " + std::to_string(katgpu_device_count()) + " CUDA devices visible");
-        all.assign(gpus, nullptr);
-        for (int r = 0; r < gpus; r++) gpu_check(katgpu_init(dev0 + r, &all[r]));
-        c = all[0];
-        if (gpus > 1) {
-            unsigned char id[128];
-            gpu_check(katgpu_dist_unique_id(id));
-            run_on_all(gpus, [&](int r) { gpu_check(katgpu_dist_init(all[r], r, gpus, id)); });
-        }
-    }
-    int n() const { return (int)all.size(); }
-    ~Ctx() {
-        run_on_all(n(), [&](int r) { katgpu_shutdown(all[r]); });
-    }
-};
-int gpus_option(const Parsed &a) {
-    const char *e = getenv("KATGPU_GPUS");
-    return (int)to_u64(a.get("gpus", e ? e : "1"), "gpus");
-}
-void free_tables(Ctx &ctx, Input &in) {
-    run_on_all(ctx.n(), [&](int r) {
-        if (r < (int)in.tables.size()) katgpu_table_free(in.tables[r]);
-    });
-    in.tables.clear();
-    in.table = nullptr;
-}
-// Feed one parsed base stream: on a job, GPU r takes the r-th share of the k-mer START positions;
-// its bytes run k-1 past the share's end so that every k-mer is complete on exactly one GPU (a
-// start inside that tail has fewer than k bases left and yields nothing).
-void feed_all(Ctx &ctx, Input &in, int k, const char *b, size_t n) {
-    if (ctx.n() == 1) {
-        gpu_check(katgpu_count_feed(in.table, b, n));
-        return;
-    }
-    run_on_all(ctx.n(), [&](int r) {
-        const size_t lo = n * (size_t)r / ctx.n(), hi = n * (size_t)(r + 1) / ctx.n();
-        const size_t end = std::min(n, hi + (size_t)k - 1);
-        gpu_check(katgpu_count_feed(in.tables[r], b + lo, hi > lo ? end - lo : 0));
-    });
-}
-
-// InputHandler::count (lib/src/input_handler.cc:180-202) on the GPU
-void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_streaming = true) {
-    Timer t;
-    if (allow_streaming) {
-        cout << "Input " << in.index << " is a sequence file.  Counting kmers for input " << in.index << " (" << join(in.files, false) << ") ...";
-        cout.flush();
-    }
-    in.tables.assign(ctx.n(), nullptr);
-    // a job shares the k-mers out: every GPU's table needs room for its 1/N of the distinct ones
-    const uint64_t per_gpu_slots = ctx.n() > 1 ? std::max<uint64_t>(in.hash_size / ctx.n(), 1024) : in.hash_size;
-    run_on_all(ctx.n(), [&](int r) { gpu_check(katgpu_count_begin(ctx.all[r], k, in.canonical ? 1 : 0, per_gpu_slots, allow_grow ? 1 : 0, &in.tables[r])); });
-    in.table = in.tables[0];
-    { // size the library's pending-key buffers once, for the whole input (about one k-mer per two file bytes of FASTQ)
-        uint64_t bytes = 0;
-        for (auto &f : in.files) bytes += file_size_or_zero(f);
-        if (bytes >= ((uint64_t)64 << 20)) run_on_all(ctx.n(), [&](int r) { gpu_check(katgpu_count_reserve(in.tables[r], bytes / 2 / (uint64_t)ctx.n())); });
-    }
-    const size_t stream_from = env_size("KAT_STREAM_BYTES", (size_t)2 << 30), block = env_size("KAT_STREAM_BLOCK", (size_t)512 << 20);
-    std::vector<unsigned char> raw;
-    std::string bases;
-    // KAT_GPU_PARSE=0 keeps FASTQ parsing on the host
-    const bool gpu_parse = allow_streaming && env_size("KAT_GPU_PARSE", 1) != 0;
-    for (size_t i = 0; i < in.files.size(); i++) {
-        string err;
-        if (gpu_parse) { // plain 4-line FASTQ: the raw bytes go to the GPU(s) and are parsed there
-            const int r = kat_host::stream_fastq_raw(in.files[i], env_size("KAT_RAW_BLOCK", (size_t)256 << 20) * (size_t)ctx.n(), ctx.n(),
-                                                     [&](const char *const *parts, const size_t *lens) {
-                                                         vector<int> regular(ctx.n(), 0);
-                                                         run_on_all(ctx.n(), [&](int rk) {
-                                                             gpu_check(katgpu_count_feed_fastq(in.tables[rk], parts[rk], lens[rk], in.trim5p[i], &regular[rk]));
-                                                         });
-                                                         int n_reg = 0;
-                                                         for (int rk = 0; rk < ctx.n(); rk++) n_reg += regular[rk] != 0;
-                                                         // some GPUs counted their share, others refused theirs: start over
-                                                         return n_reg == ctx.n() ? 1 : n_reg == 0 ? 0 : -1;
-                                                     }, err);
-            if (r == 1) continue;
-            if (r < 0) { // irregular after some blocks were counted: start this input over with host parsing
-                free_tables(ctx, in);
-                count_input(ctx, in, k, allow_grow, false);
-                return;
-            }
-        }
-        if (allow_streaming && file_size_or_zero(in.files[i]) >= stream_from) {
-            katgpu_status bad = KATGPU_OK;
-            const int r = kat_host::stream_regular_file(in.files[i], in.trim5p[i], block, [&](const char *b, size_t n) {
-                feed_all(ctx, in, k, b, n);
-                return true;
-            }, err);
-            gpu_check(bad);
-            if (r == 1) continue;
-            if (r < 0) { // irregular after some blocks were counted: start this input over, whole files at a time
-                free_tables(ctx, in);
-                count_input(ctx, in, k, allow_grow, false);
-                return;
-            }
-        }
-        if (!kat_host::read_file(in.files[i], raw, err)) throw KatError(4, err);
-        bases.clear();
-        const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), k, in.trim5p[i], bases);
-        if (st == kat_host::ParseStatus::UnsupportedFormat) {
-            cerr << "warning: " << in.files[i] << ": Unsupported format (the reference silently stops reading this input here)" << endl;
-            break;
-        }
-        if (!bases.empty()) feed_all(ctx, in, k, bases.data(), bases.size());
-        if (st == kat_host::ParseStatus::InvalidFastq) {
-            cerr << "warning: " << in.files[i] << ": Invalid fastq sequence; like the reference, the rest of this input is ignored" << endl;
-            break;
-        }
-    }
-    run_on_all(ctx.n(), [&](int r) {
-        uint64_t nd = 0, nt = 0;
-        gpu_check(katgpu_count_end(in.tables[r], &nd, &nt)); // on a job: the job's totals, on every rank
-        if (r == 0) in.n_distinct = nd, in.n_total = nt;
-    });
-    phase_done(t);
-}
-
-// InputHandler::loadHeader + loadHash (lib/src/input_handler.cc:138-142,204-219) via
-// HashLoader::loadHash (lib/src/jellyfish_helper.cc:97-187): only the FIRST file of the group is
-// read; k and the canonical flag come from its header.  Returns the file's mer length.
-kat_host::JfHeader read_jf_header(const string &path, std::ifstream &f) {
-    f.open(path.c_str(), std::ios::in | std::ios::binary);
-    kat_host::JfHeader h;
-    string err;
-    if (!f.good() || !kat_host::jf_read_header(f, h, err)) throw KatError(4, "Failed to parse header of file: " + path);
-    if (h.format == "bloomcounter")
-        throw KatError(4, "KAT does not currently support bloom counted kmer hashes.  Please create a binary hash with jellyfish or KAT and use that instead.");
-    if (h.format == "text/sorted")
-        throw KatError(4, "Processing a text format hash will be painfully slow, so we don't support it.  Please create a binary hash with jellyfish or KAT and use that instead.");
-    if (h.format != "binary/sorted") throw KatError(4, "Unknown format '" + h.format + "'");
-    return h;
-}
-int load_input(katgpu_ctx *ctx, Input &in) {
-    std::ifstream f;
-    const kat_host::JfHeader h = read_jf_header(in.files[0], f);
-    const int k = (int)(h.key_len / 2);
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); the hash holds " + std::to_string(k) + "-mers");
-    struct stat st;
-    uint64_t n_records = 0;
-    if (stat(in.files[0].c_str(), &st) == 0 && (uint64_t)st.st_size >= h.offset) {
-        const uint64_t data = (uint64_t)st.st_size - h.offset;
-        if (data % h.record_bytes())
-            throw KatError(4, "Size of database (" + std::to_string(data) + ") must be a multiple of the length of a record (" + std::to_string(h.record_bytes()) + ")");
-        n_records = data / h.record_bytes();
-    }
-    in.canonical = h.canonical;
-    // the reference sizes the new array at 2 * nbRecords rounded up to a power of two (:149-150)
-    gpu_check(katgpu_count_begin(ctx, k, in.canonical ? 1 : 0, std::max<uint64_t>(2 * n_records, 1024), 1, &in.table));
-    string err;
-    katgpu_status first_bad = KATGPU_OK;
-    const bool ok = kat_host::jf_read_records(f, h, (size_t)1 << 22, [&](const uint64_t *keys, const uint64_t *counts, size_t n) {
-        if (first_bad == KATGPU_OK) first_bad = katgpu_count_add_pairs(in.table, keys, counts, n);
-    }, err);
-    gpu_check(first_bad);
-    if (!ok) throw KatError(4, err);
-    gpu_check(katgpu_count_end(in.table, &in.n_distinct, &in.n_total));
-    return k;
-}
-void load_inputs_phase(Ctx &gpus, Input *ins, int n_in, int &k) { // the "Loading hashes into memory..." phase
-    if (gpus.n() > 1) throw KatError(4, "jellyfish hash inputs are loaded on one GPU: run without --gpus");
-    katgpu_ctx *ctx = gpus.c;
-    Timer t;
-    cout << "Loading hashes into memory...";
-    cout.flush();
-    for (int i = 0; i < n_in; i++)
-        if (ins[i].load_mode) {
-            const int kk = load_input(ctx, ins[i]);
-            ins[i].tables.assign(1, ins[i].table);
-            if (n_in == 1) k = kk; // hist / gcp take merLen from the loaded hash (InputHandler::loadHash)
-        }
-    phase_done(t);
-}
-
-// InputHandler::dump (lib/src/input_handler.cc:221-243): a counted input is written as a
-// jellyfish binary/sorted hash (JellyfishHelper::dumpHash: 4-byte counters, one file), a
-// loaded one is symlinked.
-void dump_input(Input &in, int k, const string &out_path) {
-    struct stat st;
-    if (lstat(out_path.c_str(), &st) == 0) unlink(out_path.c_str());
-    if (in.load_mode) {
-        if (symlink(in.files[0].c_str(), out_path.c_str()) != 0) throw KatError(4, "Could not create symlink " + out_path);
-        return;
-    }
-    Timer t;
-    cout << "Dumping hash to " << out_path << " ...";
-    cout.flush();
-    vector<uint64_t> keys(std::max<uint64_t>(in.n_distinct, 1)), counts(keys.size());
-    uint64_t n = 0;
-    gpu_check(katgpu_table_export(in.table, keys.data(), counts.data(), keys.size(), &n));
-    keys.resize((size_t)std::min<uint64_t>(n, keys.size()));
-    counts.resize(keys.size());
-    kat_host::JfHeader h;
-    kat_host::jf_prepare_dump(h, (unsigned)k, in.canonical, keys.size(), keys, counts);
-    std::ofstream out(out_path.c_str(), std::ios::out | std::ios::binary);
-    kat_host::jf_write_file(out, h, keys, counts);
-    out.close();
-    if (!out.good()) throw KatError(4, "Could not write " + out_path);
-    phase_done(t);
-}
-
-void ensure_parent_dir(const string &prefix) { // KatFS::ensureDirectoryExists(absolute(prefix).parent_path())
-    string p = prefix;
-    if (p.empty() || p[0] != '/') {
-        char cwd[4096];
-        if (!getcwd(cwd, sizeof cwd)) return;
-        p = string(cwd) + "/" + p;
-    }
-    const size_t s = p.find_last_of('/');
-    if (s == string::npos || s == 0) return;
-    const string dir = p.substr(0, s);
-    string cur;
-    std::stringstream ss(dir);
-    string part;
-    while (std::getline(ss, part, '/')) {
-        if (part.empty()) continue;
-        cur += "/" + part;
-        if (!exists(cur) && mkdir(cur.c_str(), 0777) != 0 && !exists(cur))
-            throw KatError(4, "Could not create output directory: " + dir);
-    }
-}
-
-// SparseMatrix::printMatrix / getMaxVal (lib/include/kat/sparse_matrix.hpp:162-173,269-277)
-void print_matrix(std::ostream &out, const vector<uint64_t> &mx, uint32_t rows, uint32_t cols) {
-    for (uint32_t i = 0; i < rows; i++) {
-        out << mx[(size_t)i * cols];
-        for (uint32_t j = 1; j < cols; j++) out << " " << mx[(size_t)i * cols + j];
-        out << endl;
-    }
-}
-uint64_t max_val(const vector<uint64_t> &mx) {
-    uint64_t m = 0;
-    for (auto v : mx) m = std::max(m, v);
-    return m;
-}
-// boost::filesystem::path::operator<< : quoted, '&' escapes '"' and '&'
-string quoted_path(const string &p) {
-    string s = "\"";
-    for (char c : p) {
-        if (c == '"' || c == '&') s += '&';
-        s += c;
-    }
-    return s + "\"";
-}
-
-// Distance metrics with the reference's arithmetic (lib/include/kat/distance_metrics.hpp:50-126)
-double minkowski(const vector<uint64_t> &a, const vector<uint64_t> &b, int p) {
-    uint64_t sum = 0;
-    for (size_t i = 0; i < a.size(); i++) {
-        const uint64_t diff = a[i] < b[i] ? b[i] - a[i] : a[i] - b[i];
-        sum += std::pow(diff, p); // double -> uint64 at every step, as the reference
-    }
-    return p == 1 ? (double)sum : std::pow((double)sum, 1.0 / (double)p);
-}
-double cosine(const vector<uint64_t> &a, const vector<uint64_t> &b) {
-    double dot = 0.0, da = 0.0, db = 0.0;
-    for (size_t i = 0; i < a.size(); i++) {
-        dot += a[i] * b[i]; // uint64 product (wraps) before the double add, as the reference
-        da += std::pow(a[i], 2);
-        db += std::pow(b[i], 2);
-    }
-    return 1.0 - (dot / (std::sqrt(da) * std::sqrt(db)));
-}
-double canberra(const vector<uint64_t> &a, const vector<uint64_t> &b) {
-    double sum = 0.0;
-    for (size_t i = 0; i < a.size(); i++) {
-        const double diff = (double)a[i] - (double)b[i];
-        const double s = a[i] + b[i];
-        if (s > 0) sum += std::abs(diff) / s;
-    }
-    return sum;
-}
-double jaccard(const vector<uint64_t> &a, const vector<uint64_t> &b) {
-    double mn = 0.0, mx = 0.0;
-    for (size_t i = 0; i < a.size(); i++) mn += std::min(a[i], b[i]);
-    for (size_t i = 0; i < a.size(); i++) mx += std::max(a[i], b[i]);
-    return 1.0 - (mn / mx);
-}
-void print_distances(std::ostream &out, const vector<uint64_t> &a, const vector<uint64_t> &b) {
-    out << " - Manhattan distance: " << minkowski(a, b, 1) << endl;
-    out << " - Euclidean distance: " << minkowski(a, b, 2) << endl;
-    out << " - Cosine distance: " << cosine(a, b) << endl;
-    out << " - Canberra distance: " << canberra(a, b) << endl;
-    out << " - Jaccard distance: " << jaccard(a, b) << endl;
-}
-
-
-// =============================== kat hist ========================================
-int hist_main(int argc, char **argv) {
-    const vector<OptSpec> specs = {{'o', "output_prefix", true}, {'t', "threads", true}, {'l', "low", true}, {'h', "high", true},
-                                   {'i', "inc", true}, {0, "5ptrim", true}, {'N', "non_canonical", false}, {'m', "mer_len", true},
-                                   {'H', "hash_size", true}, {'d', "dump_hash", false}, {'p', "output_type", true},
-                                   {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
-    const Parsed a = parse_args(argc, argv, specs);
-    if (a.has("help") || argc <= 1) {
-        cout << "Usage: kat hist [options] (<input>)+\n\nCreate an histogram of k-mer occurrences from the input.\n\n"
-                "Options: -o prefix (kat.hist) -t threads -l low (1) -h high (10000) -i inc (1) --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -v --help\n" << endl;
-        return 1;
-    }
-    const uint64_t low = to_u64(a.get("low", "1"), "low"), high = to_u64(a.get("high", "10000"), "high"), inc = to_u64(a.get("inc", "1"), "inc");
-    int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    Timer total;
-    cout << "Running KAT in HIST mode" << endl << "------------------------" << endl << endl;
-    Input in;
-    in.files = a.positional;
-    in.set_trim(parse_trim(a.get("5ptrim", "0")));
-    in.canonical = !a.has("non_canonical");
-    in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
-    const string prefix = a.get("output_prefix", "kat.hist");
-    // Histogram ctor, src/histogram.cc:57-71, src/histogram.hpp:172-178
-    const uint64_t base = low > 1 ? (1 >= low ? 1 : low - 1) : 1, ceil = high + 1, nb = ceil + 1 - base;
-    if (high < low) throw KatError(4, "High count value must be >= to low count value.  High: " + std::to_string(high) + "; Low: " + std::to_string(low));
-    if (inc == 0) throw KatError(4, "Increment must be >= 1");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
-    in.validate();
-    ensure_parent_dir(prefix);
-    Ctx ctx(gpus_option(a));
-    if (a.has("dump_hash") && ctx.n() > 1) throw KatError(4, "--dump_hash writes one GPU's table: run without --gpus");
-    if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
-    else count_input(ctx, in, k, true);
-    vector<uint64_t> bins(nb);
-    {
-        Timer t;
-        cout << "Bining kmers ...";
-        cout.flush();
-        vector<vector<uint64_t>> other(ctx.n()); // every GPU of a job receives the all-reduced bins
-        run_on_all(ctx.n(), [&](int r) {
-            if (r) other[r].resize(nb);
-            gpu_check(katgpu_hist(in.tables[r], base, ceil, inc, nb, r ? other[r].data() : bins.data()));
-        });
-        phase_done(t);
-    }
-    if (a.has("dump_hash")) dump_input(in, k, prefix + "-hash.jf" + std::to_string(k));
-    {
-        Timer t;
-        cout << "Saving results to disk ...";
-        cout.flush();
-        std::ofstream out(prefix.c_str());
-        out << "# Title:" << k << "-mer spectra for: " << join(in.files, true) << endl;
-        out << "# XLabel:" << k << "-mer frequency" << endl;
-        out << "# YLabel:# distinct " << k << "-mers" << endl;
-        out << "# Kmer value:" << k << endl;
-        out << "# Input 1:" << join(in.files, false) << endl;
-        out << "###" << endl;
-        uint64_t col = base;
-        for (uint64_t i = 0; i < nb; i++, col += inc) out << col << " " << bins[i] << "\n";
-        out.close();
-        phase_done(t);
-    }
-    free_tables(ctx, in);
-    char b[96];
-    snprintf(b, sizeof b, "KAT HIST completed.\nTotal runtime: %.1fs\n\n", total.secs());
-    cout << b;
-    return 0;
-}
-
-// =============================== kat gcp =========================================
-int gcp_main(int argc, char **argv) {
-    const vector<OptSpec> specs = {{'o', "output_prefix", true}, {'t', "threads", true}, {'x', "cvg_scale", true}, {'y', "cvg_bins", true},
-                                   {0, "5ptrim", true}, {'N', "non_canonical", false}, {'m', "mer_len", true}, {'H', "hash_size", true},
-                                   {'d', "dump_hash", false}, {'p', "output_type", true}, {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
-    const Parsed a = parse_args(argc, argv, specs);
-    if (a.has("help") || argc <= 1) {
-        cout << "Usage: kat gcp [options] (<input>)+\n\nCompares GC content and K-mer coverage from the input.\n\n"
-                "Options: -o prefix (kat-gcp) -t threads -x cvg_scale (1.0) -y cvg_bins (1000) --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -v --help\n" << endl;
-        return 1;
-    }
-    const double scale = to_double(a.get("cvg_scale", "1.0"), "cvg_scale");
-    const uint32_t bins = (uint32_t)to_u64(a.get("cvg_bins", "1000"), "cvg_bins");
-    int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    Timer total;
-    cout << "Running KAT in GCP mode" << endl << "------------------------" << endl << endl;
-    Input in;
-    in.files = a.positional;
-    in.set_trim(parse_trim(a.get("5ptrim", "0")));
-    in.canonical = !a.has("non_canonical");
-    in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
-    const string prefix = a.get("output_prefix", "kat-gcp");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
-    in.validate();
-    ensure_parent_dir(prefix);
-    Ctx ctx(gpus_option(a));
-    if (a.has("dump_hash") && ctx.n() > 1) throw KatError(4, "--dump_hash writes one GPU's table: run without --gpus");
-    if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
-    else count_input(ctx, in, k, true);
-    vector<uint64_t> mx((size_t)k * (bins + 1));
-    {
-        Timer t;
-        cout << "Analysing kmers in hash ...";
-        cout.flush();
-        vector<vector<uint64_t>> other(ctx.n());
-        run_on_all(ctx.n(), [&](int r) {
-            if (r) other[r].resize(mx.size());
-            gpu_check(katgpu_gcp(in.tables[r], scale, bins, r ? other[r].data() : mx.data()));
-        });
-        phase_done(t);
-        if (a.has("dump_hash")) dump_input(in, k, prefix + "-hash.jf" + std::to_string(k));
-    }
-    {
-        Timer t;
-        cout << "Saving results to disk ...";
-        cout.flush();
-        std::ofstream out((prefix + ".mx").c_str());
-        out << "# Title:K-mer coverage vs GC count plot for: " << join(in.files, true) << endl;
-        out << "# XLabel:" << k << "-mer frequency" << endl;
-        out << "# YLabel:GC count" << endl;
-        out << "# ZLabel:# distinct " << k << "-mers" << endl;
-        out << "# Columns:" << bins + 1 << endl;
-        out << "# Rows:" << k << endl;
-        out << "# MaxVal:" << max_val(mx) << endl;
-        out << "# Transpose:0" << endl;
-        out << "# Kmer value:" << k << endl;
-        out << "# Input 1:" << join(in.files, false) << endl;
-        out << "###" << endl;
-        print_matrix(out, mx, (uint32_t)k, bins + 1);
-        out.close();
-        phase_done(t);
-    }
-    free_tables(ctx, in);
-    char b[96];
-    snprintf(b, sizeof b, "KAT GCP completed.\nTotal runtime: %.1fs\n\n", total.secs());
-    cout << b;
-    return 0;
-}
-
-// =============================== kat comp ========================================
-void print_comp_counts(std::ostream &out, const katgpu_comp_counters &c, const string &p1, const string &p2, const string &p3,
-                       const vector<uint64_t> &sp1, const vector<uint64_t> &sp2, const vector<uint64_t> &ssp1,
-                       const vector<uint64_t> &ssp2) { // CompCounters::printCounts, lib/src/comp_counters.cc:144-206
-    out << "K-mer statistics for: " << endl;
-    out << " - Hash 1: " << quoted_path(p1) << endl;
-    out << " - Hash 2: " << quoted_path(p2) << endl;
-    if (c.hash3_total > 0) out << " - Hash 3: " << quoted_path(p3) << endl;
-    out << endl;
-    out << "Total K-mers in: " << endl;
-    out << " - Hash 1: " << c.hash1_total << endl;
-    out << " - Hash 2: " << c.hash2_total << endl;
-    if (c.hash3_total > 0) out << " - Hash 3: " << c.hash3_total << endl;
-    out << endl;
-    out << "Distinct K-mers in:" << endl;
-    out << " - Hash 1: " << c.hash1_distinct << endl;
-    out << " - Hash 2: " << c.hash2_distinct << endl;
-    if (c.hash3_total > 0) out << " - Hash 3: " << c.hash3_distinct << endl;
-    out << endl;
-    out << "Total K-mers only found in:" << endl;
-    out << " - Hash 1: " << c.hash1_only_total << endl;
-    out << " - Hash 2: " << c.hash2_only_total << endl;
-    out << endl;
-    out << "Distinct K-mers only found in:" << endl;
-    out << " - Hash 1: " << c.hash1_only_distinct << endl;
-    out << " - Hash 2: " << c.hash2_only_distinct << endl << endl;
-    out << "Shared K-mers:" << endl;
-    out << " - Total shared found in hash 1: " << c.shared_hash1_total << endl;
-    out << " - Total shared found in hash 2: " << c.shared_hash2_total << endl;
-    out << " - Distinct shared K-mers: " << c.shared_distinct << endl << endl;
-    out << "Distance between spectra 1 and 2 (all k-mers):" << endl;
-    print_distances(out, sp1, sp2);
-    out << endl;
-    out << "Distance between spectra 1 and 2 (shared k-mers):" << endl;
-    print_distances(out, ssp1, ssp2);
-    out << endl;
-}
-
-int comp_main(int argc, char **argv) {
-    const vector<OptSpec> specs = {{'o', "output_prefix", true}, {'t', "threads", true}, {'x', "d1_scale", true}, {'y', "d2_scale", true},
-                                   {'i', "d1_bins", true}, {'j', "d2_bins", true}, {0, "d1_5ptrim", true}, {0, "d2_5ptrim", true},
-                                   {'N', "non_canonical_1", false}, {'O', "non_canonical_2", false}, {'P', "non_canonical_3", false},
-                                   {'m', "mer_len", true}, {'H', "hash_size_1", true}, {'I', "hash_size_2", true}, {'J', "hash_size_3", true},
-                                   {'d', "dump_hashes", false}, {'g', "disable_hash_grow", false}, {'n', "density_plot", false},
-                                   {'p', "output_type", true}, {'h', "output_hists", false}, {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
-    const Parsed a = parse_args(argc, argv, specs);
-    if (a.has("help") || argc <= 1) {
-        cout << "Usage: kat comp [options] <input_1> <input_2> [<input_3>]\n\nCompares jellyfish K-mer count hashes.\n\n"
-                "Options: -o prefix (kat-comp) -t threads -x d1_scale -y d2_scale -i d1_bins (1001) -j d2_bins (1001) --d1_5ptrim --d2_5ptrim "
-                "-N -O -P -m mer_len (27) -H -I -J hash sizes (1e8) -g -n -h -v --help\n" << endl;
-        return 1;
-    }
-    Timer total;
-    cout << "Running KAT in COMP mode" << endl << "------------------------" << endl << endl;
-    if (a.positional.size() < 1) throw KatError(4, "Nothing specified for input group 1");
-    if (a.positional.size() < 2) throw KatError(4, "Nothing specified for input group 2");
-    const bool three = a.positional.size() >= 3;
-    int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
-    const double d1s = to_double(a.get("d1_scale", "1.0"), "d1_scale"), d2s = to_double(a.get("d2_scale", "1.0"), "d2_scale");
-    const uint32_t d1b = (uint32_t)to_u64(a.get("d1_bins", "1001"), "d1_bins"), d2b = (uint32_t)to_u64(a.get("d2_bins", "1001"), "d2_bins");
-    if (d1b == 0 || d2b == 0) throw KatError(4, "d1_bins and d2_bins must be >= 1");
-    Input in[3];
-    const char *nc[3] = {"non_canonical_1", "non_canonical_2", "non_canonical_3"};
-    const char *hs[3] = {"hash_size_1", "hash_size_2", "hash_size_3"};
-    for (int i = 0; i < (three ? 3 : 2); i++) {
-        in[i].files = glob_group(a.positional[i]);
-        in[i].index = i + 1;
-        in[i].canonical = !a.has(nc[i]);
-        in[i].hash_size = to_u64(a.get(hs[i], "100000000"), hs[i]);
-    }
-    in[0].set_trim(parse_trim(a.get("d1_5ptrim", "0")));
-    in[1].set_trim(parse_trim(a.get("d2_5ptrim", "0")));
-    if (three) in[2].set_trim({});
-    const string prefix = a.get("output_prefix", "kat-comp");
-    for (int i = 0; i < (three ? 3 : 2); i++) in[i].validate();
-    ensure_parent_dir(prefix);
-    Ctx ctx(gpus_option(a));
-    if (a.has("dump_hashes") && ctx.n() > 1) throw KatError(4, "--dump_hashes writes one GPU's table: run without --gpus");
-    if (ctx.n() > 1)
-        for (int i = 0; i < (three ? 3 : 2); i++)
-            if (!in[i].canonical) throw KatError(4, "with --gpus every input must be counted canonically (no -N/-O/-P): the shared-k-mer walk is local to the GPU that owns a k-mer");
-    const int n_in = three ? 3 : 2;
-    // Comp::execute (src/comp.cc:140-167): count the sequence inputs, then read the headers of
-    // the hash inputs; when every input is a hash the mer length comes from the first header;
-    // every hash must hold k-mers of the mer length in use (InputHandler::validateMerLen).
-    for (int i = 0; i < n_in; i++)
-        if (!in[i].load_mode) count_input(ctx, in[i], k, !a.has("disable_hash_grow"));
-    bool any_load = false, all_load = true;
-    vector<unsigned> hash_k(n_in, 0);
-    for (int i = 0; i < n_in; i++) {
-        if (in[i].load_mode) {
-            std::ifstream f;
-            hash_k[i] = read_jf_header(in[i].files[0], f).key_len / 2;
-            any_load = true;
-        } else
-            all_load = false;
-    }
-    if (all_load) k = (int)hash_k[0];
-    for (int i = 0; i < n_in; i++)
-        if (in[i].load_mode && (int)hash_k[i] != k)
-            throw KatError(4, "Cannot process hashes that were created with different K-mer lengths.  Expected: " + std::to_string(k) +
-                                  ".  Key length was " + std::to_string(hash_k[i]) + " for : " + in[i].files[0]);
-    if (any_load) {
-        int k_unused = k;
-        load_inputs_phase(ctx, in, n_in, k_unused);
-    }
-    const size_t cells = (size_t)d1b * d2b, len = std::min(d1b, d2b);
-    vector<uint64_t> main_mx(cells), ends, middle, mixed, spectra(4 * len);
-    if (three) {
-        ends.resize(cells);
-        middle.resize(cells);
-        mixed.resize(cells);
-    }
-    katgpu_comp_counters cc;
-    {
-        Timer t;
-        cout << "Comparing hashes ...";
-        cout.flush();
-        run_on_all(ctx.n(), [&](int r) {
-            if (r == 0) {
-                gpu_check(katgpu_comp(in[0].tables[0], in[1].tables[0], three ? in[2].tables[0] : nullptr, d1s, d2s, d1b, d2b, main_mx.data(),
-                                      three ? ends.data() : nullptr, three ? middle.data() : nullptr, three ? mixed.data() : nullptr, &cc,
-                                      spectra.data()));
-                return;
-            }
-            vector<uint64_t> m(cells), e, mi, mx2, sp(4 * len); // the other GPUs' copies of the all-reduced result
-            if (three) e.resize(cells), mi.resize(cells), mx2.resize(cells);
-            katgpu_comp_counters c2;
-            gpu_check(katgpu_comp(in[0].tables[r], in[1].tables[r], three ? in[2].tables[r] : nullptr, d1s, d2s, d1b, d2b, m.data(),
-                                  three ? e.data() : nullptr, three ? mi.data() : nullptr, three ? mx2.data() : nullptr, &c2, sp.data()));
-        });
-        phase_done(t);
-    }
-    if (a.has("dump_hashes")) // src/comp.cc:174-179
-        for (int i = 0; i < n_in; i++) dump_input(in[i], k, prefix + "-hash" + std::to_string(in[i].index) + ".jf" + std::to_string(k));
-    const vector<uint64_t> sp1(spectra.begin(), spectra.begin() + len), sp2(spectra.begin() + len, spectra.begin() + 2 * len),
-        ssp1(spectra.begin() + 2 * len, spectra.begin() + 3 * len), ssp2(spectra.begin() + 3 * len, spectra.end());
-    const string p1 = in[0].files[0], p2 = in[1].files[0], p3 = three ? in[2].files[0] : "";
-    {
-        Timer t;
-        cout << "Saving results to disk ...";
-        cout.flush();
-        {
-            std::ofstream out((prefix + "-main.mx").c_str()); // Comp::printMainMatrix, src/comp.cc:308-326
-            out << "# Title:K-mer comparison plot" << endl
-                << "# XLabel:" << k << "-mer frequency for: " << join(in[0].files, true) << endl
-                << "# YLabel:" << k << "-mer frequency for: " << join(in[1].files, true) << endl
-                << "# ZLabel:# distinct " << k << "-mers" << endl
-                << "# Columns:" << d2b << endl
-                << "# Rows:" << d1b << endl
-                << "# MaxVal:" << max_val(main_mx) << endl
-                << "# Transpose:1" << endl
-                << "# Kmer value:" << k << endl
-                << "# Input 1:" << join(in[0].files, false) << endl
-                << "# Input 2:" << join(in[1].files, false) << endl
-                << "###" << endl;
-            print_matrix(out, main_mx, d1b, d2b);
-        }
-        if (three) { // src/comp.cc:330-356
-            std::ofstream e((prefix + "-ends.mx").c_str());
-            e << "# Each row represents K-mer frequency for: " << p1 << endl;
-            e << "# Each column represents K-mer frequency for sequence ends: " << p3 << endl;
-            print_matrix(e, ends, d1b, d2b);
-            std::ofstream m((prefix + "-middle.mx").c_str());
-            m << "# Each row represents K-mer frequency for: " << p1 << endl;
-            m << "# Each column represents K-mer frequency for sequence middles: " << p2 << endl;
-            print_matrix(m, middle, d1b, d2b);
-            std::ofstream x((prefix + "-mixed.mx").c_str());
-            x << "# Each row represents K-mer frequency for hash file 1: " << p1 << endl;
-            x << "# Each column represents K-mer frequency for mixed: " << p2 << " and " << p3 << endl;
-            print_matrix(x, mixed, d1b, d2b);
-        }
-        {
-            std::ofstream out((prefix + ".stats").c_str());
-            print_comp_counts(out, cc, p1, p2, p3, sp1, sp2, ssp1, ssp2);
-        }
-        if (a.has("output_hists")) { // Comp::printHist, src/comp.cc:235-246
-            for (int i = 0; i < 2; i++) {
-                std::ofstream out((prefix + "." + std::to_string(i + 1) + ".hist").c_str());
-                out << "# Title:" << k << "-mer spectra for: " << join(in[i].files, false) << endl;
-                out << "# XLabel:" << k << "-mer frequency" << endl;
-                out << "# YLabel:# distinct " << k << "-mers" << endl;
-                out << "###" << endl;
-                const vector<uint64_t> &h = i == 0 ? sp1 : sp2;
-                for (uint64_t j = 0; j < h.size(); j++) out << j << " " << h[j] << "\n";
-            }
-        }
-        phase_done(t);
-    }
-    cout << endl << "Summary statistics" << endl << "------------------" << endl << endl;
-    print_comp_counts(cout, cc, p1, p2, p3, sp1, sp2, ssp1, ssp2);
-    for (int i = 0; i < (three ? 3 : 2); i++) free_tables(ctx, in[i]);
-    char b[96];
-    snprintf(b, sizeof b, "KAT COMP completed.\nTotal runtime: %.1fs\n\n", total.secs());
-    cout << b;
-    return 0;
-}
-
-} // namespace
+namespace kat_front {
+int hist_main(int argc, char **argv);
+int gcp_main(int argc, char **argv);
+int comp_main(int argc, char **argv);
+int sect_main(int argc, char **argv);
+} // namespace kat_front
+using namespace kat_front;
 
 int main(int argc, char **argv) {
     try {
         if (argc < 2 || !strcmp(argv[1], "--help") || !strcmp(argv[1], "-h")) {
             cout << "The K-mer Analysis Toolkit (KAT), GPU spectra engine.\n\nUsage: kat <mode> [options]\n\n"
-                    "Modes: hist, gcp, comp (counting and spectra on the GPU through libkatgpu).\n"
-                    "sect, cold, filter and plot are not part of this build.\n" << endl;
+                    "Modes: hist, gcp, comp, sect (counting, spectra and coverage lookups on the GPU through libkatgpu).\n"
+                    "cold, filter and plot are not part of this build.\n" << endl;
             return 1;
         }
         if (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V")) {
@@ -1030,8 +115,9 @@ int main(int argc, char **argv) {
         if (mode == "hist") return hist_main(argc - 1, argv + 1);
         if (mode == "gcp") return gcp_main(argc - 1, argv + 1);
         if (mode == "comp") return comp_main(argc - 1, argv + 1);
-        if (mode == "sect" || mode == "cold" || mode == "filter" || mode == "plot")
-            throw KatError(4, "KAT mode '" + mode + "' is outside this GPU build's scope (hist, gcp, comp)");
+        if (mode == "sect") return sect_main(argc - 1, argv + 1);
+        if (mode == "cold" || mode == "filter" || mode == "plot")
+            throw KatError(4, "KAT mode '" + mode + "' is outside this GPU build's scope (hist, gcp, comp, sect)");
         throw KatError(4, "Unrecognised KAT mode: " + mode);
     } catch (const KatError &e) {
         cerr << (e.code == 5 ? "Error: " : "") << e.what() << endl;

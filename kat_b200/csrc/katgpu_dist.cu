@@ -352,7 +352,9 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
         if (tiled) {
             // segments s = j, j + G, ... go to level-1 CTA j
             const uint32_t G = t->pend_segs;
-            const uint64_t per_cta = (uint64_t)((double)expected / G * 1.05) + kBinTile;
+            // (`expected` counts k-mer STARTS, as the hint the segments were sized from does: reads lose k-1 starts each,
+            // so this already over-estimates real read sets by ~20 %; an under-estimate only sends keys to the side list)
+            const uint64_t per_cta = expected / G + kBinTile / 4;
             const double F = (double)(1u << t->pend_Pb);
             auto fill_of = [&](uint64_t keys) { return (double)keys / F + 4.5 * std::sqrt((double)keys / F) + 16.0; };
             if (t->dist_cta_keys && fill_of(t->dist_cta_keys + per_cta) > (double)t->pend_seg_cap) {

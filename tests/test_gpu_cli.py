@@ -162,3 +162,24 @@ def test_cli_dev_paths_are_pipes(workdir):
         assert head[0] == "# Title:21-mer spectra for: c.fa" and head[4] == "# Input 1:<pipe>"
     finally:
         shutil.rmtree(d, ignore_errors=True)
+
+
+# ---- kat sect: per-position coverage through batched GPU lookups ------
+SECT_MANIFEST = json.load(open(os.path.join(G.GOLDEN, "sect", "cases.json")))
+
+
+@pytest.mark.parametrize("case", SECT_MANIFEST, ids=lambda c: c["name"])
+def test_cli_sect_output_files_byte_identical(case, tmp_path):
+    """`kat sect` (src/sect.cc): counts.cvg, stats.tsv, counts.gc and the region FASTA files equal the
+    files written by the reference binary (tests/golden/sect, make_sect_golden.py)."""
+    shutil.copytree(os.path.join(G.GOLDEN, "inputs"), tmp_path / "inputs")
+    out = os.path.join("sect", case["name"])
+    os.makedirs(tmp_path / out)
+    args = [a.replace("OUT", out) for a in case["args"]]
+    r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    assert sorted(os.listdir(tmp_path / out)) == case["files"]
+    for f in case["files"]:
+        p = os.path.join(G.GOLDEN, "sect", case["name"], f)
+        want = open(p, "rb").read() if os.path.exists(p) else gzip.open(p + ".gz", "rb").read()
+        assert open(tmp_path / out / f, "rb").read() == want, f"{case['name']}/{f} differs from the reference's file"
