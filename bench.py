@@ -197,17 +197,27 @@ def sample_slots(sample_reads):
 
 def run_product_cli_hist(fastq, slots, workdir):
     """The product's own `kat hist` binary (C++ front-end over libkatgpu) on the same FASTQ file
-    with the same options: file open -> parse -> count -> bin -> output file written.
-    Returns (wall seconds, output path)."""
+    with the same options: file open -> (device) parse -> count -> bin -> output file written.
+    Returns (wall seconds, output path, phase dict parsed from its own output and KATGPU_TRACE lines)."""
     kat = os.path.join(ROOT, "kat_b200", "bin", "kat")
     out = os.path.join(workdir, "ours.hist")
     t0 = time.perf_counter()
     r = subprocess.run([kat, "hist", f"-m{K}", f"-H{slots}", "-o", out, fastq], cwd=workdir, stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True, timeout=1800)
+                       stderr=subprocess.STDOUT, text=True, timeout=1800, env=dict(os.environ, KATGPU_TRACE="1"))
     wall = time.perf_counter() - t0
     if r.returncode != 0:
         raise RuntimeError("kat_b200/bin/kat failed: " + r.stdout[-400:])
-    return wall, out
+    ph = {}
+    m = re.search(r"katgpu_init\s+([0-9.]+) ms", r.stdout)
+    if m:
+        ph["katgpu_init_s"] = float(m.group(1)) / 1e3  # CUDA context creation + module load of a fresh process
+    m = re.search(r"Counting kmers.*?Time taken: ([0-9.]+)s", r.stdout, re.S)
+    if m:
+        ph["count_s"] = float(m.group(1))
+    m = re.search(r"Total runtime: ([0-9.]+)s", r.stdout)
+    if m:
+        ph["total_runtime_s"] = float(m.group(1))
+    return wall, out, ph
 
 
 def multi_gpu_parity(ctx, dist, rank, world, local_rank, reads_per_rank=150_000):
@@ -280,16 +290,21 @@ def cpu_baseline_leg(ctx, d_bases, n_reads, threads, args, line):
                     "attempts": r["attempts"], "rejected_runs": r["rejected"][:6],
                     "parity_on_sample": bool(np.array_equal(gbins, r["bins"]))})
         ref_hist_bytes = open(r["hist"], "rb").read()
-        # R2 of SURVEY.md §8(d): the same FILE through the product's CLI, output FILE compared byte for byte
+        # R2 of SURVEY.md §8(d): the same FILE through the product's CLI, output FILE compared byte for byte.
+        # Measured as a user would run it: no other process holds the GPU (this process gives its memory back first).
         try:
+            ctx.release_cached_memory()
             run_product_cli_hist(fq, slots, work)  # first run pays the page-in of a new binary
-            cli_wall, ours = run_product_cli_hist(fq, slots, work)
+            runs = [run_product_cli_hist(fq, slots, work) for _ in range(3)]
+            cli_wall, ours, ph = min(runs, key=lambda x: x[0])
             a_ = open(ours, "rb").read()
             same = a_ == ref_hist_bytes
             line["cli_file"] = {"wall_s": cli_wall, "reference_wall_s": r["wall"], "output_file_identical": bool(same),
-                                "value": n_inst / cli_wall, "unit": "k-mers/s",
+                                "value": n_inst / cli_wall, "unit": "k-mers/s", "wall_s_all_runs": [round(x[0], 3) for x in runs],
+                                "phases": ph, "reference_phases": r["phases"],
                                 "what": f"kat_b200/bin/kat hist -m27 -H{slots} on the sample FASTQ ({os.path.getsize(fq)} bytes, in /dev/shm): "
-                                        "process start, file read, parse, H2D, count, bin, hist file written"}
+                                        "process start, CUDA context, file mapped, FASTQ parsed on the GPU, count, bin, hist file written; best of 3 "
+                                        "(katgpu_init = CUDA context creation of a fresh process, the floor of any CUDA program here)"}
             if not same:
                 for la, lb in zip(a_.splitlines(), ref_hist_bytes.splitlines()):
                     if la != lb:

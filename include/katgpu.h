@@ -243,6 +243,9 @@ katgpu_status katgpu_ipc_export(void *dev, void *handle64);
 katgpu_status katgpu_ipc_import(const void *handle64, void **out_dev);
 void katgpu_ipc_close(void *dev);
 katgpu_status katgpu_synchronize(katgpu_ctx *ctx);
+/* The library keeps freed device blocks (tables, pending-key buffers) for the next job of the
+ * context — the reference likewise keeps its mmap'd arena; this gives them back to the driver. */
+katgpu_status katgpu_release_cached_memory(katgpu_ctx *ctx);
 
 /* ---- measurement ------------------------------------------------------------ */
 

@@ -68,6 +68,7 @@ SIGNATURES = {
     "katgpu_ipc_import": (_i, [_vp, C.POINTER(_vp)]),
     "katgpu_ipc_close": (None, [_vp]),
     "katgpu_synchronize": (_i, [_vp]),
+    "katgpu_release_cached_memory": (_i, [_vp]),
     "katgpu_dist_unique_id": (_i, [_vp]),
     "katgpu_dist_init": (_i, [_vp, _i, _i, _vp]),
     "katgpu_dist_rank": (_i, [_vp]),
@@ -168,6 +169,10 @@ class Context:
 
     def synchronize(self):
         _check(lib().katgpu_synchronize(self.h))
+
+    def release_cached_memory(self):
+        """Give the device blocks cached for reuse back to the driver (katgpu_release_cached_memory)."""
+        _check(lib().katgpu_release_cached_memory(self.h))
 
     # --- multi-GPU job (one context per GPU) ------------------------------------
     def dist_init(self, rank, n_ranks, unique_id: bytes):

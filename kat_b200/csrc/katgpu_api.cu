@@ -221,6 +221,14 @@ extern "C" katgpu_status katgpu_synchronize(katgpu_ctx *c) {
     CU(cudaStreamSynchronize(c->stream));
     return KATGPU_OK;
 }
+extern "C" katgpu_status katgpu_release_cached_memory(katgpu_ctx *c) {
+    if (!c) return fail(KATGPU_ERR_INVALID, "katgpu_release_cached_memory: NULL context");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    CU(cudaStreamSynchronize(c->copy_stream));
+    pool_flush(c);
+    return KATGPU_OK;
+}
 extern "C" katgpu_status katgpu_memcpy_d2h(katgpu_ctx *c, void *dst, const void *src, size_t n) {
     if (!c) return fail(KATGPU_ERR_INVALID, "katgpu_memcpy_d2h: NULL context");
     CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, c->stream));
@@ -557,7 +565,7 @@ katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) {
     Pb = std::min<int>(Pb, (int)t->g.Lb - 2);
     if (tiled) // level 1 of two: leave at least one bit for level 2 (slice -> 64 KB tile)
         Pb = std::max(1, std::min(9, (int)t->g.Lb - kTileBucketsLog2 - 1));
-    const uint64_t tile_pos = tiled ? kBinTile : kTile; // positions one CTA bins between two flushes
+    const uint64_t tile_pos = tiled ? (c->dist ? kBinTile : kBin1Tile) : kTile; // positions one CTA bins between two flushes
     // level-1 segment columns = CTAs of the kernel that fills them: bin_bases_kernel (bps_bin1 per SM), or on a
     // multi-GPU job bin_hashed_kernel (one per SM)
     const uint64_t nparts = 1ull << Pb, n_segs = (uint64_t)c->sm_count * (c->dist ? 1 : tiled ? c->bps_bin1 : c->bps_part);
@@ -609,7 +617,9 @@ katgpu_status pend_alloc(katgpu_table *t, uint64_t kmers_hint, bool &ok) {
     t->tiled = tiled;
     if (tiled) {
         // bps_bin1 CTAs of bin_bases_kernel per SM (two: <= 111 KB each), 16.5 KB of it fixed
-        t->ring1 = ring_slots((uint32_t)nparts, kBinTile, ((c->bps_bin1 >= 3 ? 74u : 111u) << 10) - 16896, kBin1Granule);
+        // (one CTA per SM in the wide shape: ~200 KB, 21 KB of it fixed)
+        const size_t ring1_bytes = KATGPU_BIN1_WIDE ? ((size_t)200 << 10) - 21504 : ((c->bps_bin1 >= 3 ? (size_t)74 : (size_t)111) << 10) - 16896;
+        t->ring1 = ring_slots((uint32_t)nparts, kBin1Tile, ring1_bytes, kBin1Granule);
         // side list: keys that leave the fast path (~1 % at load 0.3, ~5 % at 0.55)
         t->side_cap = std::min<uint64_t>(std::max<uint64_t>(hint / 8, 4u << 20), 512u << 20);
         if (const char *e = getenv("KATGPU_SIDE_CAP")) t->side_cap = std::max<uint64_t>(16, strtoull(e, nullptr, 10)); // tests: force deferred tiles
@@ -914,7 +924,7 @@ static katgpu_status feed_partitioned(katgpu_table *t, const uint8_t *dev, uint6
     // keys one CTA tile sends to one slice: mean m (every position a k-mer) + up to 3 padding keys;
     // after T tiles the fullest segment holds about T*(m+2) + 4*sqrt(T*m) (a segment that still
     // overflows falls back to direct insertion inside the kernel, so this only has to be a good guess)
-    const uint64_t tile_pos = t->tiled ? kBinTile : kTile;
+    const uint64_t tile_pos = t->tiled ? (in_keys ? kBinTile : kBin1Tile) : kTile;
     const double m = (double)tile_pos / (double)(1u << t->pend_Pb), pad = t->tiled ? 0.0 : 2.0;
     auto fill_after = [&](uint64_t tiles) { return (double)tiles * (m + pad) + 4.0 * std::sqrt((double)tiles * m); };
     uint64_t done = 0;

@@ -192,9 +192,9 @@ __device__ __forceinline__ void hll_sample(uint32_t *hll, uint64_t h, uint32_t s
 
 // ---- B1: base stream -> level-1 segments -------------------------------------------------------
 struct __align__(128) BinBasesHead {
-    uint8_t ascii[kBinTile + kHalo];
-    uint32_t W[2][kBinGroups + 2];
-    uint32_t B[2][kBinGroups + 2];
+    uint8_t ascii[kBin1Tile + kHalo];
+    uint32_t W[2][kBin1Groups + 2];
+    uint32_t B[2][kBin1Groups + 2];
     uint64_t mbar;
     uint32_t hll[kTileHllM];
 };
@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(c
     for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin1Threads) S.hll[i] = 0;
     SideTally tally;
 
-    auto tile_tma = [&](int t) { return P.tma_ok && ((uint64_t)(t + 1) * kBinTile + kHalo <= P.n_valid); };
+    auto tile_tma = [&](int t) { return P.tma_ok && ((uint64_t)(t + 1) * kBin1Tile + kHalo <= P.n_valid); };
     // static striding (per-CTA segment fill is predictable), rotated so that successive launches
     // hand their first tiles to different CTAs
     int tile = (int)((blockIdx.x + gridDim.x - P.cta_rot % gridDim.x) % gridDim.x);
@@ -222,28 +222,28 @@ __global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(c
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         if (tile < P.n_tiles && tile_tma(tile)) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            mbar_expect_tx(&S.mbar, kBinTile + kHalo);
-            tma_load_1d(S.ascii, P.bases + (uint64_t)tile * kBinTile, kBinTile + kHalo, &S.mbar);
+            mbar_expect_tx(&S.mbar, kBin1Tile + kHalo);
+            tma_load_1d(S.ascii, P.bases + (uint64_t)tile * kBin1Tile, kBin1Tile + kHalo, &S.mbar);
         }
     }
     __syncthreads();
     uint32_t parity = 0, buf = 0;
 
     for (; tile < P.n_tiles; tile += gridDim.x, buf ^= 1) {
-        const uint64_t tile_base = (uint64_t)tile * kBinTile;
+        const uint64_t tile_base = (uint64_t)tile * kBin1Tile;
         if (tile_tma(tile)) {
             while (!mbar_try_wait(&S.mbar, parity)) {
             }
             parity ^= 1;
         } else { // ragged tail / unaligned input: guarded loads, bytes past n_valid read as 0 (= not a base)
-            for (int i = tid; i < (kBinTile + kHalo); i += kBin1Threads) {
+            for (int i = tid; i < (kBin1Tile + kHalo); i += kBin1Threads) {
                 const uint64_t p = tile_base + i;
                 S.ascii[i] = p < P.n_valid ? P.bases[p] : (uint8_t)0;
             }
             __syncthreads();
         }
         uint32_t *Wb = S.W[buf], *Bb = S.B[buf];
-        for (int gi = tid; gi < kBinGroups + 2; gi += kBin1Threads) {
+        for (int gi = tid; gi < kBin1Groups + 2; gi += kBin1Threads) {
             const uint4 v = reinterpret_cast<const uint4 *>(S.ascii)[gi];
             uint32_t c0, c1, c2, c3, b0, b1, b2, b3;
             pack4(v.x, c0, b0);
@@ -258,18 +258,19 @@ __global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(c
             const int nt = tile + gridDim.x;
             if (nt < P.n_tiles && tile_tma(nt)) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                mbar_expect_tx(&S.mbar, kBinTile + kHalo);
-                tma_load_1d(S.ascii, P.bases + (uint64_t)nt * kBinTile, kBinTile + kHalo, &S.mbar);
+                mbar_expect_tx(&S.mbar, kBin1Tile + kHalo);
+                tma_load_1d(S.ascii, P.bases + (uint64_t)nt * kBin1Tile, kBin1Tile + kHalo, &S.mbar);
             }
         }
-        // 16 k-mers per thread (kBinGroups == kBin1Threads)
-        const uint64_t p0 = tile_base + (uint64_t)tid * 16;
-        const uint64_t bad48 = ((uint64_t)Bb[tid] << 32) | ((uint64_t)Bb[tid + 1] << 16) | Bb[tid + 2];
+        // kBin1PerThread k-mers per thread: a thread owns (half of) one 16-base group and sees its 48-base window
+        const uint32_t grp = kBin1PerThread == 16 ? (uint32_t)tid : ((uint32_t)tid & (uint32_t)(kBin1Groups - 1));
+        const bool second_half = kBin1PerThread != 16 && (uint32_t)tid >= (uint32_t)kBin1Groups; // warp-uniform
+        const uint64_t p0 = tile_base + (uint64_t)grp * 16;
+        const uint64_t bad48 = ((uint64_t)Bb[grp] << 32) | ((uint64_t)Bb[grp + 1] << 16) | Bb[grp + 2];
         const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
         Cut16 cut;
-        cut.init(Wb[tid], Wb[tid + 1], Wb[tid + 2], bad48, k, nst);
-#pragma unroll
-        for (uint32_t r = 0; r < 16; r++) {
+        cut.init(Wb[grp], Wb[grp + 1], Wb[grp + 2], bad48, k, nst);
+        auto one = [&](uint32_t r) { // r is a compile-time constant after unrolling
             uint32_t lo, hi;
             cut.key<CANON, WIDE>(r, kmask_lo, kmask_hi, lo, hi);
             const uint64_t h = mix_words<WIDE>(lo, hi, sh, kmask_lo, kmask_hi);
@@ -277,6 +278,13 @@ __global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(c
                 C.append(h, P.side, g, tally);
                 hll_sample(S.hll, h, sshift);
             }
+        };
+        if (!second_half) {
+#pragma unroll
+            for (uint32_t r = 0; r < (uint32_t)kBin1PerThread; r++) one(r);
+        } else {
+#pragma unroll
+            for (uint32_t r = 16 - kBin1PerThread; r < 16; r++) one(r);
         }
         C.flush(false, P.side, g, tally);
     }
@@ -483,42 +491,55 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
             P.side.keys[idx] = h;
             atomicAdd(&S.pushed, 1u);
         };
-        // general form: any tag width, retries when a CAS is lost
-        auto insert_general = [&](uint64_t h) {
-            const uint32_t bsm = slots_s + ((((uint32_t)(h >> rbits)) & ((1u << kTileBucketsLog2) - 1)) << 5);
-            const uint64_t want = (h & rmask) | probe1;
-            bool park = false;
-            for (int attempt = 0;; attempt++) {
-                uint64_t w0, w1, w2, w3;
-                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(bsm));
-                asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "r"(bsm + 16));
-                const bool m0 = (w0 & tagmask) == want, m1 = (w1 & tagmask) == want, m2 = (w2 & tagmask) == want, m3 = (w3 & tagmask) == want;
-                if (m0 | m1 | m2 | m3) {
-                    const uint32_t hit = m0 ? 0u : m1 ? 8u : m2 ? 16u : 24u;
-                    const uint32_t seen_hi = (uint32_t)((m0 ? w0 : m1 ? w1 : m2 ? w2 : w3) >> 32);
-                    if ((seen_hi >> cshift_hi) < safe_below) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(bsm + hit + 4), "r"(inc_hi) : "memory");
-                    else park = true;
-                    break;
-                }
-                if (w3 != 0 || attempt >= 6) { // home bucket full (or a pathological CAS storm)
+        // general form: any tag width, retries when a CAS is lost, and follows the probe sequence while it
+        // stays inside the tile (probe j looks at bucket home + j(j+1)/2, table.cuh): at load 0.56 one key in
+        // 120 finds its home bucket full, and all but a few of those find room one or three buckets on
+        auto insert_general = [&](uint64_t h, uint32_t j0) {
+            const uint32_t home = ((uint32_t)(h >> rbits)) & ((1u << kTileBucketsLog2) - 1);
+            bool park = false, done = false;
+            for (uint32_t j = j0; j < (uint32_t)kTileProbes && !done && !park; j++) {
+                const uint32_t bucket = home + ((j * (j + 1)) >> 1);
+                if (bucket >= (1u << kTileBucketsLog2)) { // the probe leaves the tile
                     park = true;
                     break;
                 }
-                const uint32_t emp = w0 == 0 ? 0u : w1 == 0 ? 8u : w2 == 0 ? 16u : 24u;
-                unsigned long long old;
-                asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(bsm + emp), "l"(0ULL), "l"(want | one) : "memory");
-                if (old == 0) {
-                    my_new++;
-                    break;
-                } // else: somebody took the slot (maybe for this very key); look at the bucket again
+                const uint32_t bsm = slots_s + (bucket << 5);
+                const uint64_t want = (h & rmask) | ((uint64_t)(j + 1) << rbits);
+                for (int attempt = 0;; attempt++) {
+                    uint64_t w0, w1, w2, w3;
+                    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "r"(bsm));
+                    asm volatile("ld.shared.v2.u64 {%0, %1}, [%2];" : "=l"(w2), "=l"(w3) : "r"(bsm + 16));
+                    const bool m0 = (w0 & tagmask) == want, m1 = (w1 & tagmask) == want, m2 = (w2 & tagmask) == want, m3 = (w3 & tagmask) == want;
+                    if (m0 | m1 | m2 | m3) {
+                        const uint32_t hit = m0 ? 0u : m1 ? 8u : m2 ? 16u : 24u;
+                        const uint32_t seen_hi = (uint32_t)((m0 ? w0 : m1 ? w1 : m2 ? w2 : w3) >> 32);
+                        if ((seen_hi >> cshift_hi) < safe_below) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(bsm + hit + 4), "r"(inc_hi) : "memory");
+                        else park = true;
+                        done = true;
+                        break;
+                    }
+                    if (w3 != 0) break; // this bucket is full and does not hold the key: next probe
+                    if (attempt >= 6) { // a pathological CAS storm
+                        park = true;
+                        break;
+                    }
+                    const uint32_t emp = w0 == 0 ? 0u : w1 == 0 ? 8u : w2 == 0 ? 16u : 24u;
+                    unsigned long long old;
+                    asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(bsm + emp), "l"(0ULL), "l"(want | one) : "memory");
+                    if (old == 0) {
+                        my_new++;
+                        done = true;
+                        break;
+                    } // else: somebody took the slot (maybe for this very key); look at the bucket again
+                }
             }
-            if (park) park_key(h);
+            if (park || !done) park_key(h);
         };
         // TAG32: rem + probe live in the low word, so does the "occupied" test (probe >= 1); one
         // straight-line pass covers a hit, a claim and a full bucket; only a lost CAS re-reads.
         auto insert_one = [&](uint64_t h) {
             if (!TAG32) {
-                insert_general(h);
+                insert_general(h, 0);
                 return;
             }
             const uint32_t bsm = slots_s + ((((uint32_t)(h >> rbits)) & ((1u << kTileBucketsLog2) - 1)) << 5);
@@ -534,15 +555,15 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
                 else park_key(h);
                 return;
             }
-            if (l3 != 0) { // home bucket full
-                park_key(h);
+            if (l3 != 0) { // home bucket full: on along the probe sequence
+                insert_general(h, 1);
                 return;
             }
             const uint32_t emp = l0 == 0 ? 0u : l1 == 0 ? 8u : l2 == 0 ? 16u : 24u;
             unsigned long long old;
             asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(bsm + emp), "l"(0ULL), "l"(((uint64_t)inc_hi << 32) | want32) : "memory");
             if (old == 0) my_new++;
-            else insert_general(h); // lost the slot: look again
+            else insert_general(h, 0); // lost the slot: look again
         };
         for (uint32_t q = 0; q < P.parts; q++) {
             const uint32_t n = len[q];

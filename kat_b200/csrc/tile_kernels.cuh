@@ -6,9 +6,26 @@
 
 namespace katgpu {
 
-constexpr int kBinTile = 4096;        // k-mer start positions per tile of the level-1 kernel (256 threads x 16)
+constexpr int kBinTile = 4096;        // keys (k-mer starts) per tile of the route / hashed-key binning kernels
 constexpr int kBinGroups = kBinTile / 16;
-constexpr int kBin1Threads = 256;
+// bin_bases_kernel comes in two shapes (KATGPU_BIN1_WIDE):
+//   0  256 threads x 16 k-mer starts, 4 KiB tiles, two CTAs per SM (16 warps), 32-byte granules;
+//   1  1024 threads x 8 starts, 8 KiB tiles, one CTA per SM (32 warps, <= 64 registers): twice the warps for the
+//      latency-bound extraction loop, and a ring deep enough (16 keys per bin and tile) for 64-byte granules,
+//      i.e. half the scattered-write requests.
+#ifndef KATGPU_BIN1_WIDE
+#define KATGPU_BIN1_WIDE 0
+#endif
+#if KATGPU_BIN1_WIDE
+constexpr int kBin1Tile = 8192, kBin1Threads = 1024, kBin1PerThread = 8;
+#define KATGPU_BIN1_MIN_CTAS 1
+#ifndef KATGPU_BIN1_GRANULE
+#define KATGPU_BIN1_GRANULE 8
+#endif
+#else
+constexpr int kBin1Tile = 4096, kBin1Threads = 256, kBin1PerThread = 16;
+#endif
+constexpr int kBin1Groups = kBin1Tile / 16;
 #ifndef KATGPU_BIN1_MIN_CTAS
 #define KATGPU_BIN1_MIN_CTAS 2
 #endif
@@ -54,6 +71,7 @@ constexpr uint32_t kBinHGranule = KATGPU_BINH_GRANULE; // level-1 segments writt
 constexpr uint32_t kBin2Granule = KATGPU_BIN2_GRANULE; // level-2 (per-tile) segments
 constexpr int kTileBucketsLog2 = 11;  // a table tile = 2048 buckets = 8192 slots = 64 KB
 constexpr int kTileBytes = (1 << kTileBucketsLog2) * 32;
+constexpr int kTileProbes = 4;        // probes (home, +1, +3, +6 buckets) the tile kernel follows before it parks a key
 constexpr int kMaxBins = 1024;        // fan-out of one binning pass
 constexpr int kTileHllBits = 10;      // HyperLogLog registers of the level-1 kernel (as partition_kernel)
 constexpr int kTileHllM = 1 << kTileHllBits;
