@@ -494,10 +494,13 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
         // general form: any tag width, retries when a CAS is lost, and follows the probe sequence while it
         // stays inside the tile (probe j looks at bucket home + j(j+1)/2, table.cuh): at load 0.56 one key in
         // 120 finds its home bucket full, and all but a few of those find room one or three buckets on
-        auto insert_general = [&](uint64_t h, uint32_t j0) {
+        // In the key loop only the home bucket is looked at (j_end = 1): a lane that walked on would hold its
+        // whole warp back (one warp iteration in four has such a lane at load 0.56: measured 43 -> 80 ms).
+        // Keys that need more are parked in shared memory and finished after the loop, densely, by all threads.
+        auto insert_general = [&](uint64_t h, uint32_t j0, uint32_t j_end) {
             const uint32_t home = ((uint32_t)(h >> rbits)) & ((1u << kTileBucketsLog2) - 1);
-            bool park = false, done = false;
-            for (uint32_t j = j0; j < (uint32_t)kTileProbes && !done && !park; j++) {
+            bool park = j0 >= j_end, done = false;
+            for (uint32_t j = j0; j < j_end && !done && !park; j++) {
                 const uint32_t bucket = home + ((j * (j + 1)) >> 1);
                 if (bucket >= (1u << kTileBucketsLog2)) { // the probe leaves the tile
                     park = true;
@@ -539,7 +542,7 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
         // straight-line pass covers a hit, a claim and a full bucket; only a lost CAS re-reads.
         auto insert_one = [&](uint64_t h) {
             if (!TAG32) {
-                insert_general(h, 0);
+                insert_general(h, 0, 1);
                 return;
             }
             const uint32_t bsm = slots_s + ((((uint32_t)(h >> rbits)) & ((1u << kTileBucketsLog2) - 1)) << 5);
@@ -555,15 +558,15 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
                 else park_key(h);
                 return;
             }
-            if (l3 != 0) { // home bucket full: on along the probe sequence
-                insert_general(h, 1);
+            if (l3 != 0) { // home bucket full: parked, finished after the loop
+                park_key(h);
                 return;
             }
             const uint32_t emp = l0 == 0 ? 0u : l1 == 0 ? 8u : l2 == 0 ? 16u : 24u;
             unsigned long long old;
             asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(bsm + emp), "l"(0ULL), "l"(((uint64_t)inc_hi << 32) | want32) : "memory");
             if (old == 0) my_new++;
-            else insert_general(h, 0); // lost the slot: look again
+            else insert_general(h, 0, 1); // lost the slot: look again
         };
         for (uint32_t q = 0; q < P.parts; q++) {
             const uint32_t n = len[q];
@@ -580,6 +583,23 @@ __global__ void __launch_bounds__(kTileThreads, KATGPU_TILE_MIN_CTAS) tile_inser
             }
         }
         __syncthreads();
+        { // second chance for the parked keys: the probe sequence inside the tile, then the side list
+            const uint32_t n_park = min(S.park_n, kParkCap);
+            constexpr uint32_t kMine = (kParkCap + kTileThreads - 1) / kTileThreads;
+            uint64_t mine[kMine];
+#pragma unroll
+            for (uint32_t u = 0; u < kMine; u++) {
+                const uint32_t i = tid + u * kTileThreads;
+                mine[u] = i < n_park ? S.park[i] : 0;
+            }
+            __syncthreads();
+            if (tid == 0) S.park_n = 0; // survivors are collected in the same buffer
+            __syncthreads();
+#pragma unroll
+            for (uint32_t u = 0; u < kMine; u++)
+                if (tid + u * kTileThreads < n_park) insert_general(mine[u], 0, (uint32_t)kTileProbes);
+            __syncthreads();
+        }
         const uint32_t parked = min(S.park_n, kParkCap);
         if (tid == 0) {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

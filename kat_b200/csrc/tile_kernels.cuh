@@ -14,7 +14,7 @@ constexpr int kBinGroups = kBinTile / 16;
 //      latency-bound extraction loop, and a ring deep enough (16 keys per bin and tile) for 64-byte granules,
 //      i.e. half the scattered-write requests.
 #ifndef KATGPU_BIN1_WIDE
-#define KATGPU_BIN1_WIDE 0
+#define KATGPU_BIN1_WIDE 1
 #endif
 #if KATGPU_BIN1_WIDE
 constexpr int kBin1Tile = 8192, kBin1Threads = 1024, kBin1PerThread = 8;
