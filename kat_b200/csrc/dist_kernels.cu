@@ -102,18 +102,20 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
                 tma_load_1d(S.ascii, P.bases + (uint64_t)nt * kBinTile, kBinTile + kHalo, &S.mbar);
             }
         }
-        // 16 k-mers per thread, kept in registers until every key of the tile has its place
-        const uint64_t p0 = tile_base + (uint64_t)tid * 16;
-        const uint64_t bad48 = ((uint64_t)Bb[tid] << 32) | ((uint64_t)Bb[tid + 1] << 16) | Bb[tid + 2];
+        // kRoutePerThread k-mers per thread, kept in registers until every key of the tile has its place; a thread
+        // owns (half of) one 16-base group and sees its 48-base window
+        const uint32_t grp = kRoutePerThread == 16 ? (uint32_t)tid : ((uint32_t)tid & (uint32_t)(kBinGroups - 1));
+        const bool second_half = kRoutePerThread != 16 && (uint32_t)tid >= (uint32_t)kBinGroups; // warp-uniform
+        const uint64_t p0 = tile_base + (uint64_t)grp * 16;
+        const uint64_t bad48 = ((uint64_t)Bb[grp] << 32) | ((uint64_t)Bb[grp + 1] << 16) | Bb[grp + 2];
         const uint32_t nst = p0 >= P.n_starts ? 0u : (uint32_t)min((uint64_t)16, P.n_starts - p0);
         Cut16 cut;
-        cut.init(Wb[tid], Wb[tid + 1], Wb[tid + 2], bad48, k, nst);
-        uint64_t hk[16];
-        uint32_t meta[8]; // two keys per word: bit 15 valid, bits 12-14 owner, bits 0-11 rank inside the owner's run
+        cut.init(Wb[grp], Wb[grp + 1], Wb[grp + 2], bad48, k, nst);
+        uint64_t hk[kRoutePerThread];
+        uint32_t meta[kRoutePerThread / 2]; // two keys per word: bit 15 valid, bits 12-14 owner, bits 0-11 rank inside the owner's run
 #pragma unroll
-        for (uint32_t r = 0; r < 8; r++) meta[r] = 0;
-#pragma unroll
-        for (uint32_t r = 0; r < 16; r++) {
+        for (uint32_t i = 0; i < (uint32_t)kRoutePerThread / 2; i++) meta[i] = 0;
+        auto one = [&](uint32_t r, uint32_t i) { // r = start inside the group, i = slot in this thread's registers: both constants after unrolling
             uint32_t lo, hi;
             cut.key<CANON, WIDE>(r, kmask_lo, kmask_hi, lo, hi);
             const uint64_t h = mix_words<WIDE>(lo, hi, sh, kmask_lo, kmask_hi);
@@ -124,8 +126,15 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
             uint32_t base = 0;
             if (ok && (int)lane == leader) base = atomicAdd(&S.cnt[o], (uint32_t)__popc(peers));
             base = __shfl_sync(0xffffffffu, base, leader);
-            hk[r] = h;
-            if (ok) meta[r >> 1] |= (0x8000u | (o << 12) | (base + (uint32_t)__popc(peers & lt_mask))) << (16 * (r & 1));
+            hk[i] = h;
+            if (ok) meta[i >> 1] |= (0x8000u | (o << 12) | (base + (uint32_t)__popc(peers & lt_mask))) << (16 * (i & 1));
+        };
+        if (!second_half) {
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)kRoutePerThread; i++) one(i, i);
+        } else {
+#pragma unroll
+            for (uint32_t i = 0; i < (uint32_t)kRoutePerThread; i++) one(16 - kRoutePerThread + i, i);
         }
         __syncthreads();
         if (tid == 0) {
@@ -146,7 +155,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
             if (j < S.nc[d]) S.pool[S.off[d] + j] = S.carry[d][j];
         }
 #pragma unroll
-        for (uint32_t r = 0; r < 16; r++) {
+        for (uint32_t r = 0; r < (uint32_t)kRoutePerThread; r++) {
             const uint32_t m = (meta[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
             const uint32_t d = (m >> 12) & 7u;
             if (m & 0x8000u) S.pool[S.off[d] + S.nc[d] + (m & 0xFFFu)] = hk[r];

@@ -9,7 +9,13 @@
 
 namespace katgpu {
 
-constexpr int kRouteThreads = 256; // x 16 k-mer starts = one kBinTile of the base stream per iteration
+// 512 threads x 8 k-mer starts = one kBinTile of the base stream per iteration; two CTAs per SM = 32 warps
+// (the extraction loop is latency bound: the same change took bin_bases_kernel from 57.3 to 52.1 ms)
+#ifndef KATGPU_ROUTE_PER_THREAD
+#define KATGPU_ROUTE_PER_THREAD 8
+#endif
+constexpr int kRoutePerThread = KATGPU_ROUTE_PER_THREAD; // 8 or 16
+constexpr int kRouteThreads = kBinTile / kRoutePerThread;
 
 // Owner rank of a hashed key (any rank count 1..kMaxRanks; independent of the bucket bits).
 // Same function as table.cuh owner_of; restated in kat_b200/routing.py for the CPU tests.
