@@ -160,7 +160,11 @@ extern "C" katgpu_status katgpu_dist_init(katgpu_ctx *c, int rank, int n_ranks, 
     // of base stream per round keeps it at 16 GiB whatever N.
     uint64_t round_mb = std::max(128, std::min(512, 1024 / n_ranks));
     if (const char *e = getenv("KATGPU_DIST_ROUND_MB")) round_mb = std::max(1, atoi(e));
-    d->grid = (uint32_t)(c->sm_count * d->bps_route);
+    // ONE route CTA per SM (512 threads, 58 registers, 47 KB): the other half of the SM belongs to the owner-side
+    // binning of the previous round (KATGPU_DIST_ROUTE_CTAS=2 gives the route kernel the whole SM instead)
+    int route_ctas = 1;
+    if (const char *e = getenv("KATGPU_DIST_ROUTE_CTAS")) route_ctas = std::max(1, std::min(atoi(e), d->bps_route));
+    d->grid = (uint32_t)(c->sm_count * route_ctas);
     const uint64_t tiles = ((round_mb << 20) + kBinTile - 1) / kBinTile;
     const uint64_t tiles_per_cta = (tiles + d->grid - 1) / d->grid;
     d->round_positions = tiles_per_cta * d->grid * (uint64_t)kBinTile;
@@ -369,13 +373,10 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
             D.shift = t->g.b - t->pend_Pb;
             D.mask = (1u << t->pend_Pb) - 1;
             D.F = 1u << t->pend_Pb;
-            // bin_hashed_kernel runs one 1024-thread CTA per SM: its staging ring may take most of the shared memory
-            const size_t ringh_bytes = ((size_t)190 << 10) - kTileHllM * 4;
-            uint32_t cpf = 3; // tiles between two flushes: as many as the ring takes with 3.5 sigma of head room (as sweep_tiled does for level 2)
-            for (; cpf > 1; cpf--) {
-                const double mean = (double)(kBinTile * cpf) / D.F;
-                if (((double)kBinHGranule + mean + 3.5 * std::sqrt(mean) + 1.0) * D.F * 8.0 + D.F * 8.0 + 16.0 <= (double)ringh_bytes) break;
-            }
+            // bin_hashed_kernel<512>: one CTA per SM on HALF an SM (<= 64 registers, <= 100 KB), beside the route
+            // kernel's one CTA per SM
+            const size_t ringh_bytes = ((size_t)100 << 10) - kTileHllM * 4;
+            const uint32_t cpf = 1;
             D.R = ring_slots(D.F, kBinTile * cpf, ringh_bytes, kBinHGranule);
             BinKeysParams B{};
             B.g = t->g;

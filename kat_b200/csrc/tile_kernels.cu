@@ -296,7 +296,11 @@ __global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(c
 }
 
 // ---- level 1 of keys that are already hashed (received from other ranks): keys -> level-1 segments ---
-__global__ void __launch_bounds__(kBin2Threads, 1) bin_hashed_kernel(const __grid_constant__ BinKeysParams P) {
+// Two shapes: 1024 threads (one CTA owns an SM; the single-GPU flat source) and 512 threads with at most 64
+// registers (multi-GPU rounds: half an SM, so that the route kernel of the NEXT round — one 512-thread CTA per
+// SM, NVLink bound from 4 GPUs on — runs beside it instead of leaving the SMs idle).
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2) bin_hashed_kernel(const __grid_constant__ BinKeysParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint32_t *hll = reinterpret_cast<uint32_t *>(smem_raw); // [kTileHllM]
     const TableGeom &g = P.g;
@@ -304,10 +308,10 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_hashed_kernel(const __gri
     SideTally tally;
     BinCore<kBinHGranule> C1; // per-CTA destination segments; one CTA per SM, so its ring may use most of the shared memory
     C1.init(P.dst, blockIdx.x, smem_raw + kTileHllM * 4);
-    for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads) hll[i] = 0;
+    for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += THREADS) hll[i] = 0;
     __syncthreads();
     const uint32_t sshift = P.dst.shift - kTileHllSampleShift;
-    constexpr int kU = kBinTile / kBin2Threads; // keys per thread per tile of kBinTile keys; host: P.tile_keys == kBinTile * P.cpf sizes the ring
+    constexpr int kU = kBinTile / THREADS; // keys per thread per tile of kBinTile keys; host: P.tile_keys == kBinTile * P.cpf sizes the ring
     // tiles first, first + step, ... of `n` keys at `keys`
     const uint32_t cpf = P.cpf ? P.cpf : 1u; // tiles binned between two flushes (the ring is sized for them)
     uint32_t since_flush = 0;
@@ -315,17 +319,21 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_hashed_kernel(const __gri
         const uint64_t n_tiles = (n + kBinTile - 1) / kBinTile;
         for (uint64_t tile = first; tile < n_tiles; tile += step) {
             const uint64_t lo = tile * kBinTile;
-            uint64_t kc[kU];
+            constexpr int kSub = 4; // keys per thread whose loads are in flight together
+#pragma unroll 1
+            for (int u0 = 0; u0 < kU; u0 += kSub) {
+                uint64_t kc[kSub];
 #pragma unroll
-            for (int u = 0; u < kU; u++) { // every load in flight before the first key is binned
-                const uint64_t i = lo + (uint64_t)u * kBin2Threads + tid;
-                kc[u] = i < n ? __ldg(keys + i) : 0;
-            }
+                for (int u = 0; u < kSub; u++) { // every load of the batch in flight before its first key is binned
+                    const uint64_t i = lo + (uint64_t)(u0 + u) * THREADS + tid;
+                    kc[u] = i < n ? __ldg(keys + i) : 0;
+                }
 #pragma unroll
-            for (int u = 0; u < kU; u++) {
-                if (lo + (uint64_t)u * kBin2Threads + tid < n) {
-                    C1.append(kc[u], P.side, g, tally);
-                    hll_sample(hll, kc[u], sshift);
+                for (int u = 0; u < kSub; u++) {
+                    if (lo + (uint64_t)(u0 + u) * THREADS + tid < n) {
+                        C1.append(kc[u], P.side, g, tally);
+                        hll_sample(hll, kc[u], sshift);
+                    }
                 }
             }
             if (++since_flush >= cpf) {
@@ -340,7 +348,7 @@ __global__ void __launch_bounds__(kBin2Threads, 1) bin_hashed_kernel(const __gri
         for (uint32_t sgm = blockIdx.x; sgm < P.n_src; sgm += gridDim.x) bin_tiles(P.seg_keys + (size_t)sgm * P.seg_cap, P.seg_len[sgm], 0, 1);
     C1.flush(true, P.side, g, tally);
     C1.store_lengths();
-    for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += kBin2Threads)
+    for (uint32_t i = tid; i < (uint32_t)kTileHllM; i += THREADS)
         if (hll[i]) atomicMax(P.hll + i, hll[i]);
     tally_flush(g, tally);
 }
@@ -676,7 +684,8 @@ cudaError_t tile_configure(int *bps_bases, int *bps_tile) {
     if ((e = cudaFuncSetAttribute(bin_bases_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(bin_bases_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(bin_keys_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
-    if ((e = cudaFuncSetAttribute(bin_hashed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(bin_hashed_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(bin_hashed_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, big)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tile_insert_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem))) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(tile_insert_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(TileSmem))) != cudaSuccess) return e;
     *bps_bases = kBin1MinCtas; // the host sizes the staging ring so that this many CTAs fit an SM
@@ -695,7 +704,8 @@ void launch_bin_bases(const BinBasesParams &P, int grid, cudaStream_t st) {
     else bin_bases_kernel<false, false><<<grid, kBin1Threads, smem, st>>>(P);
 }
 void launch_bin_keys(const BinKeysParams &P, int grid, cudaStream_t st) {
-    if (P.in_keys || P.seg_keys) bin_hashed_kernel<<<grid, kBin2Threads, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
+    if (P.seg_keys) bin_hashed_kernel<512><<<grid, 512, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
+    else if (P.in_keys) bin_hashed_kernel<1024><<<grid, 1024, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
     else bin_keys_kernel<<<grid, kBin2Threads, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
 }
 void launch_tile_insert(const TileParams &P, int grid, cudaStream_t st) {
