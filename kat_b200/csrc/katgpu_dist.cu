@@ -160,9 +160,8 @@ extern "C" katgpu_status katgpu_dist_init(katgpu_ctx *c, int rank, int n_ranks, 
     // of base stream per round keeps it at 16 GiB whatever N.
     uint64_t round_mb = std::max(128, std::min(512, 1024 / n_ranks));
     if (const char *e = getenv("KATGPU_DIST_ROUND_MB")) round_mb = std::max(1, atoi(e));
-    // ONE route CTA per SM (512 threads, 58 registers, 47 KB): the other half of the SM belongs to the owner-side
-    // binning of the previous round (KATGPU_DIST_ROUTE_CTAS=2 gives the route kernel the whole SM instead)
-    int route_ctas = 1;
+    // two route CTAs per SM (512 threads, 58 registers, 47 KB each); KATGPU_DIST_ROUTE_CTAS=1 leaves half of every SM free
+    int route_ctas = d->bps_route;
     if (const char *e = getenv("KATGPU_DIST_ROUTE_CTAS")) route_ctas = std::max(1, std::min(atoi(e), d->bps_route));
     d->grid = (uint32_t)(c->sm_count * route_ctas);
     const uint64_t tiles = ((round_mb << 20) + kBinTile - 1) / kBinTile;
@@ -373,10 +372,15 @@ static katgpu_status route_round(katgpu_table *t, const uint8_t *dev, uint64_t n
             D.shift = t->g.b - t->pend_Pb;
             D.mask = (1u << t->pend_Pb) - 1;
             D.F = 1u << t->pend_Pb;
-            // bin_hashed_kernel<512>: one CTA per SM on HALF an SM (<= 64 registers, <= 100 KB), beside the route
-            // kernel's one CTA per SM
-            const size_t ringh_bytes = ((size_t)100 << 10) - kTileHllM * 4;
-            const uint32_t cpf = 1;
+            // bin_hashed_kernel: one 1024-thread CTA per SM, its staging ring may take most of the shared memory;
+            // as many tiles between two flushes as the ring takes with 3.5 sigma of head room
+            const bool half_sm = getenv("KATGPU_BINH_THREADS") && atoi(getenv("KATGPU_BINH_THREADS")) == 512;
+            const size_t ringh_bytes = ((size_t)(half_sm ? 100 : 190) << 10) - kTileHllM * 4;
+            uint32_t cpf = half_sm ? 1 : 3;
+            for (; cpf > 1; cpf--) {
+                const double mean = (double)(kBinTile * cpf) / D.F;
+                if (((double)kBinHGranule + mean + 3.5 * std::sqrt(mean) + 1.0) * D.F * 8.0 + D.F * 8.0 + 16.0 <= (double)ringh_bytes) break;
+            }
             D.R = ring_slots(D.F, kBinTile * cpf, ringh_bytes, kBinHGranule);
             BinKeysParams B{};
             B.g = t->g;

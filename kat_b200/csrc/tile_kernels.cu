@@ -23,6 +23,8 @@
 // Replaces the same reference loop as count_kernels.cu (lib/src/jellyfish_helper.cc:202-211,
 // JFI/hash_counter.hpp:98-130, JFI/large_hash_array.hpp:298-302).
 #include "tile_kernels.cuh"
+
+#include <cstdlib>
 #include "extract.cuh"
 
 namespace katgpu {
@@ -296,9 +298,11 @@ __global__ void __launch_bounds__(kBin1Threads, kBin1MinCtas) bin_bases_kernel(c
 }
 
 // ---- level 1 of keys that are already hashed (received from other ranks): keys -> level-1 segments ---
-// Two shapes: 1024 threads (one CTA owns an SM; the single-GPU flat source) and 512 threads with at most 64
-// registers (multi-GPU rounds: half an SM, so that the route kernel of the NEXT round — one 512-thread CTA per
-// SM, NVLink bound from 4 GPUs on — runs beside it instead of leaving the SMs idle).
+// Two shapes: 1024 threads (one CTA owns an SM: the default) and 512 threads with at most 64 registers (half an
+// SM, so that the route kernel of the NEXT round — NVLink bound from 4 GPUs on — could run beside it).  The half-SM
+// pair was measured and lost: 4 GPUs 354 ms per step against 258 with whole-SM kernels that alternate (the small
+// ring of the half-SM binning costs more than the idle SMs it fills); it stays selectable for experiments
+// (KATGPU_BINH_THREADS=512 KATGPU_DIST_ROUTE_CTAS=1).
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2) bin_hashed_kernel(const __grid_constant__ BinKeysParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -704,8 +708,10 @@ void launch_bin_bases(const BinBasesParams &P, int grid, cudaStream_t st) {
     else bin_bases_kernel<false, false><<<grid, kBin1Threads, smem, st>>>(P);
 }
 void launch_bin_keys(const BinKeysParams &P, int grid, cudaStream_t st) {
-    if (P.seg_keys) bin_hashed_kernel<512><<<grid, 512, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
-    else if (P.in_keys) bin_hashed_kernel<1024><<<grid, 1024, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
+    // (KATGPU_BINH_THREADS=512: the half-SM shape, measured slower — see the comment at the kernel)
+    static const bool half = getenv("KATGPU_BINH_THREADS") && atoi(getenv("KATGPU_BINH_THREADS")) == 512;
+    if (P.seg_keys && half) bin_hashed_kernel<512><<<grid, 512, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
+    else if (P.in_keys || P.seg_keys) bin_hashed_kernel<1024><<<grid, 1024, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
     else bin_keys_kernel<<<grid, kBin2Threads, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
 }
 void launch_tile_insert(const TileParams &P, int grid, cudaStream_t st) {
