@@ -769,13 +769,13 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
         // keys binned between two flushes of bin_keys_kernel and its ring (one CTA per SM, <= 200 KB)
         // keys bin_keys_kernel bins between two flushes: as many chunks as its ring (one CTA per SM) can take
         // without cutting into the 4-sigma head room
-        const size_t ring2_bytes = (196u << 10) - kTileHllM * 4;
-        uint32_t cpf = (uint32_t)kBin2MaxCpf;
+        const size_t ring2_bytes = (196u << 10) - kBin2StageBytes;
+        uint32_t cpf = (uint32_t)kBin2MaxCpf * 2; // in pieces of kBin2Piece keys
         for (; cpf > 1; cpf--) {
-            const double mean = (double)(kBin2Threads * kBin2Unroll * cpf) / F2;
+            const double mean = (double)(kBin2Piece * cpf) / F2;
             if (((double)kBin2Granule + mean + 3.5 * std::sqrt(mean) + 1.0) * F2 * 8.0 + F2 * 8.0 + 16.0 <= (double)ring2_bytes) break; // (ring_slots then takes what fits: >= 3.5 sigma)
         }
-        const uint32_t tile2 = kBin2Threads * kBin2Unroll * cpf;
+        const uint32_t tile2 = kBin2Piece * cpf;
         const uint32_t ring2 = ring_slots(F2, tile2, ring2_bytes, kBin2Granule);
         if (getenv("KATGPU_TRACE"))
             fprintf(stderr, "[katgpu] sweep_tiled: F1=%u F2=%u slices/group=%u parts=%u cap2=%llu ring1=%u ring2=%u tile2=%u level-2 buffer %.1f MB side cap %llu\n",

@@ -358,46 +358,87 @@ __global__ void __launch_bounds__(THREADS, 2048 / THREADS / 2) bin_hashed_kernel
 }
 
 // ---- B2: the level-1 segments of one slice, one share of them per CTA -> per-tile segments --------
+// The keys arrive through a ring of TMA bulk copies (one elected thread issues them kBin2Stages - 1 pieces
+// ahead; full / empty mbarriers), so no warp ever waits on a global load and no register holds a prefetched key.
+struct B2Cursor {
+    uint32_t s, base, len;
+    const uint64_t *src;
+};
 __global__ void __launch_bounds__(kBin2Threads, 1) bin_keys_kernel(const __grid_constant__ BinKeysParams P) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    uint64_t(*kbuf)[kBin2Piece] = reinterpret_cast<uint64_t(*)[kBin2Piece]>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kBin2Stages * kBin2Piece * 8), *empty = full + kBin2Stages;
     const TableGeom &g = P.g;
     const uint32_t tid = threadIdx.x;
     SideTally tally;
     BinCore<kBin2Granule> C;
     const uint32_t s_local = blockIdx.x / P.parts, q = blockIdx.x % P.parts;
-    C.init(P.dst, (s_local * P.dst.F) * P.parts + q, smem_raw + kTileHllM * 4);
-    __syncthreads();
+    C.init(P.dst, (s_local * P.dst.F) * P.parts + q, smem_raw + kBin2StageBytes);
     const uint32_t seg_lo = (uint32_t)(((uint64_t)P.src_segs * q) / P.parts), seg_hi = (uint32_t)(((uint64_t)P.src_segs * (q + 1)) / P.parts);
-    // Chunks of kBin2Unroll keys per thread: every load of a chunk is in flight before the
-    // first key is binned, and the next chunk is requested before this one is flushed.
-    const uint32_t chunk = kBin2Threads * kBin2Unroll; // x P.cpf == P.tile_keys (host)
-    uint32_t since_flush = 0;                          // chunks in the ring since the last flush
-    uint64_t kn[kBin2Unroll];
-    for (uint32_t s = seg_lo; s < seg_hi; s++) {
-        const size_t sidx = (size_t)(P.first_slice + s_local) * P.src_segs + s;
-        const uint32_t len = P.src_len[sidx];
-        const uint64_t *src = P.src_keys + sidx * P.src_cap;
-        auto fetch = [&](uint32_t base) {
-#pragma unroll
-            for (int u = 0; u < kBin2Unroll; u++) {
-                const uint32_t i = base + u * kBin2Threads + tid;
-                kn[u] = i < len ? __ldg(src + i) : 0;
+    // the pieces of this CTA: every non-empty source segment in kBin2Piece-key steps (the same walk for the
+    // producer, ahead, and for the consumers)
+    auto seek = [&](B2Cursor &c) { // position on the next non-empty segment at or after c.s
+        for (; c.s < seg_hi; c.s++) {
+            const size_t sidx = (size_t)(P.first_slice + s_local) * P.src_segs + c.s;
+            c.len = P.src_len[sidx];
+            if (c.len) {
+                c.src = P.src_keys + sidx * P.src_cap;
+                c.base = 0;
+                return;
             }
-        };
-        if (KATGPU_BIN2_PREFETCH && len) fetch(0);
-        for (uint32_t base = 0; base < len; base += chunk) {
-            if (!KATGPU_BIN2_PREFETCH) fetch(base);
-            uint64_t kc[kBin2Unroll];
-#pragma unroll
-            for (int u = 0; u < kBin2Unroll; u++) kc[u] = kn[u];
-            if (KATGPU_BIN2_PREFETCH && base + chunk < len) fetch(base + chunk);
-#pragma unroll
-            for (int u = 0; u < kBin2Unroll; u++)
-                if (base + u * kBin2Threads + tid < len) C.append(kc[u], P.side, g, tally);
-            if (++since_flush >= P.cpf) { // (uniform: every thread counts the same chunks)
-                C.flush(false, P.side, g, tally);
-                since_flush = 0;
+        }
+    };
+    auto advance = [&](B2Cursor &c) {
+        c.base += kBin2Piece;
+        if (c.base >= c.len) {
+            c.s++;
+            seek(c);
+        }
+    };
+    B2Cursor cons{seg_lo, 0, 0, nullptr};
+    seek(cons);
+    B2Cursor prod = cons;
+    uint32_t issued = 0, consumed = 0, since_flush = 0;
+    if (tid == 0) {
+        for (int i = 0; i < kBin2Stages; i++) {
+            mbar_init(&full[i], 1);
+            mbar_init(&empty[i], kBin2Threads);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto issue = [&]() { // thread 0: piece number `issued` into its stage, once every thread has read the stage's previous piece
+        const uint32_t st = issued % kBin2Stages;
+        if (issued >= (uint32_t)kBin2Stages)
+            while (!mbar_try_wait(&empty[st], ((issued / kBin2Stages) - 1) & 1)) {
             }
+        const uint32_t n = min((uint32_t)kBin2Piece, prod.len - prod.base);
+        const uint32_t bytes = (n * 8 + 15) & ~15u; // (segment capacities are multiples of 16 keys: the round-up stays inside)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(&full[st], bytes);
+        tma_load_1d(kbuf[st], prod.src + prod.base, bytes, &full[st]);
+        issued++;
+        advance(prod);
+    };
+    if (tid == 0)
+        for (int i = 0; i < kBin2Stages - 1 && prod.s < seg_hi; i++) issue();
+    while (cons.s < seg_hi) {
+        if (tid == 0 && prod.s < seg_hi) issue();
+        const uint32_t st = consumed % kBin2Stages;
+        while (!mbar_try_wait(&full[st], (consumed / kBin2Stages) & 1)) {
+        }
+        const uint32_t n = min((uint32_t)kBin2Piece, cons.len - cons.base);
+        uint64_t k0 = 0, k1 = 0;
+        if (tid < n) k0 = kbuf[st][tid];
+        if (tid + kBin2Threads < n) k1 = kbuf[st][tid + kBin2Threads];
+        mbar_arrive(&empty[st]); // this thread is done with the stage
+        if (tid < n) C.append(k0, P.side, g, tally);
+        if (tid + kBin2Threads < n) C.append(k1, P.side, g, tally);
+        consumed++;
+        advance(cons);
+        if (++since_flush >= P.cpf) { // (uniform: every thread walks the same pieces)
+            C.flush(false, P.side, g, tally);
+            since_flush = 0;
         }
     }
     C.flush(true, P.side, g, tally);
@@ -679,6 +720,7 @@ __global__ void __launch_bounds__(256) insert_deferred_kernel(const __grid_const
 static size_t ring_bytes(uint32_t F, uint32_t R) { return (((size_t)F * 8 + 15) & ~(size_t)15) + (size_t)F * R * 8; }
 size_t bin_bases_smem(uint32_t F, uint32_t R) { return sizeof(BinBasesHead) + ring_bytes(F, R); }
 size_t bin_keys_smem(uint32_t F, uint32_t R) { return (size_t)kTileHllM * 4 + ring_bytes(F, R); }
+size_t bin_keys_b_smem(uint32_t F, uint32_t R) { return (size_t)kBin2StageBytes + ring_bytes(F, R); }
 
 cudaError_t tile_configure(int *bps_bases, int *bps_tile) {
     const int big = 200 << 10;
@@ -712,7 +754,7 @@ void launch_bin_keys(const BinKeysParams &P, int grid, cudaStream_t st) {
     static const bool half = getenv("KATGPU_BINH_THREADS") && atoi(getenv("KATGPU_BINH_THREADS")) == 512;
     if (P.seg_keys && half) bin_hashed_kernel<512><<<grid, 512, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
     else if (P.in_keys || P.seg_keys) bin_hashed_kernel<1024><<<grid, 1024, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
-    else bin_keys_kernel<<<grid, kBin2Threads, bin_keys_smem(P.dst.F, P.dst.R), st>>>(P);
+    else bin_keys_kernel<<<grid, kBin2Threads, bin_keys_b_smem(P.dst.F, P.dst.R), st>>>(P);
 }
 void launch_tile_insert(const TileParams &P, int grid, cudaStream_t st) {
     if (P.g.tagmask <= 0xFFFFFFFFULL) tile_insert_kernel<true><<<grid, kTileThreads, sizeof(TileSmem), st>>>(P);

@@ -45,6 +45,11 @@ constexpr int kBin2Unroll = KATGPU_BIN2_UNROLL; // keys per thread and chunk of 
 // barriers and a pass over all bins, so fewer, fuller flushes are cheaper (measured 70.9 / 59.1 / 57.6 ms
 // for 1 / 2 / 3 at 512 bins); the host picks the largest count whose ring still fits shared memory.
 constexpr int kBin2MaxCpf = KATGPU_BIN2_CPF;
+// bin_keys_kernel reads its source segments through a ring of TMA bulk copies (ncu of the register-prefetch form:
+// long-scoreboard stalls 9.9 per issue, issue active 29 %): kBin2Stages buffers of kBin2Piece keys, full/empty mbarriers.
+constexpr int kBin2Piece = 2048;
+constexpr int kBin2Stages = 3;
+constexpr int kBin2StageBytes = kBin2Stages * kBin2Piece * 8 + 64; // key buffers + 2 x kBin2Stages mbarriers
 #ifndef KATGPU_TILE_THREADS
 #define KATGPU_TILE_THREADS 384
 #endif
@@ -130,7 +135,7 @@ struct BinKeysParams {
     const uint32_t *src_len;
     uint32_t src_segs, src_cap, first_slice, parts;
     uint32_t tile_keys;       // keys binned between two flushes
-    uint32_t cpf;             // chunks (source B: of kBin2Threads * kBin2Unroll keys; sources A, C: of kBinTile keys) between two flushes
+    uint32_t cpf;             // pieces (source B: of kBin2Piece keys; sources A, C: of kBinTile keys) between two flushes
     BinDst dst;
     SideList side;
     uint32_t *hll;            // source A only
@@ -147,7 +152,8 @@ struct TileParams {
 };
 
 size_t bin_bases_smem(uint32_t F, uint32_t R);
-size_t bin_keys_smem(uint32_t F, uint32_t R);
+size_t bin_keys_smem(uint32_t F, uint32_t R);   // bin_hashed_kernel: HyperLogLog registers + ring
+size_t bin_keys_b_smem(uint32_t F, uint32_t R); // bin_keys_kernel: TMA stages + ring
 cudaError_t tile_configure(int *bps_bases, int *bps_tile);
 void launch_bin_bases(const BinBasesParams &P, int grid, cudaStream_t st);
 void launch_bin_keys(const BinKeysParams &P, int grid, cudaStream_t st);
