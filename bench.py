@@ -55,9 +55,9 @@ B_ALG = READ_LEN / KMERS_PER_READ + 16.0
 # measured DRAM bytes per k-mer instance of K1 = partition_kernel + sweep_kernel, from the ncu --set full
 # captures summarised in profiles/r1_v2_partition_sweep_ncu.txt (dram__bytes_read.sum + dram__bytes_write.sum)
 TRAFFIC_B_PER_KMER_PARTITIONED = 26.0
-# ... and of K1 = bin_bases_kernel + bin_keys_kernel + tile_insert_kernel (profiles/r1_v3_tiled_ncu.txt):
-# 9.22 (stream read once + 8 B key written) + 15.85 (key read + written) + 16.4 (key read, 64 KB tile read + written)
-TRAFFIC_B_PER_KMER_TILED = 41.5
+# ... and of K1 = bin_bases_kernel + bin_keys_kernel + tile_insert_kernel (profiles/r2_k1_walks_route_ncu.txt, 4.09 G k-mers):
+# 9.2 (stream read once + 8 B key written) + 15.5 (key read + written) + 15.7 (key read, 64 KB tiles read + written)
+TRAFFIC_B_PER_KMER_TILED = 40.4
 
 
 def measured_peaks():
@@ -742,7 +742,7 @@ def main():
                 "traffic": (TRAFFIC_B_PER_KMER_PARTITIONED * k_inst / args.steps) if fam == ["partition", "sweep"] else
                            (TRAFFIC_B_PER_KMER_TILED * k_inst / args.steps) if fam[:3] == ["bin1", "bin2", "tile"] and world == 1 else None,
                 "traffic_source": "ncu dram__bytes_read.sum+dram__bytes_write.sum of the K1 kernels at 5 Gbp, scaled per k-mer to one step "
-                                  "(profiles/r1_v3_tiled_ncu.txt; r1_v2_partition_sweep_ncu.txt for the L2-sweep path)",
+                                  "(profiles/r2_k1_walks_route_ncu.txt; r1_v2_partition_sweep_ncu.txt for the L2-sweep path)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_kmer": B_ALG, "kernel_ms_total": k_ms, "kernel_launches": k_launches, "k1_passes": k_n,
                 "kernel_ms_by_family": {f: prof[f][0] for f in fam},
