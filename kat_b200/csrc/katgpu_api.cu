@@ -1115,8 +1115,8 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
     for (int b = 0; b < ring; b++) CU(cudaEventRecord(c->chunk_free[b], c->stream));
     // With the partitioned path and a long feed, insert the first half of the keys while the
     // second half is still crossing PCIe: the copy engine keeps filling the ring during the sweep.
-    // (KATGPU_MID_SWEEPS: how many; default 2 = after each third, measured best of 0..3)
-    int mid_sweeps = 2;
+    // (KATGPU_MID_SWEEPS: how many; default 3 = after each quarter: e2e 269 / 225 / 217 / 238 ms for 1 / 2 / 3 / 4 with a 2^31-slot table)
+    int mid_sweeps = 3;
     if (const char *e = getenv("KATGPU_MID_SWEEPS")) mid_sweeps = std::max(0, std::min(atoi(e), 8));
     const bool mid_ok = n_chunks >= 16 && mid_sweeps > 0 && use_partition(t, n);
     size_t issued = 0;
