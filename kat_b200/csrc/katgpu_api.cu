@@ -1,6 +1,7 @@
-// katgpu_api.cu — C-ABI of libkatgpu (include/katgpu.h): contexts, table
-// lifetime (allocation, admission control, doubling), the host->device feed
-// pipeline and the launch glue around the kernels.
+// katgpu_api.cu — C-ABI of libkatgpu (include/katgpu.h): contexts, the device block cache, table
+// lifetime (geometry, allocation, admission control, doubling), the counting paths and the host->device
+// feed pipeline.  The raw-FASTQ feed is in katgpu_fastq.cu, the table walks in katgpu_walks.cu, the
+// multi-GPU engine in katgpu_dist.cu.
 #include "katgpu_internal.cuh"
 #include "synth.cuh"
 
@@ -1137,151 +1138,6 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
     return KATGPU_OK;
 }
 
-// ---- raw FASTQ feed: file bytes in, parsed on the device (parse_kernels.cu) ------------------------
-// Host -> device copy of pageable memory at more than one core's memcpy rate: `threads` host threads
-// copy 8 MiB pieces into pinned bounce buffers and queue the DMA of each piece themselves.
-static katgpu_status staged_h2d(katgpu_ctx *c, uint8_t *dst, const char *src, size_t n) {
-    cudaPointerAttributes at{};
-    if (cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost) { // already pinned: one DMA
-        CU(cudaMemcpyAsync(dst, src, n, cudaMemcpyHostToDevice, c->copy_stream));
-        return KATGPU_OK;
-    }
-    cudaGetLastError();
-    const size_t piece = (size_t)8 << 20;
-    const int n_bounce = 8;
-    if (!c->bounce[0]) {
-        for (int i = 0; i < n_bounce; i++) {
-            CU(cudaMallocHost((void **)&c->bounce[i], piece));
-            CU(cudaEventCreateWithFlags(&c->bounce_free[i], cudaEventDisableTiming));
-        }
-        c->bounce_bytes = piece;
-    }
-    const size_t n_pieces = (n + piece - 1) / piece;
-    int threads = 4;
-    if (const char *e = getenv("KATGPU_COPY_THREADS")) threads = std::max(1, std::min(atoi(e), n_bounce));
-    threads = (int)std::min<size_t>(threads, n_pieces);
-    std::atomic<int> failed{0};
-    auto work = [&](int tix) {
-        cudaSetDevice(c->device);
-        // thread tix owns bounce buffers tix, tix + threads, ... and pieces tix, tix + threads, ...
-        int slot = tix;
-        for (size_t i = tix; i < n_pieces && !failed.load(); i += threads) {
-            const size_t off = i * piece, len = std::min(piece, n - off);
-            if (cudaEventSynchronize(c->bounce_free[slot]) != cudaSuccess) failed = 1;
-            memcpy(c->bounce[slot], src + off, len);
-            if (cudaMemcpyAsync(dst + off, c->bounce[slot], len, cudaMemcpyHostToDevice, c->copy_stream) != cudaSuccess) failed = 1;
-            if (cudaEventRecord(c->bounce_free[slot], c->copy_stream) != cudaSuccess) failed = 1;
-            slot += threads;
-            if (slot >= n_bounce) slot = tix;
-        }
-    };
-    std::vector<std::thread> th;
-    for (int t = 1; t < threads; t++) th.emplace_back(work, t);
-    work(0);
-    for (auto &x : th) x.join();
-    if (failed.load()) return fail(KATGPU_ERR_CUDA, "staged host->device copy failed: %s", cudaGetErrorString(cudaGetLastError()));
-    return KATGPU_OK;
-}
-
-extern "C" katgpu_status katgpu_count_feed_fastq(katgpu_table *t, const char *bytes, size_t n, unsigned trim5p, int *regular) {
-    TraceScope trace__("katgpu_count_feed_fastq");
-    if (!t || !regular || (!bytes && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_feed_fastq: NULL argument");
-    if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_feed_fastq: table already finished");
-    if (n > ((size_t)1 << 30)) return fail(KATGPU_ERR_INVALID, "katgpu_count_feed_fastq: at most 1 GiB of whole records per call");
-    katgpu_ctx *c = t->ctx;
-    CU(cudaSetDevice(c->device));
-    *regular = 0;
-    // a job's feeds are collective: a rank without data still takes part (with an empty stream)
-    if (n == 0 || bytes[n - 1] != '\n') {
-        if (n == 0) *regular = 1;
-        if (c->dist) return dist_feed_device(t, nullptr, 0);
-        return KATGPU_OK;
-    }
-    if (c->raw_cap < n + 64) {
-        CU(cudaDeviceSynchronize()); // nothing reads the old buffers any more (compute, copy and route streams)
-        const size_t cap = std::max<size_t>((n + 64 + ((size_t)64 << 20) - 1) / ((size_t)64 << 20) * ((size_t)64 << 20), c->raw_cap);
-        for (int i = 0; i < 2; i++) {
-            if (c->raw[i]) pool_free(c, c->raw[i], c->raw_cap);
-            c->raw[i] = nullptr;
-        }
-        for (int i = 0; i < 2; i++) {
-            void *p = nullptr;
-            CU(pool_alloc(c, cap, &p));
-            c->raw[i] = (uint8_t *)p;
-            if (!c->raw_free[i]) CU(cudaEventCreateWithFlags(&c->raw_free[i], cudaEventDisableTiming));
-            CU(cudaEventRecord(c->raw_free[i], c->stream));
-        }
-        c->raw_cap = cap;
-    }
-    const uint32_t n_tiles = nl_tiles(n);
-    const size_t nl_need = n / 2 + 16; // the shortest regular record, "@\nA\n+\nI\n", has a newline every 2 bytes
-    if (c->nl_cap < nl_need || c->nl_tiles_cap < n_tiles) {
-        CU(cudaStreamSynchronize(c->stream));
-        if (c->nl_buf) pool_free(c, c->nl_buf, c->nl_cap * 4);
-        if (c->nl_tiles_buf) pool_free(c, c->nl_tiles_buf, c->nl_tiles_cap * 4);
-        void *p = nullptr;
-        c->nl_cap = std::max(nl_need, c->nl_cap);
-        c->nl_tiles_cap = std::max<size_t>(n_tiles, c->nl_tiles_cap);
-        CU(pool_alloc(c, c->nl_cap * 4, &p));
-        c->nl_buf = (uint32_t *)p;
-        CU(pool_alloc(c, c->nl_tiles_cap * 4, &p));
-        c->nl_tiles_buf = (uint32_t *)p;
-        if (!c->parse_flags) {
-            CU(pool_alloc(c, 256, &p));
-            c->parse_flags = (uint32_t *)p;
-        }
-    }
-    const int b = c->raw_next;
-    c->raw_next ^= 1;
-    uint8_t *raw = c->raw[b];
-    // the buffer is free once the kernels of the feed two calls back have read it
-    CU(cudaStreamWaitEvent(c->copy_stream, c->raw_free[b], 0));
-    KT(staged_h2d(c, raw, bytes, n));
-    CU(cudaEventRecord(c->chunk_ready[0], c->copy_stream));
-    CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[0], 0));
-    CU(cudaMemsetAsync(c->parse_flags, 0, 8, c->stream));
-    {
-        ProfScope ps(c, "parse", c->stream);
-        launch_nl_count(raw, n, c->nl_tiles_buf, n_tiles, c->stream);
-        launch_nl_scan(c->nl_tiles_buf, n_tiles, c->parse_flags + 1, c->stream);
-    }
-    c->launches += 2;
-    uint32_t h_flags[2] = {0, 0};
-    CU(cudaMemcpyAsync(h_flags, c->parse_flags, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaGetLastError());
-    const uint32_t n_nl = h_flags[1];
-    if (n_nl == 0 || (n_nl & 3u) || n_nl > nl_need) { // not four lines per record (or lines too short to be one)
-        CU(cudaEventRecord(c->raw_free[b], c->stream));
-        if (c->dist) return dist_feed_device(t, nullptr, 0); // the other ranks' feeds are collective: take part, with nothing
-        return KATGPU_OK;
-    }
-    {
-        ProfScope ps(c, "parse", c->stream);
-        launch_nl_scatter(raw, n, c->nl_tiles_buf, n_tiles, c->nl_buf, (uint32_t)std::min<size_t>(c->nl_cap, 0xFFFFFFFFu), c->stream);
-        launch_fastq_mask(raw, c->nl_buf, n_nl / 4, trim5p, c->parse_flags, c->sm_count * 8, c->stream);
-    }
-    c->launches += 2;
-    CU(cudaMemcpyAsync(h_flags, c->parse_flags, 4, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    CU(cudaGetLastError());
-    if (h_flags[0] != 0) { // some record is not in the regular layout: nothing was counted
-        CU(cudaEventRecord(c->raw_free[b], c->stream));
-        if (c->dist) return dist_feed_device(t, nullptr, 0);
-        return KATGPU_OK;
-    }
-    *regular = 1;
-    katgpu_status st;
-    if (c->dist) st = dist_feed_device(t, raw, n);
-    else {
-        TableCounters ctr;
-        KT(read_counters(t, ctr));
-        st = feed_device_range(t, raw, n, n, ctr, n / 2);
-    }
-    KT(st);
-    return record_feed_consumed(c, c->raw_free[b]);
-}
-
 extern "C" katgpu_status katgpu_count_reserve(katgpu_table *t, uint64_t expected_kmers) {
     if (!t) return fail(KATGPU_ERR_INVALID, "katgpu_count_reserve: NULL table");
     if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_reserve: table already finished");
@@ -1459,199 +1315,6 @@ extern "C" katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void
         CU(cudaGetLastError());
         done += granted;
         KT(settle(t, ctr));
-    }
-    return KATGPU_OK;
-}
-
-// ---- table walks ----
-static katgpu_status finished(katgpu_table *t, const char *who) {
-    if (!t) return fail(KATGPU_ERR_INVALID, "%s: NULL table", who);
-    if (!t->ended) return fail(KATGPU_ERR_STATE, "%s: call katgpu_count_end first", who);
-    return KATGPU_OK;
-}
-
-struct DevBuf { // zeroed device scratch, freed on scope exit
-    void *p = nullptr;
-    ~DevBuf() {
-        if (p) cudaFree(p);
-    }
-};
-
-extern "C" katgpu_status katgpu_hist(katgpu_table *t, uint64_t base, uint64_t ceil_, uint64_t inc, uint64_t nb,
-                                     uint64_t *bins_out) {
-    TraceScope trace__("katgpu_hist");
-    KT(finished(t, "katgpu_hist"));
-    if (!bins_out || nb == 0 || inc == 0 || nb > 0x7fffffffULL) return fail(KATGPU_ERR_INVALID, "katgpu_hist: bad arguments");
-    katgpu_ctx *c = t->ctx;
-    CU(cudaSetDevice(c->device));
-    DevBuf d;
-    CU(cudaMalloc(&d.p, nb * 8));
-    CU(cudaMemsetAsync(d.p, 0, nb * 8, c->stream));
-    {
-        ProfScope ps(c, "hist", c->stream);
-        launch_hist(t->g, t->n_slots, base, ceil_, inc, (uint32_t)nb, (unsigned long long *)d.p, c->sm_count * 4, c->stream);
-    }
-    c->launches++;
-    CU(cudaGetLastError());
-    if (c->dist) KT(dist_allreduce_u64(c, d.p, nb)); // ranks own disjoint k-mers: bins add up
-    CU(cudaMemcpyAsync(bins_out, d.p, nb * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return KATGPU_OK;
-}
-
-extern "C" katgpu_status katgpu_gcp(katgpu_table *t, double cvg_scale, uint32_t cvg_bins, uint64_t *mx_out) {
-    KT(finished(t, "katgpu_gcp"));
-    if (!mx_out) return fail(KATGPU_ERR_INVALID, "katgpu_gcp: NULL output");
-    katgpu_ctx *c = t->ctx;
-    CU(cudaSetDevice(c->device));
-    const size_t cells = (size_t)t->g.k * ((size_t)cvg_bins + 1);
-    DevBuf d;
-    CU(cudaMalloc(&d.p, cells * 8));
-    CU(cudaMemsetAsync(d.p, 0, cells * 8, c->stream));
-    {
-        ProfScope ps(c, "gcp", c->stream);
-        launch_gcp(t->g, t->n_slots, cvg_scale, cvg_bins, (unsigned long long *)d.p, c->sm_count, c->stream);
-    }
-    c->launches++;
-    CU(cudaGetLastError());
-    if (c->dist) KT(dist_allreduce_u64(c, d.p, cells));
-    CU(cudaMemcpyAsync(mx_out, d.p, cells * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return KATGPU_OK;
-}
-
-extern "C" katgpu_status katgpu_comp(katgpu_table *t1, katgpu_table *t2, katgpu_table *t3, double d1_scale,
-                                     double d2_scale, uint32_t d1_bins, uint32_t d2_bins, uint64_t *main_mx,
-                                     uint64_t *ends_mx, uint64_t *middle_mx, uint64_t *mixed_mx,
-                                     katgpu_comp_counters *counters, uint64_t *spectra) {
-    KT(finished(t1, "katgpu_comp"));
-    KT(finished(t2, "katgpu_comp"));
-    if (t3) KT(finished(t3, "katgpu_comp"));
-    if (!main_mx || !counters || !spectra || d1_bins == 0 || d2_bins == 0) return fail(KATGPU_ERR_INVALID, "katgpu_comp: bad arguments");
-    if (t3 && (!ends_mx || !middle_mx || !mixed_mx)) return fail(KATGPU_ERR_INVALID, "katgpu_comp: 3-input mode needs ends/middle/mixed outputs");
-    if (t1->g.k != t2->g.k || (t3 && t3->g.k != t1->g.k)) return fail(KATGPU_ERR_INVALID, "katgpu_comp: tables were counted with different k");
-    if (t1->ctx != t2->ctx || (t3 && t3->ctx != t1->ctx)) return fail(KATGPU_ERR_INVALID, "katgpu_comp: tables live on different contexts");
-    katgpu_ctx *c = t1->ctx;
-    // Multi-GPU: the dual-hash walk is local because both inputs place a k-mer on the same owner rank.
-    // That holds for the stored k-mer; a probe that re-canonicalises a non-canonical stored k-mer
-    // (src/comp.cc:400,447) may belong to another rank.
-    if (c->dist && !(t1->g.canonical && t2->g.canonical && (!t3 || t3->g.canonical)))
-        return fail(KATGPU_ERR_INVALID, "katgpu_comp: on a multi-GPU context every input must be counted canonically");
-    CU(cudaSetDevice(c->device));
-    const uint32_t len = std::min(d1_bins, d2_bins);
-    const size_t cells = (size_t)d1_bins * d2_bins;
-    const size_t n_mx = t3 ? 4 : 1;
-    const size_t words = n_mx * cells + 16 + 4 * (size_t)len;
-    DevBuf d;
-    CU(cudaMalloc(&d.p, words * 8));
-    CU(cudaMemsetAsync(d.p, 0, words * 8, c->stream));
-    unsigned long long *base = (unsigned long long *)d.p;
-    CompParams P{};
-    P.d1_scale = d1_scale;
-    P.d2_scale = d2_scale;
-    P.d1_bins = d1_bins;
-    P.d2_bins = d2_bins;
-    P.len = len;
-    P.main_mx = base;
-    P.ends_mx = t3 ? base + cells : nullptr;
-    P.middle_mx = t3 ? base + 2 * cells : nullptr;
-    P.mixed_mx = t3 ? base + 3 * cells : nullptr;
-    P.counters = base + n_mx * cells;
-    unsigned long long *spec = P.counters + 16;
-    const int grid = c->sm_count * 2;
-    {
-        ProfScope ps(c, "comp", c->stream);
-        // pass 1: walk hash1, probe hash2 (canonicalised iff input 2 is canonical, src/comp.cc:400) and hash3
-        P.pass = 1;
-        P.ga = t1->g;
-        P.n_slots = t1->n_slots;
-        P.gb = t2->g;
-        P.canon_b = t2->g.canonical;
-        P.have_c = t3 != nullptr;
-        if (t3) {
-            P.gc = t3->g;
-            P.canon_c = t3->g.canonical;
-        }
-        P.spec_walk = spec;
-        P.spec_shared1 = spec + 2 * (size_t)len;
-        P.spec_shared2 = spec + 3 * (size_t)len;
-        launch_comp(P, grid, c->stream);
-        // pass 2: walk hash2, probe hash1 — always canonicalised (src/comp.cc:447)
-        P.pass = 2;
-        P.ga = t2->g;
-        P.n_slots = t2->n_slots;
-        P.gb = t1->g;
-        P.canon_b = 1;
-        P.have_c = 0;
-        P.spec_walk = spec + len;
-        launch_comp(P, grid, c->stream);
-        c->launches += 2;
-        if (t3) { // pass 3: hash3 totals (src/comp.cc:466-479)
-            P.pass = 3;
-            P.ga = t3->g;
-            P.n_slots = t3->n_slots;
-            launch_comp(P, grid, c->stream);
-            c->launches++;
-        }
-    }
-    CU(cudaGetLastError());
-    if (c->dist) KT(dist_allreduce_u64(c, d.p, words)); // matrices, counters and spectra in one all-reduce
-    CU(cudaMemcpyAsync(main_mx, P.main_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (t3) {
-        CU(cudaMemcpyAsync(ends_mx, P.ends_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(middle_mx, P.middle_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaMemcpyAsync(mixed_mx, P.mixed_mx, cells * 8, cudaMemcpyDeviceToHost, c->stream));
-    }
-    static_assert(sizeof(katgpu_comp_counters) == 13 * 8, "counter block layout");
-    CU(cudaMemcpyAsync(counters, P.counters, sizeof(katgpu_comp_counters), cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaMemcpyAsync(spectra, spec, 4 * (size_t)len * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return KATGPU_OK;
-}
-
-extern "C" katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, size_t n, int canonicalise,
-                                       uint64_t *counts_out) {
-    KT(finished(t, "katgpu_lookup"));
-    if ((!keys || !counts_out) && n) return fail(KATGPU_ERR_INVALID, "katgpu_lookup: NULL argument");
-    if (n == 0) return KATGPU_OK;
-    katgpu_ctx *c = t->ctx;
-    CU(cudaSetDevice(c->device));
-    DevBuf dk, dc;
-    CU(cudaMalloc(&dk.p, n * 8));
-    CU(cudaMalloc(&dc.p, n * 8));
-    CU(cudaMemcpyAsync(dk.p, keys, n * 8, cudaMemcpyHostToDevice, c->stream));
-    const int grid = (int)std::min<uint64_t>((n + 255) / 256, (uint64_t)c->sm_count * 8);
-    launch_lookup(t->g, (const uint64_t *)dk.p, n, canonicalise, (uint64_t *)dc.p, grid, c->stream);
-    c->launches++;
-    CU(cudaGetLastError());
-    if (c->dist) KT(dist_allreduce_u64(c, dc.p, n)); // the owner rank answers, everybody else holds 0
-    CU(cudaMemcpyAsync(counts_out, dc.p, n * 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    return KATGPU_OK;
-}
-
-extern "C" katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t *counts_out, size_t cap,
-                                             uint64_t *n_out) {
-    KT(finished(t, "katgpu_table_export"));
-    if (!n_out || ((!keys_out || !counts_out) && cap)) return fail(KATGPU_ERR_INVALID, "katgpu_table_export: NULL argument");
-    katgpu_ctx *c = t->ctx;
-    CU(cudaSetDevice(c->device));
-    DevBuf dk, dc, dn;
-    CU(cudaMalloc(&dk.p, std::max<size_t>(cap, 1) * 8));
-    CU(cudaMalloc(&dc.p, std::max<size_t>(cap, 1) * 8));
-    CU(cudaMalloc(&dn.p, 8));
-    CU(cudaMemsetAsync(dn.p, 0, 8, c->stream));
-    launch_export(t->g, t->n_slots, (uint64_t *)dk.p, (uint64_t *)dc.p, cap, (unsigned long long *)dn.p, c->sm_count * 8, c->stream);
-    c->launches++;
-    CU(cudaGetLastError());
-    unsigned long long n = 0;
-    CU(cudaMemcpyAsync(&n, dn.p, 8, cudaMemcpyDeviceToHost, c->stream));
-    CU(cudaStreamSynchronize(c->stream));
-    *n_out = n;
-    const size_t m = std::min<size_t>(cap, n);
-    if (m) {
-        CU(cudaMemcpy(keys_out, dk.p, m * 8, cudaMemcpyDeviceToHost));
-        CU(cudaMemcpy(counts_out, dc.p, m * 8, cudaMemcpyDeviceToHost));
     }
     return KATGPU_OK;
 }

@@ -8,7 +8,7 @@ mkdir -p kat_b200/lib/variants build/variants
 while [ $# -ge 2 ]; do
   name=$1; flags=$2; shift 2
   d=build/variants/$name; mkdir -p $d
-  for f in count_kernels partition_kernels tile_kernels dist_kernels parse_kernels reduce_kernels katgpu_api katgpu_dist; do
+  for f in count_kernels partition_kernels tile_kernels dist_kernels parse_kernels reduce_kernels katgpu_api katgpu_fastq katgpu_walks katgpu_dist; do
     nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC $flags -c kat_b200/csrc/$f.cu -o $d/$f.o &
   done
   wait
