@@ -66,6 +66,26 @@ int main(int argc, char **argv) {
             fwrite(bases.data(), 1, bases.size(), stdout);
             return st == kat_host::ParseStatus::Ok ? 0 : st == kat_host::ParseStatus::UnsupportedFormat ? 2 : 3;
         }
+        if (mode == "_rawsplit") { // test hook, no GPU: how stream_fastq_raw cuts a file into blocks and per-GPU shares of whole records
+            if (argc != 5) throw KatError(1, "usage: kat _rawsplit <file.fastq> <block_bytes> <n_parts>");
+            string err;
+            size_t total = 0, blocks = 0;
+            const int n_parts = atoi(argv[4]);
+            const int r = kat_host::stream_fastq_raw(argv[2], (size_t)strtoull(argv[3], nullptr, 10), n_parts,
+                                                     [&](const char *const *parts, const size_t *lens) {
+                                                         printf("block %zu:", blocks++);
+                                                         for (int p = 0; p < n_parts; p++) {
+                                                             const bool whole = lens[p] == 0 || (parts[p][0] == '@' && parts[p][lens[p] - 1] == '\n');
+                                                             printf(" %zu%s", lens[p], whole ? "" : "!");
+                                                             total += lens[p];
+                                                             if (p + 1 < n_parts && parts[p] + lens[p] != parts[p + 1]) printf("?");
+                                                         }
+                                                         printf("\n");
+                                                         return 1;
+                                                     }, err);
+            printf("rc %d total %zu\n", r, total);
+            return 0;
+        }
         if (mode == "_jfdump") { // test hook, no GPU: header summary + records of a jellyfish hash, in file order
             if (argc != 3) throw KatError(1, "usage: kat _jfdump <hash.jf>");
             std::ifstream f;

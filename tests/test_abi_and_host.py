@@ -225,3 +225,31 @@ def test_host_streaming_route_gives_up_on_irregular_files(mutate_at, tmp_path, m
     assert b"stream route: rc 1" not in r.stderr
     want, st = O.parse_file(data, 21, 0)
     assert r.stdout == want
+
+
+def test_raw_fastq_blocks_are_whole_records(tmp_path):
+    """stream_fastq_raw (the host side of the device FASTQ parser): a file is handed out in blocks, and every
+    block in per-GPU shares, that start at a record and end with a newline, are contiguous and cover the file once —
+    also when quality lines start with '@' or '+'.  A file that is not FASTQ or lacks the final newline is declined."""
+    rng = np.random.default_rng(3)
+    recs = []
+    for i in range(3000):
+        L = int(rng.integers(20, 200))
+        seq = bytes(rng.choice(list(b"ACGTN"), L).tolist())
+        q = bytes(rng.choice(list(b"@+I#"), L).tolist())
+        recs.append(b"@r%d some text\n" % i + seq + b"\n+\n" + q + b"\n")
+    data = b"".join(recs)
+    p = tmp_path / "r.fq"
+    p.write_bytes(data)
+    kat = os.path.join(ROOT, "kat_b200", "bin", "kat")
+    for block, parts in ((4096, 1), (50_000, 3), (10_000_000, 8), (7777, 2)):
+        out = subprocess.run([kat, "_rawsplit", str(p), str(block), str(parts)], capture_output=True, text=True, check=True).stdout
+        assert "!" not in out and "?" not in out, out[-400:]
+        assert out.strip().splitlines()[-1] == "rc 1 total %d" % len(data)
+        if block < len(data):
+            assert out.count("block ") > 1
+    (tmp_path / "nonl.fq").write_bytes(data[:-1])
+    (tmp_path / "x.fa").write_bytes(b">a\nACGT\n")
+    for name in ("nonl.fq", "x.fa"):
+        out = subprocess.run([kat, "_rawsplit", str(tmp_path / name), "4096", "2"], capture_output=True, text=True, check=True).stdout
+        assert out.strip().splitlines()[-1].startswith("rc 0")
