@@ -67,6 +67,8 @@ struct BinCore {
     uint32_t *cnt;   // [F] keys staged (may run past R: those keys went to the side list)
     uint32_t *cur;   // [F] keys already in the destination segment
     uint32_t F, R, shift, mask;
+    uint32_t ge;            // effective granule: 8 keys (64 bytes, written by a lane pair in ONE store instruction) when the
+                            // CTA has two threads per bin, else 4 keys (one 32-byte sector per thread)
     uint32_t cnt_s, ring_s; // the same arrays as 32-bit shared-window addresses (append: no generic-address arithmetic per key)
     uint64_t *seg0;  // destination segment of bin 0
     uint64_t seg_stride; // keys between the segments of consecutive bins
@@ -76,6 +78,7 @@ struct BinCore {
 
     __device__ __forceinline__ void init(const BinDst &d, uint32_t offset, unsigned char *smem) {
         F = d.F, R = d.R, shift = d.shift, mask = d.mask, cap = d.cap;
+        ge = (G == 8 && blockDim.x == 2 * F) ? 8u : (G == 8 && (F & 31u) == 0 && KATGPU_OLD_G8 ? 8u : 4u);
         cnt = reinterpret_cast<uint32_t *>(smem);
         cur = cnt + F;
         ring = reinterpret_cast<uint64_t *>(smem + (((size_t)F * 8 + 15) & ~(size_t)15));
@@ -106,7 +109,7 @@ struct BinCore {
             return;
         }
         uint64_t *seg = seg0 + (uint64_t)d * seg_stride;
-        const uint32_t aligned_end = (c + n) & ~(G - 1);
+        const uint32_t aligned_end = (c + n) & ~(ge - 1);
         const uint32_t w = final ? n : (aligned_end > c ? aligned_end - c : 0u);
         uint32_t i = 0;
         for (; i < w && ((c + i) & 3u); i++) seg[c + i] = ring[(size_t)i * F + d]; // head of a segment a previous launch left unaligned
@@ -129,7 +132,36 @@ struct BinCore {
     // ~35 G scattered write requests per second whatever their size.
     __device__ __forceinline__ void flush(bool final, const SideList &S, const TableGeom &g, SideTally &t) {
         __syncthreads();
-        if (G == 8 && (F & 31u) == 0 && !final) {
+        if (G == 8 && blockDim.x == 2 * F && !final) {
+            // two threads per bin: lanes 2j and 2j+1 write the two sectors of each 64-byte granule of bin j in the
+            // same store instruction -> one 64-byte request; no state has to travel between lanes
+            const uint32_t d = threadIdx.x >> 1, sub = threadIdx.x & 1u;
+            const uint32_t n = min(cnt[d], R), c = cur[d];
+            const bool simple = n > 0 && (c & 7u) == 0 && c + n <= cap;
+            const uint32_t w = simple ? (n & ~7u) : 0u;
+            const uint64_t *col = ring + d;
+            uint64_t *dst = seg0 + (uint64_t)d * seg_stride + c;
+            for (uint32_t i = 4 * sub; i < w; i += 8) {
+                const uint64_t k0 = col[(size_t)i * F], k1 = col[(size_t)(i + 1) * F], k2 = col[(size_t)(i + 2) * F], k3 = col[(size_t)(i + 3) * F];
+                asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "l"(k0), "l"(k1), "l"(k2), "l"(k3) : "memory");
+            }
+            __syncwarp(); // both lanes of the pair have read the bin's rows before its leftover moves
+            if (sub == 0) {
+                if (simple) {
+                    const uint32_t r = n - w; // < 8
+                    if (w)
+                        for (uint32_t j = 0; j < r; j++) ring[(size_t)j * F + d] = ring[(size_t)(w + j) * F + d];
+                    cnt[d] = r;
+                    cur[d] = c + w;
+                } else if (n)
+                    flush_bin_serial(d, n, c, false, S, g, t); // unaligned head (a previous launch ended there) or a full segment
+                else
+                    cnt[d] = 0;
+            }
+            __syncthreads();
+            return;
+        }
+        if (ge == 8 && !final) {
             const uint32_t lane = threadIdx.x & 31u, sub = lane & 1u;
             for (uint32_t d = threadIdx.x; d < F; d += blockDim.x) { // warp-uniform trip count (F and blockDim are multiples of 32)
                 const uint32_t n = min(cnt[d], R), c = cur[d];

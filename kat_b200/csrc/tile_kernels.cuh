@@ -68,6 +68,9 @@ constexpr int kTileThreads = KATGPU_TILE_THREADS;
 #ifndef KATGPU_BIN2_GRANULE
 #define KATGPU_BIN2_GRANULE 4
 #endif
+#ifndef KATGPU_OLD_G8
+#define KATGPU_OLD_G8 0 // 1: 64-byte granules also when a CTA has fewer than two threads per bin (round 1's shuffle-based flush; slower)
+#endif
 #ifndef KATGPU_BINH_GRANULE
 #define KATGPU_BINH_GRANULE 4
 #endif
