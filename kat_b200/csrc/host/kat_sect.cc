@@ -10,74 +10,13 @@
 //   <prefix>-non_repetitive.fa / -repetitive.fa  with -E / -F                (printRegions, :385-420)
 // The reference builds a contamination matrix as well but never writes it (Sect::save is not called
 // from Sect::main, :733-735), so neither do we.
-#include "kat_front.hpp"
+#include "kat_seqlookup.hpp"
 
 #include <iomanip>
 
 namespace kat_front {
 
 namespace {
-
-struct SeqRecord {
-    string name, seq;
-};
-
-inline bool is_ws(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
-
-// SeqAn 2.0 readRecord for FASTA / FASTQ into CharStrings (seqan/seq_io/fasta_fastq.h): the id is the
-// header line without its marker and line end; the sequence is every non-whitespace character up to
-// the next '>' (FASTA) or up to the '+' that opens the quality block (FASTQ); qualities are skipped
-// by count, ignoring whitespace.
-vector<SeqRecord> read_records(const string &path) {
-    std::vector<unsigned char> raw;
-    string err;
-    if (!kat_host::read_file(path, raw, err)) throw KatError(4, err);
-    vector<SeqRecord> out;
-    size_t i = 0;
-    const size_t n = raw.size();
-    while (i < n && is_ws(raw[i])) i++;
-    if (i >= n) return out;
-    const bool fastq = raw[i] == '@';
-    if (!fastq && raw[i] != '>') throw KatError(4, "Unknown sequence file format: " + path);
-    while (i < n) {
-        if (raw[i] != (fastq ? '@' : '>')) throw KatError(4, "Malformed record in " + path);
-        i++;
-        SeqRecord r;
-        while (i < n && raw[i] != '\n' && raw[i] != '\r') r.name += (char)raw[i++];
-        while (i < n && (raw[i] == '\n' || raw[i] == '\r')) i++;
-        const unsigned char stop = fastq ? '+' : '>';
-        while (i < n && raw[i] != stop) {
-            if (!is_ws(raw[i])) r.seq += (char)raw[i];
-            i++;
-        }
-        if (fastq) {
-            while (i < n && raw[i] != '\n') i++; // the '+' line
-            size_t q = 0;
-            while (i < n && q < r.seq.size()) {
-                if (!is_ws(raw[i])) q++;
-                i++;
-            }
-            while (i < n && is_ws(raw[i])) i++;
-        }
-        out.push_back(std::move(r));
-    }
-    return out;
-}
-
-inline bool valid_base(char c) { // validKmer, lib/include/kat/str_utils.hpp:183-201
-    switch (c) {
-    case 'A': case 'a': case 'C': case 'c': case 'G': case 'g': case 'T': case 't': return true;
-    default: return false;
-    }
-}
-inline uint64_t base_code(char c) { // mer_dna::code, JFI/mer_dna.hpp:46-63
-    switch (c) {
-    case 'C': case 'c': return 1;
-    case 'G': case 'g': return 2;
-    case 'T': case 't': return 3;
-    default: return 0;
-    }
-}
 
 void print_regions(std::ostream &out, const vector<SeqRecord> &recs, const vector<vector<uint64_t>> &counts, uint32_t k, uint32_t min_count, uint32_t max_count) {
     for (size_t i = 0; i < recs.size(); i++) {
@@ -159,40 +98,10 @@ int sect_main(int argc, char **argv) {
     cout.flush();
     const vector<SeqRecord> recs = read_records(seq_file);
     const uint32_t K = (uint32_t)k;
-    // every k-mer position of every sequence: packed key (0 for a window with a non-ACGT character) + validity
-    vector<size_t> first(recs.size() + 1, 0);
-    for (size_t i = 0; i < recs.size(); i++) first[i + 1] = first[i] + (recs[i].seq.size() >= K ? recs[i].seq.size() - K + 1 : 0);
-    const size_t n_pos = first.back();
-    vector<uint64_t> keys(n_pos), found(n_pos, 0);
-    vector<uint8_t> valid(n_pos, 0);
-    const uint64_t kmask = K == 32 ? ~0ULL : ((1ULL << (2 * K)) - 1);
-    for (size_t i = 0; i < recs.size(); i++) {
-        const string &s = recs[i].seq;
-        uint64_t m = 0;
-        uint32_t run = 0;
-        for (size_t j = 0; j < s.size(); j++) {
-            if (valid_base(s[j])) {
-                m = ((m << 2) | base_code(s[j])) & kmask;
-                run++;
-            } else
-                run = 0;
-            if (j + 1 >= K) {
-                const size_t p = first[i] + (j + 1 - K);
-                keys[p] = run >= K ? m : 0;
-                valid[p] = run >= K;
-            }
-        }
-    }
-    // JellyfishHelper::getCount(hash, mer, canonical) per position, batched on the GPU(s)
-    const size_t batch = (size_t)1 << 26;
-    for (size_t off = 0; off < n_pos; off += batch) {
-        const size_t m = std::min(batch, n_pos - off);
-        vector<vector<uint64_t>> other(ctx.n());
-        run_on_all(ctx.n(), [&](int r) {
-            if (r) other[r].resize(m);
-            gpu_check(katgpu_lookup(in.tables[r], keys.data() + off, m, in.canonical ? 1 : 0, r ? other[r].data() : found.data() + off));
-        });
-    }
+    const SeqPositions pos = kmer_positions(recs, K);
+    const vector<size_t> &first = pos.first;
+    const vector<uint8_t> &valid = pos.valid;
+    const vector<uint64_t> found = lookup_positions(ctx, in, pos.keys);
     std::ofstream stats((prefix + "-stats.tsv").c_str());
     stats << "seq_name\tmedian\tmean\tgc%\tseq_length\tkmers_in_seq\tinvalid_kmers\t%_invalid\tnon_zero_kmers\t%_non_zero\t%_non_zero_corrected" << endl;
     stats << std::fixed << std::setprecision(5);

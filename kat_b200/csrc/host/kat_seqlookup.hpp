@@ -1,0 +1,119 @@
+// kat_seqlookup.hpp — what `kat sect` and `kat cold` share: reading the records of a sequence file the way SeqAn's
+// readRecords does, and looking up every k-mer position of every record on the GPU(s) in batches
+// (JellyfishHelper::getCount per position in the reference: src/sect.cc:524-541, src/cold.cc:338-356).
+#pragma once
+#include "kat_front.hpp"
+
+namespace kat_front {
+
+struct SeqRecord {
+    string name, seq;
+};
+
+inline bool is_ws(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+// SeqAn 2.0 readRecord for FASTA / FASTQ into CharStrings (seqan/seq_io/fasta_fastq.h): the id is the
+// header line without its marker and line end; the sequence is every non-whitespace character up to
+// the next '>' (FASTA) or up to the '+' that opens the quality block (FASTQ); qualities are skipped
+// by count, ignoring whitespace.
+inline vector<SeqRecord> read_records(const string &path) {
+    std::vector<unsigned char> raw;
+    string err;
+    if (!kat_host::read_file(path, raw, err)) throw KatError(4, err);
+    vector<SeqRecord> out;
+    size_t i = 0;
+    const size_t n = raw.size();
+    while (i < n && is_ws(raw[i])) i++;
+    if (i >= n) return out;
+    const bool fastq = raw[i] == '@';
+    if (!fastq && raw[i] != '>') throw KatError(4, "Unknown sequence file format: " + path);
+    while (i < n) {
+        if (raw[i] != (fastq ? '@' : '>')) throw KatError(4, "Malformed record in " + path);
+        i++;
+        SeqRecord r;
+        while (i < n && raw[i] != '\n' && raw[i] != '\r') r.name += (char)raw[i++];
+        while (i < n && (raw[i] == '\n' || raw[i] == '\r')) i++;
+        const unsigned char stop = fastq ? '+' : '>';
+        while (i < n && raw[i] != stop) {
+            if (!is_ws(raw[i])) r.seq += (char)raw[i];
+            i++;
+        }
+        if (fastq) {
+            while (i < n && raw[i] != '\n') i++; // the '+' line
+            size_t q = 0;
+            while (i < n && q < r.seq.size()) {
+                if (!is_ws(raw[i])) q++;
+                i++;
+            }
+            while (i < n && is_ws(raw[i])) i++;
+        }
+        out.push_back(std::move(r));
+    }
+    return out;
+}
+
+inline bool valid_base(char c) { // validKmer, lib/include/kat/str_utils.hpp:183-201
+    switch (c) {
+    case 'A': case 'a': case 'C': case 'c': case 'G': case 'g': case 'T': case 't': return true;
+    default: return false;
+    }
+}
+inline uint64_t base_code(char c) { // mer_dna::code, JFI/mer_dna.hpp:46-63
+    switch (c) {
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': return 3;
+    default: return 0;
+    }
+}
+
+
+// Every k-mer position of every record: packed key (0 where the window holds a non-ACGT character) and validity;
+// first[i] = index of record i's first position.
+struct SeqPositions {
+    vector<size_t> first;
+    vector<uint64_t> keys;
+    vector<uint8_t> valid;
+};
+inline SeqPositions kmer_positions(const vector<SeqRecord> &recs, uint32_t K) {
+    SeqPositions P;
+    P.first.assign(recs.size() + 1, 0);
+    for (size_t i = 0; i < recs.size(); i++) P.first[i + 1] = P.first[i] + (recs[i].seq.size() >= K ? recs[i].seq.size() - K + 1 : 0);
+    P.keys.assign(P.first.back(), 0);
+    P.valid.assign(P.first.back(), 0);
+    const uint64_t kmask = K == 32 ? ~0ULL : ((1ULL << (2 * K)) - 1);
+    for (size_t i = 0; i < recs.size(); i++) {
+        const string &s = recs[i].seq;
+        uint64_t m = 0;
+        uint32_t run = 0;
+        for (size_t j = 0; j < s.size(); j++) {
+            if (valid_base(s[j])) {
+                m = ((m << 2) | base_code(s[j])) & kmask;
+                run++;
+            } else
+                run = 0;
+            if (j + 1 >= K) {
+                const size_t p = P.first[i] + (j + 1 - K);
+                P.keys[p] = run >= K ? m : 0;
+                P.valid[p] = run >= K;
+            }
+        }
+    }
+    return P;
+}
+// JellyfishHelper::getCount(hash, mer, canonical) for every position, batched on the GPU(s) (collective on a job)
+inline vector<uint64_t> lookup_positions(Ctx &ctx, Input &in, const vector<uint64_t> &keys) {
+    vector<uint64_t> found(keys.size(), 0);
+    const size_t batch = (size_t)1 << 26;
+    for (size_t off = 0; off < keys.size(); off += batch) {
+        const size_t m = std::min(batch, keys.size() - off);
+        vector<vector<uint64_t>> other(ctx.n());
+        run_on_all(ctx.n(), [&](int r) {
+            if (r) other[r].resize(m);
+            gpu_check(katgpu_lookup(in.tables[r], keys.data() + off, m, in.canonical ? 1 : 0, r ? other[r].data() : found.data() + off));
+        });
+    }
+    return found;
+}
+
+} // namespace kat_front

@@ -21,6 +21,10 @@ CASES = [
     ("sect_edge_short_iupac_k5", ["sect", "-m5", "-g", "-E", "-o", "OUT/s", "inputs/edge1.fa", "inputs/edge1.fa"]),
     ("sect_multiline_fastq_nc_k5", ["sect", "-m5", "-N", "-o", "OUT/s", "inputs/edge2.fq", "inputs/edge2.fq"]),
     ("sect_no_count_stats_k27", ["sect", "-m27", "-n", "-o", "OUT/s", "inputs/long.fa", "inputs/synth_c.fa"]),
+    # kat cold <assembly> <reads...>: contig-level read coverage and assembly copy number
+    ("cold_asm_vs_reads_k21", ["cold", "-m21", "-o", "OUT/c", "inputs/synth_c.fa", "inputs/synth_a.fq", "inputs/synth_b.fq"]),
+    ("cold_edge_k5", ["cold", "-m5", "-o", "OUT/c", "inputs/edge1.fa", "inputs/edge1.fa"]),
+    ("cold_trim_k17", ["cold", "-m17", "--5ptrim", "4", "-H", "5000", "-o", "OUT/c", "inputs/synth_c.fa", "inputs/synth_a.fq"]),
 ]
 
 

@@ -169,8 +169,8 @@ SECT_MANIFEST = json.load(open(os.path.join(G.GOLDEN, "sect", "cases.json")))
 
 
 @pytest.mark.parametrize("case", SECT_MANIFEST, ids=lambda c: c["name"])
-def test_cli_sect_output_files_byte_identical(case, tmp_path):
-    """`kat sect` (src/sect.cc): counts.cvg, stats.tsv, counts.gc and the region FASTA files equal the
+def test_cli_sect_and_cold_output_files_byte_identical(case, tmp_path):
+    """`kat sect` (src/sect.cc) and `kat cold` (src/cold.cc): counts.cvg, stats.tsv, counts.gc and the region FASTA files equal the
     files written by the reference binary (tests/golden/sect, make_sect_golden.py)."""
     shutil.copytree(os.path.join(G.GOLDEN, "inputs"), tmp_path / "inputs")
     out = os.path.join("sect", case["name"])
