@@ -26,6 +26,13 @@ namespace katgpu {
 // so each owner's run is stored from its line-aligned position and the < 16 keys that do not fill
 // a line wait in shared memory for the next tile.
 constexpr uint32_t kRouteLine = 16;
+// KATGPU_ROUTE_TMA_STORE=1: the runs leave the SM as TMA bulk stores (cp.async.bulk.global.shared::cta) from a
+// double-buffered pool — asynchronous, so the wire works while the next tile is hashed — instead of per-thread
+// 32-byte stores in a burst after every tile.
+#ifndef KATGPU_ROUTE_TMA_STORE
+#define KATGPU_ROUTE_TMA_STORE 0
+#endif
+constexpr uint32_t kRoutePools = KATGPU_ROUTE_TMA_STORE ? 2 : 1;
 struct __align__(128) RouteSmem {
     uint8_t ascii[kBinTile + kHalo];
     uint32_t W[2][kBinGroups + 2];
@@ -37,7 +44,7 @@ struct __align__(128) RouteSmem {
     uint32_t goff[kMaxRanks + 1];// exclusive prefix of the 4-key groups each owner's run stores in this tile
     uint32_t cur[kMaxRanks];     // keys this CTA has already written to each owner's segment (multiple of kRouteLine)
     uint64_t carry[kMaxRanks][kRouteLine];
-    uint64_t pool[kBinTile + kMaxRanks * kRouteLine]; // the tile's keys, sorted by owner
+    alignas(128) uint64_t pool[kRoutePools][kBinTile + kMaxRanks * (kRouteLine + 2)]; // the tile's keys, sorted by owner
 };
 
 template <bool CANON, bool WIDE>
@@ -70,6 +77,7 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
     uint32_t parity = 0, buf = 0;
 
     for (; tile < P.n_tiles; tile += gridDim.x, buf ^= 1) {
+        uint64_t *pool = S.pool[KATGPU_ROUTE_TMA_STORE ? buf : 0];
         const uint64_t tile_base = (uint64_t)tile * kBinTile;
         if (tile_tma(tile)) {
             while (!mbar_try_wait(&S.mbar, parity)) {
@@ -139,7 +147,11 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
         __syncthreads();
         if (tid == 0) {
             uint32_t a = 0, ga = 0;
+#if KATGPU_ROUTE_TMA_STORE
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); // the stores out of THIS pool (two tiles ago) have read it
+#endif
             for (uint32_t d = 0; d < n_ranks; d++) {
+                a = (a + 1u) & ~1u; // runs start 16-byte aligned in the pool (bulk-copy source)
                 S.off[d] = a;
                 S.goff[d] = ga;
                 const uint32_t m = S.nc[d] + S.cnt[d];
@@ -152,15 +164,28 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
         __syncthreads();
         if (tid < (int)(n_ranks * kRouteLine)) { // carried keys open each run
             const uint32_t d = tid / kRouteLine, j = tid % kRouteLine;
-            if (j < S.nc[d]) S.pool[S.off[d] + j] = S.carry[d][j];
+            if (j < S.nc[d]) pool[S.off[d] + j] = S.carry[d][j];
         }
 #pragma unroll
         for (uint32_t r = 0; r < (uint32_t)kRoutePerThread; r++) {
             const uint32_t m = (meta[r >> 1] >> (16 * (r & 1))) & 0xFFFFu;
             const uint32_t d = (m >> 12) & 7u;
-            if (m & 0x8000u) S.pool[S.off[d] + S.nc[d] + (m & 0xFFFu)] = hk[r];
+            if (m & 0x8000u) pool[S.off[d] + S.nc[d] + (m & 0xFFFu)] = hk[r];
         }
         __syncthreads();
+#if KATGPU_ROUTE_TMA_STORE
+        if (tid == 0) { // one bulk store per owner: whole lines, local HBM for the own rank, NVLink for the others
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            for (uint32_t d = 0; d < n_ranks; d++) {
+                const uint32_t w = (S.nc[d] + S.cnt[d]) / kRouteLine * kRouteLine;
+                if (w)
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(P.seg[d] + (size_t)blockIdx.x * P.cap + S.cur[d]),
+                                 "r"(smem_u32(pool + S.off[d])), "r"(w * 8u)
+                                 : "memory");
+            }
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+#else
         // copy-out: every thread stores 32 bytes, a warp 1 KiB of consecutive lines — local HBM for
         // the own rank, NVLink for the others
         const uint32_t groups = S.goff[n_ranks];
@@ -169,15 +194,16 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
 #pragma unroll
             for (uint32_t j = 1; j < (uint32_t)kMaxRanks; j++) d += (j < n_ranks && gi >= S.goff[j]) ? 1u : 0u;
             const uint32_t q = (gi - S.goff[d]) * 4;
-            const uint64_t *src = S.pool + S.off[d] + q;
+            const uint64_t *src = pool + S.off[d] + q;
             uint64_t *dst = P.seg[d] + (size_t)blockIdx.x * P.cap + S.cur[d] + q;
             asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(dst), "l"(src[0]), "l"(src[1]), "l"(src[2]), "l"(src[3]) : "memory");
         }
+#endif
         __syncthreads();
         if (tid < (int)(n_ranks * kRouteLine)) { // what did not fill a line waits for the next tile
             const uint32_t d = tid / kRouteLine, j = tid % kRouteLine;
             const uint32_t m = S.nc[d] + S.cnt[d], w = m / kRouteLine * kRouteLine;
-            if (j < m - w) S.carry[d][j] = S.pool[S.off[d] + w + j];
+            if (j < m - w) S.carry[d][j] = pool[S.off[d] + w + j];
         }
         __syncthreads();
         if (tid < (int)n_ranks) {
@@ -189,6 +215,9 @@ __global__ void __launch_bounds__(kRouteThreads, 2) route_bases_kernel(const __g
         // (the pack phase of the next iteration ends with a barrier before cnt / nc are touched again)
     }
     __syncthreads();
+#if KATGPU_ROUTE_TMA_STORE
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // every run has landed before the lengths are published
+#endif
     if (tid < (int)(n_ranks * kRouteLine)) { // the last, partial line of every run
         const uint32_t d = tid / kRouteLine, j = tid % kRouteLine;
         if (j < S.nc[d]) P.seg[d][(size_t)blockIdx.x * P.cap + S.cur[d] + j] = S.carry[d][j];
