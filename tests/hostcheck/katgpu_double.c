@@ -1,0 +1,156 @@
+/*
+ * katgpu_double.c — a TEST DOUBLE of libkatgpu for machines without a GPU.
+ *
+ * TEST INFRASTRUCTURE ONLY (tests/test_host_frontend.py).  It exports the part of include/katgpu.h the
+ * C++ front-end (kat_b200/bin/kat) calls and answers every call with the CPU oracle
+ * (oracle/libkatoracle.so), so that the front-end's HOST logic — option handling, input groups,
+ * the FASTA/FASTQ readers, LOAD mode, the text and jellyfish-hash writers, sect/cold/filter
+ * arithmetic — is checked against the reference-written golden files in the `-m "not gpu"` suite.
+ * It is never built into, shipped with or found by the product: kat_b200/bin/kat resolves
+ * libkatgpu.so through its RUNPATH ($ORIGIN/../lib); the tests put THIS library in front with
+ * LD_LIBRARY_PATH.  What the GPU computes is checked by the `-m gpu` tests, which run the same
+ * commands against the real library.
+ *
+ * Built by tests/hostcheck/Makefile into tests/hostcheck/_build/libkatgpu.so (git-ignored).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "katgpu.h"
+
+/* oracle/kat_oracle.c */
+typedef struct oracle_table oracle_table;
+oracle_table *oracle_table_new(int k, int canonical);
+void oracle_table_free(oracle_table *t);
+void oracle_table_add(oracle_table *t, const unsigned char *bases, size_t n);
+void oracle_table_add_pairs(oracle_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo, const uint64_t *counts, size_t n);
+void oracle_table_finish(oracle_table *t);
+uint64_t oracle_table_distinct(const oracle_table *t);
+uint64_t oracle_table_total(const oracle_table *t);
+void oracle_table_export_wide(const oracle_table *t, uint64_t *keys_hi, uint64_t *keys_lo, uint64_t *counts);
+uint64_t oracle_lookup_wide(const oracle_table *t, uint64_t key_hi, uint64_t key_lo, int canonicalise);
+void oracle_hist(const oracle_table *t, uint64_t base, uint64_t ceil_, uint64_t inc, uint64_t nb, uint64_t *bins);
+void oracle_gcp(const oracle_table *t, double cvg_scale, uint32_t cvg_bins, uint64_t *mx);
+void oracle_comp(const oracle_table *t1, const oracle_table *t2, const oracle_table *t3, double d1_scale, double d2_scale,
+                 uint32_t d1_bins, uint32_t d2_bins, uint64_t *main_mx, uint64_t *ends_mx, uint64_t *middle_mx, uint64_t *mixed_mx,
+                 uint64_t *counters, uint64_t *spectra);
+
+struct katgpu_ctx { int unused; };
+struct katgpu_table {
+    oracle_table *o;
+    int k, canonical, ended, allow_grow;
+    uint64_t slots;
+};
+
+static __thread char g_err[256];
+static katgpu_status fail(katgpu_status st, const char *msg) {
+    snprintf(g_err, sizeof g_err, "%s", msg);
+    return st;
+}
+const char *katgpu_last_error(void) { return g_err; }
+int katgpu_version(void) { return KATGPU_VERSION; }
+int katgpu_device_count(void) { return 1; }
+katgpu_status katgpu_init(int device, katgpu_ctx **out) {
+    (void)device;
+    *out = (katgpu_ctx *)calloc(1, sizeof(katgpu_ctx));
+    return KATGPU_OK;
+}
+void katgpu_shutdown(katgpu_ctx *ctx) { free(ctx); }
+katgpu_status katgpu_dist_unique_id(void *id128) { memset(id128, 0, 128); return KATGPU_OK; }
+katgpu_status katgpu_dist_init(katgpu_ctx *ctx, int rank, int n_ranks, const void *id128) {
+    (void)ctx; (void)rank; (void)n_ranks; (void)id128;
+    return fail(KATGPU_ERR_INVALID, "the test double has one device");
+}
+
+katgpu_status katgpu_count_begin(katgpu_ctx *ctx, int k, int canonical, uint64_t hash_size, int allow_grow, katgpu_table **out) {
+    (void)ctx;
+    if (k < 1 || k > 64) return fail(KATGPU_ERR_INVALID, "k out of 1..64");
+    katgpu_table *t = (katgpu_table *)calloc(1, sizeof *t);
+    t->o = oracle_table_new(k, canonical);
+    t->k = k, t->canonical = canonical, t->allow_grow = allow_grow;
+    t->slots = 1024;
+    while (t->slots < hash_size) t->slots <<= 1;
+    *out = t;
+    return KATGPU_OK;
+}
+katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n) {
+    if (t->ended) return fail(KATGPU_ERR_STATE, "feed after end");
+    oracle_table_add(t->o, (const unsigned char *)bases, n);
+    return KATGPU_OK;
+}
+katgpu_status katgpu_count_feed_fastq(katgpu_table *t, const char *bytes, size_t n, unsigned trim5p, int *regular) {
+    (void)t; (void)bytes; (void)n; (void)trim5p;
+    *regular = 0; /* always "not in the regular layout": the front-end takes its host route */
+    return KATGPU_OK;
+}
+katgpu_status katgpu_count_reserve(katgpu_table *t, uint64_t expected_kmers) { (void)t; (void)expected_kmers; return KATGPU_OK; }
+katgpu_status katgpu_count_add_pairs(katgpu_table *t, const uint64_t *keys, const uint64_t *counts, size_t n) {
+    if (t->k > 32) return fail(KATGPU_ERR_INVALID, "k > 32: use katgpu_count_add_pairs_wide");
+    oracle_table_add_pairs(t->o, NULL, keys, counts, n);
+    return KATGPU_OK;
+}
+katgpu_status katgpu_count_add_pairs_wide(katgpu_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo, const uint64_t *counts, size_t n) {
+    oracle_table_add_pairs(t->o, keys_hi, keys_lo, counts, n);
+    return KATGPU_OK;
+}
+katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct, uint64_t *n_total) {
+    if (!t->ended) oracle_table_finish(t->o);
+    t->ended = 1;
+    if (!t->allow_grow && oracle_table_distinct(t->o) > t->slots) return fail(KATGPU_ERR_HASH_FULL, "Hash full");
+    if (n_distinct) *n_distinct = oracle_table_distinct(t->o);
+    if (n_total) *n_total = oracle_table_total(t->o);
+    return KATGPU_OK;
+}
+void katgpu_table_free(katgpu_table *t) {
+    if (!t) return;
+    oracle_table_free(t->o);
+    free(t);
+}
+
+katgpu_status katgpu_hist(katgpu_table *t, uint64_t base, uint64_t ceil, uint64_t inc, uint64_t nb_buckets, uint64_t *bins_out) {
+    oracle_hist(t->o, base, ceil, inc, nb_buckets, bins_out);
+    return KATGPU_OK;
+}
+katgpu_status katgpu_gcp(katgpu_table *t, double cvg_scale, uint32_t cvg_bins, uint64_t *mx_out) {
+    oracle_gcp(t->o, cvg_scale, cvg_bins, mx_out);
+    return KATGPU_OK;
+}
+katgpu_status katgpu_comp(katgpu_table *t1, katgpu_table *t2, katgpu_table *t3, double d1_scale, double d2_scale, uint32_t d1_bins,
+                          uint32_t d2_bins, uint64_t *main_mx, uint64_t *ends_mx, uint64_t *middle_mx, uint64_t *mixed_mx,
+                          katgpu_comp_counters *counters, uint64_t *spectra) {
+    oracle_comp(t1->o, t2->o, t3 ? t3->o : NULL, d1_scale, d2_scale, d1_bins, d2_bins, main_mx, ends_mx, middle_mx, mixed_mx,
+                (uint64_t *)counters, spectra);
+    return KATGPU_OK;
+}
+katgpu_status katgpu_lookup_wide(katgpu_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo, size_t n, int canonicalise,
+                                 uint64_t *counts_out) {
+    for (size_t i = 0; i < n; i++) counts_out[i] = oracle_lookup_wide(t->o, keys_hi ? keys_hi[i] : 0, keys_lo[i], canonicalise);
+    return KATGPU_OK;
+}
+katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, size_t n, int canonicalise, uint64_t *counts_out) {
+    if (t->k > 32) return fail(KATGPU_ERR_INVALID, "k > 32: use katgpu_lookup_wide");
+    return katgpu_lookup_wide(t, NULL, keys, n, canonicalise, counts_out);
+}
+katgpu_status katgpu_table_export_wide(katgpu_table *t, uint64_t *keys_hi_out, uint64_t *keys_lo_out, uint64_t *counts_out, size_t cap,
+                                       uint64_t *n_out) {
+    const uint64_t n = oracle_table_distinct(t->o);
+    if (n_out) *n_out = n;
+    if (cap < n) return KATGPU_OK; /* the real library writes the first `cap`; the front-end always sizes for all */
+    uint64_t *hi = keys_hi_out ? keys_hi_out : (uint64_t *)malloc((n ? n : 1) * sizeof(uint64_t));
+    oracle_table_export_wide(t->o, hi, keys_lo_out, counts_out);
+    /* "unordered": hand the records back in a scrambled but deterministic order so that nothing depends on sortedness */
+    for (uint64_t i = 0, j = n; j > 1; i++, j--) {
+        const uint64_t r = (i * 0x9E3779B97F4A7C15ULL >> 17) % j, a = j - 1;
+        uint64_t x;
+        x = hi[a], hi[a] = hi[r], hi[r] = x;
+        x = keys_lo_out[a], keys_lo_out[a] = keys_lo_out[r], keys_lo_out[r] = x;
+        x = counts_out[a], counts_out[a] = counts_out[r], counts_out[r] = x;
+    }
+    if (!keys_hi_out) free(hi);
+    return KATGPU_OK;
+}
+katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t *counts_out, size_t cap, uint64_t *n_out) {
+    if (t->k > 32) return fail(KATGPU_ERR_INVALID, "k > 32: use katgpu_table_export_wide");
+    return katgpu_table_export_wide(t, NULL, keys_out, counts_out, cap, n_out);
+}

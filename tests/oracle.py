@@ -52,6 +52,10 @@ def lib():
     L.oracle_table_export.argtypes = [vp, u64p, u64p]
     L.oracle_lookup.restype = C.c_uint64
     L.oracle_lookup.argtypes = [vp, C.c_uint64, C.c_int]
+    L.oracle_table_export_wide.argtypes = [vp, u64p, u64p, u64p]
+    L.oracle_lookup_wide.restype = C.c_uint64
+    L.oracle_lookup_wide.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_int]
+    L.oracle_table_add_pairs.argtypes = [vp, u64p, u64p, u64p, C.c_size_t]
     L.oracle_hist_geometry.argtypes = [C.c_uint64, C.c_uint64, u64p, u64p, u64p]
     L.oracle_hist.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, u64p]
     L.oracle_gcp.argtypes = [vp, C.c_double, C.c_uint32, u64p]
@@ -146,14 +150,29 @@ class Table:
         return int(lib().oracle_table_total(self.h))
 
     def export(self):
+        """k <= 32: (keys, counts); k > 32: (keys_hi, keys_lo, counts) — sorted by key."""
         n = self.distinct
         keys = np.empty(n, dtype=np.uint64)
         counts = np.empty(n, dtype=np.uint64)
+        if self.k > 32:
+            hi = np.empty(n, dtype=np.uint64)
+            lib().oracle_table_export_wide(self.h, _ptr(hi), _ptr(keys), _ptr(counts))
+            return hi, keys, counts
         lib().oracle_table_export(self.h, _ptr(keys), _ptr(counts))
         return keys, counts
 
+    def add_pairs(self, keys, counts, keys_hi=None):
+        """count[key] += count records (HashLoader::loadHash); call before finish()."""
+        keys = np.ascontiguousarray(keys, dtype=np.uint64)
+        counts = np.ascontiguousarray(counts, dtype=np.uint64)
+        hi = None if keys_hi is None else np.ascontiguousarray(keys_hi, dtype=np.uint64)
+        lib().oracle_table_add_pairs(self.h, None if hi is None else _ptr(hi), _ptr(keys), _ptr(counts), len(keys))
+        return self
+
     def lookup(self, key, canonicalise=False):
-        return int(lib().oracle_lookup(self.h, int(key), int(canonicalise)))
+        """key: Python int (2 bits per base, first base most significant), any k <= 64."""
+        key = int(key)
+        return int(lib().oracle_lookup_wide(self.h, key >> 64, key & 0xFFFFFFFFFFFFFFFF, int(canonicalise)))
 
     def hist(self, low=1, high=10000, inc=1):
         b, c, n = C.c_uint64(), C.c_uint64(), C.c_uint64()

@@ -1,0 +1,66 @@
+"""Host logic of the C++ front-end (kat_b200/bin/kat) WITHOUT a GPU: the same commands and the same
+reference-written golden files as tests/test_gpu_cli.py, run against a test double of libkatgpu that
+answers the C-ABI calls with the CPU oracle (tests/hostcheck/katgpu_double.c, put in front of the real
+library with LD_LIBRARY_PATH).  What this covers is everything above the ABI — option handling, input
+groups, FASTA/FASTQ readers, LOAD mode and hash dumps, the text writers, sect/cold/filter arithmetic.
+What the GPU computes is covered by the `-m gpu` run of the same test functions."""
+import os
+import subprocess
+
+import pytest
+
+import test_gpu_cli as T
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DOUBLE_DIR = os.path.join(ROOT, "tests", "hostcheck", "_build")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _double_in_front():
+    if not os.access(T.KAT, os.X_OK):
+        pytest.skip("kat_b200/bin/kat is not built (python __graft_entry__.py)")
+    r = subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostcheck")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    old = os.environ.get("LD_LIBRARY_PATH")
+    os.environ["LD_LIBRARY_PATH"] = DOUBLE_DIR + (":" + old if old else "")
+    os.environ["KAT_GPU_PARSE"] = "1"  # the double refuses raw FASTQ blocks, so the host route is what runs
+    yield
+    if old is None:
+        del os.environ["LD_LIBRARY_PATH"]
+    else:
+        os.environ["LD_LIBRARY_PATH"] = old
+    os.environ.pop("KAT_GPU_PARSE", None)
+
+
+def test_the_double_is_what_runs(tmp_path):
+    """ldd resolves libkatgpu.so to the double, and the double reports one device and no multi-GPU."""
+    r = subprocess.run(["ldd", T.KAT], capture_output=True, text=True)
+    assert os.path.join("hostcheck", "_build", "libkatgpu.so") in r.stdout, r.stdout
+    g = subprocess.run([T.KAT, "hist", "-m5", "--gpus", "2", "-o", str(tmp_path / "h"), os.path.join(T.G.GOLDEN, "inputs", "edge1.fa")],
+                       capture_output=True, text=True)
+    assert g.returncode == 4 and "only 1 CUDA devices visible" in g.stderr
+
+
+# fixtures and test functions of the GPU suite, collected here without the gpu mark
+workdir = T.workdir
+jf_workdir = T.jf_workdir
+
+test_cli_sect_and_cold_output_files_byte_identical = T.test_cli_sect_and_cold_output_files_byte_identical
+test_cli_load_mode_files_byte_identical = T.test_cli_load_mode_files_byte_identical
+test_cli_comp_dump_hashes_and_symlink = T.test_cli_comp_dump_hashes_and_symlink
+test_cli_hash_full_exit_code = T.test_cli_hash_full_exit_code
+test_cli_missing_input = T.test_cli_missing_input
+test_cli_dev_paths_are_pipes = T.test_cli_dev_paths_are_pipes
+
+
+@pytest.mark.parametrize("case", T.G.cases(), ids=lambda c: c["name"])
+def test_cli_output_files_byte_identical(case, workdir):
+    T.test_cli_output_files_byte_identical(case, "direct", workdir)  # the counting path is a property of the real library
+
+
+def test_cli_c1_ecoli_k27(tmp_path):
+    T.test_cli_c1_ecoli_k27("auto", tmp_path)
+
+
+def test_cli_dump_hash_is_a_jellyfish_file(jf_workdir):
+    T.test_cli_dump_hash_is_a_jellyfish_file("direct", jf_workdir)
