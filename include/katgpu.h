@@ -166,6 +166,14 @@ katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, size_t n, int
 katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t *counts_out,
                                   size_t cap, uint64_t *n_out);
 
+/* The same walk with FilterKmer::inBounds applied on the device (src/filter_kmer.cc:257-309): a k-mer is
+ * "in bounds" when low_count <= count <= high_count and low_gc <= #G+#C <= high_gc.  inside != 0
+ * returns the k-mers in bounds, inside == 0 those out of bounds (`kat filter kmer`, its --invert
+ * and the discard set of --separate). */
+katgpu_status katgpu_table_export_filtered(katgpu_table *t, uint64_t low_count, uint64_t high_count, uint32_t low_gc,
+                                           uint32_t high_gc, int inside, uint64_t *keys_out, uint64_t *counts_out,
+                                           size_t cap, uint64_t *n_out);
+
 /* ---- table introspection / multi-GPU plumbing ---------------------------------- */
 
 typedef struct katgpu_table_info {

@@ -58,6 +58,7 @@ SIGNATURES = {
     "katgpu_comp": (_i, [_vp, _vp, _vp, _d, _d, _u32, _u32, _vp, _vp, _vp, _vp, C.POINTER(CompCounters), _vp]),
     "katgpu_lookup": (_i, [_vp, _vp, _sz, _i, _vp]),
     "katgpu_table_export": (_i, [_vp, _vp, _vp, _sz, C.POINTER(_u64)]),
+    "katgpu_table_export_filtered": (_i, [_vp, _u64, _u64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _sz, C.POINTER(_u64)]),
     "katgpu_table_get_info": (_i, [_vp, C.POINTER(TableInfo)]),
     "katgpu_debug_set_count_bits": (None, [_i]),
     "katgpu_route_device": (_i, [_vp, _vp, _sz, _i, C.POINTER(_vp), _u64, C.POINTER(_u64)]),
@@ -312,6 +313,19 @@ class Table:
             return keys[:m], counts[:m], n.value
         order = np.argsort(keys[:m], kind="stable")
         return keys[:m][order], counts[:m][order], n.value
+
+    def export_filtered(self, low_count, high_count, low_gc, high_gc, inside=True):
+        """The k-mers inside (or outside) the count / GC bounds of `kat filter kmer`, sorted by key."""
+        n = C.c_uint64()
+        args = (self.h, int(low_count), int(high_count), int(low_gc), int(high_gc), int(bool(inside)))
+        _check(lib().katgpu_table_export_filtered(*args, None, None, 0, C.byref(n)))
+        cap = n.value
+        keys = np.zeros(max(cap, 1), dtype=np.uint64)
+        counts = np.zeros(max(cap, 1), dtype=np.uint64)
+        _check(lib().katgpu_table_export_filtered(*args, _ptr(keys), _ptr(counts), cap, C.byref(n)))
+        assert n.value == cap
+        order = np.argsort(keys[:cap], kind="stable")
+        return keys[:cap][order], counts[:cap][order]
 
     def route_device(self, bases_dev, n, out_ptrs, cap_keys):
         n_ranks = len(out_ptrs)

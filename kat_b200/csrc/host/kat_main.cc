@@ -1,5 +1,5 @@
-// kat_main.cc — entry point of the `kat hist | gcp | comp | sect | cold` front-end over libkatgpu (tools: kat_hist.cc,
-// kat_gcp.cc, kat_comp.cc, kat_sect.cc, kat_cold.cc; shared helpers: kat_front.hpp, kat_seqlookup.hpp).
+// kat_main.cc — entry point of the `kat hist | gcp | comp | sect | cold | filter` front-end over libkatgpu (tools: kat_hist.cc,
+// kat_gcp.cc, kat_comp.cc, kat_sect.cc, kat_cold.cc, kat_filter.cc; shared helpers: kat_front.hpp, kat_seqlookup.hpp).
 //
 // Mirrors the reference's CLI surface and output files for the three spectra
 // tools (src/kat.cc:178-305, src/histogram.cc:257-369, src/gcp.cc:255-370,
@@ -20,6 +20,7 @@ int gcp_main(int argc, char **argv);
 int comp_main(int argc, char **argv);
 int sect_main(int argc, char **argv);
 int cold_main(int argc, char **argv);
+int filter_main(int argc, char **argv);
 } // namespace kat_front
 using namespace kat_front;
 
@@ -27,8 +28,8 @@ int main(int argc, char **argv) {
     try {
         if (argc < 2 || !strcmp(argv[1], "--help") || !strcmp(argv[1], "-h")) {
             cout << "The K-mer Analysis Toolkit (KAT), GPU spectra engine.\n\nUsage: kat <mode> [options]\n\n"
-                    "Modes: hist, gcp, comp, sect, cold (counting, spectra and coverage lookups on the GPU through libkatgpu).\n"
-                    "filter and plot are not part of this build.\n" << endl;
+                    "Modes: hist, gcp, comp, sect, cold, filter (counting, spectra, coverage lookups and filtering on the GPU through libkatgpu).\n"
+                    "plot is not part of this build.\n" << endl;
             return 1;
         }
         if (!strcmp(argv[1], "--version") || !strcmp(argv[1], "-V")) {
@@ -138,8 +139,8 @@ int main(int argc, char **argv) {
         if (mode == "comp") return comp_main(argc - 1, argv + 1);
         if (mode == "sect") return sect_main(argc - 1, argv + 1);
         if (mode == "cold") return cold_main(argc - 1, argv + 1);
-        if (mode == "filter" || mode == "plot")
-            throw KatError(4, "KAT mode '" + mode + "' is outside this GPU build's scope (hist, gcp, comp, sect, cold)");
+        if (mode == "filter") return filter_main(argc - 1, argv + 1);
+        if (mode == "plot") throw KatError(4, "KAT mode 'plot' is outside this GPU build's scope (hist, gcp, comp, sect, cold, filter)");
         throw KatError(4, "Unrecognised KAT mode: " + mode);
     } catch (const KatError &e) {
         cerr << (e.code == 5 ? "Error: " : "") << e.what() << endl;

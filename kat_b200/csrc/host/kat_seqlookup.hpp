@@ -7,7 +7,7 @@
 namespace kat_front {
 
 struct SeqRecord {
-    string name, seq;
+    string name, seq, qual; // qual: FASTQ only (kat filter seq writes the records back out)
 };
 
 inline bool is_ws(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
@@ -15,8 +15,8 @@ inline bool is_ws(unsigned char c) { return c == ' ' || c == '\t' || c == '\n' |
 // SeqAn 2.0 readRecord for FASTA / FASTQ into CharStrings (seqan/seq_io/fasta_fastq.h): the id is the
 // header line without its marker and line end; the sequence is every non-whitespace character up to
 // the next '>' (FASTA) or up to the '+' that opens the quality block (FASTQ); qualities are skipped
-// by count, ignoring whitespace.
-inline vector<SeqRecord> read_records(const string &path) {
+// by count, ignoring whitespace.  *is_fastq (optional) reports the detected format.
+inline vector<SeqRecord> read_records(const string &path, bool *is_fastq = nullptr) {
     std::vector<unsigned char> raw;
     string err;
     if (!kat_host::read_file(path, raw, err)) throw KatError(4, err);
@@ -26,6 +26,7 @@ inline vector<SeqRecord> read_records(const string &path) {
     while (i < n && is_ws(raw[i])) i++;
     if (i >= n) return out;
     const bool fastq = raw[i] == '@';
+    if (is_fastq) *is_fastq = fastq;
     if (!fastq && raw[i] != '>') throw KatError(4, "Unknown sequence file format: " + path);
     while (i < n) {
         if (raw[i] != (fastq ? '@' : '>')) throw KatError(4, "Malformed record in " + path);
@@ -40,9 +41,8 @@ inline vector<SeqRecord> read_records(const string &path) {
         }
         if (fastq) {
             while (i < n && raw[i] != '\n') i++; // the '+' line
-            size_t q = 0;
-            while (i < n && q < r.seq.size()) {
-                if (!is_ws(raw[i])) q++;
+            while (i < n && r.qual.size() < r.seq.size()) {
+                if (!is_ws(raw[i])) r.qual += (char)raw[i];
                 i++;
             }
             while (i < n && is_ws(raw[i])) i++;

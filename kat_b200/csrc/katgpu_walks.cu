@@ -178,10 +178,10 @@ extern "C" katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, si
     return KATGPU_OK;
 }
 
-extern "C" katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t *counts_out, size_t cap,
-                                             uint64_t *n_out) {
-    KT(finished(t, "katgpu_table_export"));
-    if (!n_out || ((!keys_out || !counts_out) && cap)) return fail(KATGPU_ERR_INVALID, "katgpu_table_export: NULL argument");
+static katgpu_status export_selected(katgpu_table *t, const ExportSel &sel, uint64_t *keys_out, uint64_t *counts_out, size_t cap,
+                                      uint64_t *n_out, const char *who) {
+    KT(finished(t, who));
+    if (!n_out || ((!keys_out || !counts_out) && cap)) return fail(KATGPU_ERR_INVALID, "%s: NULL argument", who);
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));
     DevBuf dk, dc, dn;
@@ -189,7 +189,7 @@ extern "C" katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out
     CU(cudaMalloc(&dc.p, std::max<size_t>(cap, 1) * 8));
     CU(cudaMalloc(&dn.p, 8));
     CU(cudaMemsetAsync(dn.p, 0, 8, c->stream));
-    launch_export(t->g, t->n_slots, (uint64_t *)dk.p, (uint64_t *)dc.p, cap, (unsigned long long *)dn.p, c->sm_count * 8, c->stream);
+    launch_export(t->g, t->n_slots, (uint64_t *)dk.p, (uint64_t *)dc.p, cap, (unsigned long long *)dn.p, c->sm_count * 8, c->stream, sel);
     c->launches++;
     CU(cudaGetLastError());
     unsigned long long n = 0;
@@ -202,4 +202,18 @@ extern "C" katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out
         CU(cudaMemcpy(counts_out, dc.p, m * 8, cudaMemcpyDeviceToHost));
     }
     return KATGPU_OK;
+}
+
+extern "C" katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t *counts_out, size_t cap,
+                                             uint64_t *n_out) {
+    return export_selected(t, ExportSel(), keys_out, counts_out, cap, n_out, "katgpu_table_export");
+}
+
+extern "C" katgpu_status katgpu_table_export_filtered(katgpu_table *t, uint64_t low_count, uint64_t high_count, uint32_t low_gc,
+                                                      uint32_t high_gc, int inside, uint64_t *keys_out, uint64_t *counts_out,
+                                                      size_t cap, uint64_t *n_out) {
+    ExportSel sel;
+    sel.mode = inside ? 1 : -1;
+    sel.low_count = low_count, sel.high_count = high_count, sel.low_gc = low_gc, sel.high_gc = high_gc;
+    return export_selected(t, sel, keys_out, counts_out, cap, n_out, "katgpu_table_export_filtered");
 }

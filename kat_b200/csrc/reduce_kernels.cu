@@ -285,15 +285,28 @@ __global__ void __launch_bounds__(256) lookup_kernel(const __grid_constant__ Tab
     }
 }
 
+// sel.mode 0: every (key, count); +1: only k-mers whose count and GC count lie inside the bounds
+// (FilterKmer::inBounds, src/filter_kmer.cc:296-309); -1: only those outside.
 __global__ void __launch_bounds__(256) export_kernel(const __grid_constant__ TableGeom g, uint64_t n_slots,
                                                      uint64_t *__restrict__ keys, uint64_t *__restrict__ counts,
-                                                     uint64_t cap, unsigned long long *cursor) {
+                                                     uint64_t cap, unsigned long long *cursor, const ExportSel sel) {
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t rounds = (n_slots + stride - 1) / stride;
     uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     for (uint64_t it = 0; it < rounds; it++, i += stride) {
         const uint64_t word = i < n_slots ? g.slots[i] : 0;
-        const bool occ = word != 0;
+        bool occ = word != 0;
+        uint64_t key = 0, c = 0;
+        if (occ) {
+            uint64_t h;
+            decode_slot(g, i, word, h, c);
+            key = unmix_key(g, h);
+            if (sel.mode) {
+                const uint32_t gc = (uint32_t)__popcll((key ^ (key >> 1)) & 0x5555555555555555ULL);
+                const bool in_bounds = sel.low_gc <= gc && gc <= sel.high_gc && sel.low_count <= c && c <= sel.high_count;
+                occ = in_bounds == (sel.mode > 0);
+            }
+        }
         const uint32_t m = __ballot_sync(0xffffffffu, occ);
         if (m == 0) continue;
         const int lane = threadIdx.x & 31;
@@ -303,9 +316,7 @@ __global__ void __launch_bounds__(256) export_kernel(const __grid_constant__ Tab
         if (occ) {
             const uint64_t at = basei + __popc(m & ((1u << lane) - 1));
             if (at < cap) {
-                uint64_t h, c;
-                decode_slot(g, i, word, h, c);
-                keys[at] = unmix_key(g, h);
+                keys[at] = key;
                 counts[at] = c;
             }
         }
@@ -345,8 +356,8 @@ void launch_lookup(const TableGeom &g, const uint64_t *keys, uint64_t n, int can
     lookup_kernel<<<grid, 256, 0, st>>>(g, keys, n, canonicalise, out);
 }
 void launch_export(const TableGeom &g, uint64_t n_slots, uint64_t *keys, uint64_t *counts, uint64_t cap,
-                   unsigned long long *cursor, int grid, cudaStream_t st) {
-    export_kernel<<<grid, 256, 0, st>>>(g, n_slots, keys, counts, cap, cursor);
+                   unsigned long long *cursor, int grid, cudaStream_t st, const ExportSel &sel) {
+    export_kernel<<<grid, 256, 0, st>>>(g, n_slots, keys, counts, cap, cursor, sel);
 }
 
 } // namespace katgpu

@@ -29,7 +29,12 @@ void launch_gcp(const TableGeom &g, uint64_t n_slots, double scale, uint32_t cvg
 void launch_comp(CompParams P, int grid, cudaStream_t st);
 void launch_lookup(const TableGeom &g, const uint64_t *keys, uint64_t n, int canonicalise, uint64_t *out, int grid,
                    cudaStream_t st);
+struct ExportSel { // which k-mers an export keeps (kat filter kmer, src/filter_kmer.cc:296-309)
+    int mode = 0;       // 0 all, +1 inside the bounds, -1 outside
+    uint64_t low_count = 0, high_count = ~0ULL;
+    uint32_t low_gc = 0, high_gc = ~0u;
+};
 void launch_export(const TableGeom &g, uint64_t n_slots, uint64_t *keys, uint64_t *counts, uint64_t cap,
-                   unsigned long long *cursor, int grid, cudaStream_t st);
+                   unsigned long long *cursor, int grid, cudaStream_t st, const ExportSel &sel = ExportSel());
 
 } // namespace katgpu

@@ -183,3 +183,51 @@ def test_cli_sect_and_cold_output_files_byte_identical(case, tmp_path):
         p = os.path.join(G.GOLDEN, "sect", case["name"], f)
         want = open(p, "rb").read() if os.path.exists(p) else gzip.open(p + ".gz", "rb").read()
         assert open(tmp_path / out / f, "rb").read() == want, f"{case['name']}/{f} differs from the reference's file"
+
+
+# ---- kat filter seq / kat filter kmer ----------------------------------
+FILTER_MANIFEST = json.load(open(os.path.join(G.GOLDEN, "filter", "cases.json")))
+
+
+def _filter_expected(case, f):
+    p = os.path.join(G.GOLDEN, "filter", case, f)
+    return open(p, "rb").read() if os.path.exists(p) else gzip.open(p + ".gz", "rb").read()
+
+
+@pytest.mark.parametrize("case", FILTER_MANIFEST, ids=lambda c: c["name"])
+def test_cli_filter_matches_reference(case, tmp_path):
+    """`kat filter seq` (src/filter_sequence.cc): the kept / discarded record files and the .stats table are the
+    reference's files byte for byte.  `kat filter kmer` (src/filter_kmer.cc): the hashes written hold exactly the
+    reference's (k-mer, count) records, in jellyfish's sorted order, and the printed counters are the same
+    (tests/golden/filter, make_filter_golden.py)."""
+    shutil.copytree(os.path.join(G.GOLDEN, "inputs"), tmp_path / "inputs")
+    os.makedirs(tmp_path / "jf")
+    shutil.copy(os.path.join(G.GOLDEN, "jf", "synthc_k21_jf.jf"), tmp_path / "jf")
+    out = os.path.join("filter", case["name"])
+    os.makedirs(tmp_path / out)
+    args = [a.replace("OUT", out) for a in case["args"]]
+    r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    assert sorted(os.listdir(tmp_path / out)) == case["files"]
+    assert [l for l in r.stdout.splitlines() if l.startswith(("K-mers ", "Found "))] == case["summary"]
+    for f in case["files"]:
+        if ".jf" in f:
+            d = subprocess.run([KAT, "_jfdump", os.path.join(out, f)], cwd=tmp_path, capture_output=True, text=True)
+            lines = d.stdout.splitlines()
+            assert d.returncode == 0 and lines[-1].endswith("out_of_order=0"), d.stdout[-300:] + d.stderr
+            want = _filter_expected(case["name"], f + ".dump.txt").decode().splitlines()
+            assert sorted(l for l in lines if not l.startswith("#")) == want, f"{case['name']}/{f}: records differ"
+        else:
+            assert open(tmp_path / out / f, "rb").read() == _filter_expected(case["name"], f), f"{case['name']}/{f} differs from the reference's file"
+
+
+def test_cli_filter_errors(tmp_path):
+    """Argument errors of the filter tools: exit code 4 with the reference's messages."""
+    fa = os.path.join(G.GOLDEN, "inputs", "edge1.fa")
+    for args, msg in ((["filter", "kmer", "-c", "5", "-d", "2", fa], "High kmer count value must be >= to low kmer count value"),
+                      (["filter", "kmer", "-g", "9", "-h", "2", fa], "High GC count value must be >= to low GC count value"),
+                      (["filter", "seq", "-m5", fa], "You must specify at least one sequence file to filter"),
+                      (["filter", "seq", "-m5", "--seq", "nope.fa", fa], "Could not find input file at: nope.fa"),
+                      (["filter", "nonsense", fa], "Could not recognise mode string: nonsense")):
+        r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 4 and msg in r.stderr, (args, r.returncode, r.stderr)

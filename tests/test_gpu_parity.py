@@ -192,6 +192,29 @@ def test_lookup(ctx):
             assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("k", [5, 21, 32])
+def test_export_filtered(ctx, k):
+    """katgpu_table_export_filtered = FilterKmer::inBounds on the device (src/filter_kmer.cc:296-309): the in-bounds and
+    out-of-bounds sets partition the table and equal the oracle's multiset filtered on the host; counts beyond the
+    in-slot field (overflow side table) are filtered by their full value."""
+    s = np.concatenate([seqgen.genome_reads(5_000, 4000, 150, seed=77), np.frombuffer(b"N" + b"A" * 700 + b"N" + b"GC" * 300, dtype=np.uint8)])
+    B.lib().katgpu_debug_set_count_bits(4)
+    try:
+        gt = gpu_table(ctx, [s], k, True)
+    finally:
+        B.lib().katgpu_debug_set_count_bits(0)
+    keys, counts = ora_table([s], k, True).export()
+    gc = np.zeros(keys.size, dtype=np.uint32)
+    for b in range(k):
+        c = (keys >> np.uint64(2 * b)) & np.uint64(3)
+        gc += ((c == 1) | (c == 2)).astype(np.uint32)
+    for lo_c, hi_c, lo_g, hi_g in ((1, 10000, 0, 100), (2, 5, k // 3, 2 * k // 3), (16, 1 << 40, 0, k), (3, 3, k, k)):
+        inb = (counts >= lo_c) & (counts <= hi_c) & (gc >= lo_g) & (gc <= hi_g)
+        for inside, sel in ((True, inb), (False, ~inb)):
+            gk, gc_ = gt.export_filtered(lo_c, hi_c, lo_g, hi_g, inside)
+            assert np.array_equal(gk, keys[sel]) and np.array_equal(gc_, counts[sel]), (k, lo_c, hi_c, lo_g, hi_g, inside)
+
+
 def test_synth_reads_device_equals_host(ctx):
     n_reads, L = 5000, 150
     host = B.synth_reads_host(1_000_000, 1, 2, 12345, n_reads, L)
