@@ -10,7 +10,7 @@ OBJDIR    := build
 LIB       := kat_b200/lib/libkatgpu.so
 KAT       := kat_b200/bin/kat
 
-CU_SRC  := $(CSRC)/count_kernels.cu $(CSRC)/partition_kernels.cu $(CSRC)/tile_kernels.cu $(CSRC)/dist_kernels.cu $(CSRC)/parse_kernels.cu $(CSRC)/reduce_kernels.cu $(CSRC)/katgpu_api.cu $(CSRC)/katgpu_fastq.cu $(CSRC)/katgpu_walks.cu $(CSRC)/katgpu_dist.cu
+CU_SRC  := $(CSRC)/count_kernels.cu $(CSRC)/partition_kernels.cu $(CSRC)/tile_kernels.cu $(CSRC)/dist_kernels.cu $(CSRC)/parse_kernels.cu $(CSRC)/reduce_kernels.cu $(CSRC)/katgpu_api.cu $(CSRC)/katgpu_fastq.cu $(CSRC)/katgpu_walks.cu $(CSRC)/katgpu_dist.cu $(CSRC)/wide_kernels.cu $(CSRC)/katgpu_wide.cu
 CU_OBJ  := $(patsubst $(CSRC)/%.cu,$(OBJDIR)/%.o,$(CU_SRC))
 HOST_SRC := $(wildcard $(CSRC)/host/*.cc)
 HOST_OBJ := $(patsubst $(CSRC)/host/%.cc,$(OBJDIR)/host_%.o,$(HOST_SRC))

@@ -34,7 +34,7 @@ extern "C" {
 typedef int katgpu_status;
 enum {
     KATGPU_OK = 0,
-    KATGPU_ERR_INVALID = -1,   /* bad argument (k out of 1..32, null pointer, ...)      */
+    KATGPU_ERR_INVALID = -1,   /* bad argument (k out of 1..64, null pointer, ...)      */
     KATGPU_ERR_CUDA = -2,      /* CUDA runtime error, text in katgpu_last_error()       */
     KATGPU_ERR_HASH_FULL = -3, /* table full and growth disabled: the reference's
                                   std::runtime_error("Hash full"), JFI/hash_counter.hpp:199 */
@@ -69,7 +69,8 @@ void katgpu_host_free(void *p);
  * mer_iterator (JFI/mer_iterator.hpp:59-89) and hash_counter::add
  * (JFI/hash_counter.hpp:98-130).
  *
- *   k              mer length, 1..32 (one 64-bit word; mer_dna::k, jellyfish_helper.cc:229)
+ *   k              mer length, 1..64 (mer_dna::k, jellyfish_helper.cc:229).  k <= 32: one 64-bit word per
+ *                  key; k = 33..64: two words ("wide" tables, single GPU; see the _wide entry points)
  *   canonical      count min(m, revcomp(m)) (InputHandler::canonical)
  *   hash_size      initial number of table slots, rounded up to a power of two
  *                  (InputHandler::hashSize, `-H`, default 1e8)
@@ -173,6 +174,24 @@ katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t 
 katgpu_status katgpu_table_export_filtered(katgpu_table *t, uint64_t low_count, uint64_t high_count, uint32_t low_gc,
                                            uint32_t high_gc, int inside, uint64_t *keys_out, uint64_t *counts_out,
                                            size_t cap, uint64_t *n_out);
+
+/* ---- k-mers of 33..64 bases: two words per key -----------------------------------------
+ * jellyfish::mer_dna keeps ceil(2k/64) words per k-mer (JFI/mer_dna.hpp:513-531) and KAT has no limit on k; tables
+ * counted with k > 32 ("wide" tables: their own layout and kernels, one GPU) hand keys across the ABI as two arrays:
+ * keys_lo = the last 32 bases, keys_hi = the first k-32 bases, 2 bits per base, first base most significant.
+ * katgpu_count_begin / _feed* / _end / katgpu_hist / _gcp / _comp / katgpu_table_get_info take wide tables as they are;
+ * the three calls that carry keys have _wide forms, which also accept one-word tables (keys_hi is then ignored on
+ * input — may be NULL — and zero on output). */
+katgpu_status katgpu_lookup_wide(katgpu_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo, size_t n,
+                                 int canonicalise, uint64_t *counts_out);
+katgpu_status katgpu_table_export_wide(katgpu_table *t, uint64_t *keys_hi_out, uint64_t *keys_lo_out,
+                                       uint64_t *counts_out, size_t cap, uint64_t *n_out);
+katgpu_status katgpu_table_export_filtered_wide(katgpu_table *t, uint64_t low_count, uint64_t high_count,
+                                                uint32_t low_gc, uint32_t high_gc, int inside, uint64_t *keys_hi_out,
+                                                uint64_t *keys_lo_out, uint64_t *counts_out, size_t cap,
+                                                uint64_t *n_out);
+katgpu_status katgpu_count_add_pairs_wide(katgpu_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo,
+                                          const uint64_t *counts, size_t n);
 
 /* ---- table introspection / multi-GPU plumbing ---------------------------------- */
 

@@ -59,6 +59,10 @@ SIGNATURES = {
     "katgpu_lookup": (_i, [_vp, _vp, _sz, _i, _vp]),
     "katgpu_table_export": (_i, [_vp, _vp, _vp, _sz, C.POINTER(_u64)]),
     "katgpu_table_export_filtered": (_i, [_vp, _u64, _u64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _sz, C.POINTER(_u64)]),
+    "katgpu_lookup_wide": (_i, [_vp, _vp, _vp, _sz, _i, _vp]),
+    "katgpu_table_export_wide": (_i, [_vp, _vp, _vp, _vp, _sz, C.POINTER(_u64)]),
+    "katgpu_table_export_filtered_wide": (_i, [_vp, _u64, _u64, C.c_uint32, C.c_uint32, C.c_int, _vp, _vp, _vp, _sz, C.POINTER(_u64)]),
+    "katgpu_count_add_pairs_wide": (_i, [_vp, _vp, _vp, _vp, _sz]),
     "katgpu_table_get_info": (_i, [_vp, C.POINTER(TableInfo)]),
     "katgpu_debug_set_count_bits": (None, [_i]),
     "katgpu_route_device": (_i, [_vp, _vp, _sz, _i, C.POINTER(_vp), _u64, C.POINTER(_u64)]),
@@ -269,6 +273,42 @@ class Table:
         if k.size:
             _check(lib().katgpu_count_add_pairs(self.h, _ptr(k), _ptr(c), k.size))
         return self
+
+    def add_pairs_wide(self, keys_hi, keys_lo, counts):
+        """add_pairs with two words per key (any k; keys_hi is ignored for k <= 32)."""
+        hi = np.ascontiguousarray(keys_hi, dtype=np.uint64)
+        lo = np.ascontiguousarray(keys_lo, dtype=np.uint64)
+        c = np.ascontiguousarray(counts, dtype=np.uint64)
+        assert hi.size == lo.size == c.size
+        if lo.size:
+            _check(lib().katgpu_count_add_pairs_wide(self.h, _ptr(hi), _ptr(lo), _ptr(c), lo.size))
+        return self
+
+    def lookup_wide(self, keys_hi, keys_lo, canonicalise=False):
+        """Counts of two-word keys (any k): keys_lo = last 32 bases, keys_hi = the first k-32."""
+        hi = np.ascontiguousarray(keys_hi, dtype=np.uint64)
+        lo = np.ascontiguousarray(keys_lo, dtype=np.uint64)
+        out = np.zeros(lo.size, dtype=np.uint64)
+        _check(lib().katgpu_lookup_wide(self.h, _ptr(hi), _ptr(lo), lo.size, int(canonicalise), _ptr(out)))
+        return out
+
+    def export_wide(self, bounds=None, inside=True):
+        """(keys_hi, keys_lo, counts, n) sorted by key; bounds = (low_count, high_count, low_gc, high_gc) selects the
+        k-mers inside (or outside) them as `kat filter kmer` does."""
+        n = C.c_uint64()
+
+        def call(hi, lo, cn, cap):
+            if bounds is None:
+                return lib().katgpu_table_export_wide(self.h, hi, lo, cn, cap, C.byref(n))
+            return lib().katgpu_table_export_filtered_wide(self.h, *[int(b) for b in bounds], int(bool(inside)), hi, lo, cn, cap, C.byref(n))
+
+        _check(call(None, None, None, 0))
+        cap = n.value
+        hi, lo, cn = (np.zeros(max(cap, 1), dtype=np.uint64) for _ in range(3))
+        _check(call(_ptr(hi), _ptr(lo), _ptr(cn), cap))
+        assert n.value == cap
+        order = np.lexsort((lo[:cap], hi[:cap]))
+        return hi[:cap][order], lo[:cap][order], cn[:cap][order], cap
 
     def reserve(self, expected_kmers):
         _check(lib().katgpu_count_reserve(self.h, int(expected_kmers)))

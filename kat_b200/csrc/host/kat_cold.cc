@@ -25,7 +25,7 @@ int cold_main(int argc, char **argv) {
     cout << "Running KAT in Cold mode" << endl << "------------------------" << endl << endl;
     if (a.positional.size() < 2) throw KatError(4, "kat cold needs an assembly and at least one reads input");
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    check_mer_len(k);
     const uint64_t hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
     Input reads, assembly;
     reads.files.assign(a.positional.begin() + 1, a.positional.end());
@@ -43,6 +43,7 @@ int cold_main(int argc, char **argv) {
     assembly.validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));
+    check_wide_limits(k, ctx.n(), a.has("dump_hashes"), "--dump_hashes");
     if (a.has("dump_hashes") && ctx.n() > 1) throw KatError(4, "--dump_hashes writes one GPU's table: run without --gpus");
     int k_reads = k, k_asm = k;
     if (reads.load_mode) load_inputs_phase(ctx, &reads, 1, k_reads);
@@ -57,7 +58,7 @@ int cold_main(int argc, char **argv) {
     cout.flush();
     const vector<SeqRecord> recs = read_records(assembly.files[0]);
     const SeqPositions pos = kmer_positions(recs, (uint32_t)k);
-    const vector<uint64_t> in_reads = lookup_positions(ctx, reads, pos.keys), in_asm = lookup_positions(ctx, assembly, pos.keys);
+    const vector<uint64_t> in_reads = lookup_positions(ctx, reads, pos), in_asm = lookup_positions(ctx, assembly, pos);
     std::ofstream stats((prefix + "-stats.tsv").c_str());
     stats << "seq_name\tread_median_cvg\tread_mean_cvg\tasm_cn\tgc%\tseq_length\tkmers_in_seq\tinvalid_kmers\t%_invalid\tnon_zero_kmers\t%_non_zero\t%_non_zero_corrected" << endl;
     stats << std::fixed << std::setprecision(5);

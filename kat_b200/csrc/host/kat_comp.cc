@@ -61,7 +61,7 @@ int comp_main(int argc, char **argv) {
     if (a.positional.size() < 2) throw KatError(4, "Nothing specified for input group 2");
     const bool three = a.positional.size() >= 3;
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    check_mer_len(k);
     const double d1s = to_double(a.get("d1_scale", "1.0"), "d1_scale"), d2s = to_double(a.get("d2_scale", "1.0"), "d2_scale");
     const uint32_t d1b = (uint32_t)to_u64(a.get("d1_bins", "1001"), "d1_bins"), d2b = (uint32_t)to_u64(a.get("d2_bins", "1001"), "d2_bins");
     if (d1b == 0 || d2b == 0) throw KatError(4, "d1_bins and d2_bins must be >= 1");
@@ -81,6 +81,7 @@ int comp_main(int argc, char **argv) {
     for (int i = 0; i < (three ? 3 : 2); i++) in[i].validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));
+    check_wide_limits(k, ctx.n(), a.has("dump_hashes"), "--dump_hashes");
     if (a.has("dump_hashes") && ctx.n() > 1) throw KatError(4, "--dump_hashes writes one GPU's table: run without --gpus");
     if (ctx.n() > 1)
         for (int i = 0; i < (three ? 3 : 2); i++)

@@ -35,7 +35,8 @@ int filter_kmer_main(int argc, char **argv) {
     Timer total;
     cout << "Running KAT in filter kmer mode" << endl << "-------------------------------" << endl << endl;
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    if (k < 1 || k > 32) throw KatError(4, "kat filter kmer supports mer lengths 1..32 in this build; got " + std::to_string(k));
+    check_mer_len(k);
+    check_wide_limits(k, 1, true, "kat filter kmer (it writes jellyfish hashes)");
     const uint64_t low_count = to_u64(a.get("low_count", "1"), "low_count"), high_count = to_u64(a.get("high_count", "10000"), "high_count");
     const uint32_t low_gc = (uint32_t)to_u64(a.get("low_gc", "1"), "low_gc"), high_gc = (uint32_t)to_u64(a.get("high_gc", "100"), "high_gc");
     const bool invert = a.has("invert"), separate = a.has("separate");
@@ -168,7 +169,7 @@ int filter_seq_main(int argc, char **argv) {
     if (!exists(seq1)) throw KatError(4, "Could not find input file at: " + seq1 + "; please check the path and try again.");
     if (paired && !exists(seq2)) throw KatError(4, "Could not find sequence file at: " + seq2 + "; please check the path and try again.");
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    check_mer_len(k);
     const double threshold = to_double(a.get("threshold", "0.1"), "threshold"), frequency = to_double(a.get("frequency", "0"), "frequency");
     const bool invert = a.has("invert"), separate = a.has("separate"), do_stats = a.has("stats");
     if (a.positional.empty()) throw KatError(4, "No input provided for this input group");
@@ -183,6 +184,7 @@ int filter_seq_main(int argc, char **argv) {
     const string ext = ext_of(seq1); // both mates are written with the first file's extension (:189-205)
     const SeqFormat fmt = format_of_extension(ext);
     Ctx ctx(gpus_option(a));
+    check_wide_limits(k, ctx.n(), false, "");
     if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
     else count_input(ctx, in, k, true);
 
@@ -192,12 +194,12 @@ int filter_seq_main(int argc, char **argv) {
     vector<SeqRecord> r2;
     if (paired) r2 = read_records(seq2);
     const SeqPositions p1 = kmer_positions(r1, (uint32_t)k);
-    const vector<uint64_t> f1 = lookup_positions(ctx, in, p1.keys);
+    const vector<uint64_t> f1 = lookup_positions(ctx, in, p1);
     SeqPositions p2;
     vector<uint64_t> f2;
     if (paired) {
         p2 = kmer_positions(r2, (uint32_t)k);
-        f2 = lookup_positions(ctx, in, p2.keys);
+        f2 = lookup_positions(ctx, in, p2);
     }
     std::ofstream stats, in1, out1, in2, out2;
     if (do_stats) {

@@ -147,6 +147,18 @@ inline vector<unsigned> parse_trim(const string &s) {
     return v;
 }
 
+// mer lengths: one 64-bit word per k-mer up to 32, two words for 33..64 (jellyfish::mer_dna has no limit; larger k
+// is refused).  Two-word k-mers are counted on one GPU, and the jellyfish-hash reader / writer is one-word only.
+constexpr int kMaxMerLen = 64;
+inline void check_mer_len(int k) {
+    if (k < 1 || k > kMaxMerLen) throw KatError(4, "This GPU build supports mer lengths 1..64 (one or two 64-bit words per k-mer); got " + std::to_string(k));
+}
+inline void check_wide_limits(int k, int gpus, bool dumps_or_hash_files, const char *what) {
+    if (k <= 32) return;
+    if (gpus > 1) throw KatError(4, "mer lengths above 32 are counted on one GPU: run without --gpus");
+    if (dumps_or_hash_files) throw KatError(4, string(what) + " is limited to mer lengths up to 32 in this build (jellyfish hash files with one-word keys)");
+}
+
 // ---- InputHandler (lib/src/input_handler.cc) ------------------------------------
 inline string leaf(const string &p) {
     const size_t s = p.find_last_of('/');
@@ -441,7 +453,7 @@ inline int load_input(katgpu_ctx *ctx, Input &in) {
     std::ifstream f;
     const kat_host::JfHeader h = read_jf_header(in.files[0], f);
     const int k = (int)(h.key_len / 2);
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); the hash holds " + std::to_string(k) + "-mers");
+    if (k < 1 || k > 32) throw KatError(4, "This GPU build loads jellyfish hashes of mer lengths 1..32 (one 64-bit word per k-mer); the hash holds " + std::to_string(k) + "-mers");
     struct stat st;
     uint64_t n_records = 0;
     if (stat(in.files[0].c_str(), &st) == 0 && (uint64_t)st.st_size >= h.offset) {

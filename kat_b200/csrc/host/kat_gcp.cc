@@ -25,10 +25,11 @@ int gcp_main(int argc, char **argv) {
     in.canonical = !a.has("non_canonical");
     in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
     const string prefix = a.get("output_prefix", "kat-gcp");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    check_mer_len(k);
     in.validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));
+    check_wide_limits(k, ctx.n(), a.has("dump_hash"), "--dump_hash");
     if (a.has("dump_hash") && ctx.n() > 1) throw KatError(4, "--dump_hash writes one GPU's table: run without --gpus");
     if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
     else count_input(ctx, in, k, true);

@@ -29,10 +29,11 @@ int hist_main(int argc, char **argv) {
     const uint64_t base = low > 1 ? (1 >= low ? 1 : low - 1) : 1, ceil = high + 1, nb = ceil + 1 - base;
     if (high < low) throw KatError(4, "High count value must be >= to low count value.  High: " + std::to_string(high) + "; Low: " + std::to_string(low));
     if (inc == 0) throw KatError(4, "Increment must be >= 1");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    check_mer_len(k);
     in.validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));
+    check_wide_limits(k, ctx.n(), a.has("dump_hash"), "--dump_hash");
     if (a.has("dump_hash") && ctx.n() > 1) throw KatError(4, "--dump_hash writes one GPU's table: run without --gpus");
     if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
     else count_input(ctx, in, k, true);

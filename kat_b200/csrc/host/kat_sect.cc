@@ -77,7 +77,7 @@ int sect_main(int argc, char **argv) {
     if (a.positional.size() < 2) throw KatError(4, "kat sect needs a sequence file and at least one input (sequence files to count, or a jellyfish hash)");
     const string seq_file = a.positional[0];
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build supports mer lengths 1..32 (one 64-bit word per k-mer); got " + std::to_string(k));
+    check_mer_len(k);
     Input in;
     in.files.assign(a.positional.begin() + 1, a.positional.end());
     in.set_trim(parse_trim(a.get("5ptrim", "0")));
@@ -89,6 +89,7 @@ int sect_main(int argc, char **argv) {
     in.validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));
+    check_wide_limits(k, ctx.n(), a.has("dump_hash"), "--dump_hash");
     if (a.has("dump_hash") && ctx.n() > 1) throw KatError(4, "--dump_hash writes one GPU's table: run without --gpus");
     if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
     else count_input(ctx, in, k, true);
@@ -101,7 +102,7 @@ int sect_main(int argc, char **argv) {
     const SeqPositions pos = kmer_positions(recs, K);
     const vector<size_t> &first = pos.first;
     const vector<uint8_t> &valid = pos.valid;
-    const vector<uint64_t> found = lookup_positions(ctx, in, pos.keys);
+    const vector<uint64_t> found = lookup_positions(ctx, in, pos);
     std::ofstream stats((prefix + "-stats.tsv").c_str());
     stats << "seq_name\tmedian\tmean\tgc%\tseq_length\tkmers_in_seq\tinvalid_kmers\t%_invalid\tnon_zero_kmers\t%_non_zero\t%_non_zero_corrected" << endl;
     stats << std::fixed << std::setprecision(5);

@@ -69,10 +69,11 @@ inline uint64_t base_code(char c) { // mer_dna::code, JFI/mer_dna.hpp:46-63
 
 
 // Every k-mer position of every record: packed key (0 where the window holds a non-ACGT character) and validity;
-// first[i] = index of record i's first position.
+// first[i] = index of record i's first position.  keys = the last 32 bases of the k-mer, keys_hi = the first K-32
+// (all zero for K <= 32) — mer_dna's packing, first base most significant.
 struct SeqPositions {
     vector<size_t> first;
-    vector<uint64_t> keys;
+    vector<uint64_t> keys, keys_hi;
     vector<uint8_t> valid;
 };
 inline SeqPositions kmer_positions(const vector<SeqRecord> &recs, uint32_t K) {
@@ -80,21 +81,25 @@ inline SeqPositions kmer_positions(const vector<SeqRecord> &recs, uint32_t K) {
     P.first.assign(recs.size() + 1, 0);
     for (size_t i = 0; i < recs.size(); i++) P.first[i + 1] = P.first[i] + (recs[i].seq.size() >= K ? recs[i].seq.size() - K + 1 : 0);
     P.keys.assign(P.first.back(), 0);
+    P.keys_hi.assign(P.first.back(), 0);
     P.valid.assign(P.first.back(), 0);
-    const uint64_t kmask = K == 32 ? ~0ULL : ((1ULL << (2 * K)) - 1);
+    const uint64_t lo_mask = K >= 32 ? ~0ULL : ((1ULL << (2 * K)) - 1);
+    const uint64_t hi_mask = K <= 32 ? 0ULL : K == 64 ? ~0ULL : ((1ULL << (2 * K - 64)) - 1);
     for (size_t i = 0; i < recs.size(); i++) {
         const string &s = recs[i].seq;
-        uint64_t m = 0;
+        uint64_t lo = 0, hi = 0;
         uint32_t run = 0;
         for (size_t j = 0; j < s.size(); j++) {
             if (valid_base(s[j])) {
-                m = ((m << 2) | base_code(s[j])) & kmask;
+                hi = ((hi << 2) | (lo >> 62)) & hi_mask;
+                lo = ((lo << 2) | base_code(s[j])) & lo_mask;
                 run++;
             } else
                 run = 0;
             if (j + 1 >= K) {
                 const size_t p = P.first[i] + (j + 1 - K);
-                P.keys[p] = run >= K ? m : 0;
+                P.keys[p] = run >= K ? lo : 0;
+                P.keys_hi[p] = run >= K ? hi : 0;
                 P.valid[p] = run >= K;
             }
         }
@@ -102,7 +107,8 @@ inline SeqPositions kmer_positions(const vector<SeqRecord> &recs, uint32_t K) {
     return P;
 }
 // JellyfishHelper::getCount(hash, mer, canonical) for every position, batched on the GPU(s) (collective on a job)
-inline vector<uint64_t> lookup_positions(Ctx &ctx, Input &in, const vector<uint64_t> &keys) {
+inline vector<uint64_t> lookup_positions(Ctx &ctx, Input &in, const SeqPositions &P) {
+    const vector<uint64_t> &keys = P.keys;
     vector<uint64_t> found(keys.size(), 0);
     const size_t batch = (size_t)1 << 26;
     for (size_t off = 0; off < keys.size(); off += batch) {
@@ -110,7 +116,8 @@ inline vector<uint64_t> lookup_positions(Ctx &ctx, Input &in, const vector<uint6
         vector<vector<uint64_t>> other(ctx.n());
         run_on_all(ctx.n(), [&](int r) {
             if (r) other[r].resize(m);
-            gpu_check(katgpu_lookup(in.tables[r], keys.data() + off, m, in.canonical ? 1 : 0, r ? other[r].data() : found.data() + off));
+            gpu_check(katgpu_lookup_wide(in.tables[r], P.keys_hi.data() + off, keys.data() + off, m, in.canonical ? 1 : 0,
+                                         r ? other[r].data() : found.data() + off));
         });
     }
     return found;

@@ -356,13 +356,23 @@ extern "C" katgpu_status katgpu_count_begin(katgpu_ctx *c, int k, int canonical,
     TraceScope trace__("katgpu_count_begin");
     if (!c || !out) return fail(KATGPU_ERR_INVALID, "katgpu_count_begin: NULL argument");
     *out = nullptr;
-    if (k < 1 || k > 32) return fail(KATGPU_ERR_INVALID, "katgpu_count_begin: k=%d outside 1..32 (one 64-bit word per k-mer)", k);
+    if (k < 1 || k > 64) return fail(KATGPU_ERR_INVALID, "katgpu_count_begin: k=%d outside 1..64 (one or two 64-bit words per k-mer)", k);
+    if (k > 32 && c->dist) return fail(KATGPU_ERR_INVALID, "katgpu_count_begin: k=%d > 32 is counted on one GPU (not on a multi-GPU context)", k);
     CU(cudaSetDevice(c->device));
     katgpu_table *t = new (std::nothrow) katgpu_table();
     if (!t) return fail(KATGPU_ERR_NOMEM, "katgpu_count_begin: out of host memory");
     t->ctx = c;
     t->allow_grow = allow_grow != 0;
     t->count_bits_cap = g_debug_count_bits;
+    if (k > 32) { // two-word keys: their own table layout and kernels (wide.cuh)
+        const katgpu_status stw = wide_begin(t, k, canonical, hash_size);
+        if (stw != KATGPU_OK) {
+            delete t;
+            return stw;
+        }
+        *out = t;
+        return KATGPU_OK;
+    }
     int Lb = ceil_log2(std::max<uint64_t>(hash_size, 1)) - 2; // slots -> buckets
     Lb = std::max(Lb, min_Lb(k));
     katgpu_status st = make_geom(k, canonical, Lb, t->count_bits_cap, t->g);
@@ -397,7 +407,8 @@ extern "C" void katgpu_table_free(katgpu_table *t) {
     if (!t) return;
     cudaSetDevice(t->ctx->device);
     cudaStreamSynchronize(t->ctx->stream);
-    free_table_storage(t->ctx, t->g);
+    if (t->wide) wide_free(t);
+    else free_table_storage(t->ctx, t->g);
     pend_release(t);
     delete t;
 }
@@ -405,6 +416,10 @@ extern "C" void katgpu_table_free(katgpu_table *t) {
 // Read the device counter block (synchronises the compute stream).
 katgpu_status read_counters(katgpu_table *t, TableCounters &out) {
     katgpu_ctx *c = t->ctx;
+    if (t->wide) { // wide tables keep their own counter block (katgpu_wide.cu)
+        out = TableCounters{};
+        return KATGPU_OK;
+    }
     CU(cudaMemcpyAsync(c->h_ctr, t->g.ctr, sizeof(TableCounters), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     out = *c->h_ctr;
@@ -528,6 +543,7 @@ static int count_path_mode() { // 0 auto, 1 direct, 2 partition (L2 sweep), 3 ti
 static const int kAutoPendingPath = 3; // which pending-key path "auto" picks for large jobs (2 = L2 sweep, 3 = tiled)
 static bool tiled_possible(const katgpu_table *t) { return (int)t->g.Lb >= kTileBucketsLog2 + 2; }
 bool use_partition(const katgpu_table *t, uint64_t kmers_hint) {
+    if (t->wide) return false; // two-word keys are inserted in read order
     if (t->pend_keys) return true; // keep the path the pending buffer was built for
     const int m = count_path_mode();
     if (m == 1 || t->g.Lb < 6) return false;
@@ -1033,6 +1049,7 @@ katgpu_status dist_make_room(katgpu_table *t, TableCounters &ctr, uint64_t n) {
 
 katgpu_status feed_device_range(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts,
                                        TableCounters &ctr, uint64_t kmers_hint) {
+    if (t->wide) return wide_feed_range(t, dev, n_valid, n_starts);
     // a k-mer start needs k bases
     if (n_valid < (uint64_t)t->g.k) return KATGPU_OK;
     n_starts = std::min(n_starts, n_valid - t->g.k + 1);
@@ -1098,7 +1115,8 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
     const size_t chunk = std::min(kChunkBytes, (n + 4095) / 4096 * 4096);
     const size_t n_chunks = (n + chunk - 1) / chunk;
     const int ring = (int)std::min<size_t>(kRing, std::max<size_t>(2, n_chunks));
-    KT(ensure_feed_staging(c, chunk, ring));
+    const size_t halo = t->wide ? (size_t)kWideHalo : (size_t)kHalo; // >= k-1 bases behind the last start of a chunk
+    KT(ensure_feed_staging(c, chunk + (halo - kHalo), ring));
     TableCounters ctr;
     KT(read_counters(t, ctr));
     // chunk i holds host bytes [i*chunk, (i+1)*chunk + halo): k-mers starting in
@@ -1106,7 +1124,7 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
     auto issue_copy = [&](size_t i) -> katgpu_status {
         const int b = (int)(i % ring);
         const size_t off = i * chunk;
-        const size_t len = std::min(n - off, chunk + kHalo);
+        const size_t len = std::min(n - off, chunk + halo);
         CU(cudaStreamWaitEvent(c->copy_stream, c->chunk_free[b], 0));
         CU(cudaMemcpyAsync(c->chunk[b], bases + off, len, cudaMemcpyHostToDevice, c->copy_stream));
         CU(cudaEventRecord(c->chunk_ready[b], c->copy_stream));
@@ -1125,7 +1143,7 @@ extern "C" katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, s
         while (issued < n_chunks && issued < i + (size_t)ring) KT(issue_copy(issued++)); // run ahead of the kernels
         const int b = (int)(i % ring);
         const size_t off = i * chunk;
-        const size_t len = std::min(n - off, chunk + kHalo);
+        const size_t len = std::min(n - off, chunk + halo);
         const size_t starts = std::min(n - off, chunk);
         CU(cudaStreamWaitEvent(c->stream, c->chunk_ready[b], 0));
         KT(feed_device_range(t, c->chunk[b], len, starts, ctr, n));
@@ -1153,6 +1171,13 @@ extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct,
     TraceScope trace__("katgpu_count_end");
     if (!t) return fail(KATGPU_ERR_INVALID, "katgpu_count_end: NULL table");
     CU(cudaSetDevice(t->ctx->device));
+    if (t->wide) {
+        if (!t->ended) KT(wide_totals(t, t->wide_distinct, t->wide_total));
+        t->ended = true;
+        if (n_distinct) *n_distinct = t->wide_distinct;
+        if (n_total) *n_total = t->wide_total;
+        return KATGPU_OK;
+    }
     TableCounters ctr;
     KT(read_counters(t, ctr));
     if (t->ctx->dist && !t->ended) KT(dist_count_end(t, ctr)); // every rank's last route round has been binned here
@@ -1186,6 +1211,17 @@ extern "C" katgpu_status katgpu_count_end(katgpu_table *t, uint64_t *n_distinct,
 extern "C" katgpu_status katgpu_table_get_info(katgpu_table *t, katgpu_table_info *out) {
     if (!t || !out) return fail(KATGPU_ERR_INVALID, "katgpu_table_get_info: NULL argument");
     CU(cudaSetDevice(t->ctx->device));
+    if (t->wide) {
+        *out = katgpu_table_info{};
+        out->k = (int)t->g.k;
+        out->canonical = (int)t->g.canonical;
+        out->slots = t->n_slots;
+        out->bytes = wide_bytes(t);
+        KT(wide_totals(t, out->n_distinct, out->n_total));
+        out->count_bits = 64;
+        out->grow_events = t->grow_events;
+        return KATGPU_OK;
+    }
     TableCounters ctr;
     KT(read_counters(t, ctr));
     out->k = t->g.k;
@@ -1205,6 +1241,7 @@ extern "C" katgpu_status katgpu_route_device(katgpu_table *t, const void *bases_
                                              void *const *out_dev, uint64_t cap_keys, uint64_t *counts_out) {
     if (!t || !out_dev || !counts_out || (!bases_dev && n)) return fail(KATGPU_ERR_INVALID, "katgpu_route_device: NULL argument");
     if (n_ranks < 1 || n_ranks > kMaxRanks) return fail(KATGPU_ERR_INVALID, "katgpu_route_device: n_ranks=%d outside 1..%d", n_ranks, kMaxRanks);
+    if (t->wide) return fail(KATGPU_ERR_INVALID, "katgpu_route_device: one-word keys only (k <= 32)");
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));
     for (int r = 0; r < n_ranks; r++) counts_out[r] = 0;
@@ -1243,6 +1280,7 @@ extern "C" katgpu_status katgpu_route_device(katgpu_table *t, const void *bases_
 extern "C" katgpu_status katgpu_count_add_pairs(katgpu_table *t, const uint64_t *keys, const uint64_t *counts, size_t n) {
     if (!t || ((!keys || !counts) && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_add_pairs: NULL argument");
     if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_add_pairs: table already finished");
+    if (t->wide) return fail(KATGPU_ERR_INVALID, "katgpu_count_add_pairs: k > 32 needs two words per key: katgpu_count_add_pairs_wide");
     katgpu_ctx *c = t->ctx;
     if (c->dist) return fail(KATGPU_ERR_STATE, "katgpu_count_add_pairs: not available on a multi-GPU context (load hashes on one GPU)");
     CU(cudaSetDevice(c->device));
@@ -1286,8 +1324,20 @@ extern "C" katgpu_status katgpu_count_add_pairs(katgpu_table *t, const uint64_t 
     return st;
 }
 
+// (key, count) records with two words per key; works for every k (keys_hi is ignored — may be NULL — when k <= 32)
+extern "C" katgpu_status katgpu_count_add_pairs_wide(katgpu_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo,
+                                                     const uint64_t *counts, size_t n) {
+    if (!t || ((!keys_lo || !counts) && n)) return fail(KATGPU_ERR_INVALID, "katgpu_count_add_pairs_wide: NULL argument");
+    if (!t->wide) return katgpu_count_add_pairs(t, keys_lo, counts, n);
+    if (!keys_hi && n) return fail(KATGPU_ERR_INVALID, "katgpu_count_add_pairs_wide: NULL argument");
+    if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_count_add_pairs_wide: table already finished");
+    CU(cudaSetDevice(t->ctx->device));
+    return wide_add_pairs(t, keys_hi, keys_lo, counts, n);
+}
+
 extern "C" katgpu_status katgpu_insert_hashed_device(katgpu_table *t, const void *hashed_dev, uint64_t n) {
     if (!t || (!hashed_dev && n)) return fail(KATGPU_ERR_INVALID, "katgpu_insert_hashed_device: NULL argument");
+    if (t->wide) return fail(KATGPU_ERR_INVALID, "katgpu_insert_hashed_device: one-word keys only (k <= 32)");
     if (t->ended) return fail(KATGPU_ERR_STATE, "katgpu_insert_hashed_device: table already finished");
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));

@@ -512,7 +512,7 @@ katgpu_status dist_count_end(katgpu_table *t, TableCounters &ctr) {
 // owners whose receive areas are all local memory — the kernel's own cost without NVLink.  The keys
 // are written and thrown away; *ms = kernel time (CUDA events on the compute stream), *keys = keys written.
 extern "C" katgpu_status katgpu_debug_route_local(katgpu_table *t, const void *bases_dev, size_t n, int n_ranks, double *ms, uint64_t *keys) {
-    if (!t || !bases_dev || !ms || n_ranks < 1 || n_ranks > kMaxRanks) return fail(KATGPU_ERR_INVALID, "katgpu_debug_route_local: bad arguments");
+    if (!t || !bases_dev || !ms || n_ranks < 1 || n_ranks > kMaxRanks || t->wide) return fail(KATGPU_ERR_INVALID, "katgpu_debug_route_local: bad arguments");
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));
     int bps = 2;

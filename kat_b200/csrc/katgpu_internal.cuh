@@ -9,6 +9,7 @@
 #include "tile_kernels.cuh"
 #include "reduce_kernels.cuh"
 #include "parse_kernels.cuh"
+#include "wide_kernels.cuh"
 
 #include <chrono>
 #include <cstdio>
@@ -39,6 +40,7 @@ struct ProfSpan {
 
 constexpr int kRing = 24; // host-feed staging ring: lets the copy engine run ahead of a mid-feed sweep
 struct DistState;         // katgpu_dist.cu
+struct WideTable;         // katgpu_wide.cu
 
 struct katgpu_ctx {
     int device = 0;
@@ -106,6 +108,10 @@ struct katgpu_table {
     // multi-GPU (katgpu_dist.cu): keys this rank has binned per level-1 CTA since the last sweep
     uint64_t dist_cta_keys = 0;
     uint64_t dist_global_distinct = 0, dist_global_total = 0; // after katgpu_count_end
+    // k = 33..64: the table lives in the two-word layout of wide.cuh (katgpu_wide.cu); `g` then only carries k and
+    // the canonical flag, and every entry point hands over to the wide_* functions below
+    WideTable *wide = nullptr;
+    uint64_t wide_distinct = 0, wide_total = 0; // after katgpu_count_end
 };
 
 constexpr size_t kChunkBytes = 128u << 20; // host feed granularity
@@ -169,6 +175,22 @@ bool dist_can_tile(const katgpu_table *t);                                      
 katgpu_status dist_make_room(katgpu_table *t, katgpu::TableCounters &ctr, uint64_t n); // grow until n more distinct keys fit
 // record `ev` once everything queued so far that reads feed input has run (compute stream and, on a job, the route stream)
 katgpu_status record_feed_consumed(katgpu_ctx *c, cudaEvent_t ev);
+
+// ---- two-word keys, k = 33..64 (katgpu_wide.cu) ----
+katgpu_status wide_begin(katgpu_table *t, int k, int canonical, uint64_t hash_size);
+void wide_free(katgpu_table *t);
+katgpu_status wide_feed_range(katgpu_table *t, const uint8_t *dev, uint64_t n_valid, uint64_t n_starts);
+katgpu_status wide_add_pairs(katgpu_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo, const uint64_t *counts, size_t n);
+katgpu_status wide_totals(katgpu_table *t, uint64_t &n_distinct, uint64_t &n_total);
+uint64_t wide_bytes(const katgpu_table *t);
+katgpu_status wide_hist(katgpu_table *t, uint64_t base, uint64_t ceil_, uint64_t inc, uint64_t nb, uint64_t *bins_out);
+katgpu_status wide_gcp(katgpu_table *t, double cvg_scale, uint32_t cvg_bins, uint64_t *mx_out);
+katgpu_status wide_comp(katgpu_table *t1, katgpu_table *t2, katgpu_table *t3, double d1_scale, double d2_scale, uint32_t d1_bins,
+                        uint32_t d2_bins, uint64_t *main_mx, uint64_t *ends_mx, uint64_t *middle_mx, uint64_t *mixed_mx,
+                        katgpu_comp_counters *counters, uint64_t *spectra);
+katgpu_status wide_lookup_host(katgpu_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo, size_t n, int canonicalise, uint64_t *counts_out);
+katgpu_status wide_export(katgpu_table *t, const katgpu::ExportSel &sel, uint64_t *keys_hi_out, uint64_t *keys_lo_out, uint64_t *counts_out,
+                          size_t cap, uint64_t *n_out);
 
 // ---- multi-GPU hooks (katgpu_dist.cu); all are no-ops / never called when ctx->dist is null ----
 void dist_shutdown(katgpu_ctx *c);

@@ -32,6 +32,7 @@ extern "C" katgpu_status katgpu_hist(katgpu_table *t, uint64_t base, uint64_t ce
     if (!bins_out || nb == 0 || inc == 0 || nb > 0x7fffffffULL) return fail(KATGPU_ERR_INVALID, "katgpu_hist: bad arguments");
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));
+    if (t->wide) return wide_hist(t, base, ceil_, inc, nb, bins_out);
     DevBuf d;
     CU(cudaMalloc(&d.p, nb * 8));
     CU(cudaMemsetAsync(d.p, 0, nb * 8, c->stream));
@@ -52,6 +53,7 @@ extern "C" katgpu_status katgpu_gcp(katgpu_table *t, double cvg_scale, uint32_t 
     if (!mx_out) return fail(KATGPU_ERR_INVALID, "katgpu_gcp: NULL output");
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));
+    if (t->wide) return wide_gcp(t, cvg_scale, cvg_bins, mx_out);
     const size_t cells = (size_t)t->g.k * ((size_t)cvg_bins + 1);
     DevBuf d;
     CU(cudaMalloc(&d.p, cells * 8));
@@ -86,6 +88,8 @@ extern "C" katgpu_status katgpu_comp(katgpu_table *t1, katgpu_table *t2, katgpu_
     if (c->dist && !(t1->g.canonical && t2->g.canonical && (!t3 || t3->g.canonical)))
         return fail(KATGPU_ERR_INVALID, "katgpu_comp: on a multi-GPU context every input must be counted canonically");
     CU(cudaSetDevice(c->device));
+    if (t1->wide) // same k everywhere, so every table is wide
+        return wide_comp(t1, t2, t3, d1_scale, d2_scale, d1_bins, d2_bins, main_mx, ends_mx, middle_mx, mixed_mx, counters, spectra);
     const uint32_t len = std::min(d1_bins, d2_bins);
     const size_t cells = (size_t)d1_bins * d2_bins;
     const size_t n_mx = t3 ? 4 : 1;
@@ -161,6 +165,7 @@ extern "C" katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, si
                                        uint64_t *counts_out) {
     KT(finished(t, "katgpu_lookup"));
     if ((!keys || !counts_out) && n) return fail(KATGPU_ERR_INVALID, "katgpu_lookup: NULL argument");
+    if (t->wide) return fail(KATGPU_ERR_INVALID, "katgpu_lookup: k > 32 needs two words per key: katgpu_lookup_wide");
     if (n == 0) return KATGPU_OK;
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));
@@ -178,10 +183,22 @@ extern "C" katgpu_status katgpu_lookup(katgpu_table *t, const uint64_t *keys, si
     return KATGPU_OK;
 }
 
+// Two words per key: every k.  keys_hi may be NULL for a one-word table (k <= 32).
+extern "C" katgpu_status katgpu_lookup_wide(katgpu_table *t, const uint64_t *keys_hi, const uint64_t *keys_lo, size_t n, int canonicalise,
+                                            uint64_t *counts_out) {
+    KT(finished(t, "katgpu_lookup_wide"));
+    if (!t->wide) return katgpu_lookup(t, keys_lo, n, canonicalise, counts_out);
+    if ((!keys_hi || !keys_lo || !counts_out) && n) return fail(KATGPU_ERR_INVALID, "katgpu_lookup_wide: NULL argument");
+    if (n == 0) return KATGPU_OK;
+    CU(cudaSetDevice(t->ctx->device));
+    return wide_lookup_host(t, keys_hi, keys_lo, n, canonicalise, counts_out);
+}
+
 static katgpu_status export_selected(katgpu_table *t, const ExportSel &sel, uint64_t *keys_out, uint64_t *counts_out, size_t cap,
                                       uint64_t *n_out, const char *who) {
     KT(finished(t, who));
     if (!n_out || ((!keys_out || !counts_out) && cap)) return fail(KATGPU_ERR_INVALID, "%s: NULL argument", who);
+    if (t->wide) return fail(KATGPU_ERR_INVALID, "%s: k > 32 needs two words per key: katgpu_table_export_wide", who);
     katgpu_ctx *c = t->ctx;
     CU(cudaSetDevice(c->device));
     DevBuf dk, dc, dn;
@@ -216,4 +233,30 @@ extern "C" katgpu_status katgpu_table_export_filtered(katgpu_table *t, uint64_t 
     sel.mode = inside ? 1 : -1;
     sel.low_count = low_count, sel.high_count = high_count, sel.low_gc = low_gc, sel.high_gc = high_gc;
     return export_selected(t, sel, keys_out, counts_out, cap, n_out, "katgpu_table_export_filtered");
+}
+
+// Two words per key: every k (keys_hi_out receives zeros for a one-word table and may then be NULL).
+static katgpu_status export_selected_wide(katgpu_table *t, const ExportSel &sel, uint64_t *keys_hi_out, uint64_t *keys_lo_out,
+                                           uint64_t *counts_out, size_t cap, uint64_t *n_out, const char *who) {
+    KT(finished(t, who));
+    if (!t->wide) {
+        KT(export_selected(t, sel, keys_lo_out, counts_out, cap, n_out, who));
+        if (keys_hi_out) memset(keys_hi_out, 0, std::min<size_t>(cap, *n_out) * 8);
+        return KATGPU_OK;
+    }
+    if (!n_out || ((!keys_hi_out || !keys_lo_out || !counts_out) && cap)) return fail(KATGPU_ERR_INVALID, "%s: NULL argument", who);
+    CU(cudaSetDevice(t->ctx->device));
+    return wide_export(t, sel, keys_hi_out, keys_lo_out, counts_out, cap, n_out);
+}
+extern "C" katgpu_status katgpu_table_export_wide(katgpu_table *t, uint64_t *keys_hi_out, uint64_t *keys_lo_out, uint64_t *counts_out,
+                                                  size_t cap, uint64_t *n_out) {
+    return export_selected_wide(t, ExportSel(), keys_hi_out, keys_lo_out, counts_out, cap, n_out, "katgpu_table_export_wide");
+}
+extern "C" katgpu_status katgpu_table_export_filtered_wide(katgpu_table *t, uint64_t low_count, uint64_t high_count, uint32_t low_gc,
+                                                           uint32_t high_gc, int inside, uint64_t *keys_hi_out, uint64_t *keys_lo_out,
+                                                           uint64_t *counts_out, size_t cap, uint64_t *n_out) {
+    ExportSel sel;
+    sel.mode = inside ? 1 : -1;
+    sel.low_count = low_count, sel.high_count = high_count, sel.low_gc = low_gc, sel.high_gc = high_gc;
+    return export_selected_wide(t, sel, keys_hi_out, keys_lo_out, counts_out, cap, n_out, "katgpu_table_export_filtered_wide");
 }

@@ -15,8 +15,14 @@ def cases():
         return json.load(f)
 
 
-def expected_bytes(case, fname):
-    p = os.path.join(GOLDEN, "expected", case, fname)
+def wide_cases():
+    """hist / gcp / comp commands at k = 33..64 (tests/golden/wide, make_wide_golden.py)."""
+    with open(os.path.join(GOLDEN, "wide", "cases.json")) as f:
+        return [dict(c, dir="wide") for c in json.load(f) if c["args"][0] in ("hist", "gcp", "comp")]
+
+
+def expected_bytes(case, fname, sub="expected"):
+    p = os.path.join(GOLDEN, sub, case, fname)
     if os.path.exists(p):
         return open(p, "rb").read()
     return gzip.open(p + ".gz", "rb").read()

@@ -158,9 +158,9 @@ katgpu_status katgpu_table_export(katgpu_table *t, uint64_t *keys_out, uint64_t 
 static unsigned gc_of(uint64_t hi, uint64_t lo) {
     return (unsigned)(__builtin_popcountll((lo ^ (lo >> 1)) & 0x5555555555555555ULL) + __builtin_popcountll((hi ^ (hi >> 1)) & 0x5555555555555555ULL));
 }
-katgpu_status katgpu_table_export_filtered(katgpu_table *t, uint64_t low_count, uint64_t high_count, uint32_t low_gc, uint32_t high_gc,
-                                           int inside, uint64_t *keys_out, uint64_t *counts_out, size_t cap, uint64_t *n_out) {
-    if (t->k > 32) return fail(KATGPU_ERR_INVALID, "k > 32");
+katgpu_status katgpu_table_export_filtered_wide(katgpu_table *t, uint64_t low_count, uint64_t high_count, uint32_t low_gc, uint32_t high_gc,
+                                                int inside, uint64_t *keys_hi_out, uint64_t *keys_lo_out, uint64_t *counts_out, size_t cap,
+                                                uint64_t *n_out) {
     const uint64_t n = oracle_table_distinct(t->o);
     uint64_t *hi = (uint64_t *)malloc((n ? n : 1) * 8), *lo = (uint64_t *)malloc((n ? n : 1) * 8), *cn = (uint64_t *)malloc((n ? n : 1) * 8);
     uint64_t got = 0, m = 0;
@@ -169,11 +169,19 @@ katgpu_status katgpu_table_export_filtered(katgpu_table *t, uint64_t low_count, 
         const unsigned gc = gc_of(hi[i], lo[i]);
         const int in_bounds = low_gc <= gc && gc <= high_gc && low_count <= cn[i] && cn[i] <= high_count;
         if (in_bounds == (inside != 0)) {
-            if (m < cap) keys_out[m] = lo[i], counts_out[m] = cn[i];
+            if (m < cap) {
+                if (keys_hi_out) keys_hi_out[m] = hi[i];
+                keys_lo_out[m] = lo[i], counts_out[m] = cn[i];
+            }
             m++;
         }
     }
     free(hi); free(lo); free(cn);
     *n_out = m;
     return KATGPU_OK;
+}
+katgpu_status katgpu_table_export_filtered(katgpu_table *t, uint64_t low_count, uint64_t high_count, uint32_t low_gc, uint32_t high_gc,
+                                           int inside, uint64_t *keys_out, uint64_t *counts_out, size_t cap, uint64_t *n_out) {
+    if (t->k > 32) return fail(KATGPU_ERR_INVALID, "k > 32: use katgpu_table_export_filtered_wide");
+    return katgpu_table_export_filtered_wide(t, low_count, high_count, low_gc, high_gc, inside, NULL, keys_out, counts_out, cap, n_out);
 }

@@ -231,3 +231,34 @@ def test_cli_filter_errors(tmp_path):
                       (["filter", "nonsense", fa], "Could not recognise mode string: nonsense")):
         r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, timeout=120)
         assert r.returncode == 4 and msg in r.stderr, (args, r.returncode, r.stderr)
+
+
+# ---- mer lengths above 32: two-word keys ------------------------------
+WIDE_MANIFEST = json.load(open(os.path.join(G.GOLDEN, "wide", "cases.json")))
+
+
+@pytest.mark.parametrize("case", WIDE_MANIFEST, ids=lambda c: c["name"])
+def test_cli_wide_kmers_output_files_byte_identical(case, tmp_path):
+    """hist / gcp / comp (2 and 3 inputs, mixed canonical) / sect / cold / filter seq at k = 33..64: every output file equals
+    the file the reference binary writes (tests/golden/wide, make_wide_golden.py)."""
+    shutil.copytree(os.path.join(G.GOLDEN, "inputs"), tmp_path / "inputs")
+    out = os.path.join("wide", case["name"])
+    os.makedirs(tmp_path / out)
+    args = [a.replace("OUT", out) for a in case["args"]]
+    r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    assert sorted(os.listdir(tmp_path / out)) == case["files"]
+    for f in case["files"]:
+        p = os.path.join(G.GOLDEN, "wide", case["name"], f)
+        want = open(p, "rb").read() if os.path.exists(p) else gzip.open(p + ".gz", "rb").read()
+        assert open(tmp_path / out / f, "rb").read() == want, f"{case['name']}/{f} differs from the reference's file"
+
+
+def test_cli_wide_kmers_limits(tmp_path):
+    """What two-word k-mers do not cover is refused with a message, not computed wrongly: k > 64, hash dumps, filter kmer."""
+    fa = os.path.join(G.GOLDEN, "inputs", "long.fa")
+    for args, msg in ((["hist", "-m65", fa], "mer lengths 1..64"),
+                      (["hist", "-m40", "-d", "-o", "h", fa], "--dump_hash is limited to mer lengths up to 32"),
+                      (["filter", "kmer", "-m33", "-o", "k", fa], "limited to mer lengths up to 32")):
+        r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, timeout=120)
+        assert r.returncode == 4 and msg in r.stderr, (args, r.returncode, r.stderr)

@@ -50,6 +50,8 @@ test_cli_load_mode_files_byte_identical = T.test_cli_load_mode_files_byte_identi
 test_cli_comp_dump_hashes_and_symlink = T.test_cli_comp_dump_hashes_and_symlink
 test_cli_filter_matches_reference = T.test_cli_filter_matches_reference
 test_cli_filter_errors = T.test_cli_filter_errors
+test_cli_wide_kmers_output_files_byte_identical = T.test_cli_wide_kmers_output_files_byte_identical
+test_cli_wide_kmers_limits = T.test_cli_wide_kmers_limits
 test_cli_hash_full_exit_code = T.test_cli_hash_full_exit_code
 test_cli_missing_input = T.test_cli_missing_input
 test_cli_dev_paths_are_pipes = T.test_cli_dev_paths_are_pipes
