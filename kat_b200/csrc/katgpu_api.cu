@@ -742,6 +742,23 @@ static katgpu_status sweep_tiled(katgpu_table *t, TableCounters &ctr) {
         for (;;) {
             spg = (uint32_t)std::max(1.0, std::min((double)F1, budget / (slice_keys * 8.0 * 1.3)));
             parts = std::min<uint32_t>(std::max<uint32_t>(1, std::min<uint32_t>(8, (want_ctas + spg - 1) / spg)), n_segs);
+            // bin_keys_kernel keeps ONE CTA per SM, all of equal work: a launch of ns * parts CTAs takes
+            // ceil(ns * parts / SMs) rounds whether or not the last one is full (124 slices x 2 shares = 248 CTAs on 148
+            // SMs: two rounds, a third of the second empty; 9 rounds for the 512 slices where 7 would do).  Among the
+            // group sizes the budget allows (down to half of it) and 1..8 shares per slice, take the pair that spends
+            // the fewest CTA slots over the whole sweep; ties go to fewer shares, then to larger groups.
+            if (!getenv("KATGPU_TILED_NO_WAVE_FIT")) {
+                const uint32_t spg_max = spg, sms = want_ctas;
+                double best = 1e300;
+                for (uint32_t pt = 1; pt <= std::min<uint32_t>(8, n_segs); pt++)
+                    for (uint32_t sg = spg_max; sg >= std::max<uint32_t>(1, spg_max / 2); sg--) {
+                        const uint32_t full = F1 / sg, rest = F1 % sg;
+                        const uint64_t rounds = (uint64_t)full * ((sg * pt + sms - 1) / sms) + ((uint64_t)rest * pt + sms - 1) / sms;
+                        const double cost = (double)rounds / pt * (1.0 + 0.03 * (pt - 1)) // a CTA's work goes as 1 / shares (+ its fixed part)
+                                            + 0.02 * (double)(full + (rest != 0));        // per-launch overhead, in rounds
+                        if (cost < best - 1e-9) best = cost, spg = sg, parts = pt;
+                    }
+            }
             for (;;) {
                 const double mean2 = slice_keys / ((double)F2 * parts);
                 cap2 = ((uint64_t)(mean2 + 6.0 * std::sqrt(mean2) + 32.0) + 15) / 16 * 16;
