@@ -273,6 +273,38 @@ uint64_t jf_position(const JfHeader &h, uint64_t key) {
     return h.size ? res & (h.size - 1) : res;
 }
 
+uint64_t jf_position(const JfHeader &h, uint64_t key_hi, uint64_t key_lo) {
+    uint64_t res = 0;
+    const unsigned c = h.matrix_c;
+    for (unsigned j = 0; j < c && j < 128; j++)
+        if (((j < 64 ? key_lo >> j : key_hi >> (j - 64)) & 1) != 0) res ^= h.matrix_columns[c - 1 - j];
+    return h.size ? res & (h.size - 1) : res;
+}
+
+bool jf_read_records_wide(std::istream &is, const JfHeader &h, size_t batch,
+                          const std::function<void(const uint64_t *, const uint64_t *, const uint64_t *, size_t)> &sink, std::string &err) {
+    const unsigned kb = h.key_bytes(), cb = h.counter_len, rb = kb + cb;
+    if (kb == 0 || kb > 16 || cb == 0 || cb > 8) return err = "unsupported record layout (key_len " + std::to_string(h.key_len) + " bits, counter_len " + std::to_string(cb) + ")", false;
+    if (batch == 0) batch = 1;
+    std::vector<unsigned char> raw(batch * rb);
+    std::vector<uint64_t> hi(batch), lo(batch), counts(batch);
+    for (;;) {
+        is.read(reinterpret_cast<char *>(raw.data()), (std::streamsize)raw.size());
+        const size_t got = (size_t)is.gcount();
+        if (got % rb) return err = "Size of database must be a multiple of the length of a record (" + std::to_string(rb) + ")", false;
+        const size_t n = got / rb;
+        for (size_t i = 0; i < n; i++) {
+            uint64_t w[2] = {0, 0}, c = 0;
+            memcpy(w, &raw[i * rb], kb); // little-endian words of mer_dna::data(): the low word first
+            memcpy(&c, &raw[i * rb + kb], cb);
+            lo[i] = w[0], hi[i] = w[1], counts[i] = c;
+        }
+        if (n) sink(hi.data(), lo.data(), counts.data(), n);
+        if (got < raw.size()) break;
+    }
+    return true;
+}
+
 bool jf_read_records(std::istream &is, const JfHeader &h, size_t batch,
                      const std::function<void(const uint64_t *, const uint64_t *, size_t)> &sink, std::string &err) {
     const unsigned kb = h.key_bytes(), cb = h.counter_len, rb = kb + cb;
@@ -331,7 +363,24 @@ static void sort_by_key(std::vector<uint64_t> &keys, std::vector<uint64_t> &coun
     for (size_t i = 0; i < n; i++) keys[i] = rec[i].first, counts[i] = rec[i].second;
 }
 
+static void fill_dump_header(JfHeader &h, unsigned k, bool canonical, uint64_t n);
 void jf_prepare_dump(JfHeader &h, unsigned k, bool canonical, uint64_t n, std::vector<uint64_t> &keys, std::vector<uint64_t> &counts) {
+    fill_dump_header(h, k, canonical, n);
+    // ascending (position, key) == ascending key under this matrix
+    sort_by_key(keys, counts, k);
+}
+void jf_prepare_dump_wide(JfHeader &h, unsigned k, bool canonical, uint64_t n, std::vector<uint64_t> &keys_hi, std::vector<uint64_t> &keys_lo,
+                          std::vector<uint64_t> &counts) {
+    fill_dump_header(h, k, canonical, n);
+    struct Rec {
+        uint64_t hi, lo, count;
+    };
+    std::vector<Rec> rec(keys_lo.size());
+    for (size_t i = 0; i < rec.size(); i++) rec[i] = {keys_hi[i], keys_lo[i], counts[i]};
+    std::sort(rec.begin(), rec.end(), [](const Rec &a, const Rec &b) { return a.hi < b.hi || (a.hi == b.hi && a.lo < b.lo); });
+    for (size_t i = 0; i < rec.size(); i++) keys_hi[i] = rec[i].hi, keys_lo[i] = rec[i].lo, counts[i] = rec[i].count;
+}
+static void fill_dump_header(JfHeader &h, unsigned k, bool canonical, uint64_t n) {
     h.format = "binary/sorted";
     h.key_len = 2 * k;
     h.canonical = canonical;
@@ -349,8 +398,27 @@ void jf_prepare_dump(JfHeader &h, unsigned k, bool canonical, uint64_t n, std::v
     for (unsigned j = shift; j < h.matrix_c; j++) h.matrix_columns[h.matrix_c - 1 - j] = 1ULL << (j - shift);
     h.reprobes.resize(h.max_reprobe + 1);
     for (unsigned i = 0; i <= h.max_reprobe; i++) h.reprobes[i] = i == 0 ? 1 : (uint64_t)i * (i + 1) / 2; // JF/lib/storage.cc quadratic_reprobes
-    // ascending (position, key) == ascending key under this matrix
-    sort_by_key(keys, counts, k);
+}
+
+void jf_write_file_wide(std::ostream &os, JfHeader &h, const std::vector<uint64_t> &keys_hi, const std::vector<uint64_t> &keys_lo,
+                        const std::vector<uint64_t> &counts) {
+    jf_write_header(os, h);
+    const unsigned kb = h.key_bytes(), cb = h.counter_len, rb = kb + cb;
+    const uint64_t vmax = cb >= 8 ? ~0ULL : ((1ULL << (8 * cb)) - 1);
+    std::vector<unsigned char> buf;
+    buf.reserve((size_t)rb << 16);
+    for (size_t i = 0; i < keys_lo.size(); i++) {
+        const uint64_t w[2] = {keys_lo[i], keys_hi[i]}, c = std::min(counts[i], vmax);
+        const size_t at = buf.size();
+        buf.resize(at + rb);
+        memcpy(&buf[at], w, kb);
+        memcpy(&buf[at + kb], &c, cb);
+        if (buf.size() >= ((size_t)rb << 16)) {
+            os.write(reinterpret_cast<const char *>(buf.data()), (std::streamsize)buf.size());
+            buf.clear();
+        }
+    }
+    if (!buf.empty()) os.write(reinterpret_cast<const char *>(buf.data()), (std::streamsize)buf.size());
 }
 
 void jf_write_file(std::ostream &os, JfHeader &h, const std::vector<uint64_t> &keys, const std::vector<uint64_t> &counts) {

@@ -36,13 +36,24 @@ bool jf_read_header(std::istream &is, JfHeader &h, std::string &err);
 // Write the header (sets h.offset).  fill_standard() analogue: hostname/pwd/time/exe_path are
 // filled in when empty.
 void jf_write_header(std::ostream &os, JfHeader &h);
-// Position of a key in the dumped hash: (M * key) & (size - 1).
+// Position of a key in the dumped hash: (M * key) & (size - 1).  Keys longer than 32 bases carry their upper
+// 2k - 64 bits in key_hi (mer_dna keeps ceil(2k/64) words, JFI/mer_dna.hpp:513-531).
 uint64_t jf_position(const JfHeader &h, uint64_t key);
+uint64_t jf_position(const JfHeader &h, uint64_t key_hi, uint64_t key_lo);
 
 // Read every record (key_len <= 64), handing them out in batches of at most `batch` records.
 // Returns false (err set) on a truncated file.
 bool jf_read_records(std::istream &is, const JfHeader &h, size_t batch,
                      const std::function<void(const uint64_t *keys, const uint64_t *counts, size_t n)> &sink, std::string &err);
+
+// The same for any key_len <= 128 (k <= 64): two words per key.
+bool jf_read_records_wide(std::istream &is, const JfHeader &h, size_t batch,
+                          const std::function<void(const uint64_t *keys_hi, const uint64_t *keys_lo, const uint64_t *counts, size_t n)> &sink,
+                          std::string &err);
+void jf_prepare_dump_wide(JfHeader &h, unsigned k, bool canonical, uint64_t n, std::vector<uint64_t> &keys_hi, std::vector<uint64_t> &keys_lo,
+                          std::vector<uint64_t> &counts);
+void jf_write_file_wide(std::ostream &os, JfHeader &h, const std::vector<uint64_t> &keys_hi, const std::vector<uint64_t> &keys_lo,
+                        const std::vector<uint64_t> &counts);
 
 // Prepare `h` for a dump of `n` k-mers of `k` bases and sort the records the way sorted_dumper
 // emits them: ascending (position, key).  The matrix is the top-bits selector

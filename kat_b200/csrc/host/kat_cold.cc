@@ -43,7 +43,7 @@ int cold_main(int argc, char **argv) {
     assembly.validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));
-    check_wide_limits(k, ctx.n(), a.has("dump_hashes"), "--dump_hashes");
+    check_wide_limits(k, ctx.n());
     if (a.has("dump_hashes") && ctx.n() > 1) throw KatError(4, "--dump_hashes writes one GPU's table: run without --gpus");
     int k_reads = k, k_asm = k;
     if (reads.load_mode) load_inputs_phase(ctx, &reads, 1, k_reads);

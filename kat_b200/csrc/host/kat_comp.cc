@@ -81,7 +81,7 @@ int comp_main(int argc, char **argv) {
     for (int i = 0; i < (three ? 3 : 2); i++) in[i].validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));
-    check_wide_limits(k, ctx.n(), a.has("dump_hashes"), "--dump_hashes");
+    check_wide_limits(k, ctx.n());
     if (a.has("dump_hashes") && ctx.n() > 1) throw KatError(4, "--dump_hashes writes one GPU's table: run without --gpus");
     if (ctx.n() > 1)
         for (int i = 0; i < (three ? 3 : 2); i++)

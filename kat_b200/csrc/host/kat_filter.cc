@@ -3,7 +3,7 @@
 //   filter kmer  (src/filter_kmer.cc:119-309): count or load a hash, keep the k-mers whose count and GC count lie
 //                inside (or, with -i, outside) the bounds, write them as a jellyfish hash <prefix>-in.jf<k>
 //                (and the rest as <prefix>-out.jf<k> with -s).  The walk over the table with the bounds test
-//                (FilterKmer::filterSlice / inBounds, :257-309) runs on the GPU: katgpu_table_export_filtered.
+//                (FilterKmer::filterSlice / inBounds, :257-309) runs on the GPU: katgpu_table_export_filtered(_wide).
 //   filter seq   (src/filter_sequence.cc:106-368): count or load a hash, look up every k-mer position of every
 //                record of one (or two, paired) sequence file(s) — FilterSeq::getProfile, one
 //                JellyfishHelper::getCount per position (:353-366) — as batched katgpu_lookup calls, and write
@@ -36,7 +36,6 @@ int filter_kmer_main(int argc, char **argv) {
     cout << "Running KAT in filter kmer mode" << endl << "-------------------------------" << endl << endl;
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
     check_mer_len(k);
-    check_wide_limits(k, 1, true, "kat filter kmer (it writes jellyfish hashes)");
     const uint64_t low_count = to_u64(a.get("low_count", "1"), "low_count"), high_count = to_u64(a.get("high_count", "10000"), "high_count");
     const uint32_t low_gc = (uint32_t)to_u64(a.get("low_gc", "1"), "low_gc"), high_gc = (uint32_t)to_u64(a.get("high_gc", "100"), "high_gc");
     const bool invert = a.has("invert"), separate = a.has("separate");
@@ -60,23 +59,26 @@ int filter_kmer_main(int argc, char **argv) {
     cout << "Filtering kmers ...";
     cout.flush();
     struct Set {
-        vector<uint64_t> keys, counts;
+        vector<uint64_t> keys_hi, keys, counts; // keys_hi: the first k-32 bases, all zero for k <= 32
         uint64_t total = 0;
     };
     auto select = [&](bool inside) {
         vector<Set> part(ctx.n());
         run_on_all(ctx.n(), [&](int r) {
             uint64_t n = 0;
-            gpu_check(katgpu_table_export_filtered(in.tables[r], low_count, high_count, low_gc, high_gc, inside ? 1 : 0, nullptr, nullptr, 0, &n));
+            gpu_check(katgpu_table_export_filtered_wide(in.tables[r], low_count, high_count, low_gc, high_gc, inside ? 1 : 0, nullptr, nullptr, nullptr, 0, &n));
             part[r].keys.resize((size_t)std::max<uint64_t>(n, 1));
+            part[r].keys_hi.resize(part[r].keys.size());
             part[r].counts.resize(part[r].keys.size());
-            gpu_check(katgpu_table_export_filtered(in.tables[r], low_count, high_count, low_gc, high_gc, inside ? 1 : 0, part[r].keys.data(),
-                                                   part[r].counts.data(), (size_t)n, &n));
+            gpu_check(katgpu_table_export_filtered_wide(in.tables[r], low_count, high_count, low_gc, high_gc, inside ? 1 : 0, part[r].keys_hi.data(),
+                                                        part[r].keys.data(), part[r].counts.data(), (size_t)n, &n));
             part[r].keys.resize((size_t)n);
+            part[r].keys_hi.resize((size_t)n);
             part[r].counts.resize((size_t)n);
         });
         Set s;
         for (auto &p : part) {
+            s.keys_hi.insert(s.keys_hi.end(), p.keys_hi.begin(), p.keys_hi.end());
             s.keys.insert(s.keys.end(), p.keys.begin(), p.keys.end());
             s.counts.insert(s.counts.end(), p.counts.begin(), p.counts.end());
         }
@@ -100,9 +102,14 @@ int filter_kmer_main(int argc, char **argv) {
         cout << "Dumping hash to " << path << " ...";
         cout.flush();
         kat_host::JfHeader h;
-        kat_host::jf_prepare_dump(h, (unsigned)k, in.canonical, s.keys.size(), s.keys, s.counts);
         std::ofstream out(path.c_str(), std::ios::out | std::ios::binary);
-        kat_host::jf_write_file(out, h, s.keys, s.counts);
+        if (k > 32) {
+            kat_host::jf_prepare_dump_wide(h, (unsigned)k, in.canonical, s.keys.size(), s.keys_hi, s.keys, s.counts);
+            kat_host::jf_write_file_wide(out, h, s.keys_hi, s.keys, s.counts);
+        } else {
+            kat_host::jf_prepare_dump(h, (unsigned)k, in.canonical, s.keys.size(), s.keys, s.counts);
+            kat_host::jf_write_file(out, h, s.keys, s.counts);
+        }
         out.close();
         if (!out.good()) throw KatError(4, "Could not write " + path);
         phase_done(td);
@@ -184,7 +191,7 @@ int filter_seq_main(int argc, char **argv) {
     const string ext = ext_of(seq1); // both mates are written with the first file's extension (:189-205)
     const SeqFormat fmt = format_of_extension(ext);
     Ctx ctx(gpus_option(a));
-    check_wide_limits(k, ctx.n(), false, "");
+    check_wide_limits(k, ctx.n());
     if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
     else count_input(ctx, in, k, true);
 

@@ -148,15 +148,13 @@ inline vector<unsigned> parse_trim(const string &s) {
 }
 
 // mer lengths: one 64-bit word per k-mer up to 32, two words for 33..64 (jellyfish::mer_dna has no limit; larger k
-// is refused).  Two-word k-mers are counted on one GPU, and the jellyfish-hash reader / writer is one-word only.
+// is refused).  Two-word k-mers are counted on one GPU.
 constexpr int kMaxMerLen = 64;
 inline void check_mer_len(int k) {
     if (k < 1 || k > kMaxMerLen) throw KatError(4, "This GPU build supports mer lengths 1..64 (one or two 64-bit words per k-mer); got " + std::to_string(k));
 }
-inline void check_wide_limits(int k, int gpus, bool dumps_or_hash_files, const char *what) {
-    if (k <= 32) return;
-    if (gpus > 1) throw KatError(4, "mer lengths above 32 are counted on one GPU: run without --gpus");
-    if (dumps_or_hash_files) throw KatError(4, string(what) + " is limited to mer lengths up to 32 in this build (jellyfish hash files with one-word keys)");
+inline void check_wide_limits(int k, int gpus) {
+    if (k > 32 && gpus > 1) throw KatError(4, "mer lengths above 32 are counted on one GPU: run without --gpus");
 }
 
 // ---- InputHandler (lib/src/input_handler.cc) ------------------------------------
@@ -453,7 +451,7 @@ inline int load_input(katgpu_ctx *ctx, Input &in) {
     std::ifstream f;
     const kat_host::JfHeader h = read_jf_header(in.files[0], f);
     const int k = (int)(h.key_len / 2);
-    if (k < 1 || k > 32) throw KatError(4, "This GPU build loads jellyfish hashes of mer lengths 1..32 (one 64-bit word per k-mer); the hash holds " + std::to_string(k) + "-mers");
+    if (k < 1 || k > kMaxMerLen) throw KatError(4, "This GPU build supports mer lengths 1..64 (one or two 64-bit words per k-mer); the hash holds " + std::to_string(k) + "-mers");
     struct stat st;
     uint64_t n_records = 0;
     if (stat(in.files[0].c_str(), &st) == 0 && (uint64_t)st.st_size >= h.offset) {
@@ -467,7 +465,9 @@ inline int load_input(katgpu_ctx *ctx, Input &in) {
     gpu_check(katgpu_count_begin(ctx, k, in.canonical ? 1 : 0, std::max<uint64_t>(2 * n_records, 1024), 1, &in.table));
     string err;
     katgpu_status first_bad = KATGPU_OK;
-    const bool ok = kat_host::jf_read_records(f, h, (size_t)1 << 22, [&](const uint64_t *keys, const uint64_t *counts, size_t n) {
+    const bool ok = k > 32 ? kat_host::jf_read_records_wide(f, h, (size_t)1 << 22, [&](const uint64_t *keys_hi, const uint64_t *keys_lo, const uint64_t *counts, size_t n) {
+        if (first_bad == KATGPU_OK) first_bad = katgpu_count_add_pairs_wide(in.table, keys_hi, keys_lo, counts, n);
+    }, err) : kat_host::jf_read_records(f, h, (size_t)1 << 22, [&](const uint64_t *keys, const uint64_t *counts, size_t n) {
         if (first_bad == KATGPU_OK) first_bad = katgpu_count_add_pairs(in.table, keys, counts, n);
     }, err);
     gpu_check(first_bad);
@@ -503,15 +503,22 @@ inline void dump_input(Input &in, int k, const string &out_path) {
     Timer t;
     cout << "Dumping hash to " << out_path << " ...";
     cout.flush();
-    vector<uint64_t> keys(std::max<uint64_t>(in.n_distinct, 1)), counts(keys.size());
+    vector<uint64_t> keys(std::max<uint64_t>(in.n_distinct, 1)), counts(keys.size()), keys_hi(k > 32 ? keys.size() : 0);
     uint64_t n = 0;
-    gpu_check(katgpu_table_export(in.table, keys.data(), counts.data(), keys.size(), &n));
+    if (k > 32) gpu_check(katgpu_table_export_wide(in.table, keys_hi.data(), keys.data(), counts.data(), keys.size(), &n));
+    else gpu_check(katgpu_table_export(in.table, keys.data(), counts.data(), keys.size(), &n));
     keys.resize((size_t)std::min<uint64_t>(n, keys.size()));
     counts.resize(keys.size());
     kat_host::JfHeader h;
-    kat_host::jf_prepare_dump(h, (unsigned)k, in.canonical, keys.size(), keys, counts);
     std::ofstream out(out_path.c_str(), std::ios::out | std::ios::binary);
-    kat_host::jf_write_file(out, h, keys, counts);
+    if (k > 32) { // two words per key: 2k bits = ceil(2k / 8) bytes per record key, low word first
+        keys_hi.resize(keys.size());
+        kat_host::jf_prepare_dump_wide(h, (unsigned)k, in.canonical, keys.size(), keys_hi, keys, counts);
+        kat_host::jf_write_file_wide(out, h, keys_hi, keys, counts);
+    } else {
+        kat_host::jf_prepare_dump(h, (unsigned)k, in.canonical, keys.size(), keys, counts);
+        kat_host::jf_write_file(out, h, keys, counts);
+    }
     out.close();
     if (!out.good()) throw KatError(4, "Could not write " + out_path);
     phase_done(t);

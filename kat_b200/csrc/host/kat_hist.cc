@@ -33,7 +33,7 @@ int hist_main(int argc, char **argv) {
     in.validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));
-    check_wide_limits(k, ctx.n(), a.has("dump_hash"), "--dump_hash");
+    check_wide_limits(k, ctx.n());
     if (a.has("dump_hash") && ctx.n() > 1) throw KatError(4, "--dump_hash writes one GPU's table: run without --gpus");
     if (in.load_mode) load_inputs_phase(ctx, &in, 1, k);
     else count_input(ctx, in, k, true);

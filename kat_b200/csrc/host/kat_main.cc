@@ -96,16 +96,19 @@ int main(int argc, char **argv) {
             printf("# k=%u canonical=%d counter_len=%u size=%llu format=%s offset=%zu\n", k, h.canonical ? 1 : 0, h.counter_len,
                    (unsigned long long)h.size, h.format.c_str(), h.offset);
             string err;
-            uint64_t prev_pos = 0, prev_key = 0, n_seen = 0, unsorted = 0;
-            const bool ok = kat_host::jf_read_records(f, h, 1 << 16, [&](const uint64_t *keys, const uint64_t *counts, size_t n) {
+            uint64_t prev_pos = 0, prev_key = 0, prev_hi = 0, n_seen = 0, unsorted = 0;
+            const bool ok = kat_host::jf_read_records_wide(f, h, 1 << 16, [&](const uint64_t *keys_hi, const uint64_t *keys, const uint64_t *counts, size_t n) {
                 string line;
                 for (size_t i = 0; i < n; i++) {
                     line.clear();
-                    for (unsigned j = 0; j < k; j++) line += "ACGT"[(keys[i] >> (2 * (k - 1 - j))) & 3];
+                    for (unsigned j = 0; j < k; j++) {
+                        const unsigned bit = 2 * (k - 1 - j);
+                        line += "ACGT"[((bit < 64 ? keys[i] >> bit : keys_hi[i] >> (bit - 64))) & 3];
+                    }
                     printf("%s %llu\n", line.c_str(), (unsigned long long)counts[i]);
-                    const uint64_t pos = kat_host::jf_position(h, keys[i]);
-                    if (n_seen && (pos < prev_pos || (pos == prev_pos && keys[i] <= prev_key))) unsorted++;
-                    prev_pos = pos, prev_key = keys[i], n_seen++;
+                    const uint64_t pos = kat_host::jf_position(h, keys_hi[i], keys[i]);
+                    if (n_seen && (pos < prev_pos || (pos == prev_pos && (keys_hi[i] < prev_hi || (keys_hi[i] == prev_hi && keys[i] <= prev_key))))) unsorted++;
+                    prev_pos = pos, prev_key = keys[i], prev_hi = keys_hi[i], n_seen++;
                 }
             }, err);
             if (!ok) throw KatError(4, err);
@@ -117,20 +120,29 @@ int main(int argc, char **argv) {
             if (a.positional.size() != 2) throw KatError(1, "usage: kat _jfwrite -m K [-N] <kmers.txt> <out.jf>");
             const unsigned k = (unsigned)to_u64(a.get("mer_len", "27"), "mer_len");
             std::ifstream in(a.positional[0].c_str());
-            vector<uint64_t> keys, counts;
+            vector<uint64_t> keys_hi, keys, counts;
             string km;
             uint64_t c;
             while (in >> km >> c) {
                 if (km.size() != k) throw KatError(4, "k-mer of the wrong length: " + km);
-                uint64_t key = 0;
-                for (char ch : km) key = (key << 2) | (uint64_t)(ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3);
-                keys.push_back(key);
+                uint64_t lo = 0, hi = 0;
+                for (char ch : km) {
+                    hi = (hi << 2) | (lo >> 62);
+                    lo = (lo << 2) | (uint64_t)(ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : 3);
+                }
+                keys_hi.push_back(hi);
+                keys.push_back(lo);
                 counts.push_back(c);
             }
             kat_host::JfHeader h;
-            kat_host::jf_prepare_dump(h, k, !a.has("non_canonical"), keys.size(), keys, counts);
             std::ofstream out(a.positional[1].c_str(), std::ios::out | std::ios::binary);
-            kat_host::jf_write_file(out, h, keys, counts);
+            if (k > 32) {
+                kat_host::jf_prepare_dump_wide(h, k, !a.has("non_canonical"), keys.size(), keys_hi, keys, counts);
+                kat_host::jf_write_file_wide(out, h, keys_hi, keys, counts);
+            } else {
+                kat_host::jf_prepare_dump(h, k, !a.has("non_canonical"), keys.size(), keys, counts);
+                kat_host::jf_write_file(out, h, keys, counts);
+            }
             return out.good() ? 0 : 4;
         }
         cout << "Kmer Analysis Toolkit (KAT) V" << kVersion << endl << endl;

@@ -33,9 +33,56 @@ CASES = [
 ]
 
 
+REF_JF = os.path.join(ROOT, "oracle", "_ref", "kat_jellyfish")
+# jellyfish hashes with two-word keys either side of the path: a hash written by the reference as INPUT (LOAD mode),
+# and the records of the hashes the reference dumps / filters (kat_jellyfish dump -c, sorted) to compare ours with
+HASH_CASES = [
+    ("load_hist_k41", ["hist", "-o", "OUT/h", "wide/ref_small_k41.jf"]),
+    ("load_gcp_k41", ["gcp", "-o", "OUT/g", "wide/ref_small_k41.jf"]),
+    ("load_comp_hash_vs_reads_k41", ["comp", "-m41", "-i", "40", "-j", "50", "-o", "OUT/c", "wide/ref_small_k41.jf", "inputs/synth_a.fq"]),
+    ("dump_hist_k45_nc", ["hist", "-m45", "-N", "-d", "-o", "OUT/h", "inputs/wide_small.fq"]),
+    ("fkmer_k33_separate", ["filter", "kmer", "-m33", "-c", "2", "-d", "4", "-g", "10", "-h", "20", "-s", "-o", "OUT/k", "inputs/wide_small.fq"]),
+]
+
+
+def make_hash_cases():
+    a = open(os.path.join(HERE, "inputs", "synth_a.fq")).read().splitlines(keepends=True)
+    with open(os.path.join(HERE, "inputs", "wide_small.fq"), "w") as f:
+        f.writelines(a[: 4 * 60])
+    subprocess.run([REF_KAT, "hist", "-m41", "-d", "-o", "wide/tmp_h", "inputs/wide_small.fq"], cwd=HERE, check=True, stdout=subprocess.DEVNULL)
+    os.replace(os.path.join(OUT, "tmp_h-hash.jf41"), os.path.join(OUT, "ref_small_k41.jf"))
+    os.unlink(os.path.join(OUT, "tmp_h"))
+    manifest = []
+    for name, args in HASH_CASES:
+        d = os.path.join(OUT, name)
+        os.makedirs(d)
+        a = [x.replace("OUT", os.path.join("wide", name)) for x in args]
+        r = subprocess.run([REF_KAT] + a, cwd=HERE, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        if r.returncode != 0:
+            raise SystemExit(f"reference failed on {name}: {r.stdout[-800:]}")
+        files = sorted(os.listdir(d))
+        for f in files:
+            p = os.path.join(d, f)
+            if ".jf" in f:
+                j = subprocess.run([REF_JF, "dump", "-c", p], stdout=subprocess.PIPE, text=True, check=True)
+                os.unlink(p)
+                p = p + ".dump.txt"
+                with open(p, "w") as out:
+                    out.writelines(sorted(j.stdout.splitlines(keepends=True)))
+            if os.path.getsize(p) > 30_000:
+                with open(p, "rb") as src, gzip.GzipFile(p + ".gz", "wb", mtime=0) as dst:
+                    dst.write(src.read())
+                os.unlink(p)
+        manifest.append({"name": name, "args": args, "files": files})
+        print(name, files)
+    with open(os.path.join(OUT, "hash_cases.json"), "w") as f:
+        json.dump(manifest, f, indent=1)
+
+
 def main():
     shutil.rmtree(OUT, ignore_errors=True)
     os.makedirs(OUT)
+    make_hash_cases()
     manifest = []
     for name, args in CASES:
         d = os.path.join(OUT, name)

@@ -255,10 +255,42 @@ def test_cli_wide_kmers_output_files_byte_identical(case, tmp_path):
 
 
 def test_cli_wide_kmers_limits(tmp_path):
-    """What two-word k-mers do not cover is refused with a message, not computed wrongly: k > 64, hash dumps, filter kmer."""
+    """Mer lengths outside 1..64 are refused with a message (two 64-bit words per k-mer at most)."""
     fa = os.path.join(G.GOLDEN, "inputs", "long.fa")
-    for args, msg in ((["hist", "-m65", fa], "mer lengths 1..64"),
-                      (["hist", "-m40", "-d", "-o", "h", fa], "--dump_hash is limited to mer lengths up to 32"),
-                      (["filter", "kmer", "-m33", "-o", "k", fa], "limited to mer lengths up to 32")):
+    for args, msg in ((["hist", "-m65", fa], "mer lengths 1..64"), (["comp", "-m0", fa, fa], "mer lengths 1..64"),
+                      (["sect", "-m100", fa, fa], "mer lengths 1..64")):
         r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, timeout=120)
         assert r.returncode == 4 and msg in r.stderr, (args, r.returncode, r.stderr)
+
+
+WIDE_HASH_MANIFEST = json.load(open(os.path.join(G.GOLDEN, "wide", "hash_cases.json")))
+
+
+@pytest.mark.parametrize("case", WIDE_HASH_MANIFEST, ids=lambda c: c["name"])
+def test_cli_wide_kmers_hash_files(case, tmp_path):
+    """Jellyfish hashes with two-word keys (k > 32) either side of the path: a hash written by the reference is loaded
+    (hist / gcp / comp outputs byte-identical to the reference's own LOAD run), and the hashes the product writes
+    (-d dumps, filter kmer) hold exactly the records of the reference's, in jellyfish's sorted order."""
+    shutil.copytree(os.path.join(G.GOLDEN, "inputs"), tmp_path / "inputs")
+    os.makedirs(tmp_path / "wide")
+    shutil.copy(os.path.join(G.GOLDEN, "wide", "ref_small_k41.jf"), tmp_path / "wide")
+    out = os.path.join("wide", case["name"])
+    os.makedirs(tmp_path / out)
+    r = subprocess.run([KAT] + [a.replace("OUT", out) for a in case["args"]], cwd=tmp_path, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-500:] + r.stderr[-500:]
+    assert sorted(os.listdir(tmp_path / out)) == case["files"]
+    for f in case["files"]:
+        p = os.path.join(G.GOLDEN, "wide", case["name"], f)
+        if ".jf" in f:
+            d = subprocess.run([KAT, "_jfdump", os.path.join(out, f)], cwd=tmp_path, capture_output=True, text=True)
+            lines = d.stdout.splitlines()
+            assert d.returncode == 0 and lines[-1].endswith("out_of_order=0"), d.stdout[-300:] + d.stderr
+            q = p + ".dump.txt"
+            want = (open(q, "rb").read() if os.path.exists(q) else gzip.open(q + ".gz", "rb").read()).decode().splitlines()
+            assert sorted(l for l in lines if not l.startswith("#")) == want, f"{case['name']}/{f}: records differ"
+            if os.access(REF_JF, os.X_OK):  # the unmodified jellyfish reads our file
+                j = subprocess.run([REF_JF, "dump", "-c", os.path.join(out, f)], cwd=tmp_path, capture_output=True, text=True)
+                assert j.returncode == 0 and sorted(j.stdout.splitlines()) == want
+        else:
+            want = open(p, "rb").read() if os.path.exists(p) else gzip.open(p + ".gz", "rb").read()
+            assert open(tmp_path / out / f, "rb").read() == want, f"{case['name']}/{f} differs from the reference's file"

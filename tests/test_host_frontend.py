@@ -52,6 +52,7 @@ test_cli_filter_matches_reference = T.test_cli_filter_matches_reference
 test_cli_filter_errors = T.test_cli_filter_errors
 test_cli_wide_kmers_output_files_byte_identical = T.test_cli_wide_kmers_output_files_byte_identical
 test_cli_wide_kmers_limits = T.test_cli_wide_kmers_limits
+test_cli_wide_kmers_hash_files = T.test_cli_wide_kmers_hash_files
 test_cli_hash_full_exit_code = T.test_cli_hash_full_exit_code
 test_cli_missing_input = T.test_cli_missing_input
 test_cli_dev_paths_are_pipes = T.test_cli_dev_paths_are_pipes
