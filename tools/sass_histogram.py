@@ -11,7 +11,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "kat_b200", "lib", "libkatgpu.so")
-KEYS = ["UBLKCP", "SYNCS", "ATOMS", "ATOMG", "RED", "MATCH", "STG.E.ENL2.256", "STG.E.128", "STG.E.64", "LDG.E.128", "LDG.E.ENL2.256",
+KEYS = ["UBLKCP", "SYNCS", "ATOMS", "ATOMG", "ATOMG.E.CAS.128", "RED", "MATCH", "STG.E.ENL2.256", "STG.E.128", "STG.E.64", "LDG.E.128", "LDG.E.ENL2.256",
         "LDS.128", "STS.64", "BAR.SYNC", "SHFL", "VOTE", "FLO", "POPC", "IMAD", "SHF", "LOP3", "S2R", "CALL"]
 
 
@@ -35,8 +35,9 @@ def main():
                     per[name][k] += 1
     lines = ["# SASS opcode histogram per kernel of kat_b200/lib/libkatgpu.so (sm_100a), tools/sass_histogram.py",
              "# columns: static instruction counts; UBLKCP = TMA bulk copy, SYNCS = mbarrier ops, ATOMS = shared atomics,",
-             "# ATOMG/RED = global atomics, MATCH = match.any warp aggregation, STG.E.ENL2.256 = 32-byte sector stores", ""]
-    hdr = "%-62s %6s " % ("kernel", "instr") + " ".join("%7s" % k.replace("STG.E.", "STG.").replace("LDG.E.", "LDG.")[:7] for k in KEYS)
+             "# ATOMG/RED = global atomics (ATOMG.E.CAS.128 = the 16-byte compare-and-swap that claims a two-word-key slot), MATCH = match.any warp aggregation,",
+             "# STG.E.ENL2.256 = 32-byte sector stores", ""]
+    hdr = "%-62s %6s " % ("kernel", "instr") + " ".join("%7s" % k.replace("ATOMG.E.CAS.128", "CAS.128").replace("STG.E.", "STG.").replace("LDG.E.", "LDG.")[:7] for k in KEYS)
     lines.append(hdr)
     for name, c in per.items():
         lines.append("%-62s %6d " % (name[:62], c["_total"]) + " ".join("%7d" % c[k] for k in KEYS))
