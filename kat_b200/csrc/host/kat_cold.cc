@@ -57,12 +57,13 @@ int cold_main(int argc, char **argv) {
     cout << "Calculating kmer coverage across sequences ...";
     cout.flush();
     const vector<SeqRecord> recs = read_records(assembly.files[0]);
-    const SeqPositions pos = kmer_positions(recs, (uint32_t)k);
-    const vector<uint64_t> in_reads = lookup_positions(ctx, reads, pos), in_asm = lookup_positions(ctx, assembly, pos);
+    LookupWindow W(ctx, {&reads, &assembly}, recs, (uint32_t)k);
     std::ofstream stats((prefix + "-stats.tsv").c_str());
     stats << "seq_name\tread_median_cvg\tread_mean_cvg\tasm_cn\tgc%\tseq_length\tkmers_in_seq\tinvalid_kmers\t%_invalid\tnon_zero_kmers\t%_non_zero\t%_non_zero_corrected" << endl;
     stats << std::fixed << std::setprecision(5);
     for (size_t i = 0; i < recs.size(); i++) { // Cold::processSeq, src/cold.cc:303-410; printStatTable, :253-271
+        W.ensure(i);
+        const vector<uint64_t> &in_reads = W.found[0], &in_asm = W.found[1];
         const string &s = recs[i].seq;
         const uint64_t len = s.size();
         const int64_t nb = (int64_t)len - k + 1;
@@ -72,8 +73,8 @@ int cold_main(int argc, char **argv) {
         if (nb > 0) {
             vector<uint64_t> rc((size_t)nb, 0), ac((size_t)nb, 0);
             for (size_t p = 0; p < (size_t)nb; p++) {
-                const size_t q = pos.first[i] + p;
-                if (!pos.valid[q]) {
+                const size_t q = W.at(i) + p;
+                if (!W.P.valid[q]) {
                     invalid++;
                     continue;
                 }

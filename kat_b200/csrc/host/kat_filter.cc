@@ -200,14 +200,7 @@ int filter_seq_main(int argc, char **argv) {
     const vector<SeqRecord> r1 = read_records(seq1);
     vector<SeqRecord> r2;
     if (paired) r2 = read_records(seq2);
-    const SeqPositions p1 = kmer_positions(r1, (uint32_t)k);
-    const vector<uint64_t> f1 = lookup_positions(ctx, in, p1);
-    SeqPositions p2;
-    vector<uint64_t> f2;
-    if (paired) {
-        p2 = kmer_positions(r2, (uint32_t)k);
-        f2 = lookup_positions(ctx, in, p2);
-    }
+    LookupWindow w1(ctx, {&in}, r1, (uint32_t)k), w2(ctx, {&in}, r2, (uint32_t)k);
     std::ofstream stats, in1, out1, in2, out2;
     if (do_stats) {
         stats.open((prefix + ".stats").c_str());
@@ -222,10 +215,12 @@ int filter_seq_main(int argc, char **argv) {
     std::random_device rd;
     std::mt19937 gen(rd());
     std::uniform_real_distribution<> urd;
-    auto hits = [](const SeqPositions &p, const vector<uint64_t> &found, size_t i, uint64_t &n_pos) {
+    auto hits = [](LookupWindow &w, size_t i, uint64_t &n_pos) { // FilterSeq::getProfile, :330-368
+        w.ensure(i);
         uint64_t h = 0;
-        for (size_t q = p.first[i]; q < p.first[i + 1]; q++) h += p.valid[q] && found[q] > 0;
-        n_pos += p.first[i + 1] - p.first[i];
+        const size_t q0 = w.at(i), n = w.n_positions(i);
+        for (size_t q = q0; q < q0 + n; q++) h += w.P.valid[q] && w.found[0][q] > 0;
+        n_pos += n;
         return h;
     };
     uint64_t keepers = 0, n_total = 0;
@@ -233,8 +228,8 @@ int filter_seq_main(int argc, char **argv) {
         if (paired && i >= r2.size()) throw KatError(4, "Second sequence file appears to be shorter than the first.");
         const double random_val = urd(gen);
         uint64_t nb_kmers = 0;
-        uint64_t matches = hits(p1, f1, i, nb_kmers);
-        if (paired) matches += hits(p2, f2, i, nb_kmers);
+        uint64_t matches = hits(w1, i, nb_kmers);
+        if (paired) matches += hits(w2, i, nb_kmers);
         const double ratio = (double)matches / (double)nb_kmers; // 0 / 0 = NaN: such a record is never kept
         bool keep = true;
         if ((ratio >= threshold && !invert) || (invert && ratio < threshold)) {

@@ -99,10 +99,7 @@ int sect_main(int argc, char **argv) {
     cout.flush();
     const vector<SeqRecord> recs = read_records(seq_file);
     const uint32_t K = (uint32_t)k;
-    const SeqPositions pos = kmer_positions(recs, K);
-    const vector<size_t> &first = pos.first;
-    const vector<uint8_t> &valid = pos.valid;
-    const vector<uint64_t> found = lookup_positions(ctx, in, pos);
+    LookupWindow W(ctx, {&in}, recs, K);
     std::ofstream stats((prefix + "-stats.tsv").c_str());
     stats << "seq_name\tmedian\tmean\tgc%\tseq_length\tkmers_in_seq\tinvalid_kmers\t%_invalid\tnon_zero_kmers\t%_non_zero\t%_non_zero_corrected" << endl;
     stats << std::fixed << std::setprecision(5);
@@ -124,6 +121,10 @@ int sect_main(int argc, char **argv) {
         };
         vector<Row> rows(b1 - b0);
         for (size_t i = b0; i < b1; i++) { // Sect::processSeq, src/sect.cc:490-605
+            W.ensure(i);
+            const size_t first_i = W.at(i);
+            const vector<uint8_t> &valid = W.P.valid;
+            const vector<uint64_t> &found = W.found[0];
             const string &s = recs[i].seq;
             const uint64_t len = s.size();
             const int64_t nb = (int64_t)len - k + 1;
@@ -146,12 +147,12 @@ int sect_main(int argc, char **argv) {
                     }
                     if (j + 1 >= k) {
                         const size_t p = (size_t)(j + 1 - k);
-                        if (!valid[first[i] + p]) {
+                        if (!valid[first_i + p]) {
                             sc[p] = 0;
                             gc[p] = -1;
                             invalid++;
                         } else {
-                            const uint64_t cnt = found[first[i] + p];
+                            const uint64_t cnt = found[first_i + p];
                             sum += cnt;
                             sc[p] = cnt;
                             gc[p] = g; // gcCount(merstr), lib/include/kat/str_utils.hpp:151-161

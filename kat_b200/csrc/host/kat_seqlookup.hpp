@@ -72,21 +72,23 @@ inline uint64_t base_code(char c) { // mer_dna::code, JFI/mer_dna.hpp:46-63
 // first[i] = index of record i's first position.  keys = the last 32 bases of the k-mer, keys_hi = the first K-32
 // (all zero for K <= 32) — mer_dna's packing, first base most significant.
 struct SeqPositions {
-    vector<size_t> first;
+    vector<size_t> first; // relative to the first record of the range
     vector<uint64_t> keys, keys_hi;
     vector<uint8_t> valid;
 };
-inline SeqPositions kmer_positions(const vector<SeqRecord> &recs, uint32_t K) {
+// positions of records [begin, end)
+inline SeqPositions kmer_positions(const vector<SeqRecord> &recs, size_t begin, size_t end, uint32_t K) {
     SeqPositions P;
-    P.first.assign(recs.size() + 1, 0);
-    for (size_t i = 0; i < recs.size(); i++) P.first[i + 1] = P.first[i] + (recs[i].seq.size() >= K ? recs[i].seq.size() - K + 1 : 0);
+    const size_t nr = end - begin;
+    P.first.assign(nr + 1, 0);
+    for (size_t i = 0; i < nr; i++) P.first[i + 1] = P.first[i] + (recs[begin + i].seq.size() >= K ? recs[begin + i].seq.size() - K + 1 : 0);
     P.keys.assign(P.first.back(), 0);
-    P.keys_hi.assign(P.first.back(), 0);
+    if (K > 32) P.keys_hi.assign(P.first.back(), 0);
     P.valid.assign(P.first.back(), 0);
     const uint64_t lo_mask = K >= 32 ? ~0ULL : ((1ULL << (2 * K)) - 1);
     const uint64_t hi_mask = K <= 32 ? 0ULL : K == 64 ? ~0ULL : ((1ULL << (2 * K - 64)) - 1);
-    for (size_t i = 0; i < recs.size(); i++) {
-        const string &s = recs[i].seq;
+    for (size_t i = 0; i < nr; i++) {
+        const string &s = recs[begin + i].seq;
         uint64_t lo = 0, hi = 0;
         uint32_t run = 0;
         for (size_t j = 0; j < s.size(); j++) {
@@ -99,7 +101,7 @@ inline SeqPositions kmer_positions(const vector<SeqRecord> &recs, uint32_t K) {
             if (j + 1 >= K) {
                 const size_t p = P.first[i] + (j + 1 - K);
                 P.keys[p] = run >= K ? lo : 0;
-                P.keys_hi[p] = run >= K ? hi : 0;
+                if (K > 32) P.keys_hi[p] = run >= K ? hi : 0;
                 P.valid[p] = run >= K;
             }
         }
@@ -116,11 +118,42 @@ inline vector<uint64_t> lookup_positions(Ctx &ctx, Input &in, const SeqPositions
         vector<vector<uint64_t>> other(ctx.n());
         run_on_all(ctx.n(), [&](int r) {
             if (r) other[r].resize(m);
-            gpu_check(katgpu_lookup_wide(in.tables[r], P.keys_hi.data() + off, keys.data() + off, m, in.canonical ? 1 : 0,
+            gpu_check(katgpu_lookup_wide(in.tables[r], P.keys_hi.empty() ? nullptr : P.keys_hi.data() + off, keys.data() + off, m, in.canonical ? 1 : 0,
                                          r ? other[r].data() : found.data() + off));
         });
     }
     return found;
 }
+
+// The tools walk the records of a sequence file in order; the k-mer positions of a WINDOW of records (at most
+// KAT_LOOKUP_WINDOW positions, 2^26 by default: ~1.7 GB of keys, flags and counts on the host instead of 25 bytes per
+// base of the whole file) are resident at a time, looked up in every hash of the tool in one batch each.
+struct LookupWindow {
+    Ctx &ctx;
+    vector<Input *> inputs;
+    const vector<SeqRecord> &recs;
+    uint32_t K;
+    size_t max_pos;
+    size_t lo = 0, hi = 0; // records [lo, hi) are resident
+    SeqPositions P;
+    vector<vector<uint64_t>> found; // [input][position]
+    LookupWindow(Ctx &c, vector<Input *> ins, const vector<SeqRecord> &r, uint32_t k)
+        : ctx(c), inputs(std::move(ins)), recs(r), K(k), max_pos(env_size("KAT_LOOKUP_WINDOW", (size_t)1 << 26)) {}
+    void ensure(size_t i) { // make record i resident (records are visited in increasing order)
+        if (i >= lo && i < hi) return;
+        lo = i;
+        size_t n_pos = 0;
+        for (hi = lo; hi < recs.size(); hi++) {
+            const size_t np = recs[hi].seq.size() >= K ? recs[hi].seq.size() - K + 1 : 0;
+            if (hi > lo && n_pos + np > max_pos) break;
+            n_pos += np;
+        }
+        P = kmer_positions(recs, lo, hi, K);
+        found.assign(inputs.size(), {});
+        for (size_t t = 0; t < inputs.size(); t++) found[t] = lookup_positions(ctx, *inputs[t], P);
+    }
+    size_t at(size_t i) const { return P.first[i - lo]; }        // index of record i's first position in the window
+    size_t n_positions(size_t i) const { return P.first[i - lo + 1] - P.first[i - lo]; }
+};
 
 } // namespace kat_front

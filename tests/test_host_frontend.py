@@ -69,3 +69,20 @@ def test_cli_c1_ecoli_k27(tmp_path):
 
 def test_cli_dump_hash_is_a_jellyfish_file(jf_workdir):
     T.test_cli_dump_hash_is_a_jellyfish_file("direct", jf_workdir)
+
+
+@pytest.mark.parametrize("case", [c for c in T.SECT_MANIFEST if c["name"] in ("sect_regions_gc_k17", "cold_asm_vs_reads_k21", "sect_fastq_records_k13")],
+                         ids=lambda c: c["name"])
+def test_lookup_windows_do_not_change_outputs(case, tmp_path, monkeypatch):
+    """sect / cold / filter seq keep a window of records' k-mer positions resident (KAT_LOOKUP_WINDOW positions, 2^26 by
+    default); with windows of a few hundred positions — many per file, records larger than a window included — the
+    output files are still the reference's."""
+    monkeypatch.setenv("KAT_LOOKUP_WINDOW", "700")
+    T.test_cli_sect_and_cold_output_files_byte_identical(case, tmp_path)
+
+
+@pytest.mark.parametrize("case", [c for c in T.FILTER_MANIFEST if c["name"].startswith("fseq")] + [c for c in T.WIDE_MANIFEST if c["args"][0] in ("sect", "cold", "filter")],
+                         ids=lambda c: c["name"])
+def test_lookup_windows_filter_and_wide(case, tmp_path, monkeypatch):
+    monkeypatch.setenv("KAT_LOOKUP_WINDOW", "333")
+    (T.test_cli_filter_matches_reference if case in T.FILTER_MANIFEST else T.test_cli_wide_kmers_output_files_byte_identical)(case, tmp_path)
