@@ -6,12 +6,12 @@
  * (oracle/libkatoracle.so), so that the front-end's HOST logic — option handling, input groups,
  * the FASTA/FASTQ readers, LOAD mode, the text and jellyfish-hash writers, sect/cold/filter
  * arithmetic — is checked against the reference-written golden files in the `-m "not gpu"` suite.
- * It is never built into, shipped with or found by the product: kat_b200/bin/kat resolves
- * libkatgpu.so through its RUNPATH ($ORIGIN/../lib); the tests put THIS library in front with
- * LD_LIBRARY_PATH.  What the GPU computes is checked by the `-m gpu` tests, which run the same
+ * It is never built into, shipped with or found by the product: kat_b200/bin/kat links and loads the real
+ * libkatgpu.so (RUNPATH $ORIGIN/../lib); the tests interpose THIS library's symbols with LD_PRELOAD for the
+ * processes they start.  What the GPU computes is checked by the `-m gpu` tests, which run the same
  * commands against the real library.
  *
- * Built by tests/hostcheck/Makefile into tests/hostcheck/_build/libkatgpu.so (git-ignored).
+ * Built by tests/hostcheck/Makefile into tests/hostcheck/_build/libkatgpu_double.so (git-ignored, gpurun-ignored).
  */
 #include <stdio.h>
 #include <stdlib.h>
