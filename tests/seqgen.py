@@ -54,3 +54,14 @@ def encode_kmer(s):
     for ch in s.upper():
         m = (m << 2) | "ACGT".index(ch)
     return m
+
+
+SOUP_TOKENS = [b"@", b"+", b">", b"\n", b"\n", b"\n", b"\r\n", b"ACGT", b"A", b"C", b"N", b"acgt", b"IIII", b"#", b" ", b"\n\n", b"GGGGGG",
+               b"TTTTTTT", b"@r1\n", b"+\n", b">c1\n", b"ACGTACGTAC\n", b"IIIIIIIIII\n"]
+
+
+def token_soup(rng, always_marker=True):
+    """Adversarial sequence-file images: record markers, line ends, bases, quality-like bytes and blanks in random order
+    behind a FASTA or FASTQ first line — mostly malformed records (what the parsers do with them is part of the contract)."""
+    first = [b"@r0\n", b">c0\n"][int(rng.integers(0, 2))] if always_marker or rng.random() < 0.9 else b""
+    return first + b"".join(SOUP_TOKENS[int(rng.integers(0, len(SOUP_TOKENS)))] for _ in range(int(rng.integers(1, 40))))

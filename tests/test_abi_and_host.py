@@ -105,6 +105,21 @@ def test_host_parser_matches_oracle_on_random_files(seed, tmp_path):
         assert _kat_parse(str(p), k, trim) == O.parse_file(data, k, trim), (seed, k, trim)
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_host_parser_matches_oracle_on_token_soup(seed, tmp_path):
+    """Malformed input: 75 random mixtures of record markers, line ends, bases and quality-like bytes per seed; the host
+    parser emits the oracle's stream and status for each (the oracle itself is held to the reference binary on such
+    files by tests/test_oracle_pinning.py::test_oracle_vs_reference_binary_on_token_soup)."""
+    import seqgen
+    rng = np.random.default_rng(1000 + seed)
+    p = tmp_path / "soup.fq"
+    for it in range(75):
+        data = seqgen.token_soup(rng, always_marker=False)
+        p.write_bytes(data)
+        for k, trim in ((5, 0), (3, 2)):
+            assert _kat_parse(str(p), k, trim) == O.parse_file(data, k, trim), (seed, it, k, trim, data)
+
+
 # ---- the parser's fast paths (regular 4-line FASTQ / FASTA layouts, parsed piece-wise in parallel)
 def _regular_file(rng, fastq, n_records, crlf=False, tricky_quals=True, no_final_newline=False, wrap=0):
     nl = b"\r\n" if crlf else b"\n"
