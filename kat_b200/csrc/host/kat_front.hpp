@@ -376,9 +376,12 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
     std::string bases;
     // KAT_GPU_PARSE=0 keeps FASTQ parsing on the host
     const bool gpu_parse = allow_streaming && env_size("KAT_GPU_PARSE", 1) != 0;
+    // the reference parser's seq_len state, which it keeps from one file of the group to the next (seq_parser.hpp): non-zero
+    // only after a file that ended inside a FASTQ record; the regular-layout routes below then do not apply to the next file
+    size_t fastq_carry = 0;
     for (size_t i = 0; i < in.files.size(); i++) {
         string err;
-        if (gpu_parse) { // plain 4-line FASTQ: the raw bytes go to the GPU(s) and are parsed there
+        if (gpu_parse && fastq_carry == 0) { // plain 4-line FASTQ: the raw bytes go to the GPU(s) and are parsed there
             const int r = kat_host::stream_fastq_raw(in.files[i], env_size("KAT_RAW_BLOCK", (size_t)256 << 20) * (size_t)ctx.n(), ctx.n(),
                                                      [&](const char *const *parts, const size_t *lens) {
                                                          vector<int> regular(ctx.n(), 0);
@@ -397,7 +400,7 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
                 return;
             }
         }
-        if (allow_streaming && file_size_or_zero(in.files[i]) >= stream_from) {
+        if (allow_streaming && fastq_carry == 0 && file_size_or_zero(in.files[i]) >= stream_from) {
             katgpu_status bad = KATGPU_OK;
             const int r = kat_host::stream_regular_file(in.files[i], in.trim5p[i], block, [&](const char *b, size_t n) {
                 feed_all(ctx, in, k, b, n);
@@ -413,7 +416,7 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
         }
         if (!kat_host::read_file(in.files[i], raw, err)) throw KatError(4, err);
         bases.clear();
-        const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), k, in.trim5p[i], bases);
+        const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), k, in.trim5p[i], bases, &fastq_carry);
         if (st == kat_host::ParseStatus::UnsupportedFormat) {
             cerr << "warning: " << in.files[i] << ": Unsupported format (the reference silently stops reading this input here)" << endl;
             break;

@@ -38,8 +38,9 @@ int main(int argc, char **argv) {
         }
         const string mode = argv[1];
         if (mode == "_parse") { // test hook, no GPU involved: dump the base stream of one file to stdout
-            const Parsed a = parse_args(argc - 1, argv + 1, {{'m', "mer_len", true}, {0, "5ptrim", true}});
-            if (a.positional.size() != 1) throw KatError(1, "usage: kat _parse -m K [--5ptrim X] <file>");
+            const Parsed a = parse_args(argc - 1, argv + 1, {{'m', "mer_len", true}, {0, "5ptrim", true}, {0, "carry", true}});
+            if (a.positional.size() != 1) throw KatError(1, "usage: kat _parse -m K [--5ptrim X] [--carry SEQ_LEN] <file>");
+            size_t carry = (size_t)to_u64(a.get("carry", "0"), "carry"); // seq_len state inherited from the previous file of a group
             std::vector<unsigned char> raw;
             string err, bases;
             Timer t0;
@@ -61,7 +62,8 @@ int main(int argc, char **argv) {
             if (!kat_host::read_file(a.positional[0], raw, err)) throw KatError(4, err);
             const double t_read = t0.secs();
             const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), (int)to_u64(a.get("mer_len", "27"), "mer_len"),
-                                                          (unsigned)to_u64(a.get("5ptrim", "0"), "5ptrim"), bases);
+                                                          (unsigned)to_u64(a.get("5ptrim", "0"), "5ptrim"), bases, &carry);
+            fprintf(stderr, "carry_out=%zu\n", carry);
             if (getenv("KAT_TRACE"))
                 fprintf(stderr, "[kat] read %.3f s, parse %.3f s (%zu -> %zu bytes), parser: %s\n", t_read, t0.secs() - t_read, raw.size(), bases.size(),
                         kat_host::last_parse_was_fast() ? "fast" : "exact");

@@ -181,7 +181,7 @@ bool skip_quals(CharStream &is, size_t read_len) {
 }
 
 // The reference's parser, character by character (see the header of this file).
-ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out) {
+ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry) {
     CharStream is(data, n);
     const int first = is.peek();
     if (first == -1) return ParseStatus::Ok; // empty file: nothing to count
@@ -191,7 +191,7 @@ ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k
     unsigned char buf[kBuf + 8];
     const size_t seam = static_cast<size_t>(k - 1);
     bool have_seam = false;
-    size_t seq_len = 0;
+    size_t seq_len = fastq_carry ? *fastq_carry : 0; // not reset between the files of a group (see seq_parser.hpp)
     out.reserve(out.size() + n / 2 + 16);
     while (is.good()) { // one pass = one 4 KiB buffer of the reference
         size_t read = have_seam ? seam : 0;
@@ -225,6 +225,7 @@ ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k
         out.append(reinterpret_cast<const char *>(buf + start), read - start);
         have_seam = read >= seam;
     }
+    if (fastq_carry) *fastq_carry = seq_len;
     return ParseStatus::Ok;
 }
 
@@ -393,11 +394,14 @@ bool parse_regular_layout(const unsigned char *data, size_t n, bool fastq, unsig
 static bool g_last_fast = false;
 bool last_parse_was_fast() { return g_last_fast; }
 
-ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out) {
-    g_last_fast = n > 0 && (data[0] == '>' || data[0] == '@') && !getenv("KAT_PARSE_EXACT_ONLY") &&
+ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry) {
+    // a FASTQ file that inherits a non-zero seq_len is not what the regular layout describes: emulation only
+    // (a regular file leaves seq_len at 0, so the carry is untouched by the fast path)
+    const bool carried = fastq_carry && *fastq_carry != 0 && n > 0 && data[0] == '@';
+    g_last_fast = !carried && n > 0 && (data[0] == '>' || data[0] == '@') && !getenv("KAT_PARSE_EXACT_ONLY") &&
                   parse_regular_layout(data, n, data[0] == '@', trim5p, out);
     if (g_last_fast) return ParseStatus::Ok;
-    return parse_sequence_file_exact(data, n, k, trim5p, out);
+    return parse_sequence_file_exact(data, n, k, trim5p, out, fastq_carry);
 }
 
 int stream_regular_file(const std::string &path, unsigned trim5p, size_t block_bytes,

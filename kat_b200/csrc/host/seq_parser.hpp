@@ -12,7 +12,12 @@ enum class ParseStatus { Ok, UnsupportedFormat, InvalidFastq };
 bool read_file(const std::string &path, std::vector<unsigned char> &out, std::string &err);
 
 // Append the base stream of one file image to `out` (records separated by 'N').
-ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out);
+// `fastq_carry` (optional, in/out): the reference parser's per-stream `seq_len` — the bases of the FASTQ record being
+// read — survives the move to the next file of an input group (JFI/mer_overlap_sequence_parser.hpp:158-187 resets type
+// and trim only).  A file that ends inside a record (truncated, or an empty last record) leaves it non-zero; the next
+// FASTQ file's first record is then measured too long, "Invalid fastq sequence" is thrown and swallowed, and the rest
+// of the group is dropped.  A caller that parses a group passes the same variable for every file, in order.
+ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry = nullptr);
 // Large plain files in one of the regular layouts (see seq_parser.cc) block by block, without
 // holding the file or its whole base stream in memory: `sink` gets the base stream of each block
 // of whole records (no k-mer spans two records, so blocks can be counted independently).

@@ -40,6 +40,8 @@ def lib():
     u8p, u64p, vp = C.c_void_p, C.c_void_p, C.c_void_p
     L.oracle_parse_file.restype = C.c_long
     L.oracle_parse_file.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p]
+    L.oracle_parse_file_state.restype = C.c_long
+    L.oracle_parse_file_state.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p, C.POINTER(C.c_size_t)]
     L.oracle_table_new.restype = vp
     L.oracle_table_new.argtypes = [C.c_int, C.c_int]
     L.oracle_table_free.argtypes = [vp]
@@ -70,12 +72,16 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def parse_file(data: bytes, k: int, trim5p: int = 0):
+def parse_file(data: bytes, k: int, trim5p: int = 0, carry=None):
     """a1: file image -> (base stream bytes, status). status 0 ok, -1 unsupported
-    format, -2 invalid fastq (stream truncated as the reference does)."""
+    format, -2 invalid fastq (stream truncated as the reference does).  `carry`: a one-element list holding the
+    parser's seq_len state, which the reference keeps from one file of a group to the next (see kat_oracle.c)."""
     src = np.frombuffer(data, dtype=np.uint8)
     out = np.empty(len(data) + 2, dtype=np.uint8)
-    r = lib().oracle_parse_file(_ptr(src) if len(data) else None, len(data), k, trim5p, _ptr(out))
+    st = C.c_size_t(carry[0] if carry else 0)
+    r = lib().oracle_parse_file_state(_ptr(src) if len(data) else None, len(data), k, trim5p, _ptr(out), C.byref(st))
+    if carry is not None:
+        carry[0] = st.value
     if r == -1:
         return b"", -1
     if r <= -2:
@@ -90,6 +96,7 @@ def parse_files(files, k, trim5p=None):
     if len(trim5p) == 1 and len(files) > 1:
         trim5p = trim5p * len(files)
     chunks = []
+    carry = [0]
     for path, t in zip(files, trim5p):
         if isinstance(path, (bytes, bytearray)):
             data = bytes(path)
@@ -99,7 +106,7 @@ def parse_files(files, k, trim5p=None):
                 data = f.read()
             if data[:2] == b"\x1f\x8b":
                 data = gzip.decompress(data)
-        s, st = parse_file(data, k, t)
+        s, st = parse_file(data, k, t, carry)
         if st == -1:
             break
         chunks.append(s)

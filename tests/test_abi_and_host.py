@@ -53,10 +53,14 @@ def test_product_does_not_reference_the_oracle():
     assert "oracle" not in out
 
 
-def _kat_parse(path, k, trim=0, want_route=None):
-    r = subprocess.run([KAT, "_parse", "-m", str(k), "--5ptrim", str(trim), path], capture_output=True, env=dict(os.environ, KAT_TRACE="1"))
+def _kat_parse(path, k, trim=0, want_route=None, carry=None):
+    """carry: one-element list with the seq_len state inherited from the previous file of a group (updated in place)."""
+    r = subprocess.run([KAT, "_parse", "-m", str(k), "--5ptrim", str(trim), "--carry", str(carry[0] if carry else 0), path], capture_output=True,
+                       env=dict(os.environ, KAT_TRACE="1"))
     if want_route is not None:
         assert b"parser: " + want_route in r.stderr, r.stderr
+    if carry is not None and b"carry_out=" in r.stderr:
+        carry[0] = int(r.stderr.split(b"carry_out=")[1].split()[0])
     return r.stdout, {0: 0, 2: -1, 3: -2}[r.returncode]
 
 
@@ -118,6 +122,32 @@ def test_host_parser_matches_oracle_on_token_soup(seed, tmp_path):
         p.write_bytes(data)
         for k, trim in ((5, 0), (3, 2)):
             assert _kat_parse(str(p), k, trim) == O.parse_file(data, k, trim), (seed, it, k, trim, data)
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_host_parser_carries_seq_len_across_the_files_of_a_group(seed, tmp_path):
+    """The reference parser keeps `seq_len` when a stream moves to its next file (JFI/mer_overlap_sequence_parser.hpp:158-187):
+    a file that ends inside a FASTQ record makes the next FASTQ file's first record "too long" and the rest of the group is
+    dropped.  Groups of 2-4 files (soups, regular files, files with an empty or truncated last record): the host parser,
+    fed file by file with the carried state, emits the oracle's streams, statuses and final state."""
+    import seqgen
+    rng = np.random.default_rng(3000 + seed)
+    tails = [b"@t\n\n+\n\n", b"@t\nACGTACGT\n", b"@t\nACGTAC", b"@t\nACGTACGT\n+\nIIIIIIII\n", b""]
+    for it in range(25):
+        files = []
+        for j in range(int(rng.integers(2, 5))):
+            kind = rng.random()
+            body = seqgen.token_soup(rng) if kind < 0.4 else _regular_file(rng, kind < 0.8, int(rng.integers(1, 6)))
+            files.append(body + (tails[int(rng.integers(0, len(tails)))] if body.startswith(b"@") else b""))
+        host, ora = [0], [0]
+        for j, data in enumerate(files):
+            p = tmp_path / ("g%d_%d.fq" % (it, j))
+            p.write_bytes(data)
+            got = _kat_parse(str(p), 5, 0, carry=host)
+            want = O.parse_file(data, 5, 0, ora)
+            assert got == want and (want[1] != 0 or host == ora), (seed, it, j, data[-40:], host, ora)
+            if want[1] != 0:
+                break
 
 
 # ---- the parser's fast paths (regular 4-line FASTQ / FASTA layouts, parsed piece-wise in parallel)

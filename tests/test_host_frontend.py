@@ -113,3 +113,53 @@ def test_sect_and_filter_seq_against_the_reference_binary_on_random_files(seed, 
                     break
             got[who] = (r.returncode, {f: open(tmp_path / out / f, "rb").read() for f in sorted(os.listdir(tmp_path / out))})
         assert got["our"] == got["ref"], (seed, tool, got["ref"][0], got["our"][0])
+
+
+@pytest.mark.parametrize("seed", list(range(18)) + [195])
+def test_hist_gcp_comp_against_the_reference_binary_on_random_commands(seed, tmp_path):
+    """Differential run over the option space: random FASTA / FASTQ inputs (one to three per command), random k (one- and
+    two-word), -N/-O, histogram bounds, scales, bins, 5' trim, 2- and 3-input comp — the unmodified reference and the front-end
+    write the same files byte for byte.  Seed 195 is the group in which the first file ends with an empty FASTQ record and the
+    reference drops the second file (the parser's seq_len is not reset between files)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "kat")
+    if not os.access(ref, os.X_OK):
+        pytest.skip("oracle/_ref/kat not built")
+    import numpy as np
+    from test_abi_and_host import _random_file
+    rng = np.random.default_rng(seed)
+    names = []
+    for i in range(3):
+        fq = rng.random() < 0.5
+        names.append("in%d.%s" % (i, "fq" if fq else "fa"))
+        (tmp_path / names[-1]).write_bytes(_random_file(np.random.default_rng(seed * 10 + i), fq))
+    k = int(rng.choice([3, 5, 7, 11, 17, 33, 40]))
+    tool = ["hist", "gcp", "comp"][seed % 3]
+    if tool == "hist":
+        args = ["hist", "-m", str(k), "-H", "4096", "-o", "OUT/h"] + (["-N"] if rng.random() < 0.3 else [])
+        if rng.random() < 0.6:
+            args += ["-l", str(int(rng.integers(1, 5))), "-h", str(int(rng.integers(5, 40))), "-i", str(int(rng.integers(1, 4)))]
+        if rng.random() < 0.4:
+            args += ["--5ptrim", str(int(rng.integers(0, 6)))]
+        args += names[:int(rng.integers(1, 4))]
+    elif tool == "gcp":
+        args = ["gcp", "-m", str(k), "-H", "4096", "-o", "OUT/g"] + (["-N"] if rng.random() < 0.3 else [])
+        if rng.random() < 0.6:
+            args += ["-x", str(float(rng.choice([0.1, 0.5, 2.0, 1.5]))), "-y", str(int(rng.integers(1, 30)))]
+        args += names[:int(rng.integers(1, 4))]
+    else:
+        args = ["comp", "-m", str(k), "-H", "4096", "-I", "4096", "-J", "4096", "-o", "OUT/c"] + [f for f in ("-N", "-O", "-h", "-n") if rng.random() < 0.3]
+        if rng.random() < 0.6:
+            args += ["-i", str(int(rng.integers(2, 40))), "-j", str(int(rng.integers(2, 40)))]
+        if rng.random() < 0.4:
+            args += ["-x", str(float(rng.choice([0.5, 2.0]))), "-y", str(float(rng.choice([0.25, 1.5])))]
+        args += names[:(3 if rng.random() < 0.3 else 2)]
+    no_preload = {k_: v for k_, v in os.environ.items() if k_ != "LD_PRELOAD"}
+    got = {}
+    for who, exe, env in (("ref", ref, no_preload), ("our", T.KAT, os.environ)):
+        for attempt in range(3):  # (the reference may abort on the uninitialised terminal width it reads)
+            os.makedirs(tmp_path / who, exist_ok=True)
+            r = subprocess.run([exe, *[a.replace("OUT", who) for a in args], "-t1"], cwd=tmp_path, capture_output=True, text=True, env=env)
+            if r.returncode >= 0:
+                break
+        got[who] = (r.returncode, {f: open(tmp_path / who / f, "rb").read().replace(who.encode() + b"/", b"X/") for f in sorted(os.listdir(tmp_path / who))})
+    assert got["our"] == got["ref"], (seed, " ".join(args), got["ref"][0], got["our"][0])
