@@ -31,11 +31,13 @@ int cold_main(int argc, char **argv) {
     reads.files.assign(a.positional.begin() + 1, a.positional.end());
     reads.set_trim(parse_trim(a.get("5ptrim", "0")));
     reads.canonical = false;
+    reads.threads = (unsigned)to_u64(a.get("threads", "1"), "threads");
     reads.hash_size = hash_size; // Cold::setHashSize, src/cold.hpp:151-154
     reads.index = 1;
     assembly.files.assign(1, a.positional[0]);
     assembly.set_trim({});
     assembly.canonical = false;
+    assembly.threads = (unsigned)to_u64(a.get("threads", "1"), "threads");
     assembly.hash_size = hash_size / 2;
     assembly.index = 1;
     const string prefix = a.get("output_prefix", "kat-cold");

@@ -72,6 +72,7 @@ int comp_main(int argc, char **argv) {
         in[i].files = glob_group(a.positional[i]);
         in[i].index = i + 1;
         in[i].canonical = !a.has(nc[i]);
+        in[i].threads = (unsigned)to_u64(a.get("threads", "1"), "threads");
         in[i].hash_size = to_u64(a.get(hs[i], "100000000"), hs[i]);
     }
     in[0].set_trim(parse_trim(a.get("d1_5ptrim", "0")));

@@ -46,6 +46,7 @@ int filter_kmer_main(int argc, char **argv) {
     in.files = a.positional; // setMultipleInputs: every positional argument is a file of the one input group
     in.set_trim({});
     in.canonical = !a.has("non_canonical");
+    in.threads = (unsigned)to_u64(a.get("threads", "1"), "threads");
     in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
     const string prefix = a.get("output_prefix", "kat.filter.kmer");
     in.validate();
@@ -184,6 +185,7 @@ int filter_seq_main(int argc, char **argv) {
     in.files = a.positional;
     in.set_trim({});
     in.canonical = !a.has("non_canonical");
+    in.threads = (unsigned)to_u64(a.get("threads", "1"), "threads");
     in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
     const string prefix = a.get("output_prefix", "kat.filter.kmer");
     in.validate();
@@ -225,7 +227,9 @@ int filter_seq_main(int argc, char **argv) {
     };
     uint64_t keepers = 0, n_total = 0;
     for (size_t i = 0; i < r1.size(); i++) { // FilterSeq::processSeq, :267-328
-        if (paired && i >= r2.size()) throw KatError(4, "Second sequence file appears to be shorter than the first.");
+        // a second file that runs out first: SeqAn's readRecord throws UnexpectedEnd, a std::exception -> "Error: ...", exit code 5
+        // (src/filter_sequence.cc:217-219, src/kat.cc:293-295); the records written so far stay in the output files
+        if (paired && i >= r2.size()) throw KatError(5, "Unexpected end of input.");
         const double random_val = urd(gen);
         uint64_t nb_kmers = 0;
         uint64_t matches = hits(w1, i, nb_kmers);

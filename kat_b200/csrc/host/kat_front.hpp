@@ -231,6 +231,7 @@ struct Input {
     bool canonical = true;
     uint64_t hash_size = 100000000ULL; // DEFAULT_HASH_SIZE, lib/include/kat/jellyfish_helper.hpp:76
     int index = 1;
+    unsigned threads = 1;   // -t: decides how many of the group's files the reference reads side by side (count_input)
     bool load_mode = false; // InputMode::LOAD: the (first) input is a jellyfish hash
     katgpu_table *table = nullptr;        // rank 0's (the only one on a single GPU)
     vector<katgpu_table *> tables;        // one per GPU of the job
@@ -376,12 +377,62 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
     std::string bases;
     // KAT_GPU_PARSE=0 keeps FASTQ parsing on the host
     const bool gpu_parse = allow_streaming && env_size("KAT_GPU_PARSE", 1) != 0;
-    // the reference parser's seq_len state, which it keeps from one file of the group to the next (seq_parser.hpp): non-zero
-    // only after a file that ended inside a FASTQ record; the regular-layout routes below then do not apply to the next file
-    size_t fastq_carry = 0;
+    // The reference reads the group through S = min(files, threads) parser streams (lib/src/jellyfish_helper.cc:231-233).  Files
+    // are handed out in order: the first S while the parser is built, each later one to the stream that reaches the end of its
+    // file first (an empty file is skipped by the stream that opened it, which takes the next one as well).  What a stream
+    // keeps from one file to its next is `seq_len` (seq_parser.hpp: non-zero only after a file that ended inside a FASTQ
+    // record; the regular-layout routes below then do not apply) — and whether it is still alive: an exception inside
+    // produce() ends THAT stream only (JFI/cooperative_pool2.hpp:249-260), the others go on taking files; with one stream the
+    // rest of the group is lost.  Two exceptions exist:
+    //   * "Invalid fastq sequence": the buffer being filled is dropped with it (the emulation in seq_parser.cc does that);
+    //   * "Unsupported format" when the stream opens its NEXT file: produce() is still holding the last 4 KiB buffer of the
+    //     file it just finished, which is lost with it (JFI/mer_overlap_sequence_parser.hpp:132-152).  From the files opened
+    //     while the parser is built the same exception is not caught at all: the tool fails with exit code 5
+    //     (:119-122,158-187; src/kat.cc:293-295).
+    // Which live stream takes a later file is a race in the reference; it shows in the result only when a stream carries
+    // seq_len or runs into an unsupported file, and is modelled by bytes read so far.
+    struct RefStream {
+        bool alive = true, has_file = false;
+        size_t carry = 0;
+        uint64_t clock = 0;
+        std::string held; // careful mode: the last buffer of the stream's previous file (with its seam), not yet counted
+    };
+    vector<RefStream> streams(std::max<size_t>(1, std::min<size_t>(in.files.size(), std::max(1u, in.threads))));
+    // A file in no supported format anywhere in the group: fatal among the files the constructor opens (checked before
+    // anything is counted); otherwise the group is read in "careful" mode — every file through the emulation, which knows
+    // the reference's buffers, and the last buffer of each file held back until its stream has opened its next file.
+    bool careful = false;
+    {
+        size_t opened = 0; // streams that hold their first file
+        for (size_t i = 0; i < in.files.size(); i++) {
+            const int c = kat_host::first_byte_of_file(in.files[i]);
+            if (c < 0) continue;
+            const bool supported = c == '>' || c == '@';
+            if (opened < streams.size()) {
+                if (!supported) throw KatError(5, "Unsupported format");
+                opened++;
+            } else if (!supported)
+                careful = true;
+        }
+    }
+    const bool fast_routes = allow_streaming && !careful;
+    size_t built = 0; // streams that hold their first file: the parser's constructor is done when built == streams.size()
     for (size_t i = 0; i < in.files.size(); i++) {
         string err;
-        if (gpu_parse && fastq_carry == 0) { // plain 4-line FASTQ: the raw bytes go to the GPU(s) and are parsed there
+        const bool ctor = built < streams.size();
+        size_t s = built;
+        if (!ctor) {
+            s = streams.size();
+            for (size_t j = 0; j < streams.size(); j++)
+                if (streams[j].alive && (s == streams.size() || streams[j].clock < streams[s].clock)) s = j;
+            if (s == streams.size()) break; // every stream has ended: the remaining files are never opened
+        }
+        RefStream &st = streams[s];
+        st.clock += file_size_or_zero(in.files[i]);
+        auto took_file = [&]() {
+            if (ctor && !st.has_file) st.has_file = true, built++;
+        };
+        if (fast_routes && gpu_parse && st.carry == 0) { // plain 4-line FASTQ: the raw bytes go to the GPU(s) and are parsed there
             const int r = kat_host::stream_fastq_raw(in.files[i], env_size("KAT_RAW_BLOCK", (size_t)256 << 20) * (size_t)ctx.n(), ctx.n(),
                                                      [&](const char *const *parts, const size_t *lens) {
                                                          vector<int> regular(ctx.n(), 0);
@@ -393,21 +444,25 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
                                                          // some GPUs counted their share, others refused theirs: start over
                                                          return n_reg == ctx.n() ? 1 : n_reg == 0 ? 0 : -1;
                                                      }, err);
-            if (r == 1) continue;
+            if (r == 1) {
+                took_file();
+                continue;
+            }
             if (r < 0) { // irregular after some blocks were counted: start this input over with host parsing
                 free_tables(ctx, in);
                 count_input(ctx, in, k, allow_grow, false);
                 return;
             }
         }
-        if (allow_streaming && fastq_carry == 0 && file_size_or_zero(in.files[i]) >= stream_from) {
-            katgpu_status bad = KATGPU_OK;
+        if (fast_routes && st.carry == 0 && file_size_or_zero(in.files[i]) >= stream_from) {
             const int r = kat_host::stream_regular_file(in.files[i], in.trim5p[i], block, [&](const char *b, size_t n) {
                 feed_all(ctx, in, k, b, n);
                 return true;
             }, err);
-            gpu_check(bad);
-            if (r == 1) continue;
+            if (r == 1) {
+                took_file();
+                continue;
+            }
             if (r < 0) { // irregular after some blocks were counted: start this input over, whole files at a time
                 free_tables(ctx, in);
                 count_input(ctx, in, k, allow_grow, false);
@@ -415,18 +470,36 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
             }
         }
         if (!kat_host::read_file(in.files[i], raw, err)) throw KatError(4, err);
+        if (raw.empty()) continue; // open_next_file, `case EOF`: the same stream opens the next file
+        took_file();
         bases.clear();
-        const auto st = kat_host::parse_sequence_file(raw.data(), raw.size(), k, in.trim5p[i], bases, &fastq_carry);
-        if (st == kat_host::ParseStatus::UnsupportedFormat) {
-            cerr << "warning: " << in.files[i] << ": Unsupported format (the reference silently stops reading this input here)" << endl;
-            break;
+        kat_host::LastBuffer last;
+        const auto status = careful ? kat_host::parse_sequence_file_exact(raw.data(), raw.size(), k, in.trim5p[i], bases, &st.carry, &last)
+                                    : kat_host::parse_sequence_file(raw.data(), raw.size(), k, in.trim5p[i], bases, &st.carry);
+        if (status == kat_host::ParseStatus::UnsupportedFormat) { // (never while the parser is built: checked above)
+            cerr << "warning: " << in.files[i] << ": Unsupported format; like the reference, the parser stream that opened it loses the last buffer of its previous file and reads no further files" << endl;
+            st.alive = false;
+            st.held.clear();
+            continue;
         }
-        if (!bases.empty()) feed_all(ctx, in, k, bases.data(), bases.size());
-        if (st == kat_host::ParseStatus::InvalidFastq) {
-            cerr << "warning: " << in.files[i] << ": Invalid fastq sequence; like the reference, the rest of this input is ignored" << endl;
-            break;
+        if (!st.held.empty()) { // the stream has opened its next file: the buffer it was holding is queued
+            feed_all(ctx, in, k, st.held.data(), st.held.size());
+            st.held.clear();
         }
+        if (status == kat_host::ParseStatus::InvalidFastq) {
+            cerr << "warning: " << in.files[i] << ": Invalid fastq sequence; like the reference, the parser stream that read it reads no further files" << endl;
+            st.alive = false;
+            if (!bases.empty()) feed_all(ctx, in, k, bases.data(), bases.size());
+            continue;
+        }
+        if (careful) { // count up to the last buffer; hold that one (and the seam its k-mers reach back over) back
+            if (last.at > 0) feed_all(ctx, in, k, bases.data(), last.at);
+            st.held.assign(bases, last.at - last.seam, std::string::npos);
+        } else if (!bases.empty())
+            feed_all(ctx, in, k, bases.data(), bases.size());
     }
+    for (auto &st : streams) // no file left to open: every stream queues what it holds and is done
+        if (!st.held.empty()) feed_all(ctx, in, k, st.held.data(), st.held.size());
     run_on_all(ctx.n(), [&](int r) {
         uint64_t nd = 0, nt = 0;
         gpu_check(katgpu_count_end(in.tables[r], &nd, &nt)); // on a job: the job's totals, on every rank

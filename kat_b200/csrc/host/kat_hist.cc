@@ -23,6 +23,7 @@ int hist_main(int argc, char **argv) {
     in.files = a.positional;
     in.set_trim(parse_trim(a.get("5ptrim", "0")));
     in.canonical = !a.has("non_canonical");
+    in.threads = (unsigned)to_u64(a.get("threads", "1"), "threads");
     in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
     const string prefix = a.get("output_prefix", "kat.hist");
     // Histogram ctor, src/histogram.cc:57-71, src/histogram.hpp:172-178

@@ -82,6 +82,7 @@ int sect_main(int argc, char **argv) {
     in.files.assign(a.positional.begin() + 1, a.positional.end());
     in.set_trim(parse_trim(a.get("5ptrim", "0")));
     in.canonical = !a.has("non_canonical");
+    in.threads = (unsigned)to_u64(a.get("threads", "1"), "threads");
     in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
     const string prefix = a.get("output_prefix", "kat-sect");
     const uint32_t min_repeat = (uint32_t)to_u64(a.get("min_repeat", "2"), "min_repeat"), max_repeat = (uint32_t)to_u64(a.get("max_repeat", "0"), "max_repeat");

@@ -181,8 +181,10 @@ bool skip_quals(CharStream &is, size_t read_len) {
 }
 
 // The reference's parser, character by character (see the header of this file).
-ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry) {
+ParseStatus exact_impl(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry, LastBuffer *last) {
     CharStream is(data, n);
+    const size_t out_base = out.size();
+    if (last) *last = LastBuffer{};
     const int first = is.peek();
     if (first == -1) return ParseStatus::Ok; // empty file: nothing to count
     if (first != '>' && first != '@') return ParseStatus::UnsupportedFormat;
@@ -222,6 +224,7 @@ ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k
                 }
             }
         }
+        if (last) last->at = out.size() - out_base, last->seam = start; // the pass that runs into the end of the file is the last one
         out.append(reinterpret_cast<const char *>(buf + start), read - start);
         have_seam = read >= seam;
     }
@@ -401,7 +404,21 @@ ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsi
     g_last_fast = !carried && n > 0 && (data[0] == '>' || data[0] == '@') && !getenv("KAT_PARSE_EXACT_ONLY") &&
                   parse_regular_layout(data, n, data[0] == '@', trim5p, out);
     if (g_last_fast) return ParseStatus::Ok;
-    return parse_sequence_file_exact(data, n, k, trim5p, out, fastq_carry);
+    return exact_impl(data, n, k, trim5p, out, fastq_carry, nullptr);
+}
+
+ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry, LastBuffer *last) {
+    g_last_fast = false;
+    return exact_impl(data, n, k, trim5p, out, fastq_carry, last);
+}
+
+int first_byte_of_file(const std::string &path) {
+    gzFile f = gzopen(path.c_str(), "rb");
+    if (!f) return -1;
+    unsigned char c = 0;
+    const int n = gzread(f, &c, 1);
+    gzclose(f);
+    return n == 1 ? (int)c : -1;
 }
 
 int stream_regular_file(const std::string &path, unsigned trim5p, size_t block_bytes,

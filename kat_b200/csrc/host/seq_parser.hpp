@@ -18,6 +18,18 @@ bool read_file(const std::string &path, std::vector<unsigned char> &out, std::st
 // FASTQ file's first record is then measured too long, "Invalid fastq sequence" is thrown and swallowed, and the rest
 // of the group is dropped.  A caller that parses a group passes the same variable for every file, in order.
 ParseStatus parse_sequence_file(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry = nullptr);
+// The character-level emulation alone (no fast path), which also knows the reference's 4 KiB buffers.  `last`: where, in
+// the bytes this call appended, the LAST buffer's own bytes start, and how many bytes before them (the k-1 base seam) its
+// k-mers may reach back over.  The reference loses exactly that buffer when the stream that read the file then opens a
+// file in no supported format: produce() throws out of open_next_file before the buffer is queued
+// (JFI/mer_overlap_sequence_parser.hpp:132-152, JFI/cooperative_pool2.hpp:249-260) — see kat_front.hpp::count_input.
+struct LastBuffer {
+    size_t at = 0, seam = 0;
+};
+ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry = nullptr,
+                                      LastBuffer *last = nullptr);
+// The first byte of a file as the reference's streams see it (through zlib): -1 = empty or unreadable.
+int first_byte_of_file(const std::string &path);
 // Large plain files in one of the regular layouts (see seq_parser.cc) block by block, without
 // holding the file or its whole base stream in memory: `sink` gets the base stream of each block
 // of whole records (no k-mer spans two records, so blocks can be counted independently).

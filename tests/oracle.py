@@ -42,6 +42,8 @@ def lib():
     L.oracle_parse_file.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p]
     L.oracle_parse_file_state.restype = C.c_long
     L.oracle_parse_file_state.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p, C.POINTER(C.c_size_t)]
+    L.oracle_parse_file_state2.restype = C.c_long
+    L.oracle_parse_file_state2.argtypes = [u8p, C.c_size_t, C.c_int, C.c_int, u8p, C.POINTER(C.c_size_t), C.POINTER(C.c_size_t)]
     L.oracle_table_new.restype = vp
     L.oracle_table_new.argtypes = [C.c_int, C.c_int]
     L.oracle_table_free.argtypes = [vp]
@@ -72,16 +74,20 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def parse_file(data: bytes, k: int, trim5p: int = 0, carry=None):
+def parse_file(data: bytes, k: int, trim5p: int = 0, carry=None, last=None):
     """a1: file image -> (base stream bytes, status). status 0 ok, -1 unsupported
     format, -2 invalid fastq (stream truncated as the reference does).  `carry`: a one-element list holding the
-    parser's seq_len state, which the reference keeps from one file of a group to the next (see kat_oracle.c)."""
+    parser's seq_len state, which the reference keeps from one file of a group to the next (see kat_oracle.c).
+    `last`: a two-element list that receives where the last 4 KiB buffer's bytes start in the stream and the seam before it."""
     src = np.frombuffer(data, dtype=np.uint8)
     out = np.empty(len(data) + 2, dtype=np.uint8)
     st = C.c_size_t(carry[0] if carry else 0)
-    r = lib().oracle_parse_file_state(_ptr(src) if len(data) else None, len(data), k, trim5p, _ptr(out), C.byref(st))
+    lb = (C.c_size_t * 2)(0, 0)
+    r = lib().oracle_parse_file_state2(_ptr(src) if len(data) else None, len(data), k, trim5p, _ptr(out), C.byref(st), lb)
     if carry is not None:
         carry[0] = st.value
+    if last is not None:
+        last[0], last[1] = lb[0], lb[1]
     if r == -1:
         return b"", -1
     if r <= -2:
@@ -89,29 +95,71 @@ def parse_file(data: bytes, k: int, trim5p: int = 0, carry=None):
     return out[:r].tobytes(), 0
 
 
-def parse_files(files, k, trim5p=None):
-    """Whole input group -> list of per-file base streams (single-producer
-    semantics: an invalid FASTQ ends the group, cooperative_pool2.hpp:249-260)."""
+class UnsupportedFormat(RuntimeError):
+    """A file opened while the reference builds its parser starts with neither '>' nor '@': the tool fails, exit code 5."""
+
+
+def parse_files(files, k, trim5p=None, threads=1):
+    """Whole input group -> list of base-stream chunks to count (no k-mer spans two chunks).
+
+    The reference reads a group through S = min(files, threads) parser streams (lib/src/jellyfish_helper.cc:231-233).
+    Files are handed out in order: the first S while the parser is built (an empty file is skipped by the stream that
+    opened it, which takes the next one too; "Unsupported format" there is fatal), later ones to the stream that reaches
+    the end of its file first (modelled by bytes read).  A stream keeps its seq_len from file to file, and an exception
+    inside produce() — "Invalid fastq sequence", "Unsupported format" on a later file — ends THAT stream only
+    (JFI/cooperative_pool2.hpp:249-260); with one stream, the rest of the group is lost.  The second kind also costs the
+    stream the last 4 KiB buffer of the file it had just finished (kat_oracle.c, oracle_parse_file_state2)."""
     trim5p = trim5p or [0] * len(files)
     if len(trim5p) == 1 and len(files) > 1:
         trim5p = trim5p * len(files)
     chunks = []
-    carry = [0]
+    n_streams = max(1, min(len(files), max(1, threads)))
+    alive, carry, clock, has_file = [True] * n_streams, [[0] for _ in range(n_streams)], [0] * n_streams, [False] * n_streams
+    held = [b""] * n_streams  # the last buffer (with its seam) of the file a stream has just finished: queued only once the
+    built = 0                 # stream has opened its next file, lost when that file is in no supported format
     for path, t in zip(files, trim5p):
         if isinstance(path, (bytes, bytearray)):
             data = bytes(path)
+            size = len(data)
         else:
             import gzip
             with open(path, "rb") as f:
                 data = f.read()
+            size = len(data)
             if data[:2] == b"\x1f\x8b":
                 data = gzip.decompress(data)
-        s, st = parse_file(data, k, t, carry)
+        ctor = built < n_streams
+        if ctor:
+            s = built
+        else:
+            live = [j for j in range(n_streams) if alive[j]]
+            if not live:
+                break
+            s = min(live, key=lambda j: (clock[j], j))
+        clock[s] += size
+        if not data:
+            continue
+        if ctor and not has_file[s]:
+            has_file[s] = True
+            built += 1
+        last = [0, 0]
+        seq, st = parse_file(data, k, t, carry[s], last)
         if st == -1:
-            break
-        chunks.append(s)
+            if ctor:
+                raise UnsupportedFormat("Unsupported format")
+            alive[s] = False
+            held[s] = b""
+            continue
+        if held[s]:
+            chunks.append(held[s])
+            held[s] = b""
         if st == -2:
-            break
+            alive[s] = False
+            chunks.append(seq)
+            continue
+        chunks.append(seq[:last[0]])
+        held[s] = seq[last[0] - last[1]:]
+    chunks += [h for h in held if h]
     return chunks
 
 
@@ -145,8 +193,8 @@ class Table:
         return t.finish()
 
     @classmethod
-    def from_files(cls, files, k, canonical=True, trim5p=None):
-        return cls.from_chunks(parse_files(files, k, trim5p), k, canonical)
+    def from_files(cls, files, k, canonical=True, trim5p=None, threads=1):
+        return cls.from_chunks(parse_files(files, k, trim5p, threads), k, canonical)
 
     @property
     def distinct(self):

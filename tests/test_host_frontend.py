@@ -163,3 +163,20 @@ def test_hist_gcp_comp_against_the_reference_binary_on_random_commands(seed, tmp
                 break
         got[who] = (r.returncode, {f: open(tmp_path / who / f, "rb").read().replace(who.encode() + b"/", b"X/") for f in sorted(os.listdir(tmp_path / who))})
     assert got["our"] == got["ref"], (seed, " ".join(args), got["ref"][0], got["our"][0])
+
+
+import fuzz_vs_reference as F
+
+
+@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("kind", F.KINDS)
+def test_front_end_against_the_reference_binary_wider(kind, seed, tmp_path):
+    """tests/fuzz_vs_reference.py, a few seeds of every kind on each CPU run (campaigns of hundreds of seeds per kind were run
+    while the front-end was written): sect with all its switches, cold, filter kmer, filter seq single and paired (a second
+    file that runs out first ends the run like SeqAn does: "Unexpected end of input.", exit code 5), gzip'd inputs with
+    per-file trims and -t, jellyfish hashes in both directions, and file groups read by several parser streams (-t): a
+    broken FASTQ record ends one stream and the others go on, a file in no supported format is fatal while the parser is
+    built and later costs its stream the last 4 KiB buffer of the previous file."""
+    if not os.access(F.REF, os.X_OK):
+        pytest.skip("oracle/_ref/kat not built")
+    F.case(kind, seed, tmp_path)
