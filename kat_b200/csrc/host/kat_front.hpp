@@ -406,8 +406,8 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
         size_t opened = 0; // streams that hold their first file
         for (size_t i = 0; i < in.files.size(); i++) {
             const int c = kat_host::first_byte_of_file(in.files[i]);
-            if (c < 0) continue;
-            const bool supported = c == '>' || c == '@';
+            if (c == -1) continue;
+            const bool supported = c == '>' || c == '@' || c == -2; // (a pipe is taken for a sequence stream; the parser has the last word)
             if (opened < streams.size()) {
                 if (!supported) throw KatError(5, "Unsupported format");
                 opened++;

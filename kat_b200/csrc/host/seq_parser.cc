@@ -413,6 +413,8 @@ ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k
 }
 
 int first_byte_of_file(const std::string &path) {
+    struct stat st;
+    if (stat(path.c_str(), &st) != 0 || !S_ISREG(st.st_mode)) return -2; // a pipe must not be read twice
     gzFile f = gzopen(path.c_str(), "rb");
     if (!f) return -1;
     unsigned char c = 0;

@@ -28,7 +28,8 @@ struct LastBuffer {
 };
 ParseStatus parse_sequence_file_exact(const unsigned char *data, size_t n, int k, unsigned trim5p, std::string &out, size_t *fastq_carry = nullptr,
                                       LastBuffer *last = nullptr);
-// The first byte of a file as the reference's streams see it (through zlib): -1 = empty or unreadable.
+// The first byte of a regular file as the reference's streams see it (through zlib): -1 = empty or unreadable,
+// -2 = not a regular file (a pipe can be read only once: not looked at).
 int first_byte_of_file(const std::string &path);
 // Large plain files in one of the regular layouts (see seq_parser.cc) block by block, without
 // holding the file or its whole base stream in memory: `sink` gets the base stream of each block

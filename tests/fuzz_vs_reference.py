@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KAT = os.path.join(ROOT, "kat_b200", "bin", "kat")
 REF = os.path.join(ROOT, "oracle", "_ref", "kat")
 REF_JF = os.path.join(ROOT, "oracle", "_ref", "kat_jellyfish")
-KINDS = ("sect", "cold", "fkmer", "fseq", "gz", "load", "group")
+KINDS = ("sect", "cold", "fkmer", "fseq", "gz", "load", "group", "compgroups")
 
 
 def records(rng, n_rec, fastq, max_len=300, alphabet=b"ACGTacgtNRY-", p=(.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .01, .01)):
@@ -169,6 +169,27 @@ def _command(kind, rng, d):
             open(os.path.join(d, names[-1]), "wb").write(data)
         tool = ["hist", "gcp"][int(rng.integers(0, 2))]
         return [[tool, "-m", str(int(rng.choice([3, 5, 9]))), "-H", "4096", "-t", str(threads), "-o", "out/o"] + flag("-N") + names]
+    if kind == "compgroups":
+        # comp whose inputs are GROUPS of files: space-separated names and glob patterns in one argument, a trim per file of
+        # the group, 2 or 3 inputs, -t
+        names = _seq_files(rng, d, 5, allow_gz=True)
+        rng.shuffle(names)
+        n_in = 3 if rng.random() < 0.3 else 2
+        cuts = sorted(rng.choice(np.arange(1, 5), n_in - 1, replace=False).tolist())
+        groups = [names[a:b] for a, b in zip([0] + cuts, cuts + [5])]
+        args = ["comp", "-m", str(k), "-H", "4096", "-I", "4096", "-J", "4096", "-o", "out/c", "-t", str(int(rng.integers(1, 4)))]
+        args += flag("-N") + flag("-O") + flag("-h") + flag("-n")
+        if n_in == 3:
+            args += flag("-P")
+        if rng.random() < 0.5:
+            args += ["-i", str(int(rng.integers(2, 40))), "-j", str(int(rng.integers(2, 40)))]
+        if rng.random() < 0.4:
+            args += ["-x", str(float(rng.choice([0.5, 2.0]))), "-y", str(float(rng.choice([0.25, 1.5])))]
+        for opt, g in zip(("--d1_5ptrim", "--d2_5ptrim"), groups):
+            if rng.random() < 0.4:
+                args += [opt, ",".join(str(int(rng.integers(0, 5))) for _ in range(len(g) if rng.random() < 0.7 else 1))]
+        as_arg = lambda g: " ".join(g) if rng.random() < 0.7 or len(g) == 1 else "in[%s].*" % "".join(n[2] for n in g)
+        return [args + [as_arg(g) for g in groups]]
     if kind == "load":
         # (k >= 5: the reference's LOAD mode sizes its table at 2x the records and ignores add()'s result, lib/src/jellyfish_helper.cc:
         # 160-172 — with the 32 canonical 3-mers and counts beyond the 7-bit field, which take a second slot each, it
