@@ -536,6 +536,10 @@ inline int load_input(katgpu_ctx *ctx, Input &in) {
             throw KatError(4, "Size of database (" + std::to_string(data) + ") must be a multiple of the length of a record (" + std::to_string(h.record_bytes()) + ")");
         n_records = data / h.record_bytes();
     }
+    // a hash without records: the reference asks for an array of 2^ceilLog2(0) slots, whose hash matrix has no rows —
+    // std::runtime_error("Invalid matrix size 0x<key bits>"), exit code 5 (lib/src/jellyfish_helper.cc:149-165,
+    // deps/jellyfish-2.2.0/lib/rectangular_binary_matrix.cc:24-28)
+    if (n_records == 0) throw KatError(5, "Invalid matrix size 0x" + std::to_string(h.key_len));
     in.canonical = h.canonical;
     // the reference sizes the new array at 2 * nbRecords rounded up to a power of two (:149-150)
     gpu_check(katgpu_count_begin(ctx, k, in.canonical ? 1 : 0, std::max<uint64_t>(2 * n_records, 1024), 1, &in.table));

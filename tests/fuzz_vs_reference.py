@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KAT = os.path.join(ROOT, "kat_b200", "bin", "kat")
 REF = os.path.join(ROOT, "oracle", "_ref", "kat")
 REF_JF = os.path.join(ROOT, "oracle", "_ref", "kat_jellyfish")
-KINDS = ("sect", "cold", "fkmer", "fseq", "gz", "load", "group", "compgroups")
+KINDS = ("sect", "cold", "fkmer", "fseq", "gz", "load", "group", "compgroups", "jfcount")
 
 
 def records(rng, n_rec, fastq, max_len=300, alphabet=b"ACGTacgtNRY-", p=(.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .01, .01)):
@@ -190,6 +190,33 @@ def _command(kind, rng, d):
                 args += [opt, ",".join(str(int(rng.integers(0, 5))) for _ in range(len(g) if rng.random() < 0.7 else 1))]
         as_arg = lambda g: " ".join(g) if rng.random() < 0.7 or len(g) == 1 else "in[%s].*" % "".join(n[2] for n in g)
         return [args + [as_arg(g) for g in groups]]
+    if kind == "jfcount":
+        # hashes written by the unmodified `jellyfish count` with its own options (table size, counter bits, counter bytes in
+        # the file, -L / -U bounds, canonical or not) as inputs of hist / gcp / comp / sect / filter kmer (LOAD mode)
+        # (k >= 11 keeps the counts small: the reference's LOAD mode ignores add()'s result and loses records when the chained
+        # large-count entries of a narrow counter field fill its 2x-sized table, see "load" below; a hash without records makes
+        # it fail with "Invalid matrix size 0x<key bits>", exit code 5, which the front-end reproduces; tables started very small,
+        # `-s 64`, put a short reprobe limit into the header, with which the same silent loss happens at any load)
+        names = _seq_files(rng, d, 3)
+        k = max(k, 11)
+        jf = ["!jellyfish", "count", "-m", str(k), "-s", str(int(rng.choice([1000, 20000, 300000]))), "-t", str(int(rng.integers(1, 3))), "-o", "x.jf"]
+        jf += flag("-C", 0.6)
+        if rng.random() < 0.5:
+            jf += ["-c", str(int(rng.integers(2, 9)))]
+        if rng.random() < 0.5:
+            jf += ["--out-counter-len", str(int(rng.integers(1, 5)))]
+        if rng.random() < 0.3:
+            jf += ["-L", str(int(rng.integers(1, 4)))]
+        if rng.random() < 0.3:
+            jf += ["-U", str(int(rng.integers(3, 40)))]
+        jf += names[:int(rng.integers(1, 3))]
+        second = [["hist", "-o", "out/h", "-l", str(int(rng.integers(1, 4))), "-h", str(int(rng.integers(4, 300))), "x.jf"],
+                  ["gcp", "-o", "out/g", "-y", str(int(rng.integers(2, 300))), "x.jf"],
+                  ["comp", "-m", str(k), "-H", "4096", "-o", "out/c", "-i", "50", "-j", "50"] + flag("-N") + flag("-h") + ["x.jf", names[2]],
+                  ["comp", "-m", str(k), "-H", "4096", "-o", "out/c", "-i", "50", "-j", "50"] + flag("-O") + [names[2], "x.jf"],
+                  ["sect", "-o", "out/s", "-m", str(k), names[0], "x.jf"],
+                  ["filter", "kmer", "-o", "out/k", "-c", str(int(rng.integers(0, 3))), "-d", str(int(rng.integers(3, 300))), "-g", "0", "-h", str(k), "-s", "x.jf"]]
+        return [jf, second[int(rng.integers(0, len(second)))]]
     if kind == "load":
         # (k >= 5: the reference's LOAD mode sizes its table at 2x the records and ignores add()'s result, lib/src/jellyfish_helper.cc:
         # 160-172 — with the 32 canonical 3-mers and counts beyond the 7-bit field, which take a second slot each, it
@@ -211,6 +238,10 @@ def _run(exe, cmds, cwd, env):
     os.makedirs(os.path.join(cwd, "out"), exist_ok=True)
     codes = []
     for args in cmds:
+        if args[0] == "!jellyfish":  # a preparation step, run with the unmodified jellyfish on both sides
+            r = subprocess.run([REF_JF] + args[1:], cwd=cwd, capture_output=True, text=True, env={k: v for k, v in env.items() if k != "LD_PRELOAD"}, timeout=300)
+            codes.append(r.returncode)
+            continue
         for attempt in range(6):
             r = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, env=env, timeout=300)
             # the reference reads an uninitialised terminal width when stdout is no tty and may abort on it; with -t > 1 its
