@@ -10,7 +10,8 @@ line and a timestamp.  The reference needs no GPU; the front-end runs against wh
 (the real library on a GPU box, the test double of tests/hostcheck under LD_PRELOAD on a CPU-only machine).
 
 As a module: `case(kind, seed, tmp_path)` asserts one case (used by tests/test_host_frontend.py with a few seeds).
-As a script: `python tests/fuzz_vs_reference.py <kind|all> <first seed> <last seed>` runs a campaign on the CPU double."""
+As a script: `python tests/fuzz_vs_reference.py <kind|all> <first seed> <last seed>` runs a campaign on the CPU double
+(KATFUZZ_GPUS=N: the front-end as a job of N devices)."""
 import gzip
 import os
 import shutil
@@ -260,12 +261,31 @@ def _run(exe, cmds, cwd, env):
     return codes, files
 
 
-def case(kind, seed, tmp_path, our_env=None):
+def on_a_job(cmds):
+    """What `kat --gpus N` (N > 1) takes: no jellyfish hashes in or out, one-word k-mers, comp inputs all canonical."""
+    for c in cmds:
+        k = int(c[c.index("-m") + 1]) if "-m" in c else 27
+        if c[0] == "!jellyfish" or "-d" in c[:-1] and c[0] != "filter" or any(a.endswith(".jf") for a in c) or k > 32:
+            return False
+        if c[0] == "comp" and {"-N", "-O", "-P"} & set(c):
+            return False
+        if c[:2] == ["filter", "kmer"]:
+            pass
+    return True
+
+
+def case(kind, seed, tmp_path, our_env=None, gpus=1):
+    """gpus > 1: the front-end side runs as a job of that many devices (KATGPU_GPUS; on a CPU-only machine the devices of the
+    test double, KATGPU_DOUBLE_DEVICES); commands a job does not take are skipped (returns False)."""
     rng = np.random.default_rng([KINDS.index(kind), seed])
     tmp_path = str(tmp_path)
     dirs = {who: os.path.join(tmp_path, who) for who in ("ref", "our")}
     os.makedirs(dirs["ref"])
     cmds = _command(kind, rng, dirs["ref"])
+    if gpus > 1:
+        if not on_a_job(cmds):
+            return False
+        our_env = dict(os.environ if our_env is None else our_env, KATGPU_GPUS=str(gpus), KATGPU_DOUBLE_DEVICES=str(gpus))
     shutil.copytree(dirs["ref"], dirs["our"])
     no_preload = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}
     ref = _run(REF, cmds, dirs["ref"], no_preload)
@@ -303,6 +323,7 @@ if __name__ == "__main__":
     double = os.path.join(ROOT, "tests", "hostcheck", "_build", "libkatgpu_double.so")
     assert subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostcheck")], capture_output=True).returncode == 0
     env = dict(os.environ, LD_PRELOAD=double, KAT_GPU_PARSE="1")
+    gpus = int(os.environ.get("KATFUZZ_GPUS", "1"))
     bad = []
     for kind in kinds:
         for seed in range(lo, hi):
@@ -310,7 +331,7 @@ if __name__ == "__main__":
             shutil.rmtree(d, ignore_errors=True)
             os.makedirs(d)
             try:
-                case(kind, seed, d, env)
+                case(kind, seed, d, env, gpus)
                 shutil.rmtree(d, ignore_errors=True)
             except AssertionError as e:
                 bad.append((kind, seed))

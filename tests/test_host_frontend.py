@@ -33,7 +33,7 @@ def _double_in_front():
 
 
 def test_the_double_is_what_runs(tmp_path):
-    """The double answers: it reports one device (the real library reports none on a machine without a GPU) and no multi-GPU."""
+    """The double answers: it reports one device unless told otherwise (the real library reports none on a machine without a GPU)."""
     g = subprocess.run([T.KAT, "hist", "-m5", "--gpus", "2", "-o", str(tmp_path / "h"), os.path.join(T.G.GOLDEN, "inputs", "edge1.fa")],
                        capture_output=True, text=True)
     assert g.returncode == 4 and "only 1 CUDA devices visible" in g.stderr
@@ -180,3 +180,49 @@ def test_front_end_against_the_reference_binary_wider(kind, seed, tmp_path):
     if not os.access(F.REF, os.X_OK):
         pytest.skip("oracle/_ref/kat not built")
     F.case(kind, seed, tmp_path)
+
+
+@pytest.mark.parametrize("seed", range(5, 9))
+@pytest.mark.parametrize("kind", [k for k in F.KINDS if k not in ("load", "jfcount")])
+def test_front_end_as_a_job_against_the_reference_binary(kind, seed, tmp_path):
+    """The same differential cases with the front-end running as a job of 2 devices (of the test double): what a job takes
+    (tests/fuzz_vs_reference.py::on_a_job) gives the reference's files."""
+    if not os.access(F.REF, os.X_OK):
+        pytest.skip("oracle/_ref/kat not built")
+    if F.case(kind, seed, tmp_path, gpus=2) is False:
+        pytest.skip("not a command for a job (hash files, k > 32 or non-canonical comp)")
+
+
+# ---- `kat --gpus N` on the CPU: N contexts of the double joined into one job (katgpu_double.c) ----
+def _job_cases():
+    out = []
+    for c in T.G.cases():
+        out.append(("golden", c))
+    for c in T.SECT_MANIFEST:
+        out.append(("sect", c))
+    for c in T.FILTER_MANIFEST:
+        out.append(("filter", c))
+    # what a job does not do, and the front-end says so: dump or load jellyfish hashes (one GPU's table), count two-word
+    # k-mers, compare inputs that were not all counted canonically (the shared-k-mer walk is local to the owner of a k-mer)
+    def on_a_job(c):
+        a = c["args"]
+        return not ("-d" in a or "--dump_hash" in a or any(x.endswith(".jf") for x in a) or (a[0] == "comp" and {"-N", "-O", "-P"} & set(a)))
+    return [(kind, c) for kind, c in out if on_a_job(c)]
+
+
+@pytest.mark.parametrize("gpus", [2, 3])
+@pytest.mark.parametrize("kind,case", _job_cases(), ids=lambda x: x["name"] if isinstance(x, dict) else x)
+def test_cli_on_a_job_of_several_devices(kind, case, gpus, workdir, tmp_path, monkeypatch):
+    """Every golden command again as `kat --gpus 2` and `--gpus 3` (KATGPU_GPUS): the front-end creates one context per
+    device, joins them, cuts every parsed base stream into per-GPU shares of k-mer start positions with k-1 bases of
+    overlap (kat_front.hpp::feed_all), sizes the per-GPU tables, calls every walk and lookup collectively from one host
+    thread per GPU and merges per-rank parts (filter kmer) — and writes the reference's files byte for byte.  On the GPU
+    box the same is checked against the real library by tests/test_gpu_multi.py where two GPUs are present."""
+    monkeypatch.setenv("KATGPU_DOUBLE_DEVICES", str(gpus))
+    monkeypatch.setenv("KATGPU_GPUS", str(gpus))
+    if kind == "golden":
+        T.test_cli_output_files_byte_identical(case, "direct", workdir)
+    elif kind == "sect":
+        T.test_cli_sect_and_cold_output_files_byte_identical(case, tmp_path)
+    else:
+        T.test_cli_filter_matches_reference(case, tmp_path)
