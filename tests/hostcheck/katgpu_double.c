@@ -107,6 +107,9 @@ katgpu_status katgpu_dist_init(katgpu_ctx *ctx, int rank, int n_ranks, const voi
     return KATGPU_OK;
 }
 
+static void lock_job(katgpu_table *t) { if (t->ctx->job) pthread_mutex_lock(&t->ctx->job->mu); }
+static void unlock_job(katgpu_table *t) { if (t->ctx->job) pthread_mutex_unlock(&t->ctx->job->mu); }
+
 katgpu_status katgpu_count_begin(katgpu_ctx *ctx, int k, int canonical, uint64_t hash_size, int allow_grow, katgpu_table **out) {
     if (k < 1 || k > 64) return fail(KATGPU_ERR_INVALID, "k out of 1..64");
     if (k > 32 && ctx->job) return fail(KATGPU_ERR_INVALID, "k > 32 is counted on one GPU (not on a multi-GPU context)"); /* as the real library */
@@ -136,8 +139,6 @@ katgpu_status katgpu_count_begin(katgpu_ctx *ctx, int k, int canonical, uint64_t
     *out = t;
     return KATGPU_OK;
 }
-static void lock_job(katgpu_table *t) { if (t->ctx->job) pthread_mutex_lock(&t->ctx->job->mu); }
-static void unlock_job(katgpu_table *t) { if (t->ctx->job) pthread_mutex_unlock(&t->ctx->job->mu); }
 katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n) {
     if (t->sh->ended) return fail(KATGPU_ERR_STATE, "feed after end");
     lock_job(t);
@@ -145,9 +146,38 @@ katgpu_status katgpu_count_feed(katgpu_table *t, const char *bases, size_t n) {
     unlock_job(t);
     return KATGPU_OK;
 }
+/* Raw FASTQ records.  By default the double calls every block "not in the regular layout", so the front-end's host route runs.
+ * With KATGPU_DOUBLE_FASTQ=1 it takes blocks the way the real library does (katgpu_fastq.cu, parse_kernels.cu: every line
+ * '\n'-terminated, four lines per record, '@' header, sequence longer than the trim that neither starts with '@' / '+' nor
+ * holds a '+', a '+' line, quality of the sequence's length) and counts the trimmed sequences, one chunk per record —
+ * all or nothing per call — so that the front-end's raw route (blocks of whole records, per-GPU shares, starting an input
+ * over on the host route when a later block is refused) is checked on the CPU as well. */
+static const char *line_end(const char *p, const char *e) { return p < e ? (const char *)memchr(p, '\n', (size_t)(e - p)) : NULL; }
 katgpu_status katgpu_count_feed_fastq(katgpu_table *t, const char *bytes, size_t n, unsigned trim5p, int *regular) {
-    (void)t; (void)bytes; (void)n; (void)trim5p;
-    *regular = 0; /* always "not in the regular layout": the front-end takes its host route */
+    *regular = 0;
+    if (!getenv("KATGPU_DOUBLE_FASTQ")) return KATGPU_OK;
+    if (n == 0) {
+        *regular = 1;
+        return KATGPU_OK;
+    }
+    if (bytes[n - 1] != '\n') return KATGPU_OK;
+    for (int emit = 0; emit < 2; emit++) { /* validate everything, then count */
+        const char *p = bytes, *e = bytes + n;
+        while (p < e) {
+            const char *h = line_end(p, e), *s = h ? line_end(h + 1, e) : NULL, *pl = s ? line_end(s + 1, e) : NULL, *q = pl ? line_end(pl + 1, e) : NULL;
+            if (!q) return KATGPU_OK;
+            const char *seq = h + 1;
+            const size_t slen = (size_t)(s - seq), qlen = (size_t)(q - (pl + 1));
+            if (*p != '@' || s[1] != '+' || slen <= trim5p || slen != qlen || *seq == '@' || *seq == '+' || memchr(seq, '+', slen)) return KATGPU_OK;
+            if (emit) {
+                lock_job(t);
+                oracle_table_add(t->o, (const unsigned char *)seq + trim5p, slen - trim5p);
+                unlock_job(t);
+            }
+            p = q + 1;
+        }
+    }
+    *regular = 1;
     return KATGPU_OK;
 }
 katgpu_status katgpu_count_reserve(katgpu_table *t, uint64_t expected_kmers) { (void)t; (void)expected_kmers; return KATGPU_OK; }

@@ -226,3 +226,34 @@ def test_cli_on_a_job_of_several_devices(kind, case, gpus, workdir, tmp_path, mo
         T.test_cli_sect_and_cold_output_files_byte_identical(case, tmp_path)
     else:
         T.test_cli_filter_matches_reference(case, tmp_path)
+
+
+@pytest.mark.parametrize("gpus", [1, 2])
+@pytest.mark.parametrize("kind,case", [kc for kc in _job_cases() if any(a.endswith((".fq", ".fastq")) for a in kc[1]["args"])],
+                         ids=lambda x: x["name"] if isinstance(x, dict) else x)
+def test_cli_raw_fastq_route(kind, case, gpus, workdir, tmp_path, monkeypatch):
+    """The front-end's device-parsing route on the CPU: with KATGPU_DOUBLE_FASTQ=1 the double takes raw FASTQ blocks under the
+    real library's rules (all or nothing per call), so stream_fastq_raw's cutting of a file into 4 KiB blocks of whole records
+    and per-GPU shares, the per-file trims, and the fall back to the host route — from the start of the input when a later
+    block is refused — run for every golden command with a FASTQ input, on one device and on a job of two."""
+    monkeypatch.setenv("KATGPU_DOUBLE_FASTQ", "1")
+    monkeypatch.setenv("KAT_RAW_BLOCK", "4096")
+    monkeypatch.setenv("KATGPU_DOUBLE_DEVICES", str(gpus))
+    monkeypatch.setenv("KATGPU_GPUS", str(gpus))
+    if kind == "golden":
+        T.test_cli_output_files_byte_identical(case, "direct", workdir)
+    elif kind == "sect":
+        T.test_cli_sect_and_cold_output_files_byte_identical(case, tmp_path)
+    else:
+        T.test_cli_filter_matches_reference(case, tmp_path)
+
+
+@pytest.mark.parametrize("seed", range(9, 12))
+@pytest.mark.parametrize("kind", ["gz", "group", "compgroups", "cold"])
+def test_front_end_raw_fastq_route_against_the_reference_binary(kind, seed, tmp_path, monkeypatch):
+    """... and the differential cases with FASTQ inputs through the same route."""
+    if not os.access(F.REF, os.X_OK):
+        pytest.skip("oracle/_ref/kat not built")
+    monkeypatch.setenv("KATGPU_DOUBLE_FASTQ", "1")
+    monkeypatch.setenv("KAT_RAW_BLOCK", "4096")
+    F.case(kind, seed, tmp_path)
