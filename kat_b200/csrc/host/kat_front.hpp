@@ -63,6 +63,7 @@ struct Parsed {
         return it == val.end() ? dflt : it->second;
     }
 };
+inline void check_u16_options(const struct Parsed &p);
 inline Parsed parse_args(int argc, char **argv, const vector<OptSpec> &specs) {
     Parsed p;
     for (int i = 1; i < argc; i++) {
@@ -113,7 +114,18 @@ inline Parsed parse_args(int argc, char **argv, const vector<OptSpec> &specs) {
         } else
             p.val[sp->longname] = "1";
     }
+    check_u16_options(p);
     return p;
+}
+inline uint64_t to_u64(const string &s, const char *what);
+// Options the reference declares as uint16_t (po::value<uint16_t>: threads, mer_len, the bin counts, filter kmer's GC bounds):
+// a value beyond 65535 is a command-line error there, exit code 1 (src/kat.cc:286-288).
+inline void check_u16_options(const Parsed &p) {
+    for (const char *name : {"threads", "mer_len", "cvg_bins", "gc_bins", "d1_bins", "d2_bins", "low_gc", "high_gc"}) {
+        const auto it = p.val.find(name);
+        if (it != p.val.end() && to_u64(it->second, name) > 65535)
+            throw KatError(1, string("Error: Parsing Command Line: the argument ('") + it->second + "') for option '--" + name + "' is invalid");
+    }
 }
 inline uint64_t to_u64(const string &s, const char *what) {
     try {
@@ -362,6 +374,10 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
         cout << "Input " << in.index << " is a sequence file.  Counting kmers for input " << in.index << " (" << join(in.files, false) << ") ...";
         cout.flush();
     }
+    // HashCounter(hashSize, ...) (lib/src/input_handler.cc:184): a table of 2^ceilLog2(size) slots hashes with a matrix of
+    // ceilLog2(size) rows, and jellyfish refuses one without rows (deps/jellyfish-2.2.0/lib/rectangular_binary_matrix.cc:24-28):
+    // std::runtime_error, exit code 5
+    if (in.hash_size < 2) throw KatError(5, "Invalid matrix size 0x" + std::to_string(2 * k));
     in.tables.assign(ctx.n(), nullptr);
     // a job shares the k-mers out: every GPU's table needs room for its 1/N of the distinct ones
     const uint64_t per_gpu_slots = ctx.n() > 1 ? std::max<uint64_t>(in.hash_size / ctx.n(), 1024) : in.hash_size;

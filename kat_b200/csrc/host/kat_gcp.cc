@@ -56,13 +56,21 @@ int gcp_main(int argc, char **argv) {
         out << "# XLabel:" << k << "-mer frequency" << endl;
         out << "# YLabel:GC count" << endl;
         out << "# ZLabel:# distinct " << k << "-mers" << endl;
-        out << "# Columns:" << bins + 1 << endl;
+        // the matrix has `cvgBins + 1` columns in 16-bit arithmetic (src/gcp.cc:93) — none for 65535: nothing is ever found in it
+        // (inc() has no bounds check), the header says so, and printMatrix's first get() throws SparseMatrixException
+        // (boost::exception, exit code 4) with the header already in the file
+        const bool no_columns = bins == 65535;
+        out << "# Columns:" << (no_columns ? 0 : bins + 1) << endl;
         out << "# Rows:" << k << endl;
-        out << "# MaxVal:" << max_val(mx) << endl;
+        out << "# MaxVal:" << (no_columns ? 0 : max_val(mx)) << endl;
         out << "# Transpose:0" << endl;
         out << "# Kmer value:" << k << endl;
         out << "# Input 1:" << join(in.files, false) << endl;
         out << "###" << endl;
+        if (no_columns) {
+            out.close();
+            throw KatError(4, "Requested coords exceed limits of matrix.  Coords: 0,0.  Limits: " + std::to_string(k) + ",0");
+        }
         print_matrix(out, mx, (uint32_t)k, bins + 1);
         out.close();
         phase_done(t);

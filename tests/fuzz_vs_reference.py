@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KAT = os.path.join(ROOT, "kat_b200", "bin", "kat")
 REF = os.path.join(ROOT, "oracle", "_ref", "kat")
 REF_JF = os.path.join(ROOT, "oracle", "_ref", "kat_jellyfish")
-KINDS = ("sect", "cold", "fkmer", "fseq", "gz", "load", "group", "compgroups", "jfcount")
+KINDS = ("sect", "cold", "fkmer", "fseq", "gz", "load", "group", "compgroups", "jfcount", "edgeopts")
 
 
 def records(rng, n_rec, fastq, max_len=300, alphabet=b"ACGTacgtNRY-", p=(.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .01, .01)):
@@ -219,6 +219,24 @@ def _command(kind, rng, d):
                   ["sect", "-o", "out/s", "-m", str(k), names[0], "x.jf"],
                   ["filter", "kmer", "-o", "out/k", "-c", str(int(rng.integers(0, 3))), "-d", str(int(rng.integers(3, 300))), "-g", "0", "-h", str(k), "-s", "x.jf"]]
         return [jf, second[int(rng.integers(0, len(second)))]]
+    if kind == "edgeopts":
+        # option values at and beyond their edges: bounds of 0 and 1, more bins than counts, single-cell matrices, scales
+        # far from 1, the shortest and the longest mers, a hash size of 1 ("Invalid matrix size", exit code 5).  (Hash sizes of
+        # a few slots are left out: with 3-mers in 128 slots the reference itself loses a carry of 128 while it grows the table.)
+        names = _seq_files(rng, d, 3)
+        k = int(rng.choice([1, 2, 3, 4, 16, 31, 32, 33, 63, 64]))
+        pick = lambda xs: str(xs[int(rng.integers(0, len(xs)))])
+        tool = ["hist", "gcp", "comp"][int(rng.integers(0, 3))]
+        if tool == "hist":
+            args = ["hist", "-m", str(k), "-H", pick([1, 4096]), "-o", "out/h", "-l", pick([0, 1, 2, 3, 50]), "-h", pick([0, 1, 2, 3, 49, 100000]),
+                    "-i", pick([1, 2, 3, 1000])] + flag("-N") + names[:int(rng.integers(1, 3))]
+        elif tool == "gcp":
+            args = ["gcp", "-m", str(k), "-H", pick([1, 4096]), "-o", "out/g", "-x", pick([0.001, 0.01, 0.3333, 1, 3.7, 1000]), "-y", pick([1, 2, 3, 1000, 65535])]
+            args += flag("-N") + names[:int(rng.integers(1, 3))]
+        else:
+            args = ["comp", "-m", str(k), "-H", pick([1, 4096]), "-I", pick([1, 4096]), "-o", "out/c", "-i", pick([1, 2, 3, 1001]), "-j", pick([1, 2, 3, 500]),
+                    "-x", pick([0.001, 0.3333, 1, 2.5, 100]), "-y", pick([0.01, 1, 7.5])] + flag("-N") + flag("-O") + flag("-h") + flag("-n") + names[:2]
+        return [args]
     if kind == "load":
         # (k >= 5: the reference's LOAD mode sizes its table at 2x the records and ignores add()'s result, lib/src/jellyfish_helper.cc:
         # 160-172 — with the 32 canonical 3-mers and counts beyond the 7-bit field, which take a second slot each, it
