@@ -126,6 +126,11 @@ inline void check_u16_options(const Parsed &p) {
         if (it != p.val.end() && to_u64(it->second, name) > 65535)
             throw KatError(1, string("Error: Parsing Command Line: the argument ('") + it->second + "') for option '--" + name + "' is invalid");
     }
+    for (const char *name : {"min_repeat", "max_repeat"}) { // uint32_t in kat sect
+        const auto it = p.val.find(name);
+        if (it != p.val.end() && to_u64(it->second, name) > 0xFFFFFFFFull)
+            throw KatError(1, string("Error: Parsing Command Line: the argument ('") + it->second + "') for option '--" + name + "' is invalid");
+    }
 }
 inline uint64_t to_u64(const string &s, const char *what) {
     try {

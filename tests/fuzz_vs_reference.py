@@ -25,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 KAT = os.path.join(ROOT, "kat_b200", "bin", "kat")
 REF = os.path.join(ROOT, "oracle", "_ref", "kat")
 REF_JF = os.path.join(ROOT, "oracle", "_ref", "kat_jellyfish")
-KINDS = ("sect", "cold", "fkmer", "fseq", "gz", "load", "group", "compgroups", "jfcount", "edgeopts")
+KINDS = ("sect", "cold", "fkmer", "fseq", "gz", "load", "group", "compgroups", "jfcount", "edgeopts", "edgeopts2")
 
 
 def records(rng, n_rec, fastq, max_len=300, alphabet=b"ACGTacgtNRY-", p=(.22, .22, .22, .22, .02, .02, .02, .02, .01, .01, .01, .01)):
@@ -237,6 +237,25 @@ def _command(kind, rng, d):
             args = ["comp", "-m", str(k), "-H", pick([1, 4096]), "-I", pick([1, 4096]), "-o", "out/c", "-i", pick([1, 2, 3, 1001]), "-j", pick([1, 2, 3, 500]),
                     "-x", pick([0.001, 0.3333, 1, 2.5, 100]), "-y", pick([0.01, 1, 7.5])] + flag("-N") + flag("-O") + flag("-h") + flag("-n") + names[:2]
         return [args]
+    if kind == "edgeopts2":
+        # the same for sect / cold / filter: repeat bounds of 0 and in the wrong order, one-bin matrices, thresholds outside
+        # [0, 1], count and GC bounds of 0, beyond every count and in the wrong order, the shortest and longest mers
+        names = _seq_files(rng, d, 3)
+        k = int(rng.choice([1, 2, 3, 16, 31, 32, 33, 64]))
+        pick = lambda xs: str(xs[int(rng.integers(0, len(xs)))])
+        tool = ["sect", "cold", "fseq", "fkmer"][int(rng.integers(0, 4))]
+        if tool == "sect":
+            args = ["sect", "-m", str(k), "-H", "4096", "-o", "out/s", "-M", pick([0, 1, 2, 1000000]), "-G", pick([0, 1, 2, 5000000000]),
+                    "-x", pick([0, 1, 2, 1001]), "-y", pick([0, 1, 2, 1001])] + flag("-l") + flag("-g", 0.5) + flag("-E", 0.6) + flag("-F", 0.6) + flag("-n") + flag("-N")
+            return [args + [names[int(rng.integers(0, 3))]] + names[:int(rng.integers(1, 3))]]
+        if tool == "cold":
+            return [["cold", "-m", str(k), "-H", pick([2, 3, 4096]), "-o", "out/c", "-x", pick([0, 1, 1001]), "-y", pick([0, 1, 1001])] + [names[0]] + names[1:]]
+        if tool == "fseq":
+            args = ["filter", "seq", "-m", str(k), "-H", "4096", "-o", "out/f", "--stats", "-T", pick([-0.5, 0, 1e-9, 0.999999, 1, 1.5])] + flag("-i") + flag("-s", 0.6) + flag("-N")
+            return [args + ["--seq", names[1]] + names[:1]]
+        args = ["filter", "kmer", "-m", str(k), "-H", "4096", "-o", "out/k", "-c", pick([0, 1, 5, 18446744073709551615]), "-d", pick([0, 1, 4, 100000, 18446744073709551615]),
+                "-g", pick([0, 1, 30, 65535]), "-h", pick([0, 1, 29, 64, 65535])] + flag("-i") + flag("-s", 0.5) + flag("-N")
+        return [args + names[:int(rng.integers(1, 3))]]
     if kind == "load":
         # (k >= 5: the reference's LOAD mode sizes its table at 2x the records and ignores add()'s result, lib/src/jellyfish_helper.cc:
         # 160-172 — with the 32 canonical 3-mers and counts beyond the 7-bit field, which take a second slot each, it

@@ -115,8 +115,8 @@ def parse_files(files, k, trim5p=None, threads=1):
     chunks = []
     n_streams = max(1, min(len(files), max(1, threads)))
     alive, carry, clock, has_file = [True] * n_streams, [[0] for _ in range(n_streams)], [0] * n_streams, [False] * n_streams
-    held = [b""] * n_streams  # the last buffer (with its seam) of the file a stream has just finished: queued only once the
-    built = 0                 # stream has opened its next file, lost when that file is in no supported format
+    held = [None] * n_streams  # (stream of the file a stream has just finished, where its last 4 KiB buffer starts): counted whole once
+    built = 0                  # the stream has opened its next file (or none is left), without that buffer when that file is unsupported
     for path, t in zip(files, trim5p):
         if isinstance(path, (bytes, bytearray)):
             data = bytes(path)
@@ -148,19 +148,20 @@ def parse_files(files, k, trim5p=None, threads=1):
             if ctor:
                 raise UnsupportedFormat("Unsupported format")
             alive[s] = False
-            held[s] = b""
+            if held[s] is not None:
+                chunks.append(held[s][0][:held[s][1]])
+                held[s] = None
             continue
-        if held[s]:
-            chunks.append(held[s])
-            held[s] = b""
+        if held[s] is not None:
+            chunks.append(held[s][0])
+            held[s] = None
         if st == -2:
             alive[s] = False
             chunks.append(seq)
             continue
-        chunks.append(seq[:last[0]])
-        held[s] = seq[last[0] - last[1]:]
-    chunks += [h for h in held if h]
-    return chunks
+        held[s] = (seq, last[0])
+    chunks += [h[0] for h in held if h is not None]
+    return [c for c in chunks if c]
 
 
 class Table:
