@@ -32,17 +32,19 @@ def records(rng, n_rec, fastq, max_len=300, alphabet=b"ACGTacgtNRY-", p=(.22, .2
     """n_rec records, ragged lengths (a few long ones), single- or multi-line, FASTQ qualities with '@' / '+' / '>' in them."""
     out = bytearray()
     letters = np.frombuffer(alphabet, dtype=np.uint8)
+    crlf = os.environ.get("KATFUZZ_CRLF") and rng.random() < 0.5  # (campaign option: Windows line ends in half of the files)
     for i in range(n_rec):
         n = int(rng.integers(0, 6000)) if rng.random() < 0.1 else int(rng.integers(0, max_len))
         seq = bytes(rng.choice(letters, n, p=p))
         width = int(rng.integers(1, 120)) if rng.random() < 0.4 else max(n, 1)
         lines = [seq[j:j + width] for j in range(0, n, width)] or [b""]
+        head = [b"r%d/1 text", b"r%d", b"r%d\tx=1 y", b"r%d " + b"z" * 300][int(rng.integers(0, 4))] % i
         if fastq:
             q = bytes(rng.choice(np.frombuffer(b"I@+>#5", dtype=np.uint8), n))
-            out += b"@r%d/1 text\n" % i + b"\n".join(lines) + b"\n+\n" + (b"\n".join(q[j:j + width] for j in range(0, n, width)) or b"") + b"\n"
+            out += b"@" + head + b"\n" + b"\n".join(lines) + b"\n+\n" + (b"\n".join(q[j:j + width] for j in range(0, n, width)) or b"") + b"\n"
         else:
-            out += b">c%d text\n" % i + b"\n".join(lines) + b"\n"
-    return bytes(out)
+            out += b">" + head + b"\n" + b"\n".join(lines) + b"\n"
+    return bytes(out).replace(b"\n", b"\r\n") if crlf else bytes(out)
 
 
 def related(rng, src, n_rec, fastq, read_len=80):
@@ -249,7 +251,7 @@ def _command(kind, rng, d):
                     "-x", pick([0, 1, 2, 1001]), "-y", pick([0, 1, 2, 1001])] + flag("-l") + flag("-g", 0.5) + flag("-E", 0.6) + flag("-F", 0.6) + flag("-n") + flag("-N")
             return [args + [names[int(rng.integers(0, 3))]] + names[:int(rng.integers(1, 3))]]
         if tool == "cold":
-            return [["cold", "-m", str(k), "-H", pick([2, 3, 4096]), "-o", "out/c", "-x", pick([0, 1, 1001]), "-y", pick([0, 1, 1001])] + [names[0]] + names[1:]]
+            return [["cold", "-m", str(k), "-H", pick([1, 4096]), "-o", "out/c", "-x", pick([0, 1, 1001]), "-y", pick([0, 1, 1001])] + [names[0]] + names[1:]]
         if tool == "fseq":
             args = ["filter", "seq", "-m", str(k), "-H", "4096", "-o", "out/f", "--stats", "-T", pick([-0.5, 0, 1e-9, 0.999999, 1, 1.5])] + flag("-i") + flag("-s", 0.6) + flag("-N")
             return [args + ["--seq", names[1]] + names[:1]]
