@@ -383,6 +383,24 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
     // ceilLog2(size) rows, and jellyfish refuses one without rows (deps/jellyfish-2.2.0/lib/rectangular_binary_matrix.cc:24-28):
     // std::runtime_error, exit code 5
     if (in.hash_size < 2) throw KatError(5, "Invalid matrix size 0x" + std::to_string(2 * k));
+    const size_t n_streams = std::max<size_t>(1, std::min<size_t>(in.files.size(), std::max(1u, in.threads))); // parser streams, see below
+    // A file in no supported format anywhere in the group: fatal among the files the constructor opens (checked before
+    // anything is counted); otherwise the group is read in "careful" mode — every file through the emulation, which knows
+    // the reference's buffers, and the last buffer of each file held back until its stream has opened its next file.
+    bool careful = false;
+    {
+        size_t opened = 0; // streams that hold their first file
+        for (size_t i = 0; i < in.files.size(); i++) {
+            const int c = kat_host::first_byte_of_file(in.files[i]);
+            if (c == -1) continue;
+            const bool supported = c == '>' || c == '@' || c == -2; // (a pipe is taken for a sequence stream; the parser has the last word)
+            if (opened < n_streams) {
+                if (!supported) throw KatError(5, "Unsupported format");
+                opened++;
+            } else if (!supported)
+                careful = true;
+        }
+    }
     in.tables.assign(ctx.n(), nullptr);
     // a job shares the k-mers out: every GPU's table needs room for its 1/N of the distinct ones
     const uint64_t per_gpu_slots = ctx.n() > 1 ? std::max<uint64_t>(in.hash_size / ctx.n(), 1024) : in.hash_size;
@@ -418,24 +436,7 @@ inline void count_input(Ctx &ctx, Input &in, int k, bool allow_grow, bool allow_
         uint64_t clock = 0;
         std::string held; // careful mode: the last buffer of the stream's previous file (with its seam), not yet counted
     };
-    vector<RefStream> streams(std::max<size_t>(1, std::min<size_t>(in.files.size(), std::max(1u, in.threads))));
-    // A file in no supported format anywhere in the group: fatal among the files the constructor opens (checked before
-    // anything is counted); otherwise the group is read in "careful" mode — every file through the emulation, which knows
-    // the reference's buffers, and the last buffer of each file held back until its stream has opened its next file.
-    bool careful = false;
-    {
-        size_t opened = 0; // streams that hold their first file
-        for (size_t i = 0; i < in.files.size(); i++) {
-            const int c = kat_host::first_byte_of_file(in.files[i]);
-            if (c == -1) continue;
-            const bool supported = c == '>' || c == '@' || c == -2; // (a pipe is taken for a sequence stream; the parser has the last word)
-            if (opened < streams.size()) {
-                if (!supported) throw KatError(5, "Unsupported format");
-                opened++;
-            } else if (!supported)
-                careful = true;
-        }
-    }
+    vector<RefStream> streams(n_streams);
     const bool fast_routes = allow_streaming && !careful;
     size_t built = 0; // streams that hold their first file: the parser's constructor is done when built == streams.size()
     for (size_t i = 0; i < in.files.size(); i++) {
