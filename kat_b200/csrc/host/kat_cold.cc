@@ -25,7 +25,7 @@ int cold_main(int argc, char **argv) {
     cout << "Running KAT in Cold mode" << endl << "------------------------" << endl << endl;
     if (a.positional.size() < 2) throw KatError(4, "kat cold needs an assembly and at least one reads input");
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    check_mer_len(k);
+    check_mer_len(k, to_u64(a.get("hash_size", "100000000"), "hash_size"));
     const uint64_t hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
     Input reads, assembly;
     reads.files.assign(a.positional.begin() + 1, a.positional.end());

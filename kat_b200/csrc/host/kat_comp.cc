@@ -57,11 +57,12 @@ int comp_main(int argc, char **argv) {
     }
     Timer total;
     cout << "Running KAT in COMP mode" << endl << "------------------------" << endl << endl;
+    if (a.positional.size() > 3) throw KatError(1, "Error: Parsing Command Line: too many positional options have been specified on the command line");
     if (a.positional.size() < 1) throw KatError(4, "Nothing specified for input group 1");
     if (a.positional.size() < 2) throw KatError(4, "Nothing specified for input group 2");
     const bool three = a.positional.size() >= 3;
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    check_mer_len(k);
+    check_mer_len(k, to_u64(a.get("hash_size_1", "100000000"), "hash_size_1"));
     const double d1s = to_double(a.get("d1_scale", "1.0"), "d1_scale"), d2s = to_double(a.get("d2_scale", "1.0"), "d2_scale");
     const uint32_t d1b = (uint32_t)to_u64(a.get("d1_bins", "1001"), "d1_bins"), d2b = (uint32_t)to_u64(a.get("d2_bins", "1001"), "d2_bins");
     if (d1b == 0 || d2b == 0) throw KatError(4, "d1_bins and d2_bins must be >= 1");

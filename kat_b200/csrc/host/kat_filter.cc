@@ -35,7 +35,7 @@ int filter_kmer_main(int argc, char **argv) {
     Timer total;
     cout << "Running KAT in filter kmer mode" << endl << "-------------------------------" << endl << endl;
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    check_mer_len(k);
+    check_mer_len(k, to_u64(a.get("hash_size", "100000000"), "hash_size"));
     const uint64_t low_count = to_u64(a.get("low_count", "1"), "low_count"), high_count = to_u64(a.get("high_count", "10000"), "high_count");
     const uint32_t low_gc = (uint32_t)to_u64(a.get("low_gc", "1"), "low_gc"), high_gc = (uint32_t)to_u64(a.get("high_gc", "100"), "high_gc");
     const bool invert = a.has("invert"), separate = a.has("separate");
@@ -177,7 +177,7 @@ int filter_seq_main(int argc, char **argv) {
     if (!exists(seq1)) throw KatError(4, "Could not find input file at: " + seq1 + "; please check the path and try again.");
     if (paired && !exists(seq2)) throw KatError(4, "Could not find sequence file at: " + seq2 + "; please check the path and try again.");
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    check_mer_len(k);
+    check_mer_len(k, to_u64(a.get("hash_size", "100000000"), "hash_size"));
     const double threshold = to_double(a.get("threshold", "0.1"), "threshold"), frequency = to_double(a.get("frequency", "0"), "frequency");
     const bool invert = a.has("invert"), separate = a.has("separate"), do_stats = a.has("stats");
     if (a.positional.empty()) throw KatError(4, "No input provided for this input group");

@@ -159,7 +159,13 @@ inline vector<unsigned> parse_trim(const string &s) {
     vector<unsigned> v;
     std::stringstream ss(s);
     string item;
-    while (std::getline(ss, item, ',')) v.push_back((unsigned)to_u64(item, "5ptrim"));
+    while (std::getline(ss, item, ',')) {
+        try {
+            v.push_back((unsigned)to_u64(item, "5ptrim"));
+        } catch (const KatError &) { // boost::lexical_cast<uint16_t> of the list items (src/histogram.cc:345-350): a boost::exception, exit code 4
+            throw KatError(4, "bad lexical cast: source type value could not be interpreted as target");
+        }
+    }
     if (v.empty()) v.push_back(0);
     return v;
 }
@@ -167,7 +173,12 @@ inline vector<unsigned> parse_trim(const string &s) {
 // mer lengths: one 64-bit word per k-mer up to 32, two words for 33..64 (jellyfish::mer_dna has no limit; larger k
 // is refused).  Two-word k-mers are counted on one GPU.
 constexpr int kMaxMerLen = 64;
-inline void check_mer_len(int k) {
+inline void check_mer_len(int k, uint64_t hash_size = 100000000ULL) {
+    if (k == 0) { // HashCounter(hashSize, 0, ...): jellyfish refuses a hash matrix without columns, std::runtime_error -> exit code 5
+        int rows = 0;
+        while (rows < 64 && (1ULL << rows) < hash_size) rows++;
+        throw KatError(5, "Invalid matrix size " + std::to_string(hash_size < 2 ? 0 : rows) + "x0");
+    }
     if (k < 1 || k > kMaxMerLen) throw KatError(4, "This GPU build supports mer lengths 1..64 (one or two 64-bit words per k-mer); got " + std::to_string(k));
 }
 inline void check_wide_limits(int k, int gpus) {

@@ -26,7 +26,7 @@ int gcp_main(int argc, char **argv) {
     in.threads = (unsigned)to_u64(a.get("threads", "1"), "threads");
     in.hash_size = to_u64(a.get("hash_size", "100000000"), "hash_size");
     const string prefix = a.get("output_prefix", "kat-gcp");
-    check_mer_len(k);
+    check_mer_len(k, to_u64(a.get("hash_size", "100000000"), "hash_size"));
     in.validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));

@@ -30,7 +30,7 @@ int hist_main(int argc, char **argv) {
     const uint64_t base = low > 1 ? (1 >= low ? 1 : low - 1) : 1, ceil = high + 1, nb = ceil + 1 - base;
     if (high < low) throw KatError(4, "High count value must be >= to low count value.  High: " + std::to_string(high) + "; Low: " + std::to_string(low));
     if (inc == 0) throw KatError(4, "Increment must be >= 1");
-    check_mer_len(k);
+    check_mer_len(k, to_u64(a.get("hash_size", "100000000"), "hash_size"));
     in.validate();
     ensure_parent_dir(prefix);
     Ctx ctx(gpus_option(a));

@@ -148,12 +148,14 @@ int main(int argc, char **argv) {
             return out.good() ? 0 : 4;
         }
         cout << "Kmer Analysis Toolkit (KAT) V" << kVersion << endl << endl;
-        if (mode == "hist") return hist_main(argc - 1, argv + 1);
-        if (mode == "gcp") return gcp_main(argc - 1, argv + 1);
-        if (mode == "comp") return comp_main(argc - 1, argv + 1);
-        if (mode == "sect") return sect_main(argc - 1, argv + 1);
-        if (mode == "cold") return cold_main(argc - 1, argv + 1);
-        if (mode == "filter") return filter_main(argc - 1, argv + 1);
+        // the reference's main drops what a tool's main returns (src/kat.cc:259-284): a tool that only printed its help
+        // ("return 1" in the tool) still ends the process with 0; failures travel as exceptions
+        int (*const tool)(int, char **) = mode == "hist" ? hist_main : mode == "gcp" ? gcp_main : mode == "comp" ? comp_main : mode == "sect" ? sect_main
+                                          : mode == "cold" ? cold_main : mode == "filter" ? filter_main : nullptr;
+        if (tool) {
+            tool(argc - 1, argv + 1);
+            return 0;
+        }
         if (mode == "plot") throw KatError(4, "KAT mode 'plot' is outside this GPU build's scope (hist, gcp, comp, sect, cold, filter)");
         throw KatError(4, "Unrecognised KAT mode: " + mode);
     } catch (const KatError &e) {

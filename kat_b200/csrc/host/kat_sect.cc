@@ -77,7 +77,7 @@ int sect_main(int argc, char **argv) {
     if (a.positional.size() < 2) throw KatError(4, "kat sect needs a sequence file and at least one input (sequence files to count, or a jellyfish hash)");
     const string seq_file = a.positional[0];
     int k = (int)to_u64(a.get("mer_len", "27"), "mer_len");
-    check_mer_len(k);
+    check_mer_len(k, to_u64(a.get("hash_size", "100000000"), "hash_size"));
     Input in;
     in.files.assign(a.positional.begin() + 1, a.positional.end());
     in.set_trim(parse_trim(a.get("5ptrim", "0")));

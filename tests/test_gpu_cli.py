@@ -255,12 +255,13 @@ def test_cli_wide_kmers_output_files_byte_identical(case, tmp_path):
 
 
 def test_cli_wide_kmers_limits(tmp_path):
-    """Mer lengths outside 1..64 are refused with a message (two 64-bit words per k-mer at most)."""
+    """Mer lengths above 64 are refused with a message (two 64-bit words per k-mer at most); a mer length of 0 fails the way the
+    reference does (a hash matrix without columns: "Invalid matrix size 27x0", exit code 5)."""
     fa = os.path.join(G.GOLDEN, "inputs", "long.fa")
-    for args, msg in ((["hist", "-m65", fa], "mer lengths 1..64"), (["comp", "-m0", fa, fa], "mer lengths 1..64"),
-                      (["sect", "-m100", fa, fa], "mer lengths 1..64")):
+    for args, code, msg in ((["hist", "-m65", fa], 4, "mer lengths 1..64"), (["comp", "-m0", fa, fa], 5, "Invalid matrix size 27x0"),
+                            (["sect", "-m100", fa, fa], 4, "mer lengths 1..64")):
         r = subprocess.run([KAT] + args, cwd=tmp_path, capture_output=True, text=True, timeout=120)
-        assert r.returncode == 4 and msg in r.stderr, (args, r.returncode, r.stderr)
+        assert r.returncode == code and msg in r.stderr, (args, r.returncode, r.stderr)
 
 
 WIDE_HASH_MANIFEST = json.load(open(os.path.join(G.GOLDEN, "wide", "hash_cases.json")))

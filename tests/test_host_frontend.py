@@ -257,3 +257,33 @@ def test_front_end_raw_fastq_route_against_the_reference_binary(kind, seed, tmp_
     monkeypatch.setenv("KATGPU_DOUBLE_FASTQ", "1")
     monkeypatch.setenv("KAT_RAW_BLOCK", "4096")
     F.case(kind, seed, tmp_path)
+
+
+def test_usage_errors_end_like_the_reference(tmp_path):
+    """Exit codes (and the one-line messages) of commands that do no work: the reference's main drops what a tool's main returns,
+    so a tool that only printed its help ends with 0 (src/kat.cc:259-284); a fourth input of comp is a command-line error (1);
+    a trim that is no number is boost::bad_lexical_cast (4); a mer length of 0 or a hash size of 1 give a hash matrix without
+    columns / rows (5)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", "kat")
+    if not os.access(ref, os.X_OK):
+        pytest.skip("oracle/_ref/kat not built")
+    fa, fb = os.path.join(T.G.GOLDEN, "inputs", "edge1.fa"), os.path.join(T.G.GOLDEN, "inputs", "synth_c.fa")
+    no_preload = {k: v for k, v in os.environ.items() if k != "LD_PRELOAD"}
+    for args, needle in ((["hist", "--help"], ""), (["filter"], ""), (["filter", "kmer"], ""), (["filter", "seq"], ""), (["--version"], ""),
+                         (["bogus"], ""), (["comp", "-m5", "a", "b", "c", "d"], "too many positional options"),
+                         (["comp", fa], ""), (["sect", fa], ""), (["cold", fa], ""),
+                         (["hist", "-m5", "-o", "x/h", "--5ptrim", "x", fa], ""), (["hist", "-m5", "-o", "x/h", "--5ptrim", "1,2", fa], "Inconsistent number of inputs"),
+                         (["hist", "-m", "0", "-o", "x/h", fa], "Invalid matrix size 27x0"), (["hist", "-m", "0", "-H", "1", "-o", "x/h", fa], "Invalid matrix size 0x0"),
+                         (["comp", "-m", "0", "-o", "x/c", fa, fb], "Invalid matrix size 27x0"), (["gcp", "-m5", "-H", "1", "-o", "x/g", fa], "Invalid matrix size 0x10"),
+                         (["gcp", "-m5", "-y", "65536", "-o", "x/g", fa], "for option '--cvg_bins' is invalid"),
+                         (["sect", "-m5", "-G", "5000000000", "-o", "x/s", fa, fb], "for option '--max_repeat' is invalid"),
+                         (["hist", "-m5", "-t", "70000", "-o", "x/h", fa], "for option '--threads' is invalid")):
+        got = []
+        for exe, env in ((ref, no_preload), (T.KAT, os.environ)):
+            for attempt in range(5):  # (the reference may abort on the uninitialised terminal width it reads)
+                r = subprocess.run([exe] + args, cwd=tmp_path, capture_output=True, text=True, env=env, timeout=120)
+                if r.returncode >= 0:
+                    break
+            assert needle in r.stderr, (exe, args, r.stderr[-300:])
+            got.append(r.returncode)
+        assert got[0] == got[1], (args, got)
