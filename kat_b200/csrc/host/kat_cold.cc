@@ -16,6 +16,7 @@ int cold_main(int argc, char **argv) {
                                    {'g', "disable_hash_grow", false}, {'p', "output_type", true}, {'v', "verbose", false}, {0, "gpus", true},
                                    {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
+    check_path_words(a, "asm_file", "reads_files");
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat cold [options] <assembly> (<reads>)+\n\nCalculates contig level coverage and GC% from reads and an assembly.\n\n"
                 "Options: -o prefix (kat-cold) -t threads --5ptrim list -m mer_len (27) -H hash_size (1e8) -d -v --help\n" << endl;

@@ -26,6 +26,7 @@ int filter_kmer_main(int argc, char **argv) {
                                    {'N', "non_canonical", false}, {'m', "mer_len", true}, {'H', "hash_size", true}, {'v', "verbose", false},
                                    {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
+    check_path_words(a, "inputs", "inputs");
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat filter kmer [options] (<input>)+\n\nFilter k-mers to those within defined count and GC bounds.\n\n"
                 "Options: -o prefix (kat.filter.kmer) -t threads -c low_count (1) -d high_count (10000) -g low_gc (1) -h high_gc (100) -i -s -N "
@@ -162,6 +163,7 @@ int filter_seq_main(int argc, char **argv) {
                                    {'N', "non_canonical", false}, {'m', "mer_len", true}, {'H', "hash_size", true}, {'v', "verbose", false},
                                    {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
+    check_path_words(a, "inputs", "inputs", {"output_prefix", "seq", "seq2"});
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat filter seq [options] --seq <seq_file_to_filter> [--seq2 <seq_file_2>] (<input>)+\n\n"
                 "Filter sequences based on whether those sequences contain specific k-mers.\n\n"

@@ -132,6 +132,22 @@ inline void check_u16_options(const Parsed &p) {
             throw KatError(1, string("Error: Parsing Command Line: the argument ('") + it->second + "') for option '--" + name + "' is invalid");
     }
 }
+// Path-typed options (po::value<path> / vector<path>): boost reads a path up to the first white space, so a file name with a
+// blank in it is "invalid" for the reference, a command-line error with exit code 1.  positional[0] is the tool's
+// `first` hidden option, the others its `rest`.
+inline void check_path_words(const Parsed &p, const char *first, const char *rest, std::initializer_list<const char *> options = {"output_prefix"},
+                             bool positionals = true) {
+    auto bad = [](const string &v) { return v.find_first_of(" \t\n\r\f\v") != string::npos; };
+    auto fail = [](const string &v, const char *name) {
+        throw KatError(1, string("Error: Parsing Command Line: the argument ('") + v + "') for option '--" + name + "' is invalid");
+    };
+    for (const char *name : options) {
+        const auto it = p.val.find(name);
+        if (it != p.val.end() && bad(it->second)) fail(it->second, name);
+    }
+    for (size_t i = 0; positionals && i < p.positional.size(); i++)
+        if (bad(p.positional[i])) fail(p.positional[i], i == 0 ? first : rest);
+}
 inline uint64_t to_u64(const string &s, const char *what) {
     try {
         size_t pos = 0;

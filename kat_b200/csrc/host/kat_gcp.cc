@@ -9,6 +9,7 @@ int gcp_main(int argc, char **argv) {
                                    {0, "5ptrim", true}, {'N', "non_canonical", false}, {'m', "mer_len", true}, {'H', "hash_size", true},
                                    {'d', "dump_hash", false}, {'p', "output_type", true}, {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
+    check_path_words(a, "inputs", "inputs");
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat gcp [options] (<input>)+\n\nCompares GC content and K-mer coverage from the input.\n\n"
                 "Options: -o prefix (kat-gcp) -t threads -x cvg_scale (1.0) -y cvg_bins (1000) --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -v --help\n" << endl;

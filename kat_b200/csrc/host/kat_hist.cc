@@ -10,6 +10,7 @@ int hist_main(int argc, char **argv) {
                                    {'H', "hash_size", true}, {'d', "dump_hash", false}, {'p', "output_type", true},
                                    {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
+    check_path_words(a, "inputs", "inputs");
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat hist [options] (<input>)+\n\nCreate an histogram of k-mer occurrences from the input.\n\n"
                 "Options: -o prefix (kat.hist) -t threads -l low (1) -h high (10000) -i inc (1) --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -v --help\n" << endl;

@@ -67,6 +67,7 @@ int sect_main(int argc, char **argv) {
                                    {'E', "extract_nr", false}, {'F', "extract_r", false}, {'M', "min_repeat", true}, {'G', "max_repeat", true},
                                    {'d', "dump_hash", false}, {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
+    check_path_words(a, "seq_file", "counts_files");
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat sect [options] <sequence_file> (<input>)+\n\nEstimates coverage levels across sequences in the provided input sequence file.\n\n"
                 "Options: -o prefix (kat-sect) -t threads --5ptrim list -N -m mer_len (27) -H hash_size (1e8) -n -g -E -F -M min_repeat (2) -G max_repeat (0) -d -v --help\n" << endl;

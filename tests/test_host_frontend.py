@@ -277,7 +277,12 @@ def test_usage_errors_end_like_the_reference(tmp_path):
                          (["comp", "-m", "0", "-o", "x/c", fa, fb], "Invalid matrix size 27x0"), (["gcp", "-m5", "-H", "1", "-o", "x/g", fa], "Invalid matrix size 0x10"),
                          (["gcp", "-m5", "-y", "65536", "-o", "x/g", fa], "for option '--cvg_bins' is invalid"),
                          (["sect", "-m5", "-G", "5000000000", "-o", "x/s", fa, fb], "for option '--max_repeat' is invalid"),
-                         (["hist", "-m5", "-t", "70000", "-o", "x/h", fa], "for option '--threads' is invalid")):
+                         (["hist", "-m5", "-t", "70000", "-o", "x/h", fa], "for option '--threads' is invalid"),
+                         # path-typed options end at the first blank for boost: a file name with a blank is a command-line error
+                         (["hist", "-m5", "-o", "x/h", fa, "we ird.fa"], "('we ird.fa') for option '--inputs' is invalid"),
+                         (["sect", "-m5", "-o", "x/s", "we ird.fa", fa], "('we ird.fa') for option '--seq_file' is invalid"),
+                         (["cold", "-m5", "-o", "x/c", fa, "we ird.fa"], "('we ird.fa') for option '--reads_files' is invalid"),
+                         (["comp", "-m5", "-o", "x y/c", fa, fb], "('x y/c') for option '--output_prefix' is invalid")):
         got = []
         for exe, env in ((ref, no_preload), (T.KAT, os.environ)):
             for attempt in range(5):  # (the reference may abort on the uninitialised terminal width it reads)
