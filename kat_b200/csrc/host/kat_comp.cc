@@ -49,7 +49,6 @@ int comp_main(int argc, char **argv) {
                                    {'d', "dump_hashes", false}, {'g', "disable_hash_grow", false}, {'n', "density_plot", false},
                                    {'p', "output_type", true}, {'h', "output_hists", false}, {'v', "verbose", false}, {0, "gpus", true}, {0, "help", false}};
     const Parsed a = parse_args(argc, argv, specs);
-    check_path_words(a, "", "", {"output_prefix"}, false); // (comp's inputs are strings: blanks separate the files of a group)
     if (a.has("help") || argc <= 1) {
         cout << "Usage: kat comp [options] <input_1> <input_2> [<input_3>]\n\nCompares jellyfish K-mer count hashes.\n\n"
                 "Options: -o prefix (kat-comp) -t threads -x d1_scale -y d2_scale -i d1_bins (1001) -j d2_bins (1001) --d1_5ptrim --d2_5ptrim "

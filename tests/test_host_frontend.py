@@ -282,7 +282,8 @@ def test_usage_errors_end_like_the_reference(tmp_path):
                          (["hist", "-m5", "-o", "x/h", fa, "we ird.fa"], "('we ird.fa') for option '--inputs' is invalid"),
                          (["sect", "-m5", "-o", "x/s", "we ird.fa", fa], "('we ird.fa') for option '--seq_file' is invalid"),
                          (["cold", "-m5", "-o", "x/c", fa, "we ird.fa"], "('we ird.fa') for option '--reads_files' is invalid"),
-                         (["comp", "-m5", "-o", "x y/c", fa, fb], "('x y/c') for option '--output_prefix' is invalid")):
+                         (["gcp", "-m5", "-o", "x y/g", fa], "('x y/g') for option '--output_prefix' is invalid"),
+                         (["comp", "-m5", "-o", "x y/c", fa, fb], "")):  # (comp takes its prefix, like its inputs, as a string)
         got = []
         for exe, env in ((ref, no_preload), (T.KAT, os.environ)):
             for attempt in range(5):  # (the reference may abort on the uninitialised terminal width it reads)
