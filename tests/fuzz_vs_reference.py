@@ -160,6 +160,8 @@ def _command(kind, rng, d):
             data = records(rng, int(rng.integers(1, 8)), fq, max_len=120, alphabet=b"ACGTN", p=(.24, .24, .24, .24, .04))
             if rng.random() < 0.15:  # more than one 4 KiB buffer
                 data += records(rng, int(rng.integers(20, 60)), fq, max_len=400, alphabet=b"ACGTN", p=(.24, .24, .24, .24, .04))
+            if fq and not one_stream and data.endswith(b"\n\n+\n\n"):  # an empty last record leaves seq_len behind: single-stream groups only
+                data += b"@z\nACGT\n+\nIIII\n"
             x = rng.random()
             if x < 0.08:
                 data = b""
