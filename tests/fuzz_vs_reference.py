@@ -277,6 +277,10 @@ def _command(kind, rng, d):
     raise ValueError(kind)
 
 
+class ReferenceHung(RuntimeError):
+    """The reference binary did not end (it can spin in its own table growth on degenerate inputs): not a case."""
+
+
 def _run(exe, cmds, cwd, env):
     os.makedirs(os.path.join(cwd, "out"), exist_ok=True)
     codes = []
@@ -286,7 +290,12 @@ def _run(exe, cmds, cwd, env):
             codes.append(r.returncode)
             continue
         for attempt in range(6):
-            r = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, env=env, timeout=300)
+            try:
+                r = subprocess.run([exe] + args, cwd=cwd, capture_output=True, text=True, env=env, timeout=150)
+            except subprocess.TimeoutExpired:
+                if exe == REF:
+                    raise ReferenceHung(" ".join(args))
+                raise
             # the reference reads an uninitialised terminal width when stdout is no tty and may abort on it; with -t > 1 its
             # worker threads push_back into one vector unlocked (src/histogram.cc:198) and it may crash (backtrace, exit code 1)
             if r.returncode in (0, 4, 5) or exe != REF:
