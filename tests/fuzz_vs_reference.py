@@ -12,7 +12,7 @@ line and a timestamp.  The reference needs no GPU; the front-end runs against wh
 As a module: `case(kind, seed, tmp_path)` asserts one case (used by tests/test_host_frontend.py with a few seeds).
 As a script: `python tests/fuzz_vs_reference.py <kind|all> <first seed> <last seed>` runs a campaign on the CPU double
 (KATFUZZ_GPUS=N: the front-end as a job of N devices; KATFUZZ_RAW=1: the double takes raw FASTQ blocks, so the
-front-end's device-parsing route runs, in 4 KiB blocks)."""
+front-end's device-parsing route runs, in 4 KiB blocks; KATFUZZ_REAL=1 on a GPU box: no double, the real library)."""
 import gzip
 import os
 import shutil
@@ -371,9 +371,12 @@ def case(kind, seed, tmp_path, our_env=None, gpus=1):
 if __name__ == "__main__":
     kinds = KINDS if sys.argv[1] == "all" else (sys.argv[1],)
     lo, hi = int(sys.argv[2]), int(sys.argv[3])
-    double = os.path.join(ROOT, "tests", "hostcheck", "_build", "libkatgpu_double.so")
-    assert subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostcheck")], capture_output=True).returncode == 0
-    env = dict(os.environ, LD_PRELOAD=double, KAT_GPU_PARSE="1")
+    if os.environ.get("KATFUZZ_REAL"):  # on a GPU box: the real libkatgpu answers
+        env = dict(os.environ)
+    else:
+        double = os.path.join(ROOT, "tests", "hostcheck", "_build", "libkatgpu_double.so")
+        assert subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "hostcheck")], capture_output=True).returncode == 0
+        env = dict(os.environ, LD_PRELOAD=double, KAT_GPU_PARSE="1")
     gpus = int(os.environ.get("KATFUZZ_GPUS", "1"))
     if os.environ.get("KATFUZZ_RAW"):  # the double takes raw FASTQ blocks like the real library: the front-end's raw route, in 4 KiB blocks
         env.update(KATGPU_DOUBLE_FASTQ="1", KAT_RAW_BLOCK="4096")
